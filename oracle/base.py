@@ -1,0 +1,228 @@
+"""Oracle: model assembly (encoder loop, pooling, multi-head decoder).
+
+Test infrastructure only.  Restates ``Base`` (hydragnn/models/Base.py:36-982),
+``EGCLStack`` (hydragnn/models/EGCLStack.py:22-152), ``PAINNStack``
+(hydragnn/models/PAINNStack.py:27-191) and the ``create_model`` dispatch
+(hydragnn/models/create.py:112-584) for the EGNN and PAINN stacks without GPS.
+Parameter names follow the reference (PyG ``Sequential`` names its children
+``module_<i>`` [3P-memory B.5]) so state dicts interchange with the engine.
+"""
+import torch
+from torch import nn
+
+from .egnn import EGCL
+from .geometry import edge_vectors_and_lengths, graph_pool
+from .painn import PainnMessage, PainnUpdate
+
+
+def activation(name):
+    """hydragnn/utils/model/model.py:30-46."""
+    table = {
+        "relu": nn.ReLU, "selu": nn.SELU, "prelu": nn.PReLU, "elu": nn.ELU,
+        "lrelu_01": lambda: nn.LeakyReLU(0.1), "lrelu_025": lambda: nn.LeakyReLU(0.25),
+        "lrelu_05": lambda: nn.LeakyReLU(0.5), "sigmoid": nn.Sigmoid,
+    }
+    return table[name]() if name in table else None
+
+
+def loss_function(name):
+    """hydragnn/utils/model/model.py:49-62."""
+    F = torch.nn.functional
+    if name == "mse":
+        return F.mse_loss
+    if name == "mae":
+        return F.l1_loss
+    if name == "rmse":
+        return lambda a, b: torch.sqrt(F.mse_loss(a, b))
+    raise ValueError("oracle supports mse / mae / rmse, got " + str(name))
+
+
+def normalize_heads(output_heads):
+    """``update_multibranch_heads`` (hydragnn/utils/model/model.py:314-349)."""
+    out = {}
+    for key, val in output_heads.items():
+        out[key] = val if isinstance(val, list) else [{"type": "branch-0", "architecture": val}]
+    return out
+
+
+class _Conv(nn.Module):
+    """Stand-in for the PyG ``Sequential`` built by ``get_conv``; holds children under
+    the names PyG would give them."""
+
+    def __init__(self, kind, mods):
+        super().__init__()
+        self.kind = kind
+        for i, m in enumerate(mods):
+            if m is not None:
+                self.add_module("module_%d" % i, m)
+
+
+class OracleModel(nn.Module):
+    def __init__(self, mpnn_type, input_dim, hidden_dim, output_dim, output_type, output_heads,
+                 activation_function="relu", loss_function_type="mse", task_weights=None,
+                 num_conv_layers=2, num_nodes=None, edge_dim=None, num_radial=None, radius=None,
+                 equivariance=False, graph_pooling="mean", **_unused):
+        super().__init__()
+        if mpnn_type not in ("EGNN", "PAINN"):
+            raise ValueError("Unknown mpnn_type: {0}".format(mpnn_type))
+        self.mpnn_type, self.input_dim, self.hidden_dim = mpnn_type, input_dim, hidden_dim
+        self.head_dims, self.head_type = list(output_dim), list(output_type)
+        self.num_heads = len(self.head_dims)
+        self.config_heads = normalize_heads(output_heads)
+        self.activation_function = activation(activation_function)
+        self.loss_function = loss_function(loss_function_type)
+        w = list(task_weights if task_weights is not None else [1.0] * self.num_heads)
+        if len(w) != self.num_heads:
+            raise ValueError("Inconsistent number of loss weights and tasks")
+        tot = sum(abs(t) for t in w)
+        self.loss_weights = [t / tot for t in w]                           # Base.py:121-132
+        mode = graph_pooling.lower()
+        self.graph_pooling = "add" if mode == "sum" else mode
+        self.num_conv_layers, self.num_radial, self.radius = num_conv_layers, num_radial, radius
+        self.equivariance = bool(equivariance)
+        if mpnn_type == "EGNN":
+            self.edge_dim = 0 if edge_dim is None else edge_dim            # EGCLStack.py:33-35
+        else:
+            self.edge_dim = edge_dim                                        # PAINNStack.py:43
+        self.use_edge_attr = self.edge_dim is not None and self.edge_dim > 0   # Base.py:135-141
+
+        # --- conv stack: first layer at input_dim (Q4), last layer flagged (EGCLStack.py:45-70)
+        self.graph_convs = nn.ModuleList()
+        for i in range(num_conv_layers):
+            last = i == num_conv_layers - 1
+            self.graph_convs.append(self._get_conv(input_dim if i == 0 else hidden_dim, hidden_dim, last))
+
+        # --- decoder (Base.py:590-691), single or multi branch
+        act = self.activation_function
+        self.heads_NN = nn.ModuleList()          # registered before graph_shared, as in Base.__init__:83
+        self.graph_shared = nn.ModuleDict()
+        self.num_branches = 1
+        if "graph" in self.config_heads:
+            self.num_branches = len(self.config_heads["graph"])
+            for br in self.config_heads["graph"]:
+                a = br["architecture"]
+                layers = [nn.Linear(hidden_dim, a["dim_sharedlayers"]), act]
+                for _ in range(a["num_sharedlayers"] - 1):
+                    layers += [nn.Linear(a["dim_sharedlayers"], a["dim_sharedlayers"]), act]
+                self.graph_shared[br["type"]] = nn.Sequential(*layers)
+        for ih in range(self.num_heads):
+            head = nn.ModuleDict()
+            if self.head_type[ih] == "graph":
+                for br in self.config_heads["graph"]:
+                    a = br["architecture"]
+                    dims = [a["dim_sharedlayers"]] + list(a["dim_headlayers"][: a["num_headlayers"]])
+                    layers = []
+                    for d0, d1 in zip(dims[:-1], dims[1:]):
+                        layers += [nn.Linear(d0, d1), act]
+                    layers.append(nn.Linear(dims[-1], self.head_dims[ih]))
+                    head[br["type"]] = nn.Sequential(*layers)
+            elif self.head_type[ih] == "node":
+                for br in self.config_heads["node"]:
+                    a = br["architecture"]
+                    if a["type"] != "mlp":
+                        raise ValueError("oracle supports node heads of type 'mlp' only")
+                    head[br["type"]] = _MLPNode(hidden_dim, self.head_dims[ih], a["dim_headlayers"], act)
+            else:
+                raise ValueError("Unknown head type" + str(self.head_type[ih]))
+            self.heads_NN.append(head)
+
+    # EGCLStack.get_conv :72-109 / PAINNStack.get_conv :76-147
+    def _get_conv(self, fin, fout, last):
+        if self.mpnn_type == "EGNN":
+            return _Conv("egnn", [EGCL(fin, fout, self.hidden_dim, edge_attr_dim=self.edge_dim,
+                                       equivariant=self.equivariance and not last)])
+        msg = PainnMessage(fin, self.num_radial, self.radius, edge_dim=self.edge_dim)
+        upd = PainnUpdate(fin, last_layer=last)
+        s_out = nn.Sequential(nn.Linear(fin, fout), nn.Tanh(), nn.Linear(fout, fout))
+        v_out = None if last else nn.Linear(fin, fout)
+        return _Conv("painn", [msg, upd, s_out, v_out])
+
+    def forward(self, data):
+        x, pos, ei = data.x, data.pos, data.edge_index.to(torch.long)
+        shifts = getattr(data, "edge_shifts", None)
+        if shifts is None:                                                   # Base.py:466-469
+            shifts = torch.zeros(ei.shape[1], 3, dtype=pos.dtype, device=pos.device)
+        eattr = data.edge_attr if self.use_edge_attr else None
+        if self.mpnn_type == "EGNN":
+            equiv = pos
+            for conv in self.graph_convs:
+                x, equiv = conv.module_0(x, equiv, ei, eattr, shifts)
+                x = self.activation_function(x)                              # Base.py:726
+        else:
+            diff, dist = edge_vectors_and_lengths(pos, ei, shifts, normalize=True)   # PAINNStack.py:157-159
+            edge = ei.t()
+            v = torch.zeros(x.shape[0], 3, x.shape[1], dtype=x.dtype, device=x.device)
+            for conv in self.graph_convs:
+                x, v = conv.module_0(x, v, edge, diff, dist, eattr)
+                x, v = conv.module_1(x, v)
+                x = conv.module_2(x)
+                if v is not None:
+                    v = conv.module_3(v)
+                x = self.activation_function(x)
+        batch = getattr(data, "batch", None)
+        if batch is None:
+            batch = torch.zeros(x.shape[0], dtype=torch.long, device=x.device)
+        G = int(batch.max()) + 1
+        xg = graph_pool(x, batch, G, self.graph_pooling)                     # Base.py:733-738
+        ds = getattr(data, "dataset_name", None)
+        outs = []
+        for ih, (hd, head, kind) in enumerate(zip(self.head_dims, self.heads_NN, self.head_type)):
+            if self.num_branches == 1:
+                if kind == "graph":
+                    outs.append(head["branch-0"](self.graph_shared["branch-0"](xg))[:, :hd])
+                else:
+                    outs.append(head["branch-0"](x)[:, :hd])
+                continue
+            # multi-branch masking (Base.py:770-780, 816-840)
+            ids = ds[:, 0]
+            if kind == "graph":
+                out = x.new_zeros(G, hd)
+                for b in ids.unique():
+                    m = ids == b
+                    key = "branch-%d" % int(b)
+                    out[m] = head[key](self.graph_shared[key](xg[m]))[:, :hd]
+            else:
+                out = x.new_zeros(x.shape[0], hd)
+                for b in ids.unique():
+                    m = (ids == b)[batch]
+                    out[m] = head["branch-%d" % int(b)](x[m])[:, :hd]
+            outs.append(out)
+        return outs
+
+    def loss(self, pred, value, head_index):
+        """``loss_hpweighted`` (Base.py:879-906)."""
+        tot, tasks = 0, []
+        for ih in range(self.num_heads):
+            tgt = value[head_index[ih]].reshape(pred[ih].shape)
+            li = self.loss_function(pred[ih], tgt)
+            tot = tot + li * self.loss_weights[ih]
+            tasks.append(li)
+        return tot, tasks
+
+
+class _MLPNode(nn.Module):
+    """``MLPNode`` with ``node_type == 'mlp'`` (Base.py:912-964)."""
+
+    def __init__(self, fin, fout, hidden, act):
+        super().__init__()
+        dims = [fin] + list(hidden)
+        layers = []
+        for d0, d1 in zip(dims[:-1], dims[1:]):
+            layers += [nn.Linear(d0, d1), act]
+        layers.append(nn.Linear(dims[-1], fout))
+        self.mlp = nn.ModuleList([nn.Sequential(*layers)])
+
+    def forward(self, x):
+        return self.mlp[0](x)
+
+
+def create_model(**kw):
+    """Mirror of ``create_model`` (hydragnn/models/create.py:112-766): seeds the RNG
+    (:164) and wraps the stack for MLIP training when asked (:586-756)."""
+    from .mlip import MLIPWrapper
+    torch.manual_seed(0)
+    model = OracleModel(**kw)
+    if kw.get("enable_interatomic_potential", False):
+        model = MLIPWrapper(model, kw.get("energy_weight", 0.0), kw.get("energy_peratom_weight", 0.0),
+                            kw.get("force_weight", 0.0))
+    return model

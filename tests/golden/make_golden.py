@@ -1,0 +1,278 @@
+"""Generate golden vectors by running the REFERENCE's own code (run in the build
+container only; /root/reference does not exist on the GPU box).
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.pt
+
+What is real and what is stubbed
+--------------------------------
+Loaded verbatim from /root/reference (never copied into this repo):
+  hydragnn/utils/model/operations.py, hydragnn/models/Base.py,
+  hydragnn/models/EGCLStack.py, hydragnn/models/PAINNStack.py, plus (AST-extracted,
+  because their modules import absent packages at top level)
+  ``activation_function_selection`` / ``loss_function_selection`` /
+  ``unsorted_segment_mean`` from hydragnn/utils/model/model.py,
+  ``EnhancedModelWrapper.energy_force_loss`` from hydragnn/models/create.py and
+  ``RadiusGraphPBC._limit_neighbors`` / ``_remove_true_self_loops`` from
+  hydragnn/preprocess/graph_samples_checks_and_updates.py.
+Stubbed third-party packages that are absent from this image (semantics restated,
+[3P-memory] in SURVEY.md Appendix B):
+  torch_geometric.nn.Sequential (argument-string glue only), BatchNorm,
+  global_{mean,add,max}_pool (index_add / amax), torch_scatter.scatter_add,
+  hydragnn.utils.distributed.get_device (cpu), the tracer (no-op), GPSConv (unused).
+So the E_GCL / PainnMessage / PainnUpdate / Base.forward / MLIP-loss arithmetic in the
+golden files is the reference's own; only the glue named above is ours.
+"""
+import ast
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+
+def _mod(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    if "." not in name or True:
+        m.__path__ = []
+    sys.modules[name] = m
+    return m
+
+
+def _extract(path, names, glb):
+    """exec selected top-level (or nested) function/class definitions of a reference file."""
+    tree = ast.parse(open(path).read())
+    found = {}
+    for node in ast.walk(tree):
+        if isinstance(node, (ast.FunctionDef, ast.ClassDef)) and node.name in names and node.name not in found:
+            found[node.name] = node
+    for n in names:
+        code = compile(ast.Module(body=[found[n]], type_ignores=[]), path, "exec")
+        exec(code, glb)
+    return glb
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[name] = m
+    spec.loader.exec_module(m)
+    return m
+
+
+class StubSequential(torch.nn.Module):
+    """[3P-memory B.5] torch_geometric.nn.Sequential: children are named module_<i>."""
+
+    def __init__(self, input_args, modules):
+        super().__init__()
+        self.in_names = [a.strip() for a in input_args.split(",") if a.strip()]
+        self.steps = []
+        for i, item in enumerate(modules):
+            fn, desc = item
+            lhs, rhs = desc.split("->")
+            if isinstance(fn, torch.nn.Module):
+                self.add_module("module_%d" % i, fn)
+            self.steps.append((fn, [a.strip() for a in lhs.split(",") if a.strip()],
+                               [a.strip() for a in rhs.split(",") if a.strip()]))
+
+    def forward(self, *args, **kwargs):
+        env = dict(zip(self.in_names, args))
+        env.update(kwargs)
+        out = None
+        for fn, ins, outs in self.steps:
+            out = fn(*[env[k] for k in ins])
+            if len(outs) == 1:
+                env[outs[0]] = out
+            else:
+                for k, v in zip(outs, out):
+                    env[k] = v
+        return out
+
+
+def _pool(kind):
+    def f(x, batch, size=None):
+        G = int(batch.max()) + 1 if size is None else size
+        if kind == "add":
+            return x.new_zeros(G, x.shape[1]).index_add_(0, batch, x)
+        if kind == "mean":
+            s = x.new_zeros(G, x.shape[1]).index_add_(0, batch, x)
+            c = torch.bincount(batch, minlength=G).clamp(min=1).to(x.dtype)
+            return s / c[:, None]
+        out = x.new_full((G, x.shape[1]), float("-inf"))
+        return out.scatter_reduce(0, batch[:, None].expand_as(x), x, reduce="amax")
+    return f
+
+
+def install_stubs():
+    def scatter_add(src, index, dim=0):
+        shape = list(src.shape)
+        shape[dim] = int(index.max()) + 1
+        return src.new_zeros(shape).index_add_(dim, index, src)
+
+    _mod("torch_scatter", scatter_add=scatter_add, scatter=None)
+    _mod("torch_geometric")
+    _mod("torch_geometric.nn", Sequential=StubSequential, BatchNorm=torch.nn.BatchNorm1d,
+         global_add_pool=_pool("add"), global_mean_pool=_pool("mean"), global_max_pool=_pool("max"))
+    _mod("torch_geometric.typing", OptTensor=object)
+    _mod("hydragnn")
+    _mod("hydragnn.models")
+    _mod("hydragnn.utils")
+    _mod("hydragnn.utils.distributed", get_device=lambda *a, **k: torch.device("cpu"))
+    _mod("hydragnn.utils.print")
+    _mod("hydragnn.utils.print.print_utils", print_master=lambda *a, **k: None)
+    _mod("hydragnn.utils.profiling_and_tracing")
+    _mod("hydragnn.utils.profiling_and_tracing.tracer", start=lambda *a, **k: None, stop=lambda *a, **k: None)
+    _mod("hydragnn.globalAtt")
+    _mod("hydragnn.globalAtt.gps", GPSConv=None)
+    glb = {"torch": torch}
+    _extract(REF + "/hydragnn/utils/model/model.py",
+             ["activation_function_selection", "loss_function_selection", "unsorted_segment_mean"], glb)
+    _mod("hydragnn.utils.model", **{k: glb[k] for k in
+                                    ("activation_function_selection", "loss_function_selection", "unsorted_segment_mean")})
+    _load("hydragnn.utils.model.operations", REF + "/hydragnn/utils/model/operations.py")
+    _load("hydragnn.models.Base", REF + "/hydragnn/models/Base.py")
+    egcl = _load("hydragnn.models.EGCLStack", REF + "/hydragnn/models/EGCLStack.py")
+    painn = _load("hydragnn.models.PAINNStack", REF + "/hydragnn/models/PAINNStack.py")
+    return egcl, painn
+
+
+def toy_batch(gen, sizes, box, input_dim=1, dtype=torch.float32):
+    """A few random molecules + an asymmetric hand-made edge list (every atom keeps its
+    3 nearest in-graph neighbours as sources)."""
+    from hydragnn_b200.data import Batch, Data
+    samples = []
+    for n in sizes:
+        pos = torch.rand(n, 3, generator=gen, dtype=dtype) * box
+        d = torch.cdist(pos, pos) + torch.eye(n, dtype=dtype) * 1e9
+        k = min(3, n - 1)
+        nbr = d.topk(k, largest=False).indices                        # [n, k]
+        tgt = torch.arange(n)[:, None].expand(n, k)
+        ei = torch.stack([nbr.reshape(-1), tgt.reshape(-1)]).long()
+        x = torch.randint(1, 9, (n, input_dim), generator=gen).to(dtype)
+        samples.append(Data(x=x, pos=pos, edge_index=ei,
+                            edge_shifts=torch.zeros(ei.shape[1], 3, dtype=dtype),
+                            energy=torch.randn(1, generator=gen, dtype=dtype),
+                            forces=torch.randn(n, 3, generator=gen, dtype=dtype),
+                            y=torch.randn(1, 1, generator=gen, dtype=dtype)))
+    return Batch.from_data_list(samples)
+
+
+def t2d(batch):
+    return {k: v for k, v in batch.items() if torch.is_tensor(v)}
+
+
+def main():
+    egcl, painn = install_stubs()
+    gen = torch.Generator().manual_seed(20260921)
+    heads_node = {"node": [{"type": "branch-0", "architecture": {"num_headlayers": 2, "dim_headlayers": [12, 6], "type": "mlp"}}]}
+    heads_graph = {"graph": [{"type": "branch-0", "architecture": {"num_sharedlayers": 2, "dim_sharedlayers": 5,
+                                                                   "num_headlayers": 2, "dim_headlayers": [10, 7]}}]}
+
+    # ---- layer level: E_GCL (plain + equivariant), PainnMessage, PainnUpdate ------------------
+    out = {}
+    b = toy_batch(gen, [5, 7, 4], 4.0, input_dim=6)
+    for eq in (False, True):
+        torch.manual_seed(1)
+        layer = egcl.E_GCL(6, 10, 8, edge_attr_dim=0, equivariant=eq)
+        res = layer(b.x, b.pos, b.edge_index, None, b.edge_shifts)
+        out["egcl_eq%d" % eq] = {"state": layer.state_dict(), "x": b.x, "pos": b.pos, "edge_index": b.edge_index,
+                                 "out": [r.detach() for r in (res if eq else (res,))]}
+    torch.manual_seed(2)
+    msg = painn.PainnMessage(node_size=6, num_radial=5, cutoff=7.0, edge_dim=None)
+    upd = painn.PainnUpdate(node_size=6, last_layer=False)
+    upd_last = painn.PainnUpdate(node_size=6, last_layer=True)
+    ops = sys.modules["hydragnn.utils.model.operations"]
+    diff, dist = ops.get_edge_vectors_and_lengths(b.pos, b.edge_index, b.edge_shifts, normalize=True)
+    v0 = torch.randn(b.x.shape[0], 3, 6, generator=gen)
+    s1, v1 = msg(b.x, v0, b.edge_index.t(), diff, dist)
+    s2, v2 = upd(s1, v1)
+    s3 = upd_last(s1, v1)
+    out["painn_layer"] = {"msg_state": msg.state_dict(), "upd_state": upd.state_dict(), "upd_last_state": upd_last.state_dict(),
+                          "x": b.x, "v": v0, "pos": b.pos, "edge_index": b.edge_index, "diff": diff, "dist": dist,
+                          "sinc": painn.sinc_expansion(dist, 5, 7.0), "fcut": painn.cosine_cutoff(dist, 7.0),
+                          "s1": s1.detach(), "v1": v1.detach(), "s2": s2.detach(), "v2": v2.detach(), "s3": s3.detach()}
+    torch.save(out, HERE + "/layers.pt")
+
+    # ---- full models through the reference's Base.forward -----------------------------------
+    models = {}
+    # (a) EGNN MLIP, node head, the C1/C3 shape in miniature
+    b = toy_batch(gen, [6, 5, 8, 3], 4.0, input_dim=1)
+    torch.manual_seed(0)
+    m = egcl.EGCLStack("inv_node_feat, equiv_node_feat, edge_index, edge_attr, edge_shifts", "", None,
+                       1, 16, [1], 0, "", "", 0, ["node"], heads_node, "relu", "mse", False,
+                       max_neighbours=None, loss_weights=[1.0], freeze_conv=False, initial_bias=None,
+                       num_conv_layers=3, num_nodes=None, graph_pooling="mean")
+    m.eval()
+    inp = t2d(b)
+    b.pos.requires_grad_(True)
+    pred = m(b)
+    # the reference's own loss code, AST-extracted from the nested wrapper class
+    glb = {"torch": torch, "torch_scatter": sys.modules["torch_scatter"]}
+    _extract(REF + "/hydragnn/models/create.py", ["energy_force_loss"], glb)
+    fake = types.SimpleNamespace(num_heads=1, head_type=["node"], model=m, loss_function=m.loss_function,
+                                 energy_weight=1.0, energy_peratom_weight=1.0, force_weight=1.0)
+    tot, tasks = glb["energy_force_loss"](fake, pred, b, create_graph=True)
+    forces = -torch.autograd.grad(
+        sys.modules["torch_scatter"].scatter_add(pred[0], b.batch, dim=0).sum(), b.pos, retain_graph=True)[0]
+    grads = torch.autograd.grad(tot, list(m.parameters()), allow_unused=True)
+    models["egnn_mlip"] = {"state": m.state_dict(), "inputs": inp, "pred": [p.detach() for p in pred],
+                           "loss": tot.detach(), "tasks": [t.detach() for t in tasks], "forces": forces.detach(),
+                           "grads": {n: (g.detach() if g is not None else None)
+                                     for (n, _), g in zip(m.named_parameters(), grads)}}
+
+    # (b) equivariant EGNN, graph + node heads
+    b = toy_batch(gen, [6, 5, 8, 3], 4.0, input_dim=2)
+    heads_both = dict(heads_graph, **heads_node)
+    torch.manual_seed(0)
+    m = egcl.EGCLStack("inv_node_feat, equiv_node_feat, edge_index, edge_attr, edge_shifts", "", None,
+                       2, 12, [1, 3], 0, "", "", 0, ["graph", "node"], heads_both, "lrelu_01", "mse", True,
+                       max_neighbours=None, loss_weights=[1.0, 2.0], freeze_conv=False, initial_bias=None,
+                       num_conv_layers=3, num_nodes=None, graph_pooling="add")
+    m.eval()
+    pred = m(b)
+    models["egnn_equiv_multihead"] = {"state": m.state_dict(), "inputs": t2d(b), "pred": [p.detach() for p in pred]}
+
+    # (c) PaiNN, graph head, the C2 shape in miniature (input_dim = 1 -> first layer at width 1, quirk Q4)
+    for pool in ("mean", "max"):
+        b = toy_batch(gen, [9, 9, 7, 9], 5.0, input_dim=1)
+        torch.manual_seed(0)
+        m = painn.PAINNStack("inv_node_feat, equiv_node_feat, edge_index, diff, dist",
+                             "inv_node_feat, equiv_node_feat, edge_index, diff, dist", None, 5, 7.0,
+                             1, 16, [1], 0, "", "", 0, ["graph"], heads_graph, "relu", "mse", False,
+                             loss_weights=[1.0], freeze_conv=False, num_conv_layers=2, num_nodes=None,
+                             graph_pooling=pool)
+        m.eval()
+        pred = m(b)
+        loss, _ = m.loss(pred, b.y, [torch.arange(b.y.shape[0])])
+        grads = torch.autograd.grad(loss, list(m.parameters()), allow_unused=True)
+        models["painn_graph_" + pool] = {"state": m.state_dict(), "inputs": t2d(b), "pred": [p.detach() for p in pred],
+                                         "loss": loss.detach(),
+                                         "grads": {n: (g.detach() if g is not None else None)
+                                                   for (n, _), g in zip(m.named_parameters(), grads)}}
+    torch.save(models, HERE + "/models.pt")
+
+    # ---- RadiusGraphPBC numpy post-processing ---------------------------------------------
+    glb = {"np": np}
+    _extract(REF + "/hydragnn/preprocess/graph_samples_checks_and_updates.py",
+             ["_limit_neighbors", "_remove_true_self_loops"], glb)
+    rng = np.random.default_rng(7)
+    E = 200
+    src = rng.integers(0, 12, E)
+    dst = rng.integers(0, 12, E)
+    length = rng.random(E) * 5
+    S = rng.integers(-1, 2, (E, 3))
+    a = glb["_remove_true_self_loops"](None, src, dst, length, S)
+    lim = glb["_limit_neighbors"](None, *a, 6)
+    torch.save({"in": [torch.from_numpy(np.asarray(t)) for t in (src, dst, length, S)],
+                "k": 6, "out": [torch.from_numpy(np.asarray(t)) for t in lim]}, HERE + "/pbc_limit.pt")
+    print("golden vectors written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,136 @@
+"""CPU: the oracle reproduces the golden vectors produced by the reference's own code
+(tests/golden/make_golden.py).  Tolerances: fp32 arithmetic in a different association
+order -> 1e-5 relative; integer outputs bit-exact."""
+import types
+
+import numpy as np
+import torch
+
+import oracle
+from oracle.base import OracleModel
+from oracle.mlip import MLIPWrapper
+
+TOL = dict(rtol=1e-5, atol=1e-6)
+
+
+def _data(d):
+    ns = types.SimpleNamespace(**{k: v.clone() for k, v in d.items()})
+    return ns
+
+
+def test_egcl_layer(golden_dir):
+    g = torch.load(golden_dir + "/layers.pt")
+    for eq in (0, 1):
+        c = g["egcl_eq%d" % eq]
+        layer = oracle.egnn.EGCL(6, 10, 8, equivariant=bool(eq))
+        layer.load_state_dict(c["state"])
+        x, pos = layer(c["x"], c["pos"], c["edge_index"], None, None)
+        torch.testing.assert_close(x, c["out"][0], **TOL)
+        if eq:
+            torch.testing.assert_close(pos, c["out"][1], **TOL)
+
+
+def test_painn_layer(golden_dir):
+    c = torch.load(golden_dir + "/layers.pt")["painn_layer"]
+    diff, dist = oracle.geometry.edge_vectors_and_lengths(c["pos"], c["edge_index"], None, normalize=True)
+    torch.testing.assert_close(diff, c["diff"], **TOL)
+    torch.testing.assert_close(dist, c["dist"], **TOL)
+    torch.testing.assert_close(oracle.geometry.sinc_expansion(dist, 5, 7.0), c["sinc"], **TOL)
+    torch.testing.assert_close(oracle.geometry.cosine_cutoff(dist, 7.0), c["fcut"], **TOL)
+    msg = oracle.painn.PainnMessage(6, 5, 7.0)
+    msg.load_state_dict(c["msg_state"])
+    upd = oracle.painn.PainnUpdate(6, False)
+    upd.load_state_dict(c["upd_state"])
+    upl = oracle.painn.PainnUpdate(6, True)
+    upl.load_state_dict(c["upd_last_state"])
+    s1, v1 = msg(c["x"], c["v"], c["edge_index"].t(), diff, dist)
+    torch.testing.assert_close(s1, c["s1"], **TOL)
+    torch.testing.assert_close(v1, c["v1"], **TOL)
+    s2, v2 = upd(s1, v1)
+    torch.testing.assert_close(s2, c["s2"], **TOL)
+    torch.testing.assert_close(v2, c["v2"], **TOL)
+    s3, none = upl(s1, v1)
+    assert none is None
+    torch.testing.assert_close(s3, c["s3"], **TOL)
+
+
+HEADS_NODE = {"node": [{"type": "branch-0", "architecture": {"num_headlayers": 2, "dim_headlayers": [12, 6], "type": "mlp"}}]}
+HEADS_GRAPH = {"graph": [{"type": "branch-0", "architecture": {"num_sharedlayers": 2, "dim_sharedlayers": 5,
+                                                               "num_headlayers": 2, "dim_headlayers": [10, 7]}}]}
+
+MODEL_KW = {
+    "egnn_mlip": dict(mpnn_type="EGNN", input_dim=1, hidden_dim=16, output_dim=[1], output_type=["node"],
+                      output_heads=HEADS_NODE, activation_function="relu", num_conv_layers=3, task_weights=[1.0]),
+    "egnn_equiv_multihead": dict(mpnn_type="EGNN", input_dim=2, hidden_dim=12, output_dim=[1, 3],
+                                 output_type=["graph", "node"], output_heads=dict(HEADS_GRAPH, **HEADS_NODE),
+                                 activation_function="lrelu_01", num_conv_layers=3, task_weights=[1.0, 2.0],
+                                 equivariance=True, graph_pooling="add"),
+    "painn_graph_mean": dict(mpnn_type="PAINN", input_dim=1, hidden_dim=16, output_dim=[1], output_type=["graph"],
+                             output_heads=HEADS_GRAPH, activation_function="relu", num_conv_layers=2,
+                             task_weights=[1.0], num_radial=5, radius=7.0, graph_pooling="mean"),
+}
+MODEL_KW["painn_graph_max"] = dict(MODEL_KW["painn_graph_mean"], graph_pooling="max")
+
+
+def test_state_dict_keys_match_reference(golden_dir):
+    g = torch.load(golden_dir + "/models.pt")
+    for name, kw in MODEL_KW.items():
+        m = OracleModel(**kw)
+        assert list(m.state_dict().keys()) == list(g[name]["state"].keys()), name
+        m.load_state_dict(g[name]["state"], strict=True)
+
+
+def test_model_forward(golden_dir):
+    g = torch.load(golden_dir + "/models.pt")
+    for name, kw in MODEL_KW.items():
+        m = OracleModel(**kw)
+        m.load_state_dict(g[name]["state"])
+        pred = m(_data(g[name]["inputs"]))
+        for p, q in zip(pred, g[name]["pred"]):
+            torch.testing.assert_close(p, q, **TOL)
+
+
+def test_painn_loss_and_grads(golden_dir):
+    g = torch.load(golden_dir + "/models.pt")
+    for name in ("painn_graph_mean", "painn_graph_max"):
+        c = g[name]
+        m = OracleModel(**MODEL_KW[name])
+        m.load_state_dict(c["state"])
+        d = _data(c["inputs"])
+        loss, _ = m.loss(m(d), d.y, [torch.arange(d.y.shape[0])])
+        torch.testing.assert_close(loss, c["loss"], **TOL)
+        grads = torch.autograd.grad(loss, list(m.parameters()), allow_unused=True)
+        for (n, _), gr in zip(m.named_parameters(), grads):
+            ref = c["grads"][n]
+            assert (gr is None) == (ref is None), n
+            if gr is not None:
+                torch.testing.assert_close(gr, ref, rtol=1e-4, atol=1e-6)
+
+
+def test_mlip_loss_forces_and_double_backward(golden_dir):
+    c = torch.load(golden_dir + "/models.pt")["egnn_mlip"]
+    m = MLIPWrapper(OracleModel(**MODEL_KW["egnn_mlip"]), 1.0, 1.0, 1.0)
+    m.model.load_state_dict(c["state"])
+    d = _data(c["inputs"])
+    d.pos.requires_grad_(True)
+    pred = m(d)
+    torch.testing.assert_close(pred[0], c["pred"][0], **TOL)
+    tot, tasks = m.energy_force_loss(pred, d)
+    torch.testing.assert_close(tot, c["loss"], **TOL)
+    for a, b in zip(tasks, c["tasks"]):
+        torch.testing.assert_close(a, b, **TOL)
+    grads = torch.autograd.grad(tot, list(m.model.parameters()), allow_unused=True)
+    for (n, _), gr in zip(m.model.named_parameters(), grads):
+        ref = c["grads"][n]
+        assert (gr is None) == (ref is None), n
+        if gr is not None:
+            torch.testing.assert_close(gr, ref, rtol=1e-4, atol=1e-6)
+
+
+def test_pbc_limit_neighbors(golden_dir):
+    c = torch.load(golden_dir + "/pbc_limit.pt")
+    src, dst, length, S = [t.numpy() for t in c["in"]]
+    keep = ~((src == dst) & (S == 0).all(1))
+    out = oracle.radius_graph.limit_neighbors(src[keep], dst[keep], length[keep], S[keep], c["k"])
+    for a, b in zip(out, c["out"]):
+        assert np.array_equal(np.asarray(a), b.numpy())
