@@ -1,0 +1,264 @@
+// libhgb.so -- dense layers: generic fp32 GEMM (all transposes, split-K), fused linear+bias+act,
+// activation backward, column sums.
+//
+// These are the fp32 "any shape" kernels used by every Linear on the path (M = nodes/edges/graphs is
+// large, N and K are small: 1..192).  The bf16 tensor-core (tcgen05) path for the hot shapes lives in
+// hgb_tc_linear.cu; this file is the exact-fp32 path and the fallback for odd shapes.
+#include "hgb_common.cuh"
+
+#define BM 64
+#define BN 64
+#define BK 16
+#define TM 4
+#define TN 4
+
+// C[m,n] (+)= sum_k A(m,k) B(k,n), A(m,k) = a[m*lda + k] or a[k*lda + m] (TA), same for B.
+// grid.z = split-K slices; with splits > 1 each slice writes its partial to part[z, m, n].
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                   float* __restrict__ c, int m, int n, int k, int64_t lda, int64_t ldb,
+                                                   int64_t ldc, int beta_one, int k_per_split, float* __restrict__ part,
+                                                   const float* __restrict__ bias, int act, float act_param,
+                                                   float* __restrict__ zout) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(k, kbeg + k_per_split);
+  const int tx = tid % 16, ty = tid / 16;  // 16 x 16 threads, each TM x TN
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int kk = kbeg; kk < kend; kk += BK) {
+    // load A tile (BM x BK) and B tile (BK x BN): 1024 elements each, 4 per thread
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int l = tid + t * 256;
+      int am, ak;
+      if (TA) { am = l % BM; ak = l / BM; } else { ak = l % BK; am = l / BK; }   // contiguous index fastest
+      const int gm = m0 + am, gk = kk + ak;
+      float v = 0.f;
+      if (gm < m && gk < kend) v = TA ? a[(int64_t)gk * lda + gm] : a[(int64_t)gm * lda + gk];
+      As[ak][am] = v;
+      int bn, bk;
+      if (TB) { bk = l % BK; bn = l / BK; } else { bn = l % BN; bk = l / BN; }
+      const int gn = n0 + bn, gk2 = kk + bk;
+      float w = 0.f;
+      if (gn < n && gk2 < kend) w = TB ? b[(int64_t)gn * ldb + gk2] : b[(int64_t)gk2 * ldb + gn];
+      Bs[bk][bn] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < BK; ++q) {
+      float ra[TM], rb[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) ra[i] = As[q][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) rb[j] = Bs[q][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(ra[i], rb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int gm = m0 + ty * TM + i;
+    if (gm >= m) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int gn = n0 + tx * TN + j;
+      if (gn >= n) continue;
+      if (part) {
+        part[((int64_t)blockIdx.z * m + gm) * n + gn] = acc[i][j];
+      } else {
+        float v = acc[i][j];
+        if (bias) v += bias[gn];
+        if (zout) zout[(int64_t)gm * ldc + gn] = v;
+        v = hgb_act(v, act, act_param);
+        if (beta_one) v += c[(int64_t)gm * ldc + gn];
+        c[(int64_t)gm * ldc + gn] = v;
+      }
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t mn, int n, int64_t ldc,
+                                     int beta_one, float* __restrict__ c) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < mn; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += part[(int64_t)s * mn + i];
+    const int64_t o = (i / n) * ldc + (i % n);
+    c[o] = beta_one ? c[o] + acc : acc;
+  }
+}
+
+static int pick_splits(int m, int n, int k) {
+  const int tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
+  if (tiles >= HGB_NUM_SMS || k < 4096) return 1;
+  int s = (HGB_NUM_SMS * 4 + tiles - 1) / tiles;
+  const int maxs = (k + 1023) / 1024;
+  if (s > maxs) s = maxs;
+  return s < 1 ? 1 : s;
+}
+
+extern "C" int64_t hgb_gemm_workspace_bytes(int32_t m, int32_t n, int32_t k, int32_t trans_a) {
+  const int s = pick_splits(m, n, k);
+  return s > 1 ? (int64_t)s * m * n * 4 : 0;
+}
+
+template <bool TA, bool TB>
+static int launch_gemm(const float* a, const float* b, float* c, int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldc,
+                       int beta_one, void* ws, int64_t ws_bytes, const float* bias, int act, float act_param, float* z,
+                       cudaStream_t st) {
+  int splits = (bias || act || z) ? 1 : pick_splits(m, n, k);
+  if (splits > 1 && ((int64_t)splits * m * n * 4 > ws_bytes || !ws)) splits = 1;
+  int kps = (k + splits - 1) / splits;
+  kps = ((kps + BK - 1) / BK) * BK;
+  splits = (k + kps - 1) / kps;
+  if (splits < 1) splits = 1;
+  dim3 grid((n + BN - 1) / BN, (m + BM - 1) / BM, splits);
+  gemm_kernel<TA, TB><<<grid, 256, 0, st>>>(a, b, c, m, n, k, lda, ldb, ldc, beta_one, kps, splits > 1 ? (float*)ws : nullptr,
+                                            bias, act, act_param, z);
+  HGB_LAUNCH_CHECK("gemm");
+  if (splits > 1) {
+    splitk_reduce_kernel<<<hgb_grid_for((int64_t)m * n, 256), 256, 0, st>>>((const float*)ws, splits, (int64_t)m * n, n, ldc,
+                                                                            beta_one, c);
+    HGB_LAUNCH_CHECK("splitk_reduce");
+  }
+  return HGB_OK;
+}
+
+extern "C" int hgb_gemm(const float* a, const float* b, float* c, int32_t m, int32_t n, int32_t k, int32_t trans_a,
+                        int32_t trans_b, int64_t lda, int64_t ldb, int64_t ldc, int32_t beta_one, void* workspace,
+                        int64_t workspace_bytes, hgb_stream_t stream) {
+  HGB_REQUIRE(m >= 0 && n >= 0 && k >= 0 && c, "gemm: bad arguments");
+  if (m == 0 || n == 0) return HGB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (k == 0) {
+    if (!beta_one) cudaMemset2DAsync(c, ldc * 4, 0, (size_t)n * 4, m, st);
+    return HGB_OK;
+  }
+  if (trans_a && trans_b) return launch_gemm<true, true>(a, b, c, m, n, k, lda, ldb, ldc, beta_one, workspace, workspace_bytes, nullptr, 0, 0.f, nullptr, st);
+  if (trans_a) return launch_gemm<true, false>(a, b, c, m, n, k, lda, ldb, ldc, beta_one, workspace, workspace_bytes, nullptr, 0, 0.f, nullptr, st);
+  if (trans_b) return launch_gemm<false, true>(a, b, c, m, n, k, lda, ldb, ldc, beta_one, workspace, workspace_bytes, nullptr, 0, 0.f, nullptr, st);
+  return launch_gemm<false, false>(a, b, c, m, n, k, lda, ldb, ldc, beta_one, workspace, workspace_bytes, nullptr, 0, 0.f, nullptr, st);
+}
+
+extern "C" int hgb_linear_fwd(const float* x, const float* w, const float* b, int32_t m, int32_t n, int32_t k, int64_t ldx,
+                              int64_t ldw, int32_t act, float act_param, float* y, float* z, hgb_stream_t stream) {
+  HGB_REQUIRE(m >= 0 && n > 0 && k > 0 && x && w && y && ldx >= k && ldw >= k, "linear_fwd: bad arguments");
+  if (m == 0) return HGB_OK;
+  return launch_gemm<false, true>(x, w, y, m, n, k, ldx, ldw, n, 0, nullptr, 0, b, act, act_param, z, (cudaStream_t)stream);
+}
+
+// ---- activation derivative kernels -----------------------------------------------------------------
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ z,
+                               int64_t count, int act, float p, float* __restrict__ dz) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    dz[i] = dy[i] * hgb_act_grad(y ? y[i] : 0.f, z ? z[i] : 0.f, act, p);
+}
+
+extern "C" int hgb_act_bwd(const float* dy, const float* y, const float* z, int64_t count, int32_t act, float act_param,
+                           float* dz, hgb_stream_t stream) {
+  HGB_REQUIRE(count >= 0 && dy && dz, "act_bwd: bad arguments");
+  HGB_REQUIRE(act != HGB_ACT_SILU || z, "act_bwd: SiLU needs the pre-activation z");
+  HGB_REQUIRE(act == HGB_ACT_SILU || act == HGB_ACT_NONE || y, "act_bwd: needs the activation output y");
+  if (count == 0) return HGB_OK;
+  act_bwd_kernel<<<hgb_grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, z, count, act, act_param, dz);
+  HGB_LAUNCH_CHECK("act_bwd");
+  return HGB_OK;
+}
+
+// value (order 0) / first / second derivative of the activation at x
+__device__ __forceinline__ float act_deriv(float x, int act, float p, int order) {
+  if (order == 0) return hgb_act(x, act, p);
+  const float a = 1.6732632423543772848170429916717f, sc = 1.0507009873554804934193349852946f;
+  switch (act) {
+    case HGB_ACT_RELU: return order == 1 ? (x > 0.f ? 1.f : 0.f) : 0.f;
+    case HGB_ACT_LRELU: return order == 1 ? (x > 0.f ? 1.f : p) : 0.f;
+    case HGB_ACT_SILU: {
+      float s = hgb_sigmoid(x);
+      if (order == 1) return s * (1.f + x * (1.f - s));
+      return s * (1.f - s) * (2.f + x * (1.f - 2.f * s));
+    }
+    case HGB_ACT_TANH: {
+      float t = tanhf(x);
+      return order == 1 ? 1.f - t * t : -2.f * t * (1.f - t * t);
+    }
+    case HGB_ACT_SIGMOID: {
+      float s = hgb_sigmoid(x);
+      return order == 1 ? s * (1.f - s) : s * (1.f - s) * (1.f - 2.f * s);
+    }
+    case HGB_ACT_ELU: return x > 0.f ? (order == 1 ? 1.f : 0.f) : __expf(x);
+    case HGB_ACT_SELU: return x > 0.f ? (order == 1 ? sc : 0.f) : sc * a * __expf(x);
+    default: return order == 1 ? 1.f : 0.f;
+  }
+}
+
+__global__ void act_deriv_kernel(const float* __restrict__ x, int64_t count, int act, float p, int order,
+                                 float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = act_deriv(x[i], act, p, order);
+}
+
+extern "C" int hgb_act_deriv(const float* x, int64_t count, int32_t act, float act_param, int32_t order, float* out,
+                             hgb_stream_t stream) {
+  HGB_REQUIRE(count >= 0 && x && out && order >= 0 && order <= 2, "act_deriv: bad arguments");
+  if (count == 0) return HGB_OK;
+  act_deriv_kernel<<<hgb_grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(x, count, act, act_param, order, out);
+  HGB_LAUNCH_CHECK("act_deriv");
+  return HGB_OK;
+}
+
+// ---- column sums (bias gradients): two deterministic stages -------------------------------------
+#define CS_ROWS 512  // rows per block in stage 1
+__global__ void colsum_stage1(const float* __restrict__ x, int m, int n, float* __restrict__ part) {
+  // block (32 x 8): lanes over columns, 8 row-walkers; partial [blockIdx.y, n]
+  __shared__ float sm[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * CS_ROWS;
+  const int r1 = min(m, r0 + CS_ROWS);
+  float acc = 0.f;
+  if (col < n)
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) acc += x[(int64_t)r * n + col];
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    part[(int64_t)blockIdx.y * n + col] = t;
+  }
+}
+__global__ void colsum_stage2(const float* __restrict__ part, int nb, int n, float* __restrict__ out) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= n) return;
+  float acc = 0.f;
+  for (int b = 0; b < nb; ++b) acc += part[(int64_t)b * n + col];
+  out[col] = acc;
+}
+
+extern "C" int64_t hgb_colsum_workspace_bytes(int32_t m, int32_t n) {
+  return (int64_t)((m + CS_ROWS - 1) / CS_ROWS + 1) * n * 4;
+}
+
+extern "C" int hgb_colsum(const float* x, int32_t m, int32_t n, float* out, void* workspace, hgb_stream_t stream) {
+  HGB_REQUIRE(m >= 0 && n > 0 && out && workspace, "colsum: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m == 0) {
+    cudaMemsetAsync(out, 0, (size_t)n * 4, st);
+    return HGB_OK;
+  }
+  const int nb = (m + CS_ROWS - 1) / CS_ROWS;
+  colsum_stage1<<<dim3((n + 31) / 32, nb), dim3(32, 8), 0, st>>>(x, m, n, (float*)workspace);
+  HGB_LAUNCH_CHECK("colsum_stage1");
+  colsum_stage2<<<(n + 127) / 128, 128, 0, st>>>((const float*)workspace, nb, n, out);
+  HGB_LAUNCH_CHECK("colsum_stage2");
+  return HGB_OK;
+}

@@ -1,0 +1,164 @@
+// libhgb.so -- row gather, atomics-free segmented sum over a CSR view, graph pooling.
+//
+// All three are HBM-bound.  Thread mapping: a group of LANES = min(32, pow2 >= C/4) threads owns one
+// output row and walks the row with float4 loads (16 B per thread, consecutive lanes -> consecutive
+// 16 B, i.e. fully coalesced 128 B lines when C*4 >= 128), so narrow rows (C = 1..16) do not waste
+// a whole warp per row.  Summation order inside a segment is the CSR order: deterministic.
+#include "hgb_common.cuh"
+
+template <int VEC>
+struct VecT;
+template <>
+struct VecT<4> { using type = float4; };
+template <>
+struct VecT<1> { using type = float; };
+
+__device__ __forceinline__ void vadd(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ void vadd(float& a, const float& b) { a += b; }
+__device__ __forceinline__ void vzero(float4& a) { a = make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void vzero(float& a) { a = 0.f; }
+
+// picks the sub-warp group width for rows of `cv` vector elements
+static inline int group_lanes(int cv) {
+  int l = 1;
+  while (l < cv && l < 32) l <<= 1;
+  return l;
+}
+
+// ---- gather -----------------------------------------------------------------------------------
+template <int VEC>
+__global__ void gather_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, int64_t e, int cv,
+                                   int lanes, float* __restrict__ out) {
+  using V = typename VecT<VEC>::type;
+  const int gpb = blockDim.x / lanes;
+  const int sub = threadIdx.x % lanes;
+  for (int64_t row = (int64_t)blockIdx.x * gpb + threadIdx.x / lanes; row < e; row += (int64_t)gridDim.x * gpb) {
+    const V* src = reinterpret_cast<const V*>(x) + (int64_t)idx[row] * cv;
+    V* dst = reinterpret_cast<V*>(out) + row * cv;
+    for (int c = sub; c < cv; c += lanes) dst[c] = __ldg(src + c);
+  }
+}
+
+extern "C" int hgb_gather_rows(const float* x, const int32_t* idx, int64_t e, int32_t c, float* out, hgb_stream_t stream) {
+  HGB_REQUIRE(e >= 0 && c > 0 && x && idx && out, "gather_rows: bad arguments");
+  if (e == 0) return HGB_OK;
+  const bool v4 = (c % 4 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  const int cv = v4 ? c / 4 : c;
+  const int lanes = group_lanes(cv);
+  const int gpb = 256 / lanes;
+  const int grid = hgb_grid_for(e, gpb);
+  if (v4) gather_rows_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(x, idx, e, cv, lanes, out);
+  else gather_rows_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(x, idx, e, cv, lanes, out);
+  HGB_LAUNCH_CHECK("gather_rows");
+  return HGB_OK;
+}
+
+// ---- segmented sum ------------------------------------------------------------------------------
+template <int VEC>
+__global__ void segment_sum_kernel(const float* __restrict__ m, const int32_t* __restrict__ rowptr,
+                                   const int32_t* __restrict__ perm, int n, int cv, int lanes, float* __restrict__ out) {
+  using V = typename VecT<VEC>::type;
+  const int gpb = blockDim.x / lanes;
+  const int sub = threadIdx.x % lanes;
+  for (int row = blockIdx.x * gpb + threadIdx.x / lanes; row < n; row += gridDim.x * gpb) {
+    const int lo = rowptr[row], hi = rowptr[row + 1];
+    for (int c = sub; c < cv; c += lanes) {
+      V acc;
+      vzero(acc);
+      int p = lo;
+      // two independent loads in flight per lane
+      for (; p + 1 < hi; p += 2) {
+        const int e0 = perm ? perm[p] : p, e1 = perm ? perm[p + 1] : p + 1;
+        V a = __ldg(reinterpret_cast<const V*>(m) + (int64_t)e0 * cv + c);
+        V b = __ldg(reinterpret_cast<const V*>(m) + (int64_t)e1 * cv + c);
+        vadd(acc, a);
+        vadd(acc, b);
+      }
+      if (p < hi) {
+        const int e0 = perm ? perm[p] : p;
+        vadd(acc, __ldg(reinterpret_cast<const V*>(m) + (int64_t)e0 * cv + c));
+      }
+      reinterpret_cast<V*>(out)[(int64_t)row * cv + c] = acc;
+    }
+  }
+}
+
+extern "C" int hgb_segment_sum(const float* m, const int32_t* rowptr, const int32_t* perm, int32_t n, int32_t c,
+                               float* out, hgb_stream_t stream) {
+  HGB_REQUIRE(n >= 0 && c > 0 && rowptr && out, "segment_sum: bad arguments");
+  if (n == 0) return HGB_OK;
+  const bool v4 = (c % 4 == 0) && ((uintptr_t)m % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  const int cv = v4 ? c / 4 : c;
+  const int lanes = group_lanes(cv);
+  const int gpb = 256 / lanes;
+  const int grid = hgb_grid_for(n, gpb);
+  if (v4) segment_sum_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(m, rowptr, perm, n, cv, lanes, out);
+  else segment_sum_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(m, rowptr, perm, n, cv, lanes, out);
+  HGB_LAUNCH_CHECK("segment_sum");
+  return HGB_OK;
+}
+
+// ---- graph pooling (batch is sorted: a graph is a contiguous run of rows) -------------------------
+__global__ void pool_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ gptr, int g, int c, int mode,
+                                float* __restrict__ out, int32_t* __restrict__ argmax) {
+  // one warp per graph, lanes stride over channels (rows of a graph are contiguous -> coalesced)
+  const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (int k = blockIdx.x * wpb + (threadIdx.x >> 5); k < g; k += gridDim.x * wpb) {
+    const int lo = gptr[k], hi = gptr[k + 1];
+    for (int ch = lane; ch < c; ch += 32) {
+      if (mode == HGB_POOL_MAX) {
+        float best = -INFINITY;
+        int arg = -1;
+        for (int i = lo; i < hi; ++i) {
+          float v = x[(int64_t)i * c + ch];
+          if (v > best || arg < 0) { if (v > best || arg < 0) { best = v; arg = i; } }
+        }
+        out[(int64_t)k * c + ch] = arg < 0 ? 0.f : best;
+        if (argmax) argmax[(int64_t)k * c + ch] = arg;
+      } else {
+        float acc = 0.f;
+        for (int i = lo; i < hi; ++i) acc += x[(int64_t)i * c + ch];
+        if (mode == HGB_POOL_MEAN) acc /= (float)max(hi - lo, 1);
+        out[(int64_t)k * c + ch] = acc;
+      }
+    }
+  }
+}
+
+__global__ void pool_bwd_kernel(const float* __restrict__ gout, const int32_t* __restrict__ gptr,
+                                const int32_t* __restrict__ argmax, int n, int g, int c, int mode, float* __restrict__ gx) {
+  const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (int k = blockIdx.x * wpb + (threadIdx.x >> 5); k < g; k += gridDim.x * wpb) {
+    const int lo = gptr[k], hi = gptr[k + 1];
+    const float scale = mode == HGB_POOL_MEAN ? 1.f / (float)max(hi - lo, 1) : 1.f;
+    for (int ch = lane; ch < c; ch += 32) {
+      const float gv = gout[(int64_t)k * c + ch] * scale;
+      if (mode == HGB_POOL_MAX) {
+        const int arg = argmax[(int64_t)k * c + ch];
+        for (int i = lo; i < hi; ++i) gx[(int64_t)i * c + ch] = (i == arg) ? gv : 0.f;
+      } else {
+        for (int i = lo; i < hi; ++i) gx[(int64_t)i * c + ch] = gv;
+      }
+    }
+  }
+}
+
+extern "C" int hgb_pool_fwd(const float* x, const int32_t* graph_ptr, int32_t g, int32_t c, int32_t mode, float* out,
+                            int32_t* argmax, hgb_stream_t stream) {
+  HGB_REQUIRE(g >= 0 && c > 0 && graph_ptr && out && mode >= 0 && mode <= 2, "pool_fwd: bad arguments");
+  HGB_REQUIRE(mode != HGB_POOL_MAX || argmax, "pool_fwd: max pooling needs an argmax buffer");
+  if (g == 0) return HGB_OK;
+  pool_fwd_kernel<<<hgb_grid_for(g, 8), 256, 0, (cudaStream_t)stream>>>(x, graph_ptr, g, c, mode, out, argmax);
+  HGB_LAUNCH_CHECK("pool_fwd");
+  return HGB_OK;
+}
+
+extern "C" int hgb_pool_bwd(const float* gout, const int32_t* graph_ptr, const int32_t* argmax, int32_t n, int32_t g,
+                            int32_t c, int32_t mode, float* gx, hgb_stream_t stream) {
+  HGB_REQUIRE(g >= 0 && c > 0 && graph_ptr && gx && mode >= 0 && mode <= 2, "pool_bwd: bad arguments");
+  HGB_REQUIRE(mode != HGB_POOL_MAX || argmax, "pool_bwd: max pooling needs the argmax buffer");
+  if (g == 0) return HGB_OK;
+  pool_bwd_kernel<<<hgb_grid_for(g, 8), 256, 0, (cudaStream_t)stream>>>(gout, graph_ptr, argmax, n, g, c, mode, gx);
+  HGB_LAUNCH_CHECK("pool_bwd");
+  return HGB_OK;
+}

@@ -76,6 +76,8 @@ class Data:
     def clone(self):
         out = self.__class__()
         for k, v in self.__dict__.items():
+            if k.startswith("_hgb"):          # cached engine plans are tied to this object's tensors
+                continue
             out.__dict__[k] = v.clone() if torch.is_tensor(v) else copy.deepcopy(v)
         return out
 

@@ -1,0 +1,477 @@
+"""torch-facing wrappers of the libhgb.so kernels.
+
+Two layers:
+
+* ``raw_*`` -- thin launchers: check tensors, allocate outputs with torch (device memory + current
+  stream are the only things torch provides), call the C-ABI through ctypes.
+* ``torch.autograd.Function`` classes.  Two families:
+    - primitives that are closed under differentiation (``GatherRows`` <-> ``SegmentSum`` are each
+      other's adjoint, ``MatMul``'s backward is ``MatMul``): any-order differentiable, used when the
+      force loss needs ``create_graph=True`` (hydragnn/models/create.py:718-724);
+    - fused blocks with hand-written first-order backward kernels (``LinearAct``, ``PainnMessageFn``,
+      ``PainnUpdateFn``, ``PoolFn``, ``EdgeGeomFn`` ...): the fast path for ordinary training /
+      inference.  They are ``once_differentiable``: asking for a second derivative raises.
+
+Nothing here falls back to ATen/PyG scatter kernels; a missing library raises in ``_lib.lib()``.
+"""
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+ACT_CODES = {None: 0, "none": 0, "relu": 1, "silu": 2, "tanh": 3, "sigmoid": 4, "lrelu": 5, "elu": 6, "selu": 7}
+POOL_CODES = {"add": 0, "sum": 0, "mean": 1, "max": 2}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t, dtype=torch.float32):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("hydragnn_b200 ops need CUDA tensors (no CPU fallback on the hot path)")
+    if t.dtype != dtype:
+        raise RuntimeError("expected %s, got %s" % (dtype, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# =====================================================================================================
+# graph plan: int32 indices + CSR views of both rows of edge_index
+# =====================================================================================================
+class Csr:
+    """CSR view of an index vector: the entries equal to k are ``perm[rowptr[k]:rowptr[k+1]]`` (ascending)."""
+    __slots__ = ("idx", "rowptr", "perm", "n")
+
+    def __init__(self, idx, rowptr, perm, n):
+        self.idx, self.rowptr, self.perm, self.n = idx, rowptr, perm, n
+
+
+def csr_build(index64, n):
+    index64 = _chk(index64, torch.int64)
+    e = index64.numel()
+    dev = index64.device
+    idx32 = torch.empty(e, dtype=torch.int32, device=dev)
+    rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    perm = torch.empty(e, dtype=torch.int32, device=dev)
+    ws = _ws(_lib.query("hgb_csr_workspace_bytes", e, n), dev)
+    _lib.call("hgb_csr_build", _p(index64), e, n, _p(idx32), _p(rowptr), _p(perm), _p(ws), _stream())
+    return Csr(idx32, rowptr, perm, n)
+
+
+class EdgePlan:
+    """Everything index-shaped a conv layer needs, built once per batch (SURVEY hard part H3: the
+    stacks aggregate by ``edge_index[0]`` which is not the sorted row of a PyG radius graph)."""
+
+    def __init__(self, edge_index, num_nodes):
+        ei = _chk(edge_index, torch.int64)
+        self.num_nodes, self.num_edges = int(num_nodes), int(ei.shape[1])
+        self.by_row = csr_build(ei[0], self.num_nodes)
+        self.by_col = csr_build(ei[1], self.num_nodes)
+        self.row, self.col = self.by_row.idx, self.by_col.idx
+
+
+def graph_ptr_from_batch(batch, num_graphs):
+    """int32 [G+1] offsets of the (sorted) batch vector -- itself a CSR build with identity perm."""
+    return csr_build(batch, num_graphs)
+
+
+def exclusive_scan(x):
+    x = _chk(x, torch.int32)
+    out = torch.empty(x.numel() + 1, dtype=torch.int32, device=x.device)
+    ws = _ws(_lib.query("hgb_exclusive_scan_workspace_bytes", x.numel()), x.device)
+    _lib.call("hgb_exclusive_scan_i32", _p(x), _p(out), x.numel(), _p(ws), _stream())
+    return out
+
+
+# =====================================================================================================
+# raw launchers
+# =====================================================================================================
+def raw_gather(x, idx32):
+    x = _chk(x)
+    c = 1
+    for d in x.shape[1:]:
+        c *= d
+    out = torch.empty((idx32.numel(),) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    _lib.call("hgb_gather_rows", _p(x), _p(idx32), idx32.numel(), c, _p(out), _stream())
+    return out
+
+
+def raw_segment_sum(m, rowptr, perm, n):
+    m = _chk(m)
+    c = 1
+    for d in m.shape[1:]:
+        c *= d
+    out = torch.empty((n,) + tuple(m.shape[1:]), dtype=m.dtype, device=m.device)
+    _lib.call("hgb_segment_sum", _p(m), _p(rowptr), _p(perm), n, c, _p(out), _stream())
+    return out
+
+
+def raw_gemm(a, b, ta, tb, out=None, beta_one=False):
+    """op(a) @ op(b) for 2-D row-major (possibly row-strided) operands."""
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    m, k = (a.shape[1], a.shape[0]) if ta else (a.shape[0], a.shape[1])
+    k2, n = (b.shape[1], b.shape[0]) if tb else (b.shape[0], b.shape[1])
+    assert k == k2, "gemm inner dimensions differ"
+    if out is None:
+        out = torch.empty(m, n, dtype=a.dtype, device=a.device)
+    nbytes = _lib.query("hgb_gemm_workspace_bytes", m, n, k, int(ta))
+    ws = _ws(nbytes, a.device) if nbytes else None
+    _lib.call("hgb_gemm", _p(a), _p(b), _p(out), m, n, k, int(ta), int(tb), a.stride(0), b.stride(0), out.stride(0),
+              int(beta_one), _p(ws), nbytes, _stream())
+    return out
+
+
+def raw_colsum(x2d):
+    m, n = x2d.shape
+    out = torch.empty(n, dtype=x2d.dtype, device=x2d.device)
+    ws = _ws(_lib.query("hgb_colsum_workspace_bytes", m, n), x2d.device)
+    _lib.call("hgb_colsum", _p(x2d), m, n, _p(out), _p(ws), _stream())
+    return out
+
+
+def _row_major_2d(t):
+    """View an [..., k] tensor as [m, k] with unit inner stride (copying only if it has to)."""
+    k = t.shape[-1]
+    t2 = t.reshape(-1, k)
+    if t2.stride(1) != 1 or (t2.shape[0] > 1 and t2.stride(0) < k):
+        t2 = t2.contiguous()
+    return t2
+
+
+# =====================================================================================================
+# any-order differentiable primitives
+# =====================================================================================================
+class GatherRows(torch.autograd.Function):
+    """``x[idx]``; adjoint = SegmentSum over the CSR of ``idx``."""
+
+    @staticmethod
+    def forward(ctx, x, csr):
+        ctx.csr = csr
+        return raw_gather(x, csr.idx)
+
+    @staticmethod
+    def backward(ctx, g):
+        return SegmentSum.apply(g, ctx.csr), None
+
+
+class SegmentSum(torch.autograd.Function):
+    """``zeros(n).index_add_(0, idx, m)`` as a deterministic segmented reduction; adjoint = GatherRows."""
+
+    @staticmethod
+    def forward(ctx, m, csr):
+        ctx.csr = csr
+        return raw_segment_sum(m, csr.rowptr, csr.perm, csr.n)
+
+    @staticmethod
+    def backward(ctx, g):
+        return GatherRows.apply(g, ctx.csr), None
+
+
+class MatMul(torch.autograd.Function):
+    """``op(a) @ op(b)`` (2-D).  d/da and d/db are MatMuls again, so this is closed under autograd."""
+
+    @staticmethod
+    def forward(ctx, a, b, ta, tb):
+        ctx.save_for_backward(a, b)
+        ctx.ta, ctx.tb = ta, tb
+        return raw_gemm(_row_major_2d(a), _row_major_2d(b), ta, tb)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        ta, tb = ctx.ta, ctx.tb
+        ga = gb = None
+        if ctx.needs_input_grad[0]:
+            #  C = A B     : gA = G B^T      C = A^T B   : gA = B G^T
+            #  C = A B^T   : gA = G B        C = A^T B^T : gA = B^T G^T
+            ga = MatMul.apply(b, g, tb, True) if ta else MatMul.apply(g, b, False, not tb)
+        if ctx.needs_input_grad[1]:
+            #  C = A B     : gB = A^T G      C = A B^T   : gB = G^T A
+            #  C = A^T B   : gB = A G        C = A^T B^T : gB = G^T A^T
+            gb = MatMul.apply(g, a, True, ta) if tb else MatMul.apply(a, g, not ta, False)
+        return ga, gb, None, None
+
+
+def linear_any_order(x, weight, bias=None):
+    """``x @ W^T + b`` built from the closed primitives (+ an ATen broadcast add for the bias)."""
+    shp = x.shape
+    y = MatMul.apply(x.reshape(-1, shp[-1]), weight, False, True)
+    if bias is not None:
+        y = y + bias
+    return y.reshape(shp[:-1] + (weight.shape[0],))
+
+
+# =====================================================================================================
+# fused first-order blocks
+# =====================================================================================================
+class LinearAct(torch.autograd.Function):
+    """``act(x W^T + b)`` in one kernel; backward = act' kernel + two GEMMs + a column sum."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, act_param):
+        shp = x.shape
+        x2 = _row_major_2d(x)
+        w = weight if weight.stride(1) == 1 else weight.contiguous()
+        m, k = x2.shape
+        n = w.shape[0]
+        y = torch.empty(m, n, dtype=x.dtype, device=x.device)
+        code = ACT_CODES[act]
+        z = torch.empty_like(y) if code == ACT_CODES["silu"] else None
+        _lib.call("hgb_linear_fwd", _p(x2), _p(w), _p(_chk(bias)), m, n, k, x2.stride(0), w.stride(0), code,
+                  float(act_param), _p(y), _p(z), _stream())
+        ctx.save_for_backward(x2, w, y if code not in (0, ACT_CODES["silu"]) else None, z)
+        ctx.code, ctx.param, ctx.shp, ctx.has_bias = code, float(act_param), shp, bias is not None
+        return y.reshape(shp[:-1] + (n,))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x2, w, y, z = ctx.saved_tensors
+        m, k = x2.shape
+        n = w.shape[0]
+        gy2 = _chk(gy.reshape(m, n))
+        if ctx.code != 0:
+            dz = torch.empty_like(gy2)
+            _lib.call("hgb_act_bwd", _p(gy2), _p(y), _p(z), gy2.numel(), ctx.code, ctx.param, _p(dz), _stream())
+        else:
+            dz = gy2
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = raw_gemm(dz, w, False, False).reshape(ctx.shp)
+        if ctx.needs_input_grad[1]:
+            gw = raw_gemm(dz, x2, True, False)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = raw_colsum(dz)
+        return gx, gw, gb, None, None
+
+
+def linear_act(x, weight, bias=None, act=None, act_param=0.0):
+    return LinearAct.apply(x, weight, bias, act, act_param)
+
+
+class EdgeGeomFn(torch.autograd.Function):
+    """(vec, len, unit) of hydragnn/utils/model/operations.py:21-36 in one pass; the backward turns the
+    three edge gradients into one [E,3] vector and scatters it to both endpoints with segment sums."""
+
+    @staticmethod
+    def forward(ctx, pos, shifts, plan, eps):
+        pos = _chk(pos)
+        e = plan.num_edges
+        vec = torch.empty(e, 3, dtype=pos.dtype, device=pos.device)
+        ln = torch.empty(e, 1, dtype=pos.dtype, device=pos.device)
+        unit = torch.empty(e, 3, dtype=pos.dtype, device=pos.device)
+        _lib.call("hgb_edge_geom_fwd", _p(pos), _p(plan.row), _p(plan.col), _p(_chk(shifts)), e, float(eps), _p(vec), _p(ln),
+                  _p(unit), _stream())
+        ctx.save_for_backward(vec, ln)
+        ctx.plan, ctx.eps = plan, float(eps)
+        return vec, ln, unit
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_vec, g_len, g_unit):
+        vec, ln = ctx.saved_tensors
+        plan = ctx.plan
+        gv = torch.empty_like(vec)
+        _lib.call("hgb_edge_geom_bwd", _p(vec), _p(ln), ctx.eps, _p(_chk(g_vec)), _p(_chk(g_len)), _p(_chk(g_unit)),
+                  plan.num_edges, _p(gv), _stream())
+        g_pos = g_shift = None
+        if ctx.needs_input_grad[0]:
+            # vec = pos[col] - pos[row] + shift
+            g_pos = raw_segment_sum(gv, plan.by_col.rowptr, plan.by_col.perm, plan.num_nodes) - \
+                raw_segment_sum(gv, plan.by_row.rowptr, plan.by_row.perm, plan.num_nodes)
+        if ctx.needs_input_grad[1]:
+            g_shift = gv
+        return g_pos, g_shift, None, None
+
+
+class PainnEdgeEmbedFn(torch.autograd.Function):
+    """len/unit -> (dir = unit/len [quirk Q2], rbf*cutoff, cutoff) (hydragnn/models/PAINNStack.py:239-242,257)."""
+
+    @staticmethod
+    def forward(ctx, unit, ln, num_radial, cutoff):
+        e = unit.shape[0]
+        d = torch.empty_like(unit)
+        rbfc = torch.empty(e, num_radial, dtype=unit.dtype, device=unit.device)
+        fc = torch.empty(e, dtype=unit.dtype, device=unit.device)
+        _lib.call("hgb_painn_edge_embed_fwd", _p(unit), _p(ln), e, num_radial, float(cutoff), _p(d), _p(rbfc), _p(fc), _stream())
+        ctx.save_for_backward(unit, ln)
+        ctx.r, ctx.cutoff = num_radial, float(cutoff)
+        return d, rbfc, fc
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_dir, g_rbfc, g_fc):
+        unit, ln = ctx.saved_tensors
+        e = unit.shape[0]
+        g_unit = torch.empty_like(unit)
+        g_len = torch.empty_like(ln)
+        _lib.call("hgb_painn_edge_embed_bwd", _p(unit), _p(ln), _p(_chk(g_dir)), _p(_chk(g_rbfc)), _p(_chk(g_fc)), e, ctx.r,
+                  ctx.cutoff, _p(g_unit), _p(g_len), _stream())
+        return g_unit, g_len, None, None
+
+
+class PainnMessageFn(torch.autograd.Function):
+    """Fused PaiNN message (hydragnn/models/PAINNStack.py:239-270): returns (s + ds, v + dv)."""
+
+    @staticmethod
+    def forward(ctx, phi, s, v, dirs, rbfc, fc, wf, bf, efilt, plan):
+        n, f = s.shape
+        r = rbfc.shape[1]
+        phi, s, v = _chk(phi), _chk(s), _chk(v)
+        s_out, v_out = torch.empty_like(s), torch.empty_like(v)
+        agg = plan.by_row     # messages are summed into edge[:,0] = edge_index[0]
+        _lib.call("hgb_painn_message_fwd", _p(phi), _p(s), _p(v), _p(agg.rowptr), _p(agg.perm), _p(plan.col), _p(dirs),
+                  _p(rbfc), _p(fc), _p(_chk(wf)), _p(_chk(bf)), _p(_chk(efilt)), n, f, r, _p(s_out), _p(v_out), _stream())
+        ctx.save_for_backward(phi, v, dirs, rbfc, fc, wf, bf, efilt)
+        ctx.plan = plan
+        return s_out, v_out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gs_out, gv_out):
+        phi, v, dirs, rbfc, fc, wf, bf, efilt = ctx.saved_tensors
+        plan = ctx.plan
+        n, f = gs_out.shape
+        r = rbfc.shape[1]
+        gs_out, gv_out = _chk(gs_out), _chk(gv_out)
+        need_edge = ctx.needs_input_grad[3] or ctx.needs_input_grad[4] or ctx.needs_input_grad[5]
+        gphi, gv = torch.empty_like(phi), torch.empty_like(v)
+        gwf, gbf = torch.empty_like(wf), torch.empty_like(bf)
+        ncb = (f + 63) // 64 if f > 32 else 1
+        alloc = torch.zeros if ncb > 1 else torch.empty
+        g_dir = alloc(dirs.shape, dtype=dirs.dtype, device=dirs.device) if need_edge else None
+        g_rbfc = alloc(rbfc.shape, dtype=dirs.dtype, device=dirs.device) if need_edge else None
+        g_fc = alloc(fc.shape, dtype=dirs.dtype, device=dirs.device) if need_edge else None
+        g_ef = torch.empty_like(efilt) if efilt is not None else None
+        nbytes = _lib.query("hgb_painn_message_bwd_workspace_bytes", n, f, r)
+        ws = _ws(nbytes, phi.device)
+        src = plan.by_col     # the gather side: edge[:,1] = edge_index[1]
+        _lib.call("hgb_painn_message_bwd", _p(gs_out), _p(gv_out), _p(phi), _p(v), _p(src.rowptr), _p(src.perm), _p(plan.row),
+                  _p(dirs), _p(rbfc), _p(fc), _p(wf), _p(bf), _p(efilt), n, f, r, _p(gphi), _p(gv), _p(gwf), _p(gbf),
+                  _p(g_dir), _p(g_rbfc), _p(g_fc), _p(g_ef), _p(ws), nbytes, _stream())
+        return gphi, gs_out, gv, g_dir, g_rbfc, g_fc, gwf, gbf, g_ef, None
+
+
+def raw_linear(x2, w, b, code=0, param=0.0, want_z=False):
+    m, k = x2.shape
+    n = w.shape[0]
+    y = torch.empty(m, n, dtype=x2.dtype, device=x2.device)
+    z = torch.empty_like(y) if want_z else None
+    _lib.call("hgb_linear_fwd", _p(x2), _p(w), _p(b), m, n, k, x2.stride(0), w.stride(0), code, float(param), _p(y), _p(z), _stream())
+    return y, z
+
+
+def raw_act_bwd(dy, y, z, code, param=0.0):
+    dz = torch.empty_like(dy)
+    _lib.call("hgb_act_bwd", _p(dy), _p(y), _p(z), dy.numel(), code, float(param), _p(dz), _stream())
+    return dz
+
+
+class PainnUpdateFn(torch.autograd.Function):
+    """The whole PaiNN update block (hydragnn/models/PAINNStack.py:298-328) with one hand-written
+    backward: U/V linears, |Vv|, update_mlp (Linear-SiLU-Linear) and the gated residuals."""
+
+    @staticmethod
+    def forward(ctx, s, v, uw, ub, vw, vb, w1, b1, w2, b2, last):
+        n, f = s.shape
+        s, v = _chk(s), _chk(v)
+        uw, ub, vw, vb, w1, b1, w2, b2 = [_chk(t) for t in (uw, ub, vw, vb, w1, b1, w2, b2)]
+        v2 = v.reshape(3 * n, f)
+        uv, _ = raw_linear(v2, uw, ub)
+        vv, _ = raw_linear(v2, vw, vb)
+        mlp_in = torch.empty(n, 2 * f, dtype=s.dtype, device=s.device)
+        _lib.call("hgb_painn_update_pre_fwd", _p(vv), _p(s), n, f, _p(mlp_in), _stream())
+        h, z1 = raw_linear(mlp_in, w1, b1, ACT_CODES["silu"], 0.0, want_z=True)
+        a, _ = raw_linear(h, w2, b2)
+        s_out = torch.empty_like(s)
+        v_out = None if last else torch.empty_like(v)
+        _lib.call("hgb_painn_update_post_fwd", _p(a), _p(uv), _p(vv), _p(s), _p(v), n, f, int(last), _p(s_out), _p(v_out), _stream())
+        ctx.save_for_backward(v2, uv, vv, mlp_in, z1, h, a, uw, vw, w1, w2)
+        ctx.last = bool(last)
+        if last:
+            return s_out, s_out.new_zeros(0)
+        return s_out, v_out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gs_out, gv_out):
+        v2, uv, vv, mlp_in, z1, h, a, uw, vw, w1, w2 = ctx.saved_tensors
+        last = ctx.last
+        n, f = gs_out.shape
+        gs_out = _chk(gs_out)
+        gv_out = None if last else _chk(gv_out)
+        ga = torch.empty_like(a)
+        _lib.call("hgb_painn_update_post_bwd_a", _p(gs_out), _p(gv_out), _p(uv), _p(vv), n, f, int(last), _p(ga), _stream())
+        gw2 = raw_gemm(ga, h, True, False)
+        gb2 = raw_colsum(ga)
+        gh = raw_gemm(ga, w2, False, False)
+        gz1 = raw_act_bwd(gh, None, z1, ACT_CODES["silu"])
+        gw1 = raw_gemm(gz1, mlp_in, True, False)
+        gb1 = raw_colsum(gz1)
+        g_mlp_in = raw_gemm(gz1, w1, False, False)
+        guv, gvv = torch.empty_like(uv), torch.empty_like(vv)
+        gs, gv = torch.empty_like(gs_out), torch.empty_like(v2)
+        _lib.call("hgb_painn_update_bwd", _p(gs_out), _p(gv_out), _p(g_mlp_in), _p(a), _p(uv), _p(vv), _p(mlp_in), n, f,
+                  int(last), _p(guv), _p(gvv), _p(gs), _p(gv), _stream())
+        guw, gub = raw_gemm(guv, v2, True, False), raw_colsum(guv)
+        gvw, gvb = raw_gemm(gvv, v2, True, False), raw_colsum(gvv)
+        raw_gemm(guv, uw, False, False, out=gv, beta_one=True)
+        raw_gemm(gvv, vw, False, False, out=gv, beta_one=True)
+        return gs, gv.reshape(n, 3, f), guw, gub, gvw, gvb, gw1, gb1, gw2, gb2, None
+
+
+class PoolFn(torch.autograd.Function):
+    """global_{add,mean,max}_pool over a sorted batch vector (hydragnn/models/Base.py:147-170)."""
+
+    @staticmethod
+    def forward(ctx, x, gcsr, mode):
+        x = _chk(x)
+        g, c = gcsr.n, x.shape[1]
+        out = torch.empty(g, c, dtype=x.dtype, device=x.device)
+        code = POOL_CODES[mode]
+        arg = torch.empty(g, c, dtype=torch.int32, device=x.device) if code == 2 else None
+        _lib.call("hgb_pool_fwd", _p(x), _p(gcsr.rowptr), g, c, code, _p(out), _p(arg), _stream())
+        ctx.gcsr, ctx.code, ctx.n, ctx.arg = gcsr, code, x.shape[0], arg
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        g = _chk(g)
+        gx = torch.empty(ctx.n, g.shape[1], dtype=g.dtype, device=g.device)
+        _lib.call("hgb_pool_bwd", _p(g), _p(ctx.gcsr.rowptr), _p(ctx.arg), ctx.n, ctx.gcsr.n, g.shape[1], ctx.code, _p(gx), _stream())
+        return gx, None, None
+
+
+class LossFn(torch.autograd.Function):
+    """mean squared / absolute error with its gradient produced in the same pass."""
+
+    @staticmethod
+    def forward(ctx, pred, target, mode):
+        pred, target = _chk(pred), _chk(target)
+        loss = torch.empty(1, dtype=pred.dtype, device=pred.device)
+        gpred = torch.empty_like(pred)
+        _lib.call("hgb_loss_fwd_bwd", _p(pred), _p(target), pred.numel(), mode, 1.0, _p(loss), _p(gpred), _stream())
+        ctx.save_for_backward(gpred)
+        return loss.reshape(())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (gpred,) = ctx.saved_tensors
+        return gpred * g, None, None
+
+
+def adamw_step(p, g, m, v, step_dev, lr, beta1, beta2, eps, weight_decay, grad_scale=1.0):
+    _lib.call("hgb_adamw_step", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+              float(weight_decay), float(grad_scale), _p(step_dev), _stream())

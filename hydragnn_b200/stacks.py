@@ -1,0 +1,494 @@
+"""EGNN and PaiNN stacks + the shared encoder / multi-head decoder, executing on libhgb.so.
+
+Host-side mirror of the reference's plugin surface for this path:
+``hydragnn/models/Base.py`` (encoder loop :697-727, pooling :733-738, heads :742-846, losses :848-906),
+``hydragnn/models/EGCLStack.py`` and ``hydragnn/models/PAINNStack.py``.  Module / parameter names are the
+reference's (``graph_convs.<i>.module_<k>...``, ``graph_shared.branch-0...``, ``heads_NN.<i>.branch-0...``)
+so reference checkpoints load; class names ``E_GCL`` / ``PainnMessage`` / ``PainnUpdate`` are
+kept because reference tests locate the modules by class (tests/test_forces_equivariant.py:93-114).
+
+Every conv has two execution modes, selected per forward call:
+* fused (default): hand-written forward + first-order backward kernels;
+* any-order (``higher_order=True``; chosen automatically for MLIP *training*, where the force loss is
+  differentiated again -- hydragnn/models/create.py:718-724 with ``create_graph=True``): the same math
+  composed from the closed primitives GatherRows / SegmentSum / MatMul, with ATen only for elementwise glue.
+"""
+import torch
+from torch import nn
+
+from . import ops
+from .ops import GatherRows, LinearAct, MatMul, SegmentSum  # noqa: F401
+
+
+# ------------------------------------------------------------------------------------------------
+# activation / loss selection  (hydragnn/utils/model/model.py:30-62)
+# ------------------------------------------------------------------------------------------------
+def activation_function_selection(name):
+    table = {"relu": nn.ReLU, "selu": nn.SELU, "elu": nn.ELU, "sigmoid": nn.Sigmoid,
+             "lrelu_01": lambda: nn.LeakyReLU(0.1), "lrelu_025": lambda: nn.LeakyReLU(0.25),
+             "lrelu_05": lambda: nn.LeakyReLU(0.5)}
+    if name == "prelu":
+        raise ValueError("activation 'prelu' (a learnable slope) is not supported by the b200 engine")
+    if name not in table:
+        raise ValueError("Unknown activation function: " + str(name))
+    return table[name]()
+
+
+def _act_code(mod):
+    """(kernel activation name, parameter) of an nn activation module, or None if it is not one."""
+    if isinstance(mod, nn.ReLU):
+        return "relu", 0.0
+    if isinstance(mod, nn.SiLU):
+        return "silu", 0.0
+    if isinstance(mod, nn.Tanh):
+        return "tanh", 0.0
+    if isinstance(mod, nn.Sigmoid):
+        return "sigmoid", 0.0
+    if isinstance(mod, nn.LeakyReLU):
+        return "lrelu", float(mod.negative_slope)
+    if isinstance(mod, nn.ELU) and mod.alpha == 1.0:
+        return "elu", 0.0
+    if isinstance(mod, nn.SELU):
+        return "selu", 0.0
+    return None
+
+
+def loss_function_selection(name):
+    if name == "mse":
+        return _Loss(0, False)
+    if name == "mae":
+        return _Loss(1, False)
+    if name == "rmse":
+        return _Loss(0, True)
+    raise ValueError("loss_function_type %r is not supported by the b200 engine (mse / mae / rmse)" % (name,))
+
+
+class _Loss:
+    """mse / mae / rmse.  Uses the fused value+gradient kernel when only first derivatives can be asked
+    for, plain tensor arithmetic (any-order differentiable) when the prediction carries a graph that
+    will itself be differentiated (forces)."""
+
+    def __init__(self, mode, sqrt):
+        self.mode, self.sqrt = mode, sqrt
+
+    def __call__(self, pred, target, any_order=False):
+        target = target.to(pred.dtype)
+        if any_order or not pred.is_cuda:
+            d = pred - target
+            val = (d * d).mean() if self.mode == 0 else d.abs().mean()
+        else:
+            val = ops.LossFn.apply(pred.reshape(-1), target.reshape(-1), self.mode)
+        return torch.sqrt(val) if self.sqrt else val
+
+
+def run_mlp(seq, x, higher_order=False):
+    """Execute an ``nn.Sequential`` of Linear / activation modules on the engine: every Linear (with the
+    activation that follows it) is one fused kernel; in any-order mode it is MatMul + ATen glue."""
+    mods = list(seq)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        if isinstance(m, nn.Linear):
+            code = _act_code(mods[i + 1]) if i + 1 < len(mods) else None
+            if higher_order:
+                x = ops.linear_any_order(x, m.weight, m.bias)
+            elif code is not None:
+                x = ops.linear_act(x, m.weight, m.bias, code[0], code[1])
+                i += 1
+            else:
+                x = ops.linear_act(x, m.weight, m.bias)
+        else:
+            x = m(x)
+        i += 1
+    return x
+
+
+# ------------------------------------------------------------------------------------------------
+# EGNN  (hydragnn/models/EGCLStack.py:180-300)
+# ------------------------------------------------------------------------------------------------
+class E_GCL(nn.Module):
+    def __init__(self, input_channels, output_channels, hidden_channels, edge_attr_dim=0, equivariant=False):
+        super().__init__()
+        ed = edge_attr_dim or 0
+        self.equivariant = bool(equivariant)
+        self.edge_attr_dim = ed
+        self.edge_mlp = nn.Sequential(nn.Linear(2 * input_channels + 1 + ed, hidden_channels), nn.ReLU(),
+                                      nn.Linear(hidden_channels, hidden_channels), nn.ReLU())
+        self.node_mlp = nn.Sequential(nn.Linear(hidden_channels + input_channels, hidden_channels), nn.ReLU(),
+                                      nn.Linear(hidden_channels, output_channels))
+        if self.equivariant:
+            last = nn.Linear(hidden_channels, 1, bias=False)
+            nn.init.xavier_uniform_(last.weight, gain=0.001)
+            self.coord_mlp = nn.Sequential(nn.Linear(hidden_channels, hidden_channels), nn.ReLU(), last, nn.Tanh())
+
+    def forward(self, x, coord, plan, edge_attr=None, edge_shifts=None, higher_order=False):
+        n = x.shape[0]
+        # geometry with eps = 1.0 (quirk Q3, EGCLStack.py:280-282); "radial" is the length
+        if higher_order:
+            vec = GatherRows.apply(coord, plan.by_col) - GatherRows.apply(coord, plan.by_row)
+            if edge_shifts is not None:
+                vec = vec + edge_shifts
+            radial = torch.linalg.norm(vec, dim=-1, keepdim=True)
+            coord_diff = vec / (radial + 1.0)
+        else:
+            _, radial, coord_diff = ops.EdgeGeomFn.apply(coord, edge_shifts, plan, 1.0)
+        feats = [GatherRows.apply(x, plan.by_row), GatherRows.apply(x, plan.by_col), radial]
+        if edge_attr is not None:
+            feats.append(edge_attr)
+        m = run_mlp(self.edge_mlp, torch.cat(feats, dim=1), higher_order)           # :245-250
+        if self.equivariant:                                                         # :268-276
+            trans = torch.clamp(coord_diff * run_mlp(self.coord_mlp, m, higher_order), min=-100, max=100)
+            cnt = (plan.by_row.rowptr[1:] - plan.by_row.rowptr[:-1]).clamp(min=1).to(trans.dtype)
+            coord = coord + SegmentSum.apply(trans, plan.by_row) / cnt[:, None]
+        agg = SegmentSum.apply(m, plan.by_row)                                       # :257-258
+        out = run_mlp(self.node_mlp, torch.cat([x, agg], dim=1), higher_order)       # :262-263
+        return out, coord
+
+
+# ------------------------------------------------------------------------------------------------
+# PaiNN  (hydragnn/models/PAINNStack.py:194-328)
+# ------------------------------------------------------------------------------------------------
+class PainnMessage(nn.Module):
+    def __init__(self, node_size, num_radial, cutoff, edge_dim=None):
+        super().__init__()
+        self.node_size, self.num_radial, self.cutoff, self.edge_dim = node_size, num_radial, cutoff, edge_dim
+        self.scalar_message_mlp = nn.Sequential(nn.Linear(node_size, node_size), nn.SiLU(),
+                                                nn.Linear(node_size, node_size * 3))
+        self.filter_layer = nn.Linear(num_radial, node_size * 3)
+        if edge_dim is not None:
+            self.edge_filter = nn.Sequential(nn.Linear(edge_dim, node_size), nn.SiLU(),
+                                             nn.Linear(node_size, node_size * 3))
+
+    def forward(self, s, v, plan, geom, edge_attr=None, higher_order=False):
+        f = self.node_size
+        if higher_order:
+            diff, dist = geom["unit"], geom["len"]
+            n = torch.arange(1, self.num_radial + 1, device=dist.device)
+            rbf = torch.sin(dist * n * torch.pi / self.cutoff) / dist
+            fcut = torch.where(dist < self.cutoff, 0.5 * (torch.cos(torch.pi * dist / self.cutoff) + 1.0),
+                               torch.zeros_like(dist))
+            w = ops.linear_any_order(rbf, self.filter_layer.weight, self.filter_layer.bias) * fcut
+            if edge_attr is not None:
+                w = w * run_mlp(self.edge_filter, edge_attr, True)
+            phi = run_mlp(self.scalar_message_mlp, s, True)
+            fo = w * GatherRows.apply(phi, plan.by_col)
+            g_v, g_e, m_s = torch.split(fo, f, dim=1)
+            m_v = GatherRows.apply(v, plan.by_col) * g_v.unsqueeze(1) + g_e.unsqueeze(1) * (diff / dist).unsqueeze(-1)
+            return s + SegmentSum.apply(m_s, plan.by_row), v + SegmentSum.apply(m_v, plan.by_row)
+        phi = run_mlp(self.scalar_message_mlp, s)
+        efilt = run_mlp(self.edge_filter, edge_attr) if edge_attr is not None else None
+        return ops.PainnMessageFn.apply(phi, s, v, geom["dir"], geom["rbfc"], geom["fc"], self.filter_layer.weight,
+                                        self.filter_layer.bias, efilt, plan)
+
+
+class PainnUpdate(nn.Module):
+    def __init__(self, node_size, last_layer=False):
+        super().__init__()
+        self.update_U = nn.Linear(node_size, node_size)
+        self.update_V = nn.Linear(node_size, node_size)
+        self.last_layer = last_layer
+        self.update_mlp = nn.Sequential(nn.Linear(node_size * 2, node_size), nn.SiLU(),
+                                        nn.Linear(node_size, node_size * (2 if last_layer else 3)))
+
+    def forward(self, s, v, higher_order=False):
+        f = v.shape[-1]
+        if higher_order:
+            uv = ops.linear_any_order(v, self.update_U.weight, self.update_U.bias)
+            vv = ops.linear_any_order(v, self.update_V.weight, self.update_V.bias)
+            a = run_mlp(self.update_mlp, torch.cat([torch.linalg.norm(vv, dim=1), s], dim=1), True)
+            inner = (uv * vv).sum(dim=1)
+            if self.last_layer:
+                a_sv, a_ss = torch.split(a, f, dim=1)
+                return s + a_sv * inner + a_ss, None
+            a_vv, a_sv, a_ss = torch.split(a, f, dim=1)
+            return s + a_sv * inner + a_ss, v + a_vv.unsqueeze(1) * uv
+        s_out, v_out = ops.PainnUpdateFn.apply(s, v, self.update_U.weight, self.update_U.bias, self.update_V.weight,
+                                               self.update_V.bias, self.update_mlp[0].weight, self.update_mlp[0].bias,
+                                               self.update_mlp[2].weight, self.update_mlp[2].bias, self.last_layer)
+        return s_out, (None if self.last_layer else v_out)
+
+
+# ------------------------------------------------------------------------------------------------
+# conv containers: children are named module_<i> like the PyG Sequential the reference builds
+# ------------------------------------------------------------------------------------------------
+class EGNNConv(nn.Module):
+    def __init__(self, egcl):
+        super().__init__()
+        self.module_0 = egcl
+
+    def forward(self, inv_node_feat, equiv_node_feat, plan, edge_attr=None, edge_shifts=None, geom=None, higher_order=False):
+        x, pos = self.module_0(inv_node_feat, equiv_node_feat, plan, edge_attr, edge_shifts, higher_order)
+        return x, pos
+
+
+class PainnConv(nn.Module):
+    def __init__(self, msg, upd, node_embed_out, vec_embed_out):
+        super().__init__()
+        self.module_0, self.module_1, self.module_2 = msg, upd, node_embed_out
+        if vec_embed_out is not None:
+            self.module_3 = vec_embed_out
+        self.last = vec_embed_out is None
+
+    def forward(self, inv_node_feat, equiv_node_feat, plan, edge_attr=None, edge_shifts=None, geom=None, higher_order=False):
+        s, v = self.module_0(inv_node_feat, equiv_node_feat, plan, geom, edge_attr, higher_order)
+        s, v_new = self.module_1(s, v, higher_order)
+        s = run_mlp(self.module_2, s, higher_order)
+        if self.last:
+            return s, v          # PAINNStack.py:124-147: v passes through unchanged in the last layer
+        lin = self.module_3
+        v_new = ops.linear_any_order(v_new, lin.weight, lin.bias) if higher_order else ops.linear_act(v_new, lin.weight, lin.bias)
+        return s, v_new
+
+
+class MLPNode(nn.Module):
+    """Shared node-level MLP head, ``node_type == 'mlp'`` (hydragnn/models/Base.py:912-964)."""
+
+    def __init__(self, input_dim, output_dim, hidden_dim_node, activation):
+        super().__init__()
+        dims = [input_dim] + list(hidden_dim_node)
+        layers = []
+        for d0, d1 in zip(dims[:-1], dims[1:]):
+            layers += [nn.Linear(d0, d1), activation]
+        layers.append(nn.Linear(dims[-1], output_dim))
+        self.mlp = nn.ModuleList([nn.Sequential(*layers)])
+
+    def forward(self, x, higher_order=False):
+        return run_mlp(self.mlp[0], x, higher_order)
+
+
+# ------------------------------------------------------------------------------------------------
+# Base: encoder loop + pooling + multi-head decoder
+# ------------------------------------------------------------------------------------------------
+class Base(nn.Module):
+    def __init__(self, input_dim, hidden_dim, output_dim, output_type, config_heads, activation_function_type,
+                 loss_function_type, equivariance=False, loss_weights=None, freeze_conv=False, initial_bias=None,
+                 num_conv_layers=16, num_nodes=None, graph_pooling="mean"):
+        super().__init__()
+        self.input_dim, self.hidden_dim = input_dim, hidden_dim
+        self.num_conv_layers, self.num_nodes = num_conv_layers, num_nodes
+        self.head_dims, self.head_type = list(output_dim), list(output_type)
+        self.num_heads = len(self.head_dims)
+        self.config_heads = config_heads
+        self.equivariance = bool(equivariance)
+        self.activation_function = activation_function_selection(activation_function_type)
+        self.var_output = 0
+        if loss_function_type == "GaussianNLLLoss":
+            raise ValueError("GaussianNLLLoss is not supported by the b200 engine")
+        self.loss_function_type = loss_function_type
+        self.loss_function = loss_function_selection(loss_function_type)
+        self.ilossweights_hyperp, self.ilossweights_nll = 1, 0
+        loss_weights = list(loss_weights if loss_weights is not None else [1.0] * self.num_heads)
+        if len(loss_weights) != self.num_heads:
+            raise ValueError("Inconsistent number of loss weights and tasks: " + str(len(loss_weights)) + " VS " + str(self.num_heads))
+        tot = sum(abs(w) for w in loss_weights)
+        self.loss_weights = [w / tot for w in loss_weights]
+        self.use_edge_attr = getattr(self, "edge_dim", None) is not None and self.edge_dim > 0
+        mode = graph_pooling.lower()
+        mode = "add" if mode == "sum" else mode
+        if mode not in ("mean", "add", "max"):
+            raise ValueError("Unsupported graph_pooling: " + graph_pooling)
+        self.graph_pooling = mode
+        self.freeze_conv, self.initial_bias = freeze_conv, initial_bias
+        self.use_global_attn = False
+        self.embed_dim = input_dim
+        self.force_higher_order = False   # tests can force the any-order path
+        self.graph_convs = nn.ModuleList()
+        self.feature_layers = nn.ModuleList()
+        self.heads_NN = nn.ModuleList()
+        self._init_conv()
+        if freeze_conv:
+            for p in self.graph_convs.parameters():
+                p.requires_grad = False
+        self._multihead()
+        if initial_bias is not None:
+            for head, kind in zip(self.heads_NN, self.head_type):
+                if kind == "graph":
+                    for br in head.values():
+                        br[-1].bias.data.fill_(initial_bias)
+
+    # first layer at width input_dim (quirk Q4), last layer flagged (EGCLStack.py:45-70, PAINNStack.py:49-74)
+    def _init_conv(self):
+        for i in range(self.num_conv_layers):
+            last = i == self.num_conv_layers - 1
+            self.graph_convs.append(self.get_conv(self.embed_dim if i == 0 else self.hidden_dim, self.hidden_dim, last))
+            self.feature_layers.append(nn.Identity())
+
+    def _multihead(self):                                                  # Base.py:590-691
+        act = self.activation_function
+        self.graph_shared = nn.ModuleDict()
+        self.num_branches = 1
+        if "graph" in self.config_heads:
+            self.num_branches = len(self.config_heads["graph"])
+            for br in self.config_heads["graph"]:
+                a = br["architecture"]
+                layers = [nn.Linear(self.hidden_dim, a["dim_sharedlayers"]), act]
+                for _ in range(a["num_sharedlayers"] - 1):
+                    layers += [nn.Linear(a["dim_sharedlayers"], a["dim_sharedlayers"]), act]
+                self.graph_shared[br["type"]] = nn.Sequential(*layers)
+        for ih in range(self.num_heads):
+            head = nn.ModuleDict()
+            if self.head_type[ih] == "graph":
+                for br in self.config_heads["graph"]:
+                    a = br["architecture"]
+                    hid = list(a["dim_headlayers"])
+                    layers = [nn.Linear(a["dim_sharedlayers"], hid[0]), act]
+                    for j in range(a["num_headlayers"] - 1):
+                        layers += [nn.Linear(hid[j], hid[j + 1]), act]
+                    layers.append(nn.Linear(hid[-1], self.head_dims[ih]))
+                    head[br["type"]] = nn.Sequential(*layers)
+            elif self.head_type[ih] == "node":
+                for br in self.config_heads["node"]:
+                    a = br["architecture"]
+                    if a["type"] != "mlp":
+                        raise ValueError("b200 engine: node heads of type %r are not supported yet (use 'mlp')" % (a["type"],))
+                    head[br["type"]] = MLPNode(self.hidden_dim, self.head_dims[ih], a["dim_headlayers"], act)
+            else:
+                raise ValueError("Unknown head type" + str(self.head_type[ih]) + "; currently only support 'graph' or 'node'")
+            self.heads_NN.append(head)
+
+    # -- per-batch preparation -----------------------------------------------------------------------
+    @staticmethod
+    def plan_for(data):
+        plan = data.__dict__.get("_hgb_plan") if hasattr(data, "__dict__") else None
+        ei = data.edge_index
+        if plan is None or plan.num_edges != ei.shape[1] or plan.row.device != ei.device or plan._src is not ei:
+            plan = ops.EdgePlan(ei, data.pos.shape[0] if data.pos is not None else data.x.shape[0])
+            plan._src = ei
+            try:
+                data._hgb_plan = plan
+            except Exception:
+                pass
+        return plan
+
+    def _higher_order(self, data):
+        pos = data.pos
+        return bool(self.force_higher_order or
+                    (self.training and torch.is_grad_enabled() and pos is not None and pos.requires_grad))
+
+    def forward(self, data):
+        x = data.x
+        if x.dtype != torch.float32:
+            raise RuntimeError("b200 engine kernels are fp32 (bf16 via autocast-style GEMMs); got " + str(x.dtype))
+        higher = self._higher_order(data)
+        plan = self.plan_for(data)
+        inv, equiv, conv_args = self._embedding(data, plan, higher)
+        for conv, feat in zip(self.graph_convs, self.feature_layers):
+            inv, equiv = conv(inv_node_feat=inv, equiv_node_feat=equiv, plan=plan, higher_order=higher, **conv_args)
+            inv = self.activation_function(feat(inv))                        # Base.py:726
+        x = inv
+        batch = data.batch
+        if batch is None:
+            batch = torch.zeros(x.shape[0], dtype=torch.long, device=x.device)
+        num_graphs = data.__dict__.get("_num_graphs") if hasattr(data, "__dict__") else None
+        if num_graphs is None:
+            num_graphs = int(batch.max()) + 1
+        gcsr = data.__dict__.get("_hgb_gcsr") if hasattr(data, "__dict__") else None
+        if gcsr is None or gcsr.n != num_graphs or gcsr.idx.numel() != batch.numel():
+            gcsr = ops.graph_ptr_from_batch(batch, num_graphs)
+            try:
+                data._hgb_gcsr = gcsr
+            except Exception:
+                pass
+        x_graph = self.pool(x, gcsr, higher)                                  # Base.py:733-738
+        ds = getattr(data, "dataset_name", None)
+        outputs = []
+        for hd, head, kind in zip(self.head_dims, self.heads_NN, self.head_type):
+            if self.num_branches == 1:
+                if kind == "graph":
+                    h = run_mlp(self.graph_shared["branch-0"], x_graph, higher)
+                    outputs.append(run_mlp(head["branch-0"], h, higher)[:, :hd])
+                else:
+                    outputs.append(head["branch-0"](x, higher)[:, :hd])
+                continue
+            ids = ds[:, 0]                                                   # Base.py:770-780, 816-840
+            if kind == "graph":
+                out = x.new_zeros(num_graphs, hd)
+                for b in ids.unique():
+                    msk = ids == b
+                    key = "branch-%d" % int(b)
+                    out[msk] = run_mlp(head[key], run_mlp(self.graph_shared[key], x_graph[msk], higher), higher)[:, :hd]
+            else:
+                out = x.new_zeros(x.shape[0], hd)
+                for b in ids.unique():
+                    msk = (ids == b)[batch]
+                    out[msk] = head["branch-%d" % int(b)](x[msk], higher)[:, :hd]
+            outputs.append(out)
+        return outputs
+
+    def pool(self, x, gcsr, higher_order=False):
+        if higher_order and self.graph_pooling != "max":
+            out = SegmentSum.apply(x, ops.Csr(gcsr.idx, gcsr.rowptr, None, gcsr.n))
+            if self.graph_pooling == "mean":
+                cnt = (gcsr.rowptr[1:] - gcsr.rowptr[:-1]).clamp(min=1).to(x.dtype)
+                out = out / cnt[:, None]
+            return out
+        return ops.PoolFn.apply(x, gcsr, self.graph_pooling)
+
+    def loss(self, pred, value, head_index):
+        """``loss_hpweighted`` (hydragnn/models/Base.py:879-906)."""
+        tot_loss = 0
+        tasks_loss = []
+        for ihead in range(self.num_heads):
+            head_pre = pred[ihead]
+            head_val = value[head_index[ihead]].reshape(head_pre.shape)
+            li = self.loss_function(head_pre, head_val)
+            tot_loss = tot_loss + li * self.loss_weights[ihead]
+            tasks_loss.append(li)
+        return tot_loss, tasks_loss
+
+    def __str__(self):
+        return "Base"
+
+
+class EGCLStack(Base):
+    def __init__(self, edge_attr_dim, *args, max_neighbours=None, **kwargs):
+        self.edge_dim = 0 if edge_attr_dim is None else edge_attr_dim       # EGCLStack.py:33-35
+        self.is_edge_model = True
+        super().__init__(*args, **kwargs)
+
+    def get_conv(self, input_dim, output_dim, last_layer=False, edge_dim=None):
+        return EGNNConv(E_GCL(input_dim, output_dim, self.hidden_dim, edge_attr_dim=edge_dim or self.edge_dim,
+                              equivariant=self.equivariance and not last_layer))
+
+    def _embedding(self, data, plan, higher):
+        shifts = data.edge_shifts                                            # zeros if absent (EGCLStack.py:114-118)
+        return data.x, data.pos, {"edge_attr": data.edge_attr if self.use_edge_attr else None, "edge_shifts": shifts}
+
+    def __str__(self):
+        return "EGCLStack"
+
+
+class PAINNStack(Base):
+    def __init__(self, edge_dim, num_radial, radius, *args, **kwargs):
+        self.edge_dim, self.num_radial, self.radius = edge_dim, num_radial, radius
+        self.is_edge_model = True
+        super().__init__(*args, **kwargs)
+
+    def get_conv(self, input_dim, output_dim, last_layer=False, edge_dim=None):
+        hidden = output_dim if input_dim == 1 else input_dim
+        assert hidden > 1, "PainnNet requires more than one hidden dimension between input_dim and output_dim."
+        msg = PainnMessage(node_size=input_dim, num_radial=self.num_radial, cutoff=self.radius,
+                           edge_dim=edge_dim if edge_dim is not None else self.edge_dim)
+        upd = PainnUpdate(node_size=input_dim, last_layer=last_layer)
+        node_embed_out = nn.Sequential(nn.Linear(input_dim, output_dim), nn.Tanh(), nn.Linear(output_dim, output_dim))
+        vec_embed_out = nn.Linear(input_dim, output_dim) if not last_layer else None
+        return PainnConv(msg, upd, node_embed_out, vec_embed_out)
+
+    def _embedding(self, data, plan, higher):
+        assert data.pos is not None, "PAINN requires node positions (data.pos) to be set."
+        x, pos, shifts = data.x, data.pos, data.edge_shifts
+        if higher:
+            vec = GatherRows.apply(pos, plan.by_col) - GatherRows.apply(pos, plan.by_row)
+            if shifts is not None:
+                vec = vec + shifts
+            ln = torch.linalg.norm(vec, dim=-1, keepdim=True)
+            geom = {"unit": vec / (ln + 1e-9), "len": ln}
+        else:
+            _, ln, unit = ops.EdgeGeomFn.apply(pos, shifts, plan, 1e-9)      # PAINNStack.py:157-159
+            d, rbfc, fc = ops.PainnEdgeEmbedFn.apply(unit, ln, self.num_radial, self.radius)
+            geom = {"dir": d, "rbfc": rbfc, "fc": fc}
+        v = torch.zeros(x.shape[0], 3, x.shape[1], dtype=x.dtype, device=x.device)   # PAINNStack.py:190
+        return x, v, {"edge_attr": data.edge_attr if self.use_edge_attr else None, "geom": geom}
+
+    def __str__(self):
+        return "PAINNStack"

@@ -1,0 +1,87 @@
+"""Synthetic radius-graph workloads of the shapes BASELINE.json names.
+
+Everything is drawn from ``torch.Generator().manual_seed(seed)`` on the CPU so the oracle, the engine and
+every rank see identical inputs.  Positions: atoms uniform in a cube at number density ``rho`` with a minimum
+separation (rejection-resampled, vectorised over graphs).  Labels are synthetic (standard normal); there is
+no network to fetch QM9 / MD17.
+"""
+import torch
+
+from .data import Batch, Data
+
+WORKLOADS = {
+    # name: atoms/graph, density, species pool (atomic numbers), radius, max_neighbours
+    "qm9_painn": dict(n=9, rho=0.10, species=[1, 6, 7, 8, 9], radius=7.0, max_neighbours=5),
+    "md17_egnn": dict(n=21, rho=0.08, species=[6] * 9 + [1] * 8 + [8] * 4, radius=7.0, max_neighbours=5, fixed_species=True),
+    "lj_egnn": dict(n=27, lattice=3.8, radius=5.0, max_neighbours=5, pbc=True),
+}
+
+ARCH = {
+    # examples/qm9/qm9.json minus GPS, mpnn_type PAINN
+    "qm9_painn": dict(mpnn_type="PAINN", input_dim=1, hidden_dim=64, num_conv_layers=2, num_radial=5, radius=7.0,
+                      max_neighbours=5, output_dim=[1], output_type=["graph"], task_weights=[1.0],
+                      output_heads={"graph": {"num_sharedlayers": 2, "dim_sharedlayers": 5, "num_headlayers": 2,
+                                              "dim_headlayers": [50, 25]}},
+                      activation_function="relu", loss_function_type="mse", graph_pooling="mean"),
+    # examples/md17/md17_mlip.json with the three MLIP weights set to 1
+    "md17_egnn": dict(mpnn_type="EGNN", input_dim=1, hidden_dim=64, num_conv_layers=3, num_radial=5, radius=7.0,
+                      max_neighbours=5, output_dim=[1], output_type=["node"], task_weights=[1.0],
+                      output_heads={"node": {"num_headlayers": 2, "dim_headlayers": [60, 20], "type": "mlp"}},
+                      activation_function="relu", loss_function_type="mse", enable_interatomic_potential=True,
+                      energy_weight=1.0, energy_peratom_weight=1.0, force_weight=1.0),
+    # examples/LennardJones/LJ.json with mpnn_type EGNN, 2 layers
+    "lj_egnn": dict(mpnn_type="EGNN", input_dim=1, hidden_dim=32, num_conv_layers=2, radius=5.0, max_neighbours=5,
+                    output_dim=[1], output_type=["node"], task_weights=[1.0],
+                    output_heads={"node": {"num_headlayers": 2, "dim_headlayers": [60, 20], "type": "mlp"}},
+                    activation_function="relu", loss_function_type="mse", enable_interatomic_potential=True,
+                    energy_weight=1.0, energy_peratom_weight=1.0, force_weight=1.0),
+}
+
+
+def _cube_positions(gen, num_graphs, n, box, min_sep, max_iter=200):
+    pos = torch.rand(num_graphs, n, 3, generator=gen) * box
+    eye = torch.eye(n, dtype=torch.bool)
+    for _ in range(max_iter):
+        d = torch.cdist(pos, pos)
+        close = (d < min_sep) & ~eye
+        bad = torch.triu(close, 1).any(dim=1)            # the later atom of every too-close pair
+        if not bool(bad.any()):
+            break
+        pos[bad] = torch.rand(int(bad.sum()), 3, generator=gen) * box
+    return pos
+
+
+def make_samples(name, num_graphs, seed=1234, with_edges=None):
+    """List-free construction: returns one ``Batch`` (CPU) with x, pos, batch, ptr, y / energy / forces
+    (+ cell, pbc for the periodic LJ workload).  Edges are NOT built here -- that is the radius-graph kernel's
+    job (or the oracle's, on the CPU side)."""
+    w = WORKLOADS[name]
+    gen = torch.Generator().manual_seed(seed)
+    n = w["n"]
+    if "lattice" in w:                                      # 3x3x3 simple cubic, jitter +-0.05 a (LJ_data.py:310-343)
+        a = w["lattice"]
+        grid = torch.stack(torch.meshgrid(*[torch.arange(3.0)] * 3, indexing="ij"), -1).reshape(-1, 3) * a
+        pos = grid[None] + (torch.rand(num_graphs, n, 3, generator=gen) - 0.5) * 0.1 * a
+        z = torch.ones(num_graphs, n)
+    else:
+        box = (n / w["rho"]) ** (1.0 / 3.0)
+        pos = _cube_positions(gen, num_graphs, n, box, 0.9)
+        sp = torch.tensor(w["species"], dtype=torch.float32)
+        if w.get("fixed_species"):
+            z = sp[None, :].expand(num_graphs, n).clone()
+        else:
+            z = sp[torch.randint(0, len(sp), (num_graphs, n), generator=gen)]
+    out = Batch()
+    out.x = z.reshape(-1, 1).contiguous()
+    out.pos = pos.reshape(-1, 3).contiguous()
+    out.batch = torch.arange(num_graphs).repeat_interleave(n)
+    out.ptr = torch.arange(num_graphs + 1) * n
+    out._num_graphs = num_graphs
+    out.y = torch.randn(num_graphs, 1, generator=gen)
+    out.energy = torch.randn(num_graphs, generator=gen)
+    out.forces = torch.randn(num_graphs * n, 3, generator=gen)
+    if w.get("pbc"):
+        L = 3 * w["lattice"]
+        out.cell = (torch.eye(3) * L)[None].expand(num_graphs, 3, 3).contiguous()
+        out.pbc = torch.ones(num_graphs, 3, dtype=torch.bool)
+    return out

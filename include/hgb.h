@@ -1,0 +1,249 @@
+/* hgb.h -- C-ABI of libhgb.so, the sm_100a hot-path library of hydragnn-b200.
+ *
+ * The reference (ORNL/HydraGNN) is 100 % Python and has no FFI boundary of its own: every
+ * GPU instruction on its hot path is issued by ATen or a third-party wheel (torch_scatter,
+ * torch_cluster, PyG).  Each entry point below therefore cites the *reference call site* (or
+ * third-party kernel it reaches) that it replaces, file:line relative to the reference tree.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers into caller-owned buffers, sizes, a cudaStream_t.  No torch
+ *     types, no allocation, no retained pointers, no global mutable state, no implicit
+ *     synchronisation: every call only enqueues work on `stream`.
+ *   - every function returns HGB_OK (0) or a negative HGB_E* code; hgb_last_error() returns a
+ *     thread-local message for the last failure on the calling thread.
+ *   - matrices are dense row-major fp32 unless stated; index arrays handed over by the host
+ *     framework are int64 (PyG convention), internal ones int32.
+ *   - reductions are deterministic (fixed summation order given the same inputs).
+ */
+#ifndef HGB_H
+#define HGB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* hgb_stream_t; /* cudaStream_t */
+
+#define HGB_OK 0
+#define HGB_EINVAL (-1)
+#define HGB_ECUDA (-2)
+#define HGB_ECAPACITY (-3)
+
+/* activation codes (hydragnn/utils/model/model.py:30-46 plus the ones hard-wired in the stacks) */
+#define HGB_ACT_NONE 0
+#define HGB_ACT_RELU 1
+#define HGB_ACT_SILU 2
+#define HGB_ACT_TANH 3
+#define HGB_ACT_SIGMOID 4
+#define HGB_ACT_LRELU 5 /* slope in `act_param` */
+#define HGB_ACT_ELU 6
+#define HGB_ACT_SELU 7
+
+/* pooling codes (hydragnn/models/Base.py:147-170) */
+#define HGB_POOL_ADD 0
+#define HGB_POOL_MEAN 1
+#define HGB_POOL_MAX 2
+
+int hgb_version(void);
+const char* hgb_last_error(void);
+/* number of kernels this library has launched from the calling process (bench.py gpu_launches) */
+int64_t hgb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Graph construction
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces torch_cluster.radius_graph reached through PyG RadiusGraph
+ * (hydragnn/preprocess/graph_samples_checks_and_updates.py:112-117,128-133).
+ * pos [n,3] fp32, graph_ptr [g+1] int32 (nodes of graph k are graph_ptr[k]..graph_ptr[k+1]).
+ * Pass 1 writes deg [n] (in-degree of every query/target node after the max_neighbors cap).  */
+int hgb_radius_graph_count(const float* pos, const int32_t* graph_ptr, int32_t n, int32_t g,
+                           float r, int32_t max_neighbors, int32_t loop, int32_t* deg,
+                           hgb_stream_t stream);
+/* Pass 2: rowptr [n+1] = exclusive scan of deg; writes edge_index [2,e] int64
+ * (row 0 = neighbour/source, row 1 = query/target; grouped by target ascending, sources ascending). */
+int hgb_radius_graph_fill(const float* pos, const int32_t* graph_ptr, int32_t n, int32_t g, float r,
+                          int32_t max_neighbors, int32_t loop, const int32_t* rowptr, int64_t e,
+                          int64_t* edge_index, hgb_stream_t stream);
+
+/* Periodic variant: replaces RadiusGraphPBC.__call__ (graph_samples...py:149-256: vesin neighbour
+ * list + _limit_neighbors nearest-k) for a whole batch.  pos [n,3] fp32 or fp64 (pos_is_f64),
+ * cell [g,3,3] fp64 (rows are lattice vectors), pbc [g,3] int32, cutoff [g] fp64 (per-graph so the
+ * caller can run the reference's radius-growth retry).  Distances are evaluated in fp64 as the
+ * reference does (vesin works in double).
+ * Pass 0: nimg [g,3] = number of periodic images to scan along each lattice vector.               */
+int hgb_radius_pbc_range(const void* pos, int32_t pos_is_f64, const int32_t* graph_ptr,
+                         const double* cell, const int32_t* pbc, const double* cutoff, int32_t n,
+                         int32_t g, int32_t* nimg, hgb_stream_t stream);
+/* Pass 1 counts all candidates (src, S) per target node (no cap yet).                            */
+int hgb_radius_pbc_count(const void* pos, int32_t pos_is_f64, const int32_t* graph_ptr,
+                         const double* cell, const int32_t* nimg, const double* cutoff, int32_t n,
+                         int32_t g, int32_t* cand_count, hgb_stream_t stream);
+/* Pass 2: candptr [n+1] = exclusive scan of cand_count; fills cand_src [c] int32, cand_shift [c,3]
+ * int32, cand_len [c] fp64 and sorts every target's segment by (len, src, Sx, Sy, Sz).           */
+int hgb_radius_pbc_fill(const void* pos, int32_t pos_is_f64, const int32_t* graph_ptr,
+                        const double* cell, const int32_t* nimg, const double* cutoff, int32_t n,
+                        int32_t g, const int32_t* candptr, int32_t* cand_src, int32_t* cand_shift,
+                        double* cand_len, hgb_stream_t stream);
+/* Pass 3: keeps the first min(count, max_neighbors) candidates of every target.  outptr [n+1] =
+ * exclusive scan of min(cand_count, max_neighbors) (hgb_clamp_i32 + scan).  Writes edge_index
+ * [2,e] int64 (src; dst), cell_shift [e,3] int32 and edge_shifts [e,3] fp32/fp64 = S @ cell
+ * (graph_samples...py:239-247).                                                                   */
+int hgb_radius_pbc_emit(const int32_t* graph_ptr, const double* cell, int32_t n, int32_t g,
+                        const int32_t* candptr, const int32_t* cand_src, const int32_t* cand_shift,
+                        int32_t max_neighbors, const int32_t* outptr, int64_t e, int64_t* edge_index,
+                        int32_t* cell_shift, void* edge_shifts, int32_t shifts_is_f64,
+                        hgb_stream_t stream);
+/* out[i] = min(in[i], cap) */
+int hgb_clamp_i32(const int32_t* in, int32_t cap, int64_t n, int32_t* out, hgb_stream_t stream);
+
+/* exclusive prefix sum of int32 (out has n+1 entries, out[n] = total).  workspace: >= 4*(n/1024+2) bytes */
+int hgb_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* workspace,
+                           hgb_stream_t stream);
+int64_t hgb_exclusive_scan_workspace_bytes(int64_t n);
+
+/* Builds a CSR view of an arbitrary index vector: rowptr [n+1], perm [e] such that the edges whose
+ * idx == k are perm[rowptr[k] .. rowptr[k+1]) in ascending edge id (stable).  Also writes idx32 [e].
+ * This is what lets every scatter of the reference (ATen scatter_add_/index_add_,
+ * hydragnn/models/EGCLStack.py:294-300, hydragnn/models/PAINNStack.py:263-266) run as an
+ * atomics-free segmented reduction.  workspace: hgb_csr_workspace_bytes(e, n).                  */
+int hgb_csr_build(const int64_t* idx, int64_t e, int32_t n, int32_t* idx32, int32_t* rowptr,
+                  int32_t* perm, void* workspace, hgb_stream_t stream);
+int64_t hgb_csr_workspace_bytes(int64_t e, int32_t n);
+
+/* ------------------------------------------------------------------------------------------
+ * Gather / segmented reductions (mutual adjoints)
+ * ------------------------------------------------------------------------------------------ */
+
+/* out[e, :] = x[idx[e], :]      -- aten::index at hydragnn/models/EGCLStack.py:284 etc. */
+int hgb_gather_rows(const float* x, const int32_t* idx, int64_t e, int32_t c, float* out,
+                    hgb_stream_t stream);
+/* out[k, :] = sum over p in [rowptr[k], rowptr[k+1]) of m[perm[p], :]   (perm may be NULL = identity)
+ * -- ATen scatter_add_ / index_add_ / torch_scatter.scatter_add.  Algorithmic bytes:
+ * E*C*4 + E*4 + N*C*4 (SURVEY 8d "scatter primitive").                                          */
+int hgb_segment_sum(const float* m, const int32_t* rowptr, const int32_t* perm, int32_t n, int32_t c,
+                    float* out, hgb_stream_t stream);
+/* graph pooling over sorted `batch` (graph_ptr [g+1]); mode HGB_POOL_*.  argmax [g,c] int32 is
+ * written for HGB_POOL_MAX (may be NULL otherwise).  -- PyG global_*_pool, Base.py:147-170.     */
+int hgb_pool_fwd(const float* x, const int32_t* graph_ptr, int32_t g, int32_t c, int32_t mode,
+                 float* out, int32_t* argmax, hgb_stream_t stream);
+int hgb_pool_bwd(const float* gout, const int32_t* graph_ptr, const int32_t* argmax, int32_t n,
+                 int32_t g, int32_t c, int32_t mode, float* gx, hgb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense layers (cuBLAS call sites of nn.Linear in every stack / head)
+ * ------------------------------------------------------------------------------------------ */
+
+/* C[m,n] = op(A) . op(B); op = transpose when the flag is set; lda/ldb/ldc are row strides.
+ * beta_one != 0 accumulates into C.  workspace (split-K partials): hgb_gemm_workspace_bytes.     */
+int hgb_gemm(const float* a, const float* b, float* c, int32_t m, int32_t n, int32_t k,
+             int32_t trans_a, int32_t trans_b, int64_t lda, int64_t ldb, int64_t ldc, int32_t beta_one,
+             void* workspace, int64_t workspace_bytes, hgb_stream_t stream);
+int64_t hgb_gemm_workspace_bytes(int32_t m, int32_t n, int32_t k, int32_t trans_a);
+/* y = act(x . W^T + b); x [m,k] with row stride ldx, W [n,k] with row stride ldw (so a column block
+ * of a wider weight matrix can be applied without a copy), b [n] or NULL, y [m,n] dense; z
+ * (pre-activation, dense [m,n]) is written when non-NULL (needed by the SiLU backward).           */
+int hgb_linear_fwd(const float* x, const float* w, const float* b, int32_t m, int32_t n, int32_t k,
+                   int64_t ldx, int64_t ldw, int32_t act, float act_param, float* y, float* z,
+                   hgb_stream_t stream);
+/* dz = dy * act'(.) evaluated from y (or from z for SiLU, which must then be non-NULL).           */
+int hgb_act_bwd(const float* dy, const float* y, const float* z, int64_t count, int32_t act,
+                float act_param, float* dz, hgb_stream_t stream);
+/* elementwise activation value (order 0) or its order-th derivative (1..2) at x                   */
+int hgb_act_deriv(const float* x, int64_t count, int32_t act, float act_param, int32_t order,
+                  float* out, hgb_stream_t stream);
+/* out[j] = sum_i x[i, j]  (bias gradient).  workspace: hgb_colsum_workspace_bytes(m, n).          */
+int hgb_colsum(const float* x, int32_t m, int32_t n, float* out, void* workspace, hgb_stream_t stream);
+int64_t hgb_colsum_workspace_bytes(int32_t m, int32_t n);
+
+/* ------------------------------------------------------------------------------------------
+ * Edge geometry  (hydragnn/utils/model/operations.py:21-36 and the RBF / cutoff chains of
+ * hydragnn/models/PAINNStack.py:331-352)
+ * ------------------------------------------------------------------------------------------ */
+
+/* vec = pos[col] - pos[row] + shift; len = |vec|; unit = vec / (len + eps).  Any output may be NULL. */
+int hgb_edge_geom_fwd(const float* pos, const int32_t* row, const int32_t* col, const float* shifts,
+                      int64_t e, float eps, float* vec, float* len, float* unit, hgb_stream_t stream);
+/* g_vec = g_vec_in + g_len * vec/len + d(unit)/d(vec)^T g_unit   (NULL gradients are zero).       */
+int hgb_edge_geom_bwd(const float* vec, const float* len, float eps, const float* g_vec_in,
+                      const float* g_len, const float* g_unit, int64_t e, float* g_vec,
+                      hgb_stream_t stream);
+/* PaiNN edge embedding: len -> dir = unit/len (quirk Q2, PAINNStack.py:257), rbfc [e,r] =
+ * sin(n pi d / rc)/d * fcut(d), fc [e] = fcut(d).                                                 */
+int hgb_painn_edge_embed_fwd(const float* unit, const float* len, int64_t e, int32_t r, float cutoff,
+                             float* dir, float* rbfc, float* fc, hgb_stream_t stream);
+/* backward of the above: (g_dir, g_rbfc, g_fc) -> (g_unit, g_len)                                 */
+int hgb_painn_edge_embed_bwd(const float* unit, const float* len, const float* g_dir,
+                             const float* g_rbfc, const float* g_fc, int64_t e, int32_t r, float cutoff,
+                             float* g_unit, float* g_len, hgb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * PaiNN  (hydragnn/models/PAINNStack.py:194-328)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Fused message: for every node i, over its CSR segment (edges with edge[:,0] == i):
+ *   W = Wf . rbfc[e] + bf * fc[e] (* efilt[e]);  f = W * phi[src[e]];  (g_v, g_e, m_s) = split(f)
+ *   s_out[i] = s[i] + sum m_s;  v_out[i,k] = v[i,k] + sum (v[src,k] * g_v + g_e * dir[e,k])
+ * Replaces filter GEMM + 2 gathers + 2 index_add_ (PAINNStack.py:239-270); nothing per-edge is
+ * written.  Algorithmic bytes: E*(6F*4 + 2*4 + 4*(R+4)) + 12*N*F*4.
+ * phi [n,3f], s [n,f], v [n,3,f], src [e] = edge[:,1], wf [3f,r], bf [3f], efilt [e,3f] or NULL.   */
+int hgb_painn_message_fwd(const float* phi, const float* s, const float* v, const int32_t* rowptr,
+                          const int32_t* perm, const int32_t* src, const float* dir, const float* rbfc,
+                          const float* fc, const float* wf, const float* bf, const float* efilt,
+                          int32_t n, int32_t f, int32_t r, float* s_out, float* v_out,
+                          hgb_stream_t stream);
+/* Backward of the fused message, as a segmented reduction over the CSR of edge[:,1] (the gather
+ * side).  gs_out [n,f], gv_out [n,3,f] are the incoming gradients; agg [e] = edge[:,0].
+ * Outputs: gphi [n,3f]; gv [n,3,f] (= gv_out + gathered part; gs_in == gs_out is the caller's);
+ * gwf [3f,r], gbf [3f] (via workspace partials); optional per-edge g_dir [e,3], g_rbfc [e,r],
+ * g_fc [e] (all three NULL or all non-NULL) and g_efilt [e,3f] (iff efilt).                        */
+int hgb_painn_message_bwd(const float* gs_out, const float* gv_out, const float* phi, const float* v,
+                          const int32_t* rowptr_src, const int32_t* perm_src, const int32_t* agg,
+                          const float* dir, const float* rbfc, const float* fc, const float* wf,
+                          const float* bf, const float* efilt, int32_t n, int32_t f, int32_t r,
+                          float* gphi, float* gv, float* gwf, float* gbf, float* g_dir, float* g_rbfc,
+                          float* g_fc, float* g_efilt, void* workspace, int64_t workspace_bytes,
+                          hgb_stream_t stream);
+int64_t hgb_painn_message_bwd_workspace_bytes(int32_t n, int32_t f, int32_t r);
+
+/* Update block glue (PAINNStack.py:298-328).  uv, vv [n,3,f] are update_U(v), update_V(v).
+ * pre:  mlp_in [n,2f] = [ |vv| over the 3 components , s ]                                        */
+int hgb_painn_update_pre_fwd(const float* vv, const float* s, int32_t n, int32_t f, float* mlp_in,
+                             hgb_stream_t stream);
+/* post: a [n,(2|3)f] from update_mlp.  s_out = s + a_sv * sum_k(uv*vv) + a_ss;
+ *       v_out = v + a_vv * uv (skipped when last != 0: a = (a_sv, a_ss), v_out may be NULL)        */
+int hgb_painn_update_post_fwd(const float* a, const float* uv, const float* vv, const float* s,
+                              const float* v, int32_t n, int32_t f, int32_t last, float* s_out,
+                              float* v_out, hgb_stream_t stream);
+/* backward of pre+post in one pass.  Inputs: gs_out, gv_out (NULL when last), g_mlp_in [n,2f]
+ * (gradient that came back through update_mlp), a, uv, vv, mlp_in.  Outputs: ga [n,(2|3)f] is
+ * produced by *_post_bwd_a (needed before the MLP backward can run), then the rest.                */
+int hgb_painn_update_post_bwd_a(const float* gs_out, const float* gv_out, const float* uv,
+                                const float* vv, int32_t n, int32_t f, int32_t last, float* ga,
+                                hgb_stream_t stream);
+int hgb_painn_update_bwd(const float* gs_out, const float* gv_out, const float* g_mlp_in,
+                         const float* a, const float* uv, const float* vv, const float* mlp_in,
+                         int32_t n, int32_t f, int32_t last, float* guv, float* gvv, float* gs,
+                         float* gv, hgb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Loss / optimizer (hydragnn/train/train_validate_test.py:736-769, torch.optim.AdamW)
+ * ------------------------------------------------------------------------------------------ */
+
+/* loss[0] = mean((pred - target)^2) (mode 0) or mean(|pred - target|) (mode 1);
+ * gpred = d loss / d pred * gscale.  Single-block deterministic reduction.                         */
+int hgb_loss_fwd_bwd(const float* pred, const float* target, int64_t count, int32_t mode, float gscale,
+                     float* loss, float* gpred, hgb_stream_t stream);
+/* Fused AdamW over one flat parameter buffer: p, g, m, v [count]; `grad_scale` multiplies g first
+ * (1/world_size after the flat all-reduce); step is 1-based and read from device (`step_dev`, fp32,
+ * incremented by the kernel) so the launch is CUDA-graph capturable.                               */
+int hgb_adamw_step(float* p, const float* g, float* m, float* v, int64_t count, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, float grad_scale, float* step_dev,
+                   hgb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGB_H */

@@ -79,7 +79,7 @@ def _neighbor_list_ijS(pos64, cell64, pbc, cutoff):
     n = pos64.shape[0]
     if n == 0:
         z = np.zeros(0, dtype=np.int64)
-        return z, z, np.zeros((0, 3), dtype=np.int64)
+        return z, z, np.zeros((0, 3), dtype=np.int64), np.zeros(0)
     pbc = [bool(b) for b in pbc]
     nimg = [0, 0, 0]
     if any(pbc):
@@ -95,12 +95,14 @@ def _neighbor_list_ijS(pos64, cell64, pbc, cutoff):
             nimg[k] = int(np.ceil(cutoff / height + spread)) + 1
     rng = [np.arange(-m, m + 1) for m in nimg]
     S = np.stack(np.meshgrid(*rng, indexing="ij"), -1).reshape(-1, 3).astype(np.int64)
-    out_i, out_j, out_S = [], [], []
+    out_i, out_j, out_S, out_len = [], [], [], []
     c2 = cutoff * cutoff
     base = pos64[None, :, :] - pos64[:, None, :]            # [i, j] = pos[j] - pos[i]
     for s in S:
-        v = base + (s.astype(np.float64) @ cell64)[None, None, :]
-        d2 = (v * v).sum(-1)
+        # every operation individually rounded, in this order (the CUDA kernel does the same)
+        sh = (float(s[0]) * cell64[0] + float(s[1]) * cell64[1]) + float(s[2]) * cell64[2]
+        v = base + sh[None, None, :]
+        d2 = (v[..., 0] * v[..., 0] + v[..., 1] * v[..., 1]) + v[..., 2] * v[..., 2]
         ok = d2 < c2
         if not s.any():
             ok &= ~np.eye(n, dtype=bool)                    # never the zero-shift self pair
@@ -108,8 +110,14 @@ def _neighbor_list_ijS(pos64, cell64, pbc, cutoff):
         out_i.append(ii)
         out_j.append(jj)
         out_S.append(np.broadcast_to(s, (ii.size, 3)))
+        out_len.append(np.sqrt(d2[ii, jj]))
     return (np.concatenate(out_i).astype(np.int64), np.concatenate(out_j).astype(np.int64),
-            np.concatenate(out_S).astype(np.int64))
+            np.concatenate(out_S).astype(np.int64), np.concatenate(out_len))
+
+
+def _shift_vectors(S, cell64):
+    Sf = S.astype(np.float64)
+    return (Sf[:, 0:1] * cell64[0][None] + Sf[:, 1:2] * cell64[1][None]) + Sf[:, 2:3] * cell64[2][None]
 
 
 def limit_neighbors(src, dst, length, shifts, k):
@@ -146,9 +154,8 @@ def radius_graph_pbc(pos, cell, pbc, r, loop=False, max_num_neighbors=32):
     n = p64.shape[0]
     cutoff = float(r)
     for attempt in range(3):
-        src, dst, S = _neighbor_list_ijS(p64, c64, pbc_l, cutoff)
-        vec = p64[dst] - p64[src] + S.astype(np.float64) @ c64
-        length = np.linalg.norm(vec, axis=1)
+        # the reference recomputes |pos[dst]-pos[src]+S@cell| with numpy (:179-183); same values
+        src, dst, S, length = _neighbor_list_ijS(p64, c64, pbc_l, cutoff)
         if not loop:  # _remove_true_self_loops (:258-264) -- a no-op on a vesin list
             keep = ~((src == dst) & (S == 0).all(1))
             src, dst, length, S = src[keep], dst[keep], length[keep], S[keep]
@@ -170,7 +177,7 @@ def radius_graph_pbc(pos, cell, pbc, r, loop=False, max_num_neighbors=32):
         S = np.vstack([S, np.zeros((n, 3), dtype=S.dtype)])
     ei = torch.from_numpy(np.stack([src, dst]).astype(np.int64))
     np_dt = np.float32 if pos.dtype == torch.float32 else np.float64
-    shifts = torch.from_numpy((S.astype(np.float64) @ c64).astype(np_dt))
+    shifts = torch.from_numpy(_shift_vectors(S, c64).astype(np_dt))
     return ei, shifts
 
 
