@@ -59,7 +59,18 @@ def create_model_config(config, verbosity=0, use_gpu=True):
     prec = str(training.get("precision", "fp32")).lower()
     if prec in ("fp64", "float64", "double"):
         raise ValueError("the b200 engine computes in fp32 (bf16 tensor-core GEMMs under precision='bf16'); fp64 is not supported")
-    model.precision = "bf16" if prec in ("bf16", "bfloat16") else "fp32"
+    return set_precision(model, "bf16" if prec in ("bf16", "bfloat16") else "fp32")
+
+
+def set_precision(model, precision):
+    """'fp32': exact fp32 kernels everywhere.  'bf16': the large-M Linear layers run on the tcgen05 tensor-core
+    kernels (TF32 products, fp32 accumulation; parameters and activations stay fp32 like the reference's
+    autocast mode, hydragnn/train/train_validate_test.py:43-49)."""
+    if precision not in ("fp32", "bf16"):
+        raise ValueError("Unsupported precision %s" % (precision,))
+    model.precision = precision
+    for m in model.modules():
+        m.precision = precision
     return model
 
 

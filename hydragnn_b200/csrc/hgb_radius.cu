@@ -48,8 +48,8 @@ __global__ void radius_open_kernel(const float* __restrict__ pos, const int32_t*
 
 extern "C" int hgb_radius_graph_count(const float* pos, const int32_t* graph_ptr, int32_t n, int32_t g, float r,
                                       int32_t max_neighbors, int32_t loop, int32_t* deg, hgb_stream_t stream) {
-  HGB_REQUIRE(n >= 0 && g >= 0 && r > 0.f && max_neighbors > 0 && deg, "radius_graph_count: bad arguments");
   if (n == 0) return HGB_OK;
+  HGB_REQUIRE(n > 0 && g >= 0 && r > 0.f && max_neighbors > 0 && deg, "radius_graph_count: bad arguments");
   int cap = loop ? max_neighbors : (max_neighbors == INT32_MAX ? max_neighbors : max_neighbors + 1);
   radius_open_kernel<false><<<hgb_grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(pos, graph_ptr, n, g, r, cap, loop,
                                                                                    deg, nullptr, 0, nullptr);
@@ -60,8 +60,8 @@ extern "C" int hgb_radius_graph_count(const float* pos, const int32_t* graph_ptr
 extern "C" int hgb_radius_graph_fill(const float* pos, const int32_t* graph_ptr, int32_t n, int32_t g, float r,
                                      int32_t max_neighbors, int32_t loop, const int32_t* rowptr, int64_t e,
                                      int64_t* edge_index, hgb_stream_t stream) {
-  HGB_REQUIRE(n >= 0 && g >= 0 && r > 0.f && max_neighbors > 0 && rowptr, "radius_graph_fill: bad arguments");
   if (n == 0 || e == 0) return HGB_OK;
+  HGB_REQUIRE(n > 0 && g >= 0 && r > 0.f && max_neighbors > 0 && rowptr, "radius_graph_fill: bad arguments");
   int cap = loop ? max_neighbors : (max_neighbors == INT32_MAX ? max_neighbors : max_neighbors + 1);
   radius_open_kernel<true><<<hgb_grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(pos, graph_ptr, n, g, r, cap, loop,
                                                                                   nullptr, rowptr, e, edge_index);

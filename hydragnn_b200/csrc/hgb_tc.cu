@@ -1,0 +1,534 @@
+// libhgb.so -- tensor-core (tcgen05 / TMEM / TMA) dense layers for the large-M, small-N/K GEMMs of the
+// node/edge MLPs.  sm_100a only.
+//
+// Why TF32: activations live in HBM as fp32 (parameters are fp32 in every reference precision mode,
+// hydragnn/train/train_validate_test.py:43-49).  kind::tf32 consumes fp32 bit patterns straight from shared
+// memory, so the activation tiles go HBM -> smem by TMA with no conversion pass, and the result (10-bit mantissa
+// products, fp32 accumulation in TMEM) is strictly more accurate than the bf16 autocast the reference runs
+// under precision="bf16".  These GEMMs are memory-bound (AI ~ 12-24 FLOP/B), so TF32's half-rate is irrelevant.
+//
+// Three kernels:
+//   tc_linear_kernel  : Y[M,NO] = act(A[M,KR] . B^T + bias)   B = W (NO x KR, forward) or W^T (dgrad)
+//                       persistent, warp-specialised: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc),
+//                       warps 2-5 = epilogue (TMEM -> registers -> bias/act -> global).  The weight operand is
+//                       staged once per CTA; the A tiles stream through a 2-4 stage mbarrier ring; two TMEM
+//                       accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
+//   tc_wgrad_kernel   : dW[NO,KO] (+ db[NO]) = dZ[M,NO]^T . X[M,KO]: both operands MN-major straight from the
+//                       row-major tensors, reduction over M split across CTAs, per-CTA partials + deterministic
+//                       final reduce.  The bias gradient rides along as 16 extra "ones" columns of the B operand.
+#include <cuda.h>
+
+#include "hgb_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* holder, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(holder)), "r"(cols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols));
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]   (issued by ONE thread)
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread t <- lane base+t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor, SWIZZLE_128B, version 1 (cute/arch/mma_sm100_desc.hpp SmemDescriptor)
+// layout_type: 2 = SWIZZLE_128B (16-B atoms; K-major operands), 1 = SWIZZLE_128B_BASE32B (32-B atoms; what UMMA
+// needs for MN-major 32-bit operands, cute Layout_MN_SW128_32B_Atom)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+// instruction descriptor: D = f32, A = B = tf32 (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// byte offset of element (r, c) of a K-major SWIZZLE_128B operand stored as column blocks of 32 fp32:
+// block cb = c/32 is a [rows x 128 B] slab; 8-row groups are 1024 B apart; 16-B chunks are XOR-swizzled by r%8
+__device__ __forceinline__ uint32_t kmajor_sw128_off(int r, int c, int rows) {
+  const int cb = c >> 5, cc = (c & 31) >> 2, j = c & 3;
+  return (uint32_t)cb * rows * 128 + (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128 + (uint32_t)((cc ^ (r & 7)) << 4) + j * 4;
+}
+
+struct LinParams {
+  int m, kr, no;        // rows, reduction length, output columns
+  const float* w;       // weight matrix [n_w, k_w], row stride ldw
+  int64_t ldw;
+  int trans_b;          // 0: B(r, c) = w[r, c] (forward: no = n_w, kr = k_w); 1: B(r, c) = w[c, r] (dgrad: no = k_w, kr = n_w)
+  const float* bias;
+  int act;
+  float act_param;
+  float* y;
+  float* z;
+  int stages;
+  int tmem_cols;
+};
+
+constexpr int TILE_M = 128;
+
+__global__ void __launch_bounds__(192, 1) tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const LinParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int KB = p.kr >> 5;
+  const int NO = p.no;
+  const uint32_t b_bytes = (uint32_t)KB * NO * 128;
+  constexpr uint32_t a_stage = TILE_M * 128;   // one pipeline stage = one [128 x 32 fp32] k-block (16 KB)
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + ((b_bytes + 1023) & ~1023u);
+  const int S = p.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sA + (size_t)S * a_stage);
+  uint64_t* empty = full + S;
+  uint64_t* tfull = empty + S;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = (p.m + TILE_M - 1) / TILE_M;
+
+  // ---- one-time setup -------------------------------------------------------------------------------
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, (uint32_t)p.tmem_cols);
+  // stage the weight operand (generic-proxy stores, then make them visible to the async proxy)
+  {
+    const int total = NO * p.kr;
+    if (!p.trans_b) {
+      for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int r = i / p.kr, c = i - r * p.kr;
+        *reinterpret_cast<float*>(sB + kmajor_sw128_off(r, c, NO)) = __ldg(p.w + (int64_t)r * p.ldw + c);
+      }
+    } else {
+      for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int c = i / NO, r = i - c * NO;  // r fastest: w[c, r] is contiguous in r
+        *reinterpret_cast<float*>(sB + kmajor_sw128_off(r, c, NO)) = __ldg(p.w + (int64_t)c * p.ldw + r);
+      }
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t idesc = make_idesc(TILE_M, NO, 0, 0);
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(empty + s, ph ^ 1);
+          mbar_expect_tx(full + s, a_stage);
+          tma_load_2d(sA + (size_t)s * a_stage, &tmap_a, full + s, kb * 32, t * TILE_M);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int s = 0, acc = 0;
+      uint32_t ph = 0, aph = 0;
+      const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        mbar_wait(tempty + acc, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + (uint32_t)acc * NO;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(full + s, ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint64_t ad = make_desc(sA_addr + s * a_stage + k4 * 32, 16, 1024);
+            const uint64_t bd = make_desc(sB_addr + kb * NO * 128 + k4 * 32, 16, 1024);
+            umma_tf32(d_addr, ad, bd, idesc, (kb | k4) != 0);
+          }
+          umma_commit(empty + s);    // smem stage free once these MMAs have read it
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+        umma_commit(tfull + acc);    // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5, each owns the TMEM lane quarter (warp % 4) =====
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t aph = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      mbar_wait(tfull + acc, aph);
+      tc_fence_after();
+      const int row = t * TILE_M + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * NO;
+      for (int c0 = 0; c0 < NO; c0 += 32) {
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        if (row < p.m) {
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + c0 + j);
+          }
+          if (p.z) {
+            float4* zp = reinterpret_cast<float4*>(p.z + (int64_t)row * NO + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) zp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (p.act != HGB_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = hgb_act(v[j], p.act, p.act_param);
+          }
+          float4* yp = reinterpret_cast<float4*>(p.y + (int64_t)row * NO + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + acc);
+      if (++acc == 2) { acc = 0; aph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient: dW[NO, KO] (+ db[NO]) = sum_m dZ[m, NO]^T X[m, KO]
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_ROWS = 64;            // rows of dZ / X per pipeline stage (8 MMA k-steps of 8 rows)
+constexpr int WG_CHUNK = WG_ROWS * 128;  // one [64 x 32 fp32] slab = 8 KB
+
+struct WgParams {
+  int m, no, ko;
+  int chunks_per_cta;   // number of 64-row chunks each CTA reduces
+  int stages;
+  int tmem_cols;
+  int mblocks;          // ceil(no / 128)
+  int nmma;             // ko + 16 (ones columns for the bias gradient)
+  float* part;          // [gridDim.x, no, ko + 1]
+};
+
+__global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz,
+                                                          const __grid_constant__ CUtensorMap tmap_x, const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int a_chunks = p.mblocks * 4;          // allocated MN slabs of the A operand (>= no/32; the tail is never read back)
+  const int b_chunks = (p.ko >> 5) + 1;        // + the ones slab
+  const uint32_t stage_bytes = (uint32_t)(a_chunks + b_chunks) * WG_CHUNK;
+  const int S = p.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+  uint64_t* empty = full + S;
+  uint64_t* done = empty + S;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int total_chunks = (p.m + WG_ROWS - 1) / WG_ROWS;
+  const int c_beg = blockIdx.x * p.chunks_per_cta;
+  const int c_end = min(total_chunks, c_beg + p.chunks_per_cta);
+  const int nchunks = max(0, c_end - c_beg);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, (uint32_t)p.tmem_cols);
+  // ones slab of every stage (all elements equal, so the swizzle does not matter)
+  for (int s = 0; s < S; ++s) {
+    float* ones = reinterpret_cast<float*>(smem + (size_t)s * stage_bytes + (size_t)(a_chunks + b_chunks - 1) * WG_CHUNK);
+    for (int i = threadIdx.x; i < WG_CHUNK / 4; i += blockDim.x) ones[i] = 1.0f;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t idesc = make_idesc(128, p.nmma, 1, 1);
+  const uint32_t tx_bytes = (uint32_t)((p.no >> 5) + (p.ko >> 5)) * WG_CHUNK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(empty + s, ph ^ 1);
+        mbar_expect_tx(full + s, tx_bytes);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        const int row0 = (c_beg + c) * WG_ROWS;
+        for (int j = 0; j < (p.no >> 5); ++j) tma_load_2d(st + (size_t)j * WG_CHUNK, &tmap_dz, full + s, j * 32, row0);
+        for (int j = 0; j < (p.ko >> 5); ++j) tma_load_2d(st + (size_t)(a_chunks + j) * WG_CHUNK, &tmap_x, full + s, j * 32, row0);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t base = smem_u32(smem);
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(full + s, ph);
+        tc_fence_after();
+        const uint32_t st = base + s * stage_bytes;
+#pragma unroll
+        for (int ks = 0; ks < WG_ROWS / 8; ++ks) {
+          const uint64_t bd = make_desc(st + a_chunks * WG_CHUNK + ks * 1024, WG_CHUNK, 512, 1);
+          for (int mb = 0; mb < p.mblocks; ++mb) {
+            const uint64_t ad = make_desc(st + mb * 4 * WG_CHUNK + ks * 1024, WG_CHUNK, 512, 1);
+            umma_tf32(tmem_base + (uint32_t)mb * p.nmma, ad, bd, idesc, (c | ks) != 0);
+          }
+        }
+        umma_commit(empty + s);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+      umma_commit(done);
+    }
+  } else {
+    // epilogue: after the whole reduction, dump this CTA's partial
+    const int q = warp & 3;
+    mbar_wait(done, 0);
+    tc_fence_after();
+    float* part = p.part + (size_t)blockIdx.x * p.no * (p.ko + 1);
+    for (int mb = 0; mb < p.mblocks; ++mb) {
+      const int row = mb * 128 + q * 32 + lane;   // output row = weight row n
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)mb * p.nmma;
+      for (int c0 = 0; c0 < p.nmma; c0 += 32) {   // nmma = ko + 16: the last piece is read 32 wide and masked
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        if (row < p.no && nchunks > 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = c0 + j;
+            if (col <= p.ko) part[(size_t)row * (p.ko + 1) + col] = v[j];   // col == ko is the bias gradient
+          }
+        } else if (row < p.no) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = c0 + j;
+            if (col <= p.ko) part[(size_t)row * (p.ko + 1) + col] = 0.f;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+__global__ void tc_wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int no, int ko, float* __restrict__ dw,
+                                       int64_t lddw, float* __restrict__ db, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = ko + 1;
+  if (i >= no * w) return;
+  float acc = 0.f;
+  for (int b = 0; b < nparts; ++b) acc += part[(size_t)b * no * w + i];
+  const int r = i / w, c = i % w;
+  if (c == ko) {
+    if (db) db[r] = accumulate ? db[r] + acc : acc;
+  } else {
+    float* o = dw + (int64_t)r * lddw + c;
+    *o = accumulate ? *o + acc : acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major tensor [rows, cols] with row stride ld (elements); box = [box_rows x 32 cols], 128B swizzle
+int make_tmap(CUtensorMap* tm, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+              CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { hgb_set_error("tc: cuTensorMapEncodeTiled is not available from the driver"); return HGB_ECUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { hgb_set_error("tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return HGB_ECUDA; }
+  return HGB_OK;
+}
+
+int pow2_cols(int c) {
+  int p = 32;
+  while (p < c) p <<= 1;
+  return p;
+}
+
+bool shape_ok(int kr, int no) { return kr >= 32 && kr <= 256 && kr % 32 == 0 && no >= 32 && no <= 256 && no % 32 == 0; }
+
+}  // namespace
+
+extern "C" int hgb_tc_linear_supported(int32_t m, int32_t n_out, int32_t k_red) { return (m >= 128 && shape_ok(k_red, n_out)) ? 1 : 0; }
+
+// y[m, no] = act(a[m, kr] . B^T + bias);  B(r, c) = w[r, c] (trans_b = 0) or w[c, r] (trans_b = 1)
+extern "C" int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_t ldw, int32_t trans_b, const float* bias, int32_t m,
+                             int32_t n_out, int32_t k_red, int32_t act, float act_param, float* y, float* z, hgb_stream_t stream) {
+  HGB_REQUIRE(a && w && y && hgb_tc_linear_supported(m, n_out, k_red), "tc_linear: unsupported shape m=%d n=%d k=%d", m, n_out, k_red);
+  HGB_REQUIRE(lda % 4 == 0 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!z || (uintptr_t)z % 16 == 0),
+              "tc_linear: operands must be 16-byte aligned with a row stride that is a multiple of 4");
+  CUtensorMap tm;
+  int rc = make_tmap(&tm, a, m, k_red, lda, TILE_M);
+  if (rc) return rc;
+  LinParams p;
+  p.m = m; p.kr = k_red; p.no = n_out; p.w = w; p.ldw = ldw; p.trans_b = trans_b; p.bias = bias; p.act = act; p.act_param = act_param;
+  p.y = y; p.z = z;
+  const int KB = k_red / 32;
+  const size_t b_bytes = ((size_t)KB * n_out * 128 + 1023) & ~(size_t)1023;
+  const size_t a_stage = (size_t)TILE_M * 128;
+  int stages = (int)((200 * 1024 - b_bytes) / a_stage);
+  if (stages > 8) stages = 8;
+  HGB_REQUIRE(stages >= 2, "tc_linear: weight operand does not fit shared memory (n=%d k=%d)", n_out, k_red);
+  p.stages = stages;
+  p.tmem_cols = pow2_cols(2 * n_out);
+  const size_t smem = 1024 + b_bytes + stages * a_stage + (2 * stages + 4) * 8 + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  const int ntiles = (m + TILE_M - 1) / TILE_M;
+  const int grid = ntiles < HGB_NUM_SMS ? ntiles : HGB_NUM_SMS;
+  tc_linear_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tm, p);
+  HGB_LAUNCH_CHECK("tc_linear");
+  return HGB_OK;
+}
+
+extern "C" int64_t hgb_tc_wgrad_workspace_bytes(int32_t n_out, int32_t k_out) { return (int64_t)HGB_NUM_SMS * n_out * (k_out + 1) * 4; }
+
+// dw[no, ko] (row stride lddw) (+)= dz[m, no]^T x[m, ko];  db[no] (+)= column sums of dz (db may be NULL)
+extern "C" int hgb_tc_wgrad(const float* dz, int64_t lddz, const float* x, int64_t ldx, int32_t m, int32_t n_out, int32_t k_out,
+                            float* dw, int64_t lddw, float* db, int32_t accumulate, void* workspace, int64_t workspace_bytes,
+                            hgb_stream_t stream) {
+  HGB_REQUIRE(dz && x && dw && workspace && hgb_tc_linear_supported(m, n_out, k_out) && k_out + 16 <= 256,
+              "tc_wgrad: unsupported shape m=%d n=%d k=%d", m, n_out, k_out);
+  HGB_REQUIRE(lddz % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)dz % 16 == 0) && ((uintptr_t)x % 16 == 0), "tc_wgrad: operands must be 16-byte aligned");
+  HGB_REQUIRE(workspace_bytes >= hgb_tc_wgrad_workspace_bytes(n_out, k_out), "tc_wgrad: workspace too small");
+  CUtensorMap tdz, tx;
+  int rc = make_tmap(&tdz, dz, m, n_out, lddz, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc) return rc;
+  rc = make_tmap(&tx, x, m, k_out, ldx, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc) return rc;
+  WgParams p;
+  p.m = m; p.no = n_out; p.ko = k_out;
+  p.mblocks = (n_out + 127) / 128;
+  p.nmma = k_out + 16;
+  p.tmem_cols = pow2_cols(p.mblocks * p.nmma);
+  HGB_REQUIRE(p.tmem_cols <= 512, "tc_wgrad: accumulator does not fit TMEM");
+  const int a_chunks = p.mblocks * 4, b_chunks = k_out / 32 + 1;
+  const size_t stage_bytes = (size_t)(a_chunks + b_chunks) * WG_CHUNK;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 4) stages = 4;
+  HGB_REQUIRE(stages >= 2, "tc_wgrad: stage does not fit shared memory");
+  p.stages = stages;
+  const int total_chunks = (m + WG_ROWS - 1) / WG_ROWS;
+  int grid = total_chunks < HGB_NUM_SMS ? total_chunks : HGB_NUM_SMS;
+  p.chunks_per_cta = (total_chunks + grid - 1) / grid;
+  grid = (total_chunks + p.chunks_per_cta - 1) / p.chunks_per_cta;
+  p.part = (float*)workspace;
+  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 1) * 8 + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  tc_wgrad_kernel<<<grid, 192, smem, st>>>(tdz, tx, p);
+  HGB_LAUNCH_CHECK("tc_wgrad");
+  const int outs = n_out * (k_out + 1);
+  tc_wgrad_reduce_kernel<<<(outs + 127) / 128, 128, 0, st>>>(p.part, grid, n_out, k_out, dw, lddw, db, accumulate);
+  HGB_LAUNCH_CHECK("tc_wgrad_reduce");
+  return HGB_OK;
+}

@@ -139,6 +139,87 @@ def raw_colsum(x2d):
     return out
 
 
+# ---- tensor-core (tcgen05 / TF32) dense layers: enabled per model by precision="bf16" -----------------
+_TC = {"enabled": False}
+
+
+class tensor_cores:
+    """Context manager: run the large-M Linear layers on the tcgen05 TF32 kernels (hgb_tc_*)."""
+
+    def __init__(self, enabled=True):
+        self.enabled, self.prev = bool(enabled), None
+
+    def __enter__(self):
+        self.prev = _TC["enabled"]
+        _TC["enabled"] = self.enabled
+        return self
+
+    def __exit__(self, *exc):
+        _TC["enabled"] = self.prev
+        return False
+
+
+def tc_ok(m, n_out, k_red, *tensors):
+    if not _TC["enabled"]:
+        return False
+    if not _lib.query("hgb_tc_linear_supported", m, n_out, k_red):
+        return False
+    for t in tensors:
+        if t is not None and (t.data_ptr() % 16 != 0 or (t.dim() == 2 and t.stride(0) % 4 != 0)):
+            return False
+    return True
+
+
+def raw_tc_linear(a2, w, trans_b, bias, n_out, k_red, code=0, param=0.0, want_z=False):
+    m = a2.shape[0]
+    y = torch.empty(m, n_out, dtype=a2.dtype, device=a2.device)
+    z = torch.empty_like(y) if want_z else None
+    _lib.call("hgb_tc_linear", _p(a2), a2.stride(0), _p(w), w.stride(0), int(trans_b), _p(bias), m, n_out, k_red, code, float(param),
+              _p(y), _p(z), _stream())
+    return y, z
+
+
+def raw_tc_wgrad(dz, x2, want_bias=True, dw=None, db=None, accumulate=False):
+    m, n_out = dz.shape
+    k_out = x2.shape[1]
+    if dw is None:
+        dw = torch.empty(n_out, k_out, dtype=dz.dtype, device=dz.device)
+    if want_bias and db is None:
+        db = torch.empty(n_out, dtype=dz.dtype, device=dz.device)
+    nbytes = _lib.query("hgb_tc_wgrad_workspace_bytes", n_out, k_out)
+    ws = _ws(nbytes, dz.device)
+    _lib.call("hgb_tc_wgrad", _p(dz), dz.stride(0), _p(x2), x2.stride(0), m, n_out, k_out, _p(dw), dw.stride(0),
+              _p(db) if want_bias else None, int(accumulate), _p(ws), nbytes, _stream())
+    return dw, db
+
+
+def linear_fwd_dispatch(x2, w, b, code=0, param=0.0, want_z=False):
+    """y = act(x2 W^T + b) on the tensor-core kernel when the shape qualifies, else the exact-fp32 kernel."""
+    m, k = x2.shape
+    n = w.shape[0]
+    if tc_ok(m, n, k, x2):
+        return raw_tc_linear(x2, w, False, b, n, k, code, param, want_z)
+    return raw_linear(x2, w, b, code, param, want_z)
+
+
+def linear_bwd_dispatch(dz, x2, w, need_x=True, need_w=True, need_b=True):
+    """(dx, dw, db) of y = x2 W^T + b given dz."""
+    m, n = dz.shape
+    k = x2.shape[1]
+    dx = dw = db = None
+    if need_x:
+        dx = raw_tc_linear(dz, w, True, None, k, n)[0] if tc_ok(m, k, n, dz) else raw_gemm(dz, w, False, False)
+    if need_w or need_b:
+        if tc_ok(m, n, k, dz, x2) and k + 16 <= 256:
+            dw, db = raw_tc_wgrad(dz, x2, want_bias=need_b)
+        else:
+            if need_w:
+                dw = raw_gemm(dz, x2, True, False)
+            if need_b:
+                db = raw_colsum(dz)
+    return dx, dw, db
+
+
 def _row_major_2d(t):
     """View an [..., k] tensor as [m, k] with unit inner stride (copying only if it has to)."""
     k = t.shape[-1]
@@ -224,13 +305,11 @@ class LinearAct(torch.autograd.Function):
         w = weight if weight.stride(1) == 1 else weight.contiguous()
         m, k = x2.shape
         n = w.shape[0]
-        y = torch.empty(m, n, dtype=x.dtype, device=x.device)
         code = ACT_CODES[act]
-        z = torch.empty_like(y) if code == ACT_CODES["silu"] else None
-        _lib.call("hgb_linear_fwd", _p(x2), _p(w), _p(_chk(bias)), m, n, k, x2.stride(0), w.stride(0), code,
-                  float(act_param), _p(y), _p(z), _stream())
+        y, z = linear_fwd_dispatch(x2, w, _chk(bias), code, act_param, want_z=(code == ACT_CODES["silu"]))
         ctx.save_for_backward(x2, w, y if code not in (0, ACT_CODES["silu"]) else None, z)
         ctx.code, ctx.param, ctx.shp, ctx.has_bias = code, float(act_param), shp, bias is not None
+        ctx.tc = _TC["enabled"]                      # the backward runs outside the forward's precision context
         return y.reshape(shp[:-1] + (n,))
 
     @staticmethod
@@ -245,13 +324,11 @@ class LinearAct(torch.autograd.Function):
             _lib.call("hgb_act_bwd", _p(gy2), _p(y), _p(z), gy2.numel(), ctx.code, ctx.param, _p(dz), _stream())
         else:
             dz = gy2
-        gx = gw = gb = None
-        if ctx.needs_input_grad[0]:
-            gx = raw_gemm(dz, w, False, False).reshape(ctx.shp)
-        if ctx.needs_input_grad[1]:
-            gw = raw_gemm(dz, x2, True, False)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = raw_colsum(dz)
+        with tensor_cores(ctx.tc):
+            gx, gw, gb = linear_bwd_dispatch(dz, x2, w, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                             ctx.has_bias and ctx.needs_input_grad[2])
+        if gx is not None:
+            gx = gx.reshape(ctx.shp)
         return gx, gw, gb, None, None
 
 
@@ -387,17 +464,18 @@ class PainnUpdateFn(torch.autograd.Function):
         s, v = _chk(s), _chk(v)
         uw, ub, vw, vb, w1, b1, w2, b2 = [_chk(t) for t in (uw, ub, vw, vb, w1, b1, w2, b2)]
         v2 = v.reshape(3 * n, f)
-        uv, _ = raw_linear(v2, uw, ub)
-        vv, _ = raw_linear(v2, vw, vb)
+        uv, _ = linear_fwd_dispatch(v2, uw, ub)
+        vv, _ = linear_fwd_dispatch(v2, vw, vb)
         mlp_in = torch.empty(n, 2 * f, dtype=s.dtype, device=s.device)
         _lib.call("hgb_painn_update_pre_fwd", _p(vv), _p(s), n, f, _p(mlp_in), _stream())
-        h, z1 = raw_linear(mlp_in, w1, b1, ACT_CODES["silu"], 0.0, want_z=True)
-        a, _ = raw_linear(h, w2, b2)
+        h, z1 = linear_fwd_dispatch(mlp_in, w1, b1, ACT_CODES["silu"], 0.0, want_z=True)
+        a, _ = linear_fwd_dispatch(h, w2, b2)
         s_out = torch.empty_like(s)
         v_out = None if last else torch.empty_like(v)
         _lib.call("hgb_painn_update_post_fwd", _p(a), _p(uv), _p(vv), _p(s), _p(v), n, f, int(last), _p(s_out), _p(v_out), _stream())
         ctx.save_for_backward(v2, uv, vv, mlp_in, z1, h, a, uw, vw, w1, w2)
         ctx.last = bool(last)
+        ctx.tc = _TC["enabled"]
         if last:
             return s_out, s_out.new_zeros(0)
         return s_out, v_out
@@ -412,21 +490,18 @@ class PainnUpdateFn(torch.autograd.Function):
         gv_out = None if last else _chk(gv_out)
         ga = torch.empty_like(a)
         _lib.call("hgb_painn_update_post_bwd_a", _p(gs_out), _p(gv_out), _p(uv), _p(vv), n, f, int(last), _p(ga), _stream())
-        gw2 = raw_gemm(ga, h, True, False)
-        gb2 = raw_colsum(ga)
-        gh = raw_gemm(ga, w2, False, False)
-        gz1 = raw_act_bwd(gh, None, z1, ACT_CODES["silu"])
-        gw1 = raw_gemm(gz1, mlp_in, True, False)
-        gb1 = raw_colsum(gz1)
-        g_mlp_in = raw_gemm(gz1, w1, False, False)
+        with tensor_cores(ctx.tc):
+            gh, gw2, gb2 = linear_bwd_dispatch(ga, h, w2)
+            gz1 = raw_act_bwd(gh, None, z1, ACT_CODES["silu"])
+            g_mlp_in, gw1, gb1 = linear_bwd_dispatch(gz1, mlp_in, w1)
         guv, gvv = torch.empty_like(uv), torch.empty_like(vv)
         gs, gv = torch.empty_like(gs_out), torch.empty_like(v2)
         _lib.call("hgb_painn_update_bwd", _p(gs_out), _p(gv_out), _p(g_mlp_in), _p(a), _p(uv), _p(vv), _p(mlp_in), n, f,
                   int(last), _p(guv), _p(gvv), _p(gs), _p(gv), _stream())
-        guw, gub = raw_gemm(guv, v2, True, False), raw_colsum(guv)
-        gvw, gvb = raw_gemm(gvv, v2, True, False), raw_colsum(gvv)
-        raw_gemm(guv, uw, False, False, out=gv, beta_one=True)
-        raw_gemm(gvv, vw, False, False, out=gv, beta_one=True)
+        with tensor_cores(ctx.tc):
+            dv_u, guw, gub = linear_bwd_dispatch(guv, v2, uw)
+            dv_v, gvw, gvb = linear_bwd_dispatch(gvv, v2, vw)
+        gv = gv + dv_u + dv_v
         return gs, gv.reshape(n, 3, f), guw, gub, gvw, gvb, gw1, gb1, gw2, gb2, None
 
 

@@ -148,6 +148,22 @@ int64_t hgb_gemm_workspace_bytes(int32_t m, int32_t n, int32_t k, int32_t trans_
 int hgb_linear_fwd(const float* x, const float* w, const float* b, int32_t m, int32_t n, int32_t k,
                    int64_t ldx, int64_t ldw, int32_t act, float act_param, float* y, float* z,
                    hgb_stream_t stream);
+/* Tensor-core (tcgen05 kind::tf32, TMEM accumulators, TMA-fed) versions of the same dense layers for the
+ * large-M shapes of the node / edge MLPs: m >= 128, n_out and k_red multiples of 32 and <= 256.  Used under
+ * precision="bf16" (TF32 products, fp32 accumulation: tighter than the bf16 autocast of the reference).
+ * y[m,n_out] = act(a[m,k_red] . B^T + bias) with B(r,c) = w[r,c] (trans_b = 0: forward, w is [n_out,k_red])
+ * or B(r,c) = w[c,r] (trans_b = 1: the data gradient dX = dZ . W, w is [k_red,n_out]).                      */
+int hgb_tc_linear_supported(int32_t m, int32_t n_out, int32_t k_red);
+int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_t ldw, int32_t trans_b, const float* bias,
+                  int32_t m, int32_t n_out, int32_t k_red, int32_t act, float act_param, float* y, float* z,
+                  hgb_stream_t stream);
+/* dw[n_out,k_out] (row stride lddw) (+)= dz[m,n_out]^T . x[m,k_out] and db[n_out] (+)= column sums of dz
+ * (db may be NULL) in one pass: both operands are consumed MN-major straight from the row-major tensors, the
+ * bias gradient rides along as extra all-ones columns of the B operand.  Deterministic two-stage reduce.      */
+int hgb_tc_wgrad(const float* dz, int64_t lddz, const float* x, int64_t ldx, int32_t m, int32_t n_out,
+                 int32_t k_out, float* dw, int64_t lddw, float* db, int32_t accumulate, void* workspace,
+                 int64_t workspace_bytes, hgb_stream_t stream);
+int64_t hgb_tc_wgrad_workspace_bytes(int32_t n_out, int32_t k_out);
 /* dz = dy * act'(.) evaluated from y (or from z for SiLU, which must then be non-NULL).           */
 int hgb_act_bwd(const float* dy, const float* y, const float* z, int64_t count, int32_t act,
                 float act_param, float* dz, hgb_stream_t stream);

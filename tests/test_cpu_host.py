@@ -1,0 +1,196 @@
+"""CPU tests: host-side logic, the C-ABI surface (load + exported symbols, no compute calls), and the
+world_size-2 data-parallel plumbing over gloo."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import hydragnn_b200 as hb
+from hydragnn_b200 import _lib, ops
+from hydragnn_b200.synthetic import ARCH, make_samples
+from test_oracle_golden import MODEL_KW
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_library_loads_and_exports_every_declared_symbol():
+    protos = _lib.prototypes()
+    assert len(protos) >= 35
+    src = open(_lib.HEADER).read()
+    declared = set(re.findall(r"\b(hgb_\w+)\s*\(", re.sub(r"/\*.*?\*/", "", src, flags=re.S)))
+    assert declared == set(protos), declared ^ set(protos)
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    L = _lib.lib()
+    for name in protos:
+        assert hasattr(L, name), name
+    assert L.hgb_version() >= 100
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (hgb_\w+)", out))
+    assert set(protos) <= exported
+    # every signature in the header is plain C: no torch / C++ types
+    for name, (ret, args) in protos.items():
+        for t, _ in args:
+            assert re.fullmatch(r"(const )?(void|float|double|int32_t|int64_t|int|hgb_stream_t)\*?", t), (name, t)
+
+
+def test_ops_refuse_cpu_tensors_no_fallback():
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.raw_gather(torch.zeros(3, 2), torch.zeros(2, dtype=torch.int32))
+    m = hb.create_model(**MODEL_KW["painn_graph_mean"])
+    g = torch.load(os.path.join(ROOT, "tests/golden/models.pt"))["painn_graph_mean"]
+    with pytest.raises(RuntimeError):
+        m(hb.Batch(**g["inputs"]))
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libhgb.so")
+    with pytest.raises(RuntimeError, match="no CPU"):
+        _lib.lib()
+
+
+def test_create_model_reproduces_reference_initialisation(golden_dir):
+    g = torch.load(golden_dir + "/models.pt")
+    for name, kw in MODEL_KW.items():
+        sd = hb.create_model(**kw).state_dict()
+        assert list(sd.keys()) == list(g[name]["state"].keys()), name
+        for k, v in sd.items():
+            assert torch.equal(v, g[name]["state"][k]), (name, k)
+
+
+def test_create_model_errors_mirror_reference():
+    with pytest.raises(ValueError, match="Unknown mpnn_type"):
+        hb.create_model(**dict(MODEL_KW["egnn_mlip"], mpnn_type="GIN"))
+    with pytest.raises(ValueError, match="Inconsistent number of loss weights"):
+        hb.create_model(**dict(MODEL_KW["egnn_mlip"], task_weights=[1.0, 1.0]))
+    with pytest.raises(ValueError, match="Unsupported graph_pooling"):
+        hb.create_model(**dict(MODEL_KW["egnn_mlip"], graph_pooling="median"))
+    m = hb.create_model(**ARCH["md17_egnn"])
+    assert m.num_heads == 1 and m.head_type == ["node"] and m.energy_weight == 1.0 and m.graph_pooling == "mean"
+    assert str(m.model) == "EGCLStack"
+
+
+def test_create_model_config_surface():
+    cfg = {"Architecture": dict(ARCH["qm9_painn"], freeze_conv_layers=False, initial_bias=None, num_nodes=9, edge_dim=None,
+                                equivariance=None, pe_dim=0, global_attn_engine=None),
+           "Training": {"loss_function_type": "mse", "precision": "bf16"}}
+    m = hb.create_model_config(cfg)
+    assert m.precision == "bf16" and str(m) == "PAINNStack"
+    cfg["Training"]["precision"] = "fp64"
+    with pytest.raises(ValueError):
+        hb.create_model_config(cfg)
+
+
+def test_data_batch_container():
+    a = hb.Data(x=torch.ones(2, 1), pos=torch.zeros(2, 3), edge_index=torch.tensor([[0], [1]]), y=torch.ones(1, 1), energy=torch.tensor(1.0))
+    b = hb.Data(x=torch.ones(3, 1), pos=torch.zeros(3, 3), edge_index=torch.tensor([[0, 2], [1, 0]]), y=torch.ones(1, 1), energy=torch.tensor(2.0))
+    bt = hb.Batch.from_data_list([a, b])
+    assert bt.num_graphs == 2 and bt.num_nodes == 5 and bt.edge_index.tolist() == [[0, 2, 4], [1, 3, 2]]
+    assert bt.batch.tolist() == [0, 0, 1, 1, 1] and bt.energy.tolist() == [1.0, 2.0] and bt.edge_shifts is None
+    assert "x" in bt and "edge_attr" not in bt and dict(bt.items())["y"].shape == (2, 1)
+    c = bt.clone()
+    c.x += 1
+    assert float(bt.x.sum()) == 5.0 and bt["x"] is bt.x
+    assert not hasattr(bt, "dataset_name")
+
+
+def test_head_indices_and_precision():
+    m = hb.create_model(**MODEL_KW["egnn_equiv_multihead"])
+    d = hb.Batch(y=torch.zeros(100, 1), batch=torch.tensor([0, 0, 1, 1, 1]), y_loc=torch.tensor([[0, 1, 7], [0, 1, 10]]))
+    d._num_graphs = 2
+    hi = hb.get_head_indices(m, d)
+    assert hi[0].tolist() == [0, 7] and hi[1].tolist() == list(range(1, 7)) + list(range(8, 17))
+    from hydragnn_b200.train import resolve_precision
+    assert resolve_precision("bfloat16")[0] == "bf16" and resolve_precision(None)[0] == "fp32"
+    with pytest.raises(ValueError):
+        resolve_precision("fp64")
+    with pytest.raises(ValueError):
+        resolve_precision("int8")
+
+
+def test_flat_adamw_views_share_storage():
+    m = hb.create_model(**MODEL_KW["painn_graph_mean"])
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    opt = hb.FlatAdamW(m, lr=1e-3)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, before[k])
+    n = sum(p.numel() for p in m.parameters())
+    assert opt.flat_p.numel() == n
+    p0 = next(m.parameters())
+    opt.flat_p[:p0.numel()] = 7.0
+    assert float(p0.min()) == 7.0                              # parameters are views of the flat buffer
+    for p in m.parameters():
+        p.grad = torch.full_like(p, 2.0)
+    list(m.parameters())[3].grad = None                        # an unused parameter contributes zeros
+    flat = opt.gather_grads()
+    k3 = list(m.parameters())[3].numel()
+    assert float(flat.sum()) == 2.0 * (n - k3)
+
+
+WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import hydragnn_b200 as hb
+from hydragnn_b200 import ops, train
+from hydragnn_b200.synthetic import ARCH
+
+def torch_adamw(p, g, m, v, step_dev, lr, b1, b2, eps, wd, gscale=1.0):   # CPU stand-in for the CUDA kernel (test only)
+    step_dev += 1
+    t = float(step_dev)
+    g = g * gscale
+    p.mul_(1 - lr * wd); m.mul_(b1).add_(g, alpha=1 - b1); v.mul_(b2).addcmul_(g, g, value=1 - b2)
+    p.addcdiv_(m / (1 - b1 ** t), (v / (1 - b2 ** t)).sqrt() + eps, value=-lr)
+ops.adamw_step = torch_adamw
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+model = hb.create_model(**ARCH["qm9_painn"], use_gpu=False)
+if rank == 1:
+    with torch.no_grad():
+        for p in model.parameters(): p.add_(1.0)           # deliberately different starting point
+model = hb.get_distributed_model(model)                     # rank 0's weights everywhere
+opt = hb.FlatAdamW(model, lr=1e-2)
+for p in model.parameters():
+    p.grad = torch.full_like(p, float(rank + 1))            # rank-dependent gradients: mean is 1.5
+flat = opt.gather_grads()
+dist.all_reduce(flat)
+opt.step(grad_scale=1.0 / 2)
+out = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+gathered = [torch.zeros_like(out) for _ in range(2)]
+dist.all_gather(gathered, out)
+assert torch.equal(gathered[0], gathered[1]), "ranks diverged"
+if rank == 0:
+    ref = hb.create_model(**ARCH["qm9_painn"], use_gpu=False)
+    o2 = torch.optim.AdamW(ref.parameters(), lr=1e-2, weight_decay=1e-2)
+    for p in ref.parameters(): p.grad = torch.full_like(p, 1.5)
+    o2.step()
+    r = torch.cat([p.detach().reshape(-1) for p in ref.parameters()])
+    assert torch.allclose(out, r, rtol=1e-5, atol=1e-7), float((out - r).abs().max())
+    print("OK")
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_flat_allreduce_matches_single_process(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    assert "OK" in outs[0]
+
+
+def test_synthetic_workloads_shapes():
+    b = make_samples("qm9_painn", 10)
+    assert b.pos.shape == (90, 3) and b.x.shape == (90, 1) and b.num_graphs == 10 and b.ptr.tolist()[-1] == 90
+    d = torch.cdist(b.pos.reshape(10, 9, 3), b.pos.reshape(10, 9, 3)) + torch.eye(9) * 10
+    assert float(d.min()) >= 0.9
+    assert torch.equal(make_samples("qm9_painn", 10).pos, b.pos)      # deterministic in the seed
+    lj = make_samples("lj_egnn", 2)
+    assert lj.cell.shape == (2, 3, 3) and bool(lj.pbc.all())

@@ -180,6 +180,17 @@ def test_force_equivariance_and_translation_invariance():
             kw.update(output_type=["node"], output_heads={"node": {"num_headlayers": 2, "dim_headlayers": [60, 20], "type": "mlp"}},
                       enable_interatomic_potential=True, energy_weight=1.0, energy_peratom_weight=1.0, force_weight=1.0)
         m = hb.create_model(**kw).eval()
+        if name == "qm9_painn":
+            # Reference quirk: update_U / update_V / vec_embed_out are nn.Linear WITH bias applied to every
+            # Cartesian component of v (hydragnn/models/PAINNStack.py:281-282,98), which is not rotation-
+            # equivariant unless the bias is zero.  The engine reproduces that arithmetic faithfully
+            # (parity tests above); the property itself is checked with those biases zeroed.
+            with torch.no_grad():
+                for conv in m.model.graph_convs:
+                    conv.module_1.update_U.bias.zero_()
+                    conv.module_1.update_V.bias.zero_()
+                    if hasattr(conv, "module_3"):
+                        conv.module_3.bias.zero_()
         b = make_samples(name, 8).to(DEV)
         b._num_graphs = 8
         b = hb.get_radius_graph(7.0, 100000)(b)          # symmetric graph: rotation cannot change the edge set
