@@ -262,3 +262,154 @@ extern "C" int hgb_colsum(const float* x, int32_t m, int32_t n, float* out, void
   HGB_LAUNCH_CHECK("colsum_stage2");
   return HGB_OK;
 }
+
+// ---- tiny-K linear layers (K <= 8) ----------------------------------------------------------------------------
+// The reference runs its first PaiNN / PNAEq layer at node_size = input_dim (often 1, quirk Q4), so Linear(1 -> F),
+// Linear(2 -> 1), Linear(1 -> 3) ... appear at M = nodes (or 3*nodes).  They are outer products / column sums,
+// purely HBM-bound; a tiled GEMM wastes almost all of its work on them.
+#define SK_KMAX 8
+#define SK_NPT 8   // outputs per lane -> n <= 256
+
+__global__ void linear_smallk_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w, int64_t ldw,
+                                         const float* __restrict__ b, int64_t total, int n, int k, int act, float ap,
+                                         float* __restrict__ y, float* __restrict__ z) {
+  extern __shared__ float sw[];  // [n][k] + [n]
+  for (int i = threadIdx.x; i < n * k; i += blockDim.x) sw[i] = w[(int64_t)(i / k) * ldw + (i % k)];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sw[n * k + i] = b ? b[i] : 0.f;
+  __syncthreads();
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / n;
+    const int c = (int)(t - r * n);
+    float acc = sw[n * k + c];
+    for (int q = 0; q < k; ++q) acc = fmaf(__ldg(x + r * ldx + q), sw[c * k + q], acc);
+    if (z) z[t] = acc;
+    y[t] = hgb_act(acc, act, ap);
+  }
+}
+
+// one pass over (dy, y|z, x): dz = dy * act'(.), dx[m,k] = dz . W, partial dW / db per block
+__global__ void __launch_bounds__(256)
+linear_smallk_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ z,
+                         const float* __restrict__ x, int64_t ldx, const float* __restrict__ w, int64_t ldw, int m, int n, int k,
+                         int act, float ap, int rows_per_block, float* __restrict__ dx, float* __restrict__ part) {
+  extern __shared__ float sm[];  // w [n][k], then the reduction scratch [8][32]
+  float* sw = sm;
+  float* red = sm + n * k;
+  for (int i = threadIdx.y * 32 + threadIdx.x; i < n * k; i += 256) sw[i] = w[(int64_t)(i / k) * ldw + (i % k)];
+  __syncthreads();
+  const int lane = threadIdx.x, walker = threadIdx.y;
+  float gw[SK_NPT][SK_KMAX + 1];
+#pragma unroll
+  for (int j = 0; j < SK_NPT; ++j)
+#pragma unroll
+    for (int q = 0; q <= SK_KMAX; ++q) gw[j][q] = 0.f;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(m, r0 + rows_per_block);
+  for (int r = r0 + walker; r < r1; r += 8) {
+    float xr[SK_KMAX], dxp[SK_KMAX];
+#pragma unroll
+    for (int q = 0; q < SK_KMAX; ++q) { xr[q] = q < k ? __ldg(x + (int64_t)r * ldx + q) : 0.f; dxp[q] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < SK_NPT; ++j) {
+      const int c = lane + 32 * j;
+      if (c < n) {
+        const int64_t o = (int64_t)r * n + c;
+        float g = dy[o];
+        if (act != HGB_ACT_NONE) g *= hgb_act_grad(y ? y[o] : 0.f, z ? z[o] : 0.f, act, ap);
+        gw[j][SK_KMAX] += g;
+#pragma unroll
+        for (int q = 0; q < SK_KMAX; ++q)
+          if (q < k) {
+            gw[j][q] = fmaf(g, xr[q], gw[j][q]);
+            dxp[q] = fmaf(g, sw[c * k + q], dxp[q]);
+          }
+      }
+    }
+    if (dx) {
+#pragma unroll
+      for (int q = 0; q < SK_KMAX; ++q)
+        if (q < k) {
+          const float s = hgb_warp_sum(dxp[q]);
+          if (lane == 0) dx[(int64_t)r * k + q] = s;
+        }
+    }
+  }
+  // reduce the 8 row walkers -> part[blockIdx.x][n][k+1]
+  float* mypart = part + (int64_t)blockIdx.x * n * (k + 1);
+#pragma unroll
+  for (int j = 0; j < SK_NPT; ++j)
+#pragma unroll
+    for (int q = 0; q <= SK_KMAX; ++q) {
+      if ((q < k || q == SK_KMAX) && 32 * j < n) {   // uniform across the block
+        __syncthreads();
+        red[walker * 32 + lane] = gw[j][q];
+        __syncthreads();
+        if (walker == 0) {
+          float acc = 0.f;
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) acc += red[w8 * 32 + lane];
+          const int c = lane + 32 * j;
+          if (c < n) mypart[c * (k + 1) + (q == SK_KMAX ? k : q)] = acc;
+        }
+      }
+    }
+}
+
+__global__ void linear_smallk_reduce_kernel(const float* __restrict__ part, int nblocks, int n, int k, float* __restrict__ dw,
+                                            int64_t lddw, float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * (k + 1)) return;
+  float acc = 0.f;
+  for (int b = 0; b < nblocks; ++b) acc += part[(int64_t)b * n * (k + 1) + i];
+  const int r = i / (k + 1), c = i % (k + 1);
+  if (c == k) { if (db) db[r] = acc; } else if (dw) dw[(int64_t)r * lddw + c] = acc;
+}
+
+static int smallk_blocks(int m, int* rows_per_block) {
+  int rpb = (m + HGB_NUM_SMS * 4 - 1) / (HGB_NUM_SMS * 4);
+  rpb = ((rpb + 7) / 8) * 8;
+  if (rpb < 8) rpb = 8;
+  *rows_per_block = rpb;
+  return (m + rpb - 1) / rpb;
+}
+
+extern "C" int hgb_linear_smallk_supported(int32_t n, int32_t k) { return (k >= 1 && k <= SK_KMAX && n >= 1 && n <= 32 * SK_NPT) ? 1 : 0; }
+
+extern "C" int hgb_linear_smallk_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* b, int32_t m, int32_t n,
+                                     int32_t k, int32_t act, float act_param, float* y, float* z, hgb_stream_t stream) {
+  HGB_REQUIRE(x && w && y && m >= 0 && hgb_linear_smallk_supported(n, k), "linear_smallk_fwd: unsupported shape n=%d k=%d", n, k);
+  if (m == 0) return HGB_OK;
+  const int64_t total = (int64_t)m * n;
+  linear_smallk_fwd_kernel<<<hgb_grid_for(total, 256), 256, (size_t)(n * k + n) * 4, (cudaStream_t)stream>>>(x, ldx, w, ldw, b, total, n, k,
+                                                                                                       act, act_param, y, z);
+  HGB_LAUNCH_CHECK("linear_smallk_fwd");
+  return HGB_OK;
+}
+
+extern "C" int64_t hgb_linear_smallk_bwd_workspace_bytes(int32_t m, int32_t n, int32_t k) {
+  int rpb;
+  return (int64_t)smallk_blocks(m, &rpb) * n * (k + 1) * 4;
+}
+
+// dy [m,n] is the gradient of the activation OUTPUT; y (or z for SiLU) lets the kernel apply act' itself.
+extern "C" int hgb_linear_smallk_bwd(const float* dy, const float* y, const float* z, const float* x, int64_t ldx, const float* w,
+                                     int64_t ldw, int32_t m, int32_t n, int32_t k, int32_t act, float act_param, float* dx, float* dw,
+                                     int64_t lddw, float* db, void* workspace, hgb_stream_t stream) {
+  HGB_REQUIRE(dy && x && w && workspace && m >= 0 && hgb_linear_smallk_supported(n, k), "linear_smallk_bwd: unsupported shape n=%d k=%d", n, k);
+  HGB_REQUIRE(act != HGB_ACT_SILU || z, "linear_smallk_bwd: SiLU needs the pre-activation z");
+  HGB_REQUIRE(act == HGB_ACT_SILU || act == HGB_ACT_NONE || y, "linear_smallk_bwd: needs the activation output y");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m == 0) {
+    if (dw) cudaMemset2DAsync(dw, lddw * 4, 0, (size_t)k * 4, n, st);
+    if (db) cudaMemsetAsync(db, 0, (size_t)n * 4, st);
+    return HGB_OK;
+  }
+  int rpb;
+  const int nb = smallk_blocks(m, &rpb);
+  linear_smallk_bwd_kernel<<<nb, dim3(32, 8), (size_t)(n * k + 256) * 4, st>>>(dy, y, z, x, ldx, w, ldw, m, n, k, act, act_param, rpb, dx,
+                                                                             (float*)workspace);
+  HGB_LAUNCH_CHECK("linear_smallk_bwd");
+  linear_smallk_reduce_kernel<<<(n * (k + 1) + 127) / 128, 128, 0, st>>>((const float*)workspace, nb, n, k, dw, lddw, db);
+  HGB_LAUNCH_CHECK("linear_smallk_reduce");
+  return HGB_OK;
+}

@@ -12,7 +12,16 @@
 #define RMAX 8
 #define WPB 8  // warps per block
 
-template <int CPL, bool HAS_EF>
+// GROUP = lanes that share one node (32 for F >= 32; for narrow layers -- the reference's first layer runs at
+// F = input_dim, often 1 -- a warp serves 32/GROUP nodes at once instead of idling 31 lanes)
+template <int G>
+__device__ __forceinline__ float hgb_group_sum(float v, unsigned mask) {   // groups of one warp may diverge: shuffle within the group only
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+
+template <int CPL, bool HAS_EF, int GROUP>
 __global__ void __launch_bounds__(WPB * 32)
 painn_message_fwd_kernel(const float* __restrict__ phi, const float* __restrict__ s, const float* __restrict__ v,
                          const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm,
@@ -28,13 +37,15 @@ painn_message_fwd_kernel(const float* __restrict__ phi, const float* __restrict_
   for (int t = threadIdx.x; t < 3 * f; t += blockDim.x) bfs[t] = bf[t];
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int cbase = blockIdx.y * 32 * CPL;
+  constexpr int NPW = 32 / GROUP;
+  const int sub = lane % GROUP, nsub = lane / GROUP;
+  const int cbase = blockIdx.y * GROUP * CPL;
   int ch[CPL];
   bool ok[CPL];
 #pragma unroll
-  for (int t = 0; t < CPL; ++t) { ch[t] = cbase + lane + 32 * t; ok[t] = ch[t] < f; if (!ok[t]) ch[t] = 0; }
+  for (int t = 0; t < CPL; ++t) { ch[t] = cbase + sub + GROUP * t; ok[t] = ch[t] < f; if (!ok[t]) ch[t] = 0; }
   const int f3 = 3 * f;
-  for (int i = blockIdx.x * WPB + (threadIdx.x >> 5); i < n; i += gridDim.x * WPB) {
+  for (int i = (blockIdx.x * WPB + (threadIdx.x >> 5)) * NPW + nsub; i < n; i += gridDim.x * WPB * NPW) {
     const int lo = rowptr[i], hi = rowptr[i + 1];
     float as[CPL], av[CPL][3];
 #pragma unroll
@@ -92,11 +103,22 @@ extern "C" int hgb_painn_message_fwd(const float* phi, const float* s, const flo
   const size_t smem = (size_t)(3 * f * ((r | 1) + 1)) * sizeof(float);
   HGB_REQUIRE(smem <= 48 * 1024, "painn_message_fwd: hidden_dim %d too large for the filter staging", f);
   const int cpl = f <= 32 ? 1 : 2;
-  dim3 grid(hgb_grid_for(n, WPB, HGB_NUM_SMS * 8), (f + 32 * cpl - 1) / (32 * cpl));
+  int group = 32;
+  if (f < 32) { group = 1; while (group < f) group <<= 1; }
+  dim3 grid(hgb_grid_for(n, WPB * (32 / group), HGB_NUM_SMS * 8), (f + group * cpl - 1) / (group * cpl));
   cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(C, E) painn_message_fwd_kernel<C, E><<<grid, WPB * 32, smem, st>>>(phi, s, v, rowptr, perm, src, dir, rbfc, fc, wf, bf, efilt, n, f, r, s_out, v_out)
-  if (cpl == 1) { if (efilt) LAUNCH(1, true); else LAUNCH(1, false); }
-  else { if (efilt) LAUNCH(2, true); else LAUNCH(2, false); }
+#define LAUNCH(C, E, G) painn_message_fwd_kernel<C, E, G><<<grid, WPB * 32, smem, st>>>(phi, s, v, rowptr, perm, src, dir, rbfc, fc, wf, bf, efilt, n, f, r, s_out, v_out)
+#define LAUNCH_G(E)                                                  \
+  switch (group) {                                                   \
+    case 1: LAUNCH(1, E, 1); break;                                  \
+    case 2: LAUNCH(1, E, 2); break;                                  \
+    case 4: LAUNCH(1, E, 4); break;                                  \
+    case 8: LAUNCH(1, E, 8); break;                                  \
+    case 16: LAUNCH(1, E, 16); break;                                \
+    default: if (cpl == 1) LAUNCH(1, E, 32); else LAUNCH(2, E, 32);  \
+  }
+  if (efilt) { LAUNCH_G(true) } else { LAUNCH_G(false) }
+#undef LAUNCH_G
 #undef LAUNCH
   HGB_LAUNCH_CHECK("painn_message_fwd");
   return HGB_OK;
@@ -104,7 +126,7 @@ extern "C" int hgb_painn_message_fwd(const float* phi, const float* s, const flo
 
 // ---- backward ----------------------------------------------------------------------------------------
 // workspace layout: part[gridDim.x][3f][r+1]  (column r holds the bias gradient)
-template <int CPL, bool HAS_EF, bool NEED_EDGE>
+template <int CPL, bool HAS_EF, bool NEED_EDGE, int GROUP>
 __global__ void __launch_bounds__(WPB * 32)
 painn_message_bwd_kernel(const float* __restrict__ gs_out, const float* __restrict__ gv_out, const float* __restrict__ phi,
                          const float* __restrict__ v, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm,
@@ -122,12 +144,15 @@ painn_message_bwd_kernel(const float* __restrict__ gs_out, const float* __restri
   for (int t = threadIdx.x; t < 3 * f; t += blockDim.x) bfs[t] = bf[t];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int cbase = blockIdx.y * 32 * CPL;
+  constexpr int NPW = 32 / GROUP;
+  const int sub = lane % GROUP, nsub = lane / GROUP;
+  const int cbase = blockIdx.y * GROUP * CPL;
   int ch[CPL];
   bool ok[CPL];
 #pragma unroll
-  for (int t = 0; t < CPL; ++t) { ch[t] = cbase + lane + 32 * t; ok[t] = ch[t] < f; if (!ok[t]) ch[t] = 0; }
+  for (int t = 0; t < CPL; ++t) { ch[t] = cbase + sub + GROUP * t; ok[t] = ch[t] < f; if (!ok[t]) ch[t] = 0; }
   const int f3 = 3 * f;
+  const unsigned gmask = GROUP == 32 ? 0xffffffffu : (((1u << GROUP) - 1u) << (nsub * GROUP));
   float gw[CPL][3][RMAX + 1];
 #pragma unroll
   for (int t = 0; t < CPL; ++t)
@@ -136,7 +161,7 @@ painn_message_bwd_kernel(const float* __restrict__ gs_out, const float* __restri
 #pragma unroll
       for (int q = 0; q <= RMAX; ++q) gw[t][a][q] = 0.f;
 
-  for (int j = blockIdx.x * WPB + warp; j < n; j += gridDim.x * WPB) {
+  for (int j = (blockIdx.x * WPB + warp) * NPW + nsub; j < n; j += gridDim.x * WPB * NPW) {
     const int lo = rowptr[j], hi = rowptr[j + 1];
     float ph[CPL][3], vj[CPL][3], aphi[CPL][3], agv[CPL][3];
 #pragma unroll
@@ -213,9 +238,9 @@ painn_message_bwd_kernel(const float* __restrict__ gs_out, const float* __restri
       if (NEED_EDGE) {
 #pragma unroll
         for (int q = 0; q < RMAX; ++q)
-          if (q < r) e_rb[q] = hgb_warp_sum(e_rb[q]);
-        e_fc = hgb_warp_sum(e_fc); e_d0 = hgb_warp_sum(e_d0); e_d1 = hgb_warp_sum(e_d1); e_d2 = hgb_warp_sum(e_d2);
-        if (lane == 0) {
+          if (q < r) e_rb[q] = hgb_group_sum<GROUP>(e_rb[q], gmask);
+        e_fc = hgb_group_sum<GROUP>(e_fc, gmask); e_d0 = hgb_group_sum<GROUP>(e_d0, gmask); e_d1 = hgb_group_sum<GROUP>(e_d1, gmask); e_d2 = hgb_group_sum<GROUP>(e_d2, gmask);
+        if (sub == 0) {
           if (multi_cb) {  // several channel blocks contribute to the same edge
 #pragma unroll
             for (int q = 0; q < RMAX; ++q)
@@ -255,10 +280,12 @@ painn_message_bwd_kernel(const float* __restrict__ gs_out, const float* __restri
           __syncthreads();
           red[warp * 32 + lane] = gw[t][a][q];
           __syncthreads();
-          if (warp == 0) {
+          if (warp == 0 && lane < GROUP) {     // lanes with the same `sub` own the same channel
             float acc = 0.f;
 #pragma unroll
-            for (int w8 = 0; w8 < WPB; ++w8) acc += red[w8 * 32 + lane];
+            for (int w8 = 0; w8 < WPB; ++w8)
+#pragma unroll
+              for (int g = 0; g < NPW; ++g) acc += red[w8 * 32 + lane + GROUP * g];
             if (ok[t]) mypart[(a * f + ch[t]) * (r + 1) + (q == RMAX ? r : q)] = acc;
           }
         }
@@ -275,10 +302,11 @@ __global__ void painn_wgrad_reduce_kernel(const float* __restrict__ part, int nb
   if (q == r) gbf[row] = acc; else gwf[row * r + q] = acc;
 }
 
-static int painn_bwd_grid(int n) { return hgb_grid_for(n, WPB, HGB_NUM_SMS * 4); }
+static int painn_group(int f) { int g = 32; if (f < 32) { g = 1; while (g < f) g <<= 1; } return g; }
+static int painn_bwd_grid(int n, int f) { return hgb_grid_for(n, WPB * (32 / painn_group(f)), HGB_NUM_SMS * 4); }
 
 extern "C" int64_t hgb_painn_message_bwd_workspace_bytes(int32_t n, int32_t f, int32_t r) {
-  return (int64_t)painn_bwd_grid(n) * 3 * f * (r + 1) * 4;
+  return (int64_t)painn_bwd_grid(n, f) * 3 * f * (r + 1) * 4;
 }
 
 extern "C" int hgb_painn_message_bwd(const float* gs_out, const float* gv_out, const float* phi, const float* v,
@@ -304,17 +332,23 @@ extern "C" int hgb_painn_message_bwd(const float* gs_out, const float* gv_out, c
   const size_t smem = (size_t)(f3 * ((r | 1) + 1) + WPB * 32) * sizeof(float);
   HGB_REQUIRE(smem <= 48 * 1024, "painn_message_bwd: hidden_dim %d too large for the filter staging", f);
   const int cpl = f <= 32 ? 1 : 2;
-  const int ncb = (f + 32 * cpl - 1) / (32 * cpl);
-  dim3 grid(painn_bwd_grid(n), ncb);
+  const int group = painn_group(f);
+  const int ncb = (f + group * cpl - 1) / (group * cpl);
+  dim3 grid(painn_bwd_grid(n, f), ncb);
   float* part = (float*)workspace;
-#define LAUNCH(C, E, G) painn_message_bwd_kernel<C, E, G><<<grid, WPB * 32, smem, st>>>(gs_out, gv_out, phi, v, rowptr_src, perm_src, agg, dir, rbfc, fc, wf, bf, efilt, n, f, r, gphi, gv, part, g_dir, g_rbfc, g_fc, g_efilt, ncb > 1)
-  if (cpl == 1) {
-    if (efilt) { if (need_edge) LAUNCH(1, true, true); else LAUNCH(1, true, false); }
-    else { if (need_edge) LAUNCH(1, false, true); else LAUNCH(1, false, false); }
-  } else {
-    if (efilt) { if (need_edge) LAUNCH(2, true, true); else LAUNCH(2, true, false); }
-    else { if (need_edge) LAUNCH(2, false, true); else LAUNCH(2, false, false); }
+#define LAUNCH(C, E, G, W) painn_message_bwd_kernel<C, E, G, W><<<grid, WPB * 32, smem, st>>>(gs_out, gv_out, phi, v, rowptr_src, perm_src, agg, dir, rbfc, fc, wf, bf, efilt, n, f, r, gphi, gv, part, g_dir, g_rbfc, g_fc, g_efilt, ncb > 1)
+#define LAUNCH_G(E, G)                                                     \
+  switch (group) {                                                         \
+    case 1: LAUNCH(1, E, G, 1); break;                                     \
+    case 2: LAUNCH(1, E, G, 2); break;                                     \
+    case 4: LAUNCH(1, E, G, 4); break;                                     \
+    case 8: LAUNCH(1, E, G, 8); break;                                     \
+    case 16: LAUNCH(1, E, G, 16); break;                                   \
+    default: if (cpl == 1) LAUNCH(1, E, G, 32); else LAUNCH(2, E, G, 32);  \
   }
+  if (efilt) { if (need_edge) { LAUNCH_G(true, true) } else { LAUNCH_G(true, false) } }
+  else { if (need_edge) { LAUNCH_G(false, true) } else { LAUNCH_G(false, false) } }
+#undef LAUNCH_G
 #undef LAUNCH
   HGB_LAUNCH_CHECK("painn_message_bwd");
   painn_wgrad_reduce_kernel<<<(f3 * (r + 1) + 127) / 128, 128, 0, st>>>(part, grid.x, f3, r, gwf, gbf);

@@ -193,10 +193,38 @@ def raw_tc_wgrad(dz, x2, want_bias=True, dw=None, db=None, accumulate=False):
     return dw, db
 
 
+def smallk_ok(n, k):
+    return k <= 8 and bool(_lib.query("hgb_linear_smallk_supported", n, k))
+
+
+def raw_smallk_fwd(x2, w, b, code=0, param=0.0, want_z=False):
+    m, k = x2.shape
+    n = w.shape[0]
+    y = torch.empty(m, n, dtype=x2.dtype, device=x2.device)
+    z = torch.empty_like(y) if want_z else None
+    _lib.call("hgb_linear_smallk_fwd", _p(x2), x2.stride(0), _p(w), w.stride(0), _p(b), m, n, k, code, float(param), _p(y), _p(z), _stream())
+    return y, z
+
+
+def raw_smallk_bwd(dy, y, z, x2, w, code=0, param=0.0, need_x=True, need_w=True, need_b=True):
+    """One pass: applies act' to dy, returns (dx, dw, db)."""
+    m, n = dy.shape
+    k = x2.shape[1]
+    dx = torch.empty(m, k, dtype=dy.dtype, device=dy.device) if need_x else None
+    dw = torch.empty(n, k, dtype=dy.dtype, device=dy.device) if need_w else None
+    db = torch.empty(n, dtype=dy.dtype, device=dy.device) if need_b else None
+    ws = _ws(_lib.query("hgb_linear_smallk_bwd_workspace_bytes", m, n, k), dy.device)
+    _lib.call("hgb_linear_smallk_bwd", _p(dy), _p(y), _p(z), _p(x2), x2.stride(0), _p(w), w.stride(0), m, n, k, code, float(param),
+              _p(dx), _p(dw), k, _p(db), _p(ws), _stream())
+    return dx, dw, db
+
+
 def linear_fwd_dispatch(x2, w, b, code=0, param=0.0, want_z=False):
     """y = act(x2 W^T + b) on the tensor-core kernel when the shape qualifies, else the exact-fp32 kernel."""
     m, k = x2.shape
     n = w.shape[0]
+    if smallk_ok(n, k):
+        return raw_smallk_fwd(x2, w, b, code, param, want_z)
     if tc_ok(m, n, k, x2):
         return raw_tc_linear(x2, w, False, b, n, k, code, param, want_z)
     return raw_linear(x2, w, b, code, param, want_z)
@@ -206,6 +234,8 @@ def linear_bwd_dispatch(dz, x2, w, need_x=True, need_w=True, need_b=True):
     """(dx, dw, db) of y = x2 W^T + b given dz."""
     m, n = dz.shape
     k = x2.shape[1]
+    if smallk_ok(n, k):
+        return raw_smallk_bwd(dz, None, None, x2, w, 0, 0.0, need_x, need_w, need_b)
     dx = dw = db = None
     if need_x:
         dx = raw_tc_linear(dz, w, True, None, k, n)[0] if tc_ok(m, k, n, dz) else raw_gemm(dz, w, False, False)
@@ -319,6 +349,10 @@ class LinearAct(torch.autograd.Function):
         m, k = x2.shape
         n = w.shape[0]
         gy2 = _chk(gy.reshape(m, n))
+        if smallk_ok(n, k):
+            gx, gw, gb = raw_smallk_bwd(gy2, y, z, x2, w, ctx.code, ctx.param, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                        ctx.has_bias and ctx.needs_input_grad[2])
+            return (gx.reshape(ctx.shp) if gx is not None else None), gw, gb, None, None
         if ctx.code != 0:
             dz = torch.empty_like(gy2)
             _lib.call("hgb_act_bwd", _p(gy2), _p(y), _p(z), gy2.numel(), ctx.code, ctx.param, _p(dz), _stream())

@@ -148,6 +148,20 @@ int64_t hgb_gemm_workspace_bytes(int32_t m, int32_t n, int32_t k, int32_t trans_
 int hgb_linear_fwd(const float* x, const float* w, const float* b, int32_t m, int32_t n, int32_t k,
                    int64_t ldx, int64_t ldw, int32_t act, float act_param, float* y, float* z,
                    hgb_stream_t stream);
+/* Tiny-K (k <= 8, n <= 256) linear layers: the reference's first PaiNN layer runs at node_size = input_dim
+ * (quirk Q4, hydragnn/models/PAINNStack.py:81-87), so Linear(1->F), Linear(2->1) ... appear at M = nodes.
+ * fwd: y = act(x W^T + b).  bwd: ONE pass over (dy, y|z, x) applies act', writes dx [m,k] (optional) and
+ * reduces dW [n,k] / db [n] deterministically (no dz tensor is materialised).                                 */
+int hgb_linear_smallk_supported(int32_t n, int32_t k);
+int hgb_linear_smallk_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* b, int32_t m,
+                          int32_t n, int32_t k, int32_t act, float act_param, float* y, float* z,
+                          hgb_stream_t stream);
+int hgb_linear_smallk_bwd(const float* dy, const float* y, const float* z, const float* x, int64_t ldx,
+                          const float* w, int64_t ldw, int32_t m, int32_t n, int32_t k, int32_t act,
+                          float act_param, float* dx, float* dw, int64_t lddw, float* db, void* workspace,
+                          hgb_stream_t stream);
+int64_t hgb_linear_smallk_bwd_workspace_bytes(int32_t m, int32_t n, int32_t k);
+
 /* Tensor-core (tcgen05 kind::tf32, TMEM accumulators, TMA-fed) versions of the same dense layers for the
  * large-M shapes of the node / edge MLPs: m >= 128, n_out and k_red multiples of 32 and <= 256.  Used under
  * precision="bf16" (TF32 products, fp32 accumulation: tighter than the bf16 autocast of the reference).

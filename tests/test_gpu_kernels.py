@@ -130,7 +130,7 @@ ACTS = {"relu": torch.relu, "silu": torch.nn.functional.silu, "tanh": torch.tanh
 
 
 @pytest.mark.parametrize("act", list(ACTS))
-@pytest.mark.parametrize("m,k,n", [(257, 64, 192), (100, 1, 3), (33, 11, 1)])
+@pytest.mark.parametrize("m,k,n", [(257, 64, 192), (100, 1, 3), (33, 11, 1), (5000, 1, 64), (4097, 2, 1), (3000, 8, 200), (70000, 1, 1)])
 def test_linear_act_forward_backward(act, m, k, n):
     g = gen(m + k + n)
     x, w, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) * 0.3, torch.randn(n, generator=g)
