@@ -333,7 +333,7 @@ def run_engine(args):
 
 def painn_message_roofline(m, d, ops, dev):
     """CUDA-event timing of hgb_painn_message_fwd alone on the real layer-2 inputs (F = hidden_dim), L2 flushed
-    between launches.  Algorithmic bytes: E*(6F*4 + 8 + 4(R+4)) + N*(8F*4 + 4)."""
+    between launches.  Algorithmic bytes: E*(6F*4 + 8 + 48) + N*(8F*4 + 4)."""
     hbm, src = peaks()
     from hydragnn_b200.stacks import Base
     plan = Base.plan_for(d)
@@ -343,7 +343,7 @@ def painn_message_roofline(m, d, ops, dev):
     conv = m.graph_convs[-1]
     with torch.no_grad():
         _, ln, unit = ops.EdgeGeomFn.apply(d.pos.detach(), None, plan, 1e-9)
-        dr, rbfc, fc = ops.PainnEdgeEmbedFn.apply(unit, ln, r, m.radius)
+        epack = ops.PainnEdgeEmbedFn.apply(unit, ln, r, m.radius)
         s = torch.randn(n, f, device=dev)
         v = torch.randn(n, 3, f, device=dev)
         phi = torch.randn(n, 3 * f, device=dev)
@@ -354,15 +354,15 @@ def painn_message_roofline(m, d, ops, dev):
             flush.zero_()
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0.record()
-            ops.PainnMessageFn.apply(phi, s, v, dr, rbfc, fc, msg.filter_layer.weight, msg.filter_layer.bias, None, plan)
+            ops.PainnMessageFn.apply(phi, s, v, epack, msg.filter_layer.weight, msg.filter_layer.bias, None, plan)
             t1.record()
             torch.cuda.synchronize()
             if it >= 3:
                 ts.append(t0.elapsed_time(t1))
     ms = sum(ts) / len(ts)
-    alg = e * (6 * f * 4 + 8 + 4 * (r + 4)) + n * (8 * f * 4 + 4)
+    alg = e * (6 * f * 4 + 8 + 48) + n * (8 * f * 4 + 4)
     ach = alg / (ms * 1e-3) / 1e9
-    return {"kernel": "painn_message_fwd_kernel<2,false>", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
+    return {"kernel": "painn_message_fwd_kernel<2,false,32,5>", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
             "frac": ach / hbm, "traffic": None, "peak_source": src + " (burst copy figure; kernel timed alone, L2 flushed)",
             "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms}
 

@@ -177,3 +177,15 @@ extern "C" int hgb_csr_build(const int64_t* idx, int64_t e, int32_t n, int32_t* 
   }
   return HGB_OK;
 }
+
+// out[p] = idx[perm[p]]  (the neighbour of every CSR slot, so the fused kernels do one dependent index load less)
+__global__ void gather_i32_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ perm, int64_t e, int32_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) out[i] = idx[perm[i]];
+}
+extern "C" int hgb_gather_i32(const int32_t* idx, const int32_t* perm, int64_t e, int32_t* out, hgb_stream_t stream) {
+  if (e == 0) return HGB_OK;
+  HGB_REQUIRE(idx && perm && out, "gather_i32: null pointer");
+  gather_i32_kernel<<<hgb_grid_for(e, 256), 256, 0, (cudaStream_t)stream>>>(idx, perm, e, out);
+  HGB_LAUNCH_CHECK("gather_i32");
+  return HGB_OK;
+}

@@ -102,7 +102,7 @@ static int pick_splits(int m, int n, int k) {
   const int tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
   if (tiles >= HGB_NUM_SMS || k < 4096) return 1;
   int s = (HGB_NUM_SMS * 4 + tiles - 1) / tiles;
-  const int maxs = (k + 1023) / 1024;
+  const int maxs = (k + 255) / 256;
   if (s > maxs) s = maxs;
   return s < 1 ? 1 : s;
 }
@@ -355,14 +355,82 @@ linear_smallk_bwd_kernel(const float* __restrict__ dy, const float* __restrict__
     }
 }
 
+// out[i] = sum_b part[b][i]: 32 outputs x 8 partial-walkers per block, fixed summation order (deterministic)
 __global__ void linear_smallk_reduce_kernel(const float* __restrict__ part, int nblocks, int n, int k, float* __restrict__ dw,
                                             int64_t lddw, float* __restrict__ db) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n * (k + 1)) return;
+  __shared__ float red[8][33];
+  const int cnt = n * (k + 1);
+  const int i = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
-  for (int b = 0; b < nblocks; ++b) acc += part[(int64_t)b * n * (k + 1) + i];
-  const int r = i / (k + 1), c = i % (k + 1);
-  if (c == k) { if (db) db[r] = acc; } else if (dw) dw[(int64_t)r * lddw + c] = acc;
+  if (i < cnt)
+    for (int b = threadIdx.y; b < nblocks; b += 8) acc += part[(int64_t)b * cnt + i];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < cnt) {
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) t += red[w8][threadIdx.x];
+    const int r = i / (k + 1), c = i % (k + 1);
+    if (c == k) { if (db) db[r] = t; } else if (dw) dw[(int64_t)r * lddw + c] = t;
+  }
+}
+
+// n <= 8 as well: one thread per row keeps the whole n x (k+1) gradient tile in registers
+#define SK_NMAX 8
+__global__ void __launch_bounds__(256)
+linear_tiny_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ z,
+                       const float* __restrict__ x, int64_t ldx, const float* __restrict__ w, int64_t ldw, int m, int n, int k,
+                       int act, float ap, int rows_per_block, float* __restrict__ dx, float* __restrict__ part) {
+  __shared__ float sw[SK_NMAX * SK_KMAX];
+  __shared__ float red[8];
+  for (int i = threadIdx.x; i < n * k; i += blockDim.x) sw[i] = w[(int64_t)(i / k) * ldw + (i % k)];
+  __syncthreads();
+  float gw[SK_NMAX][SK_KMAX + 1];
+#pragma unroll
+  for (int j = 0; j < SK_NMAX; ++j)
+#pragma unroll
+    for (int q = 0; q <= SK_KMAX; ++q) gw[j][q] = 0.f;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(m, r0 + rows_per_block);
+  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+    float xr[SK_KMAX], dxr[SK_KMAX];
+#pragma unroll
+    for (int q = 0; q < SK_KMAX; ++q) { xr[q] = q < k ? x[(int64_t)r * ldx + q] : 0.f; dxr[q] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < SK_NMAX; ++j)
+      if (j < n) {
+        const int64_t o = (int64_t)r * n + j;
+        float g = dy[o];
+        if (act != HGB_ACT_NONE) g *= hgb_act_grad(y ? y[o] : 0.f, z ? z[o] : 0.f, act, ap);
+        gw[j][SK_KMAX] += g;
+#pragma unroll
+        for (int q = 0; q < SK_KMAX; ++q)
+          if (q < k) { gw[j][q] = fmaf(g, xr[q], gw[j][q]); dxr[q] = fmaf(g, sw[j * k + q], dxr[q]); }
+      }
+    if (dx) {
+#pragma unroll
+      for (int q = 0; q < SK_KMAX; ++q)
+        if (q < k) dx[(int64_t)r * k + q] = dxr[q];
+    }
+  }
+  float* mypart = part + (int64_t)blockIdx.x * n * (k + 1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < SK_NMAX; ++j)
+#pragma unroll
+    for (int q = 0; q <= SK_KMAX; ++q)
+      if (j < n && (q < k || q == SK_KMAX)) {
+        const float v = hgb_warp_sum(gw[j][q]);
+        __syncthreads();
+        if (lane == 0) red[warp] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          float t = 0.f;
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) t += red[w8];
+          mypart[j * (k + 1) + (q == SK_KMAX ? k : q)] = t;
+        }
+      }
 }
 
 static int smallk_blocks(int m, int* rows_per_block) {
@@ -406,10 +474,14 @@ extern "C" int hgb_linear_smallk_bwd(const float* dy, const float* y, const floa
   }
   int rpb;
   const int nb = smallk_blocks(m, &rpb);
-  linear_smallk_bwd_kernel<<<nb, dim3(32, 8), (size_t)(n * k + 256) * 4, st>>>(dy, y, z, x, ldx, w, ldw, m, n, k, act, act_param, rpb, dx,
-                                                                             (float*)workspace);
+  if (n <= SK_NMAX) {
+    linear_tiny_bwd_kernel<<<nb, 256, 0, st>>>(dy, y, z, x, ldx, w, ldw, m, n, k, act, act_param, rpb, dx, (float*)workspace);
+  } else {
+    linear_smallk_bwd_kernel<<<nb, dim3(32, 8), (size_t)(n * k + 256) * 4, st>>>(dy, y, z, x, ldx, w, ldw, m, n, k, act, act_param, rpb, dx,
+                                                                               (float*)workspace);
+  }
   HGB_LAUNCH_CHECK("linear_smallk_bwd");
-  linear_smallk_reduce_kernel<<<(n * (k + 1) + 127) / 128, 128, 0, st>>>((const float*)workspace, nb, n, k, dw, lddw, db);
+  linear_smallk_reduce_kernel<<<(n * (k + 1) + 31) / 32, dim3(32, 8), 0, st>>>((const float*)workspace, nb, n, k, dw, lddw, db);
   HGB_LAUNCH_CHECK("linear_smallk_reduce");
   return HGB_OK;
 }

@@ -61,62 +61,64 @@ extern "C" int hgb_edge_geom_bwd(const float* vec, const float* len, float eps, 
 // ---- PaiNN radial embedding --------------------------------------------------------------------
 #define HGB_PI 3.14159265358979323846f
 
+// epack [e,12] = { sin(n pi d / rc)/d * fcut for n = 1..r (zero padded to 8), fcut, unit/d (x, y, z) }
 __global__ void painn_edge_embed_fwd_kernel(const float* __restrict__ unit, const float* __restrict__ len, int64_t e, int r,
-                                            float cutoff, float* __restrict__ dir, float* __restrict__ rbfc,
-                                            float* __restrict__ fc) {
+                                            float cutoff, float* __restrict__ epack) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
     const float d = len[i];
     const float id = 1.f / d;
-    dir[3 * i] = unit[3 * i] * id; dir[3 * i + 1] = unit[3 * i + 1] * id; dir[3 * i + 2] = unit[3 * i + 2] * id;
     const float cut = d < cutoff ? 0.5f * (cosf(HGB_PI * d / cutoff) + 1.f) : 0.f;
-    fc[i] = cut;
-    for (int q = 0; q < r; ++q) rbfc[i * r + q] = sinf(d * (float)(q + 1) * HGB_PI / cutoff) * id * cut;
+    float o[12];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = q < r ? sinf(d * (float)(q + 1) * HGB_PI / cutoff) * id * cut : 0.f;
+    o[8] = cut;
+    o[9] = unit[3 * i] * id; o[10] = unit[3 * i + 1] * id; o[11] = unit[3 * i + 2] * id;
+    float4* op = reinterpret_cast<float4*>(epack + i * 12);
+    op[0] = make_float4(o[0], o[1], o[2], o[3]); op[1] = make_float4(o[4], o[5], o[6], o[7]); op[2] = make_float4(o[8], o[9], o[10], o[11]);
   }
 }
 
-extern "C" int hgb_painn_edge_embed_fwd(const float* unit, const float* len, int64_t e, int32_t r, float cutoff, float* dir,
-                                        float* rbfc, float* fc, hgb_stream_t stream) {
-  HGB_REQUIRE(e >= 0 && r > 0 && unit && len && dir && rbfc && fc, "painn_edge_embed_fwd: bad arguments");
+extern "C" int hgb_painn_edge_embed_fwd(const float* unit, const float* len, int64_t e, int32_t r, float cutoff, float* epack,
+                                        hgb_stream_t stream) {
+  HGB_REQUIRE(e >= 0 && r > 0 && r <= 8 && unit && len && epack, "painn_edge_embed_fwd: bad arguments (num_radial <= 8)");
   if (e == 0) return HGB_OK;
-  painn_edge_embed_fwd_kernel<<<hgb_grid_for(e, 256), 256, 0, (cudaStream_t)stream>>>(unit, len, e, r, cutoff, dir, rbfc, fc);
+  painn_edge_embed_fwd_kernel<<<hgb_grid_for(e, 256), 256, 0, (cudaStream_t)stream>>>(unit, len, e, r, cutoff, epack);
   HGB_LAUNCH_CHECK("painn_edge_embed_fwd");
   return HGB_OK;
 }
 
 __global__ void painn_edge_embed_bwd_kernel(const float* __restrict__ unit, const float* __restrict__ len,
-                                            const float* __restrict__ g_dir, const float* __restrict__ g_rbfc,
-                                            const float* __restrict__ g_fc, int64_t e, int r, float cutoff,
+                                            const float* __restrict__ g_epack, int64_t e, int r, float cutoff,
                                             float* __restrict__ g_unit, float* __restrict__ g_len) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
     const float d = len[i];
     const float id = 1.f / d;
-    const float gx = g_dir[3 * i], gy = g_dir[3 * i + 1], gz = g_dir[3 * i + 2];
+    const float* g = g_epack + i * 12;
+    const float gx = g[9], gy = g[10], gz = g[11];
     g_unit[3 * i] = gx * id; g_unit[3 * i + 1] = gy * id; g_unit[3 * i + 2] = gz * id;
     float gl = -(gx * unit[3 * i] + gy * unit[3 * i + 1] + gz * unit[3 * i + 2]) * id * id;
     const bool in = d < cutoff;
     const float w = HGB_PI / cutoff;
     const float cut = in ? 0.5f * (cosf(w * d) + 1.f) : 0.f;
     const float dcut = in ? -0.5f * w * sinf(w * d) : 0.f;
-    gl += g_fc[i] * dcut;
+    gl += g[8] * dcut;
     for (int q = 0; q < r; ++q) {
       const float a = (float)(q + 1) * w;
       float sn, cs;
       sincosf(a * d, &sn, &cs);
       const float sinc = sn * id;
       const float dsinc = (a * cs - sinc) * id;
-      gl += g_rbfc[i * r + q] * (dsinc * cut + sinc * dcut);
+      gl += g[q] * (dsinc * cut + sinc * dcut);
     }
     g_len[i] = gl;
   }
 }
 
-extern "C" int hgb_painn_edge_embed_bwd(const float* unit, const float* len, const float* g_dir, const float* g_rbfc,
-                                        const float* g_fc, int64_t e, int32_t r, float cutoff, float* g_unit, float* g_len,
-                                        hgb_stream_t stream) {
-  HGB_REQUIRE(e >= 0 && r > 0 && unit && len && g_dir && g_rbfc && g_fc && g_unit && g_len, "painn_edge_embed_bwd: bad arguments");
+extern "C" int hgb_painn_edge_embed_bwd(const float* unit, const float* len, const float* g_epack, int64_t e, int32_t r, float cutoff,
+                                        float* g_unit, float* g_len, hgb_stream_t stream) {
+  HGB_REQUIRE(e >= 0 && r > 0 && r <= 8 && unit && len && g_epack && g_unit && g_len, "painn_edge_embed_bwd: bad arguments");
   if (e == 0) return HGB_OK;
-  painn_edge_embed_bwd_kernel<<<hgb_grid_for(e, 256), 256, 0, (cudaStream_t)stream>>>(unit, len, g_dir, g_rbfc, g_fc, e, r, cutoff,
-                                                                                     g_unit, g_len);
+  painn_edge_embed_bwd_kernel<<<hgb_grid_for(e, 256), 256, 0, (cudaStream_t)stream>>>(unit, len, g_epack, e, r, cutoff, g_unit, g_len);
   HGB_LAUNCH_CHECK("painn_edge_embed_bwd");
   return HGB_OK;
 }

@@ -6,14 +6,19 @@
 // in registers.  Nothing per-edge is written; no atomics; summation order = ascending edge id.
 // Message backward is the mirror image over the CSR of edge[:,1] (the gather side): the warp that owns
 // source node j reads the incoming gradients of every node it sent a message to.
-// Filter weights (3F x R) sit in shared memory with an odd row stride (bank-conflict free).
+// Filter weights (3F x R) of a lane's channels are register resident.
 #include "hgb_common.cuh"
 
 #define RMAX 8
 #define WPB 8  // warps per block
 
 // GROUP = lanes that share one node (32 for F >= 32; for narrow layers -- the reference's first layer runs at
-// F = input_dim, often 1 -- a warp serves 32/GROUP nodes at once instead of idling 31 lanes)
+// F = input_dim, often 1 -- a warp serves 32/GROUP nodes at once instead of idling 31 lanes).
+// CPL  = channels per lane, adjacent (c, c+1) so that CPL = 2 reads phi / v / gradients with 8-byte loads.
+// RT   = compile-time radial count (5 or 8; weights and edge records are zero-padded up to RT).
+// Edge record "epack" [E,12] = { rbf_q * fcut (q < 8, zero padded), fcut, dir_x, dir_y, dir_z }: three 16-byte
+// broadcast loads per edge instead of nine scalar ones.  nbr[p] is the neighbour node of CSR slot p, precomputed
+// by the plan so the gather address does not hang off a second dependent index load.
 template <int G>
 __device__ __forceinline__ float hgb_group_sum(float v, unsigned mask) {   // groups of one warp may diverge: shuffle within the group only
 #pragma unroll
@@ -21,104 +26,127 @@ __device__ __forceinline__ float hgb_group_sum(float v, unsigned mask) {   // gr
   return v;
 }
 
-template <int CPL, bool HAS_EF, int GROUP>
+#define EPK 12
+
+template <int CPL>
+struct ChanVec;
+template <>
+struct ChanVec<1> {
+  static __device__ __forceinline__ void ld(const float* p, float* o) { o[0] = __ldg(p); }
+  static __device__ __forceinline__ void st(float* p, const float* o) { p[0] = o[0]; }
+};
+template <>
+struct ChanVec<2> {
+  static __device__ __forceinline__ void ld(const float* p, float* o) { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); o[0] = t.x; o[1] = t.y; }
+  static __device__ __forceinline__ void st(float* p, const float* o) { *reinterpret_cast<float2*>(p) = make_float2(o[0], o[1]); }
+};
+
+template <int CPL, bool HAS_EF, int GROUP, int RT>
 __global__ void __launch_bounds__(WPB * 32)
 painn_message_fwd_kernel(const float* __restrict__ phi, const float* __restrict__ s, const float* __restrict__ v,
                          const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm,
-                         const int32_t* __restrict__ src, const float* __restrict__ dir, const float* __restrict__ rbfc,
-                         const float* __restrict__ fc, const float* __restrict__ wf, const float* __restrict__ bf,
-                         const float* __restrict__ efilt, int n, int f, int r, float* __restrict__ s_out,
-                         float* __restrict__ v_out) {
-  extern __shared__ float sm[];
-  const int rs = r | 1;
-  float* wfs = sm;               // [3f][rs]
-  float* bfs = sm + 3 * f * rs;  // [3f]
-  for (int t = threadIdx.x; t < 3 * f * r; t += blockDim.x) wfs[(t / r) * rs + (t % r)] = wf[t];
-  for (int t = threadIdx.x; t < 3 * f; t += blockDim.x) bfs[t] = bf[t];
-  __syncthreads();
+                         const int32_t* __restrict__ nbr, const float* __restrict__ epack, const float* __restrict__ wf,
+                         const float* __restrict__ bf, const float* __restrict__ efilt, int n, int f, int r,
+                         float* __restrict__ s_out, float* __restrict__ v_out) {
   const int lane = threadIdx.x & 31;
   constexpr int NPW = 32 / GROUP;
   const int sub = lane % GROUP, nsub = lane / GROUP;
-  const int cbase = blockIdx.y * GROUP * CPL;
-  int ch[CPL];
-  bool ok[CPL];
-#pragma unroll
-  for (int t = 0; t < CPL; ++t) { ch[t] = cbase + sub + GROUP * t; ok[t] = ch[t] < f; if (!ok[t]) ch[t] = 0; }
+  const int c0 = blockIdx.y * GROUP * CPL + sub * CPL;   // first channel of this lane
+  const bool ok = c0 < f;                                // f is a multiple of CPL whenever CPL == 2
+  const int cc = ok ? c0 : 0;
   const int f3 = 3 * f;
+  // filter rows of this lane's channels, register resident: wr[part][t][q], q == RT holds the bias
+  float wr[3][CPL][RT + 1];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) {
+#pragma unroll
+      for (int q = 0; q < RT; ++q) wr[a][t][q] = q < r ? wf[(a * f + cc + t) * r + q] : 0.f;
+      wr[a][t][RT] = bf[a * f + cc + t];
+    }
   for (int i = (blockIdx.x * WPB + (threadIdx.x >> 5)) * NPW + nsub; i < n; i += gridDim.x * WPB * NPW) {
     const int lo = rowptr[i], hi = rowptr[i + 1];
-    float as[CPL], av[CPL][3];
+    float as[CPL], av[3][CPL];
 #pragma unroll
-    for (int t = 0; t < CPL; ++t) { as[t] = 0.f; av[t][0] = av[t][1] = av[t][2] = 0.f; }
+    for (int t = 0; t < CPL; ++t) { as[t] = 0.f; av[0][t] = av[1][t] = av[2][t] = 0.f; }
     for (int p = lo; p < hi; ++p) {
+      const int j = nbr[p];
       const int e = perm ? perm[p] : p;
-      const int j = src[e];
-      const float fce = fc[e];
-      const float d0 = dir[3 * (int64_t)e], d1 = dir[3 * (int64_t)e + 1], d2 = dir[3 * (int64_t)e + 2];
-      float rb[RMAX];
+      const float4* ep = reinterpret_cast<const float4*>(epack + (int64_t)e * EPK);
+      const float4 e0 = __ldg(ep), e1 = __ldg(ep + 1), e2 = __ldg(ep + 2);
+      const float rb[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+      const float fce = e2.x, d[3] = {e2.y, e2.z, e2.w};
+      const float* ph = phi + (int64_t)j * f3 + cc;
+      const float* vj = v + (int64_t)j * f3 + cc;
+      float pv[3][CPL], vv[3][CPL];
 #pragma unroll
-      for (int q = 0; q < RMAX; ++q) rb[q] = q < r ? rbfc[(int64_t)e * r + q] : 0.f;
-      const float* ph = phi + (int64_t)j * f3;
-      const float* vj = v + (int64_t)j * f3;
+      for (int a = 0; a < 3; ++a) { ChanVec<CPL>::ld(ph + a * f, pv[a]); ChanVec<CPL>::ld(vj + a * f, vv[a]); }
+      float ef[3][CPL];
+      if (HAS_EF) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) ChanVec<CPL>::ld(efilt + (int64_t)e * f3 + a * f + cc, ef[a]);
+      }
 #pragma unroll
       for (int t = 0; t < CPL; ++t) {
-        const int c = ch[t];
-        float w0 = bfs[c] * fce, w1 = bfs[f + c] * fce, w2 = bfs[2 * f + c] * fce;
+        float w[3];
 #pragma unroll
-        for (int q = 0; q < RMAX; ++q)
-          if (q < r) {
-            w0 = fmaf(wfs[c * rs + q], rb[q], w0);
-            w1 = fmaf(wfs[(f + c) * rs + q], rb[q], w1);
-            w2 = fmaf(wfs[(2 * f + c) * rs + q], rb[q], w2);
-          }
-        if (HAS_EF) {
-          const float* ef = efilt + (int64_t)e * f3;
-          w0 *= ef[c]; w1 *= ef[f + c]; w2 *= ef[2 * f + c];
+        for (int a = 0; a < 3; ++a) {
+          float acc = wr[a][t][RT] * fce;
+#pragma unroll
+          for (int q = 0; q < RT; ++q) acc = fmaf(wr[a][t][q], rb[q], acc);
+          w[a] = HAS_EF ? acc * ef[a][t] : acc;
         }
-        const float gv = w0 * __ldg(ph + c), ge = w1 * __ldg(ph + f + c), ms = w2 * __ldg(ph + 2 * f + c);
-        as[t] += ms;
-        av[t][0] += __ldg(vj + c) * gv + ge * d0;
-        av[t][1] += __ldg(vj + f + c) * gv + ge * d1;
-        av[t][2] += __ldg(vj + 2 * f + c) * gv + ge * d2;
+        const float gv = w[0] * pv[0][t], ge = w[1] * pv[1][t];
+        as[t] = fmaf(w[2], pv[2][t], as[t]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) av[k][t] += vv[k][t] * gv + ge * d[k];
       }
     }
+    if (ok) {
+      float so[CPL], tmp[CPL];
+      ChanVec<CPL>::ld(s + (int64_t)i * f + cc, so);
 #pragma unroll
-    for (int t = 0; t < CPL; ++t)
-      if (ok[t]) {
-        const int c = ch[t];
-        s_out[(int64_t)i * f + c] = s[(int64_t)i * f + c] + as[t];
+      for (int t = 0; t < CPL; ++t) so[t] += as[t];
+      ChanVec<CPL>::st(s_out + (int64_t)i * f + cc, so);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) v_out[(int64_t)i * f3 + k * f + c] = v[(int64_t)i * f3 + k * f + c] + av[t][k];
+      for (int k = 0; k < 3; ++k) {
+        ChanVec<CPL>::ld(v + (int64_t)i * f3 + k * f + cc, tmp);
+#pragma unroll
+        for (int t = 0; t < CPL; ++t) tmp[t] += av[k][t];
+        ChanVec<CPL>::st(v_out + (int64_t)i * f3 + k * f + cc, tmp);
       }
+    }
   }
 }
 
+static int painn_group(int f) { int g = 32; if (f < 32) { g = 1; while (g < f) g <<= 1; } return g; }
+static int painn_cpl(int f) { return (f >= 64 && f % 2 == 0) ? 2 : 1; }
+
 extern "C" int hgb_painn_message_fwd(const float* phi, const float* s, const float* v, const int32_t* rowptr,
-                                     const int32_t* perm, const int32_t* src, const float* dir, const float* rbfc,
-                                     const float* fc, const float* wf, const float* bf, const float* efilt, int32_t n,
-                                     int32_t f, int32_t r, float* s_out, float* v_out, hgb_stream_t stream) {
+                                     const int32_t* perm, const int32_t* nbr, const float* epack, const float* wf, const float* bf,
+                                     const float* efilt, int32_t n, int32_t f, int32_t r, float* s_out, float* v_out,
+                                     hgb_stream_t stream) {
   HGB_REQUIRE(n >= 0 && f > 0 && r > 0 && r <= RMAX, "painn_message_fwd: need 0 < num_radial <= %d (got %d)", RMAX, r);
-  HGB_REQUIRE(phi && s && v && rowptr && src && dir && rbfc && fc && wf && bf && s_out && v_out, "painn_message_fwd: null pointer");
+  HGB_REQUIRE(phi && s && v && rowptr && nbr && epack && wf && bf && s_out && v_out, "painn_message_fwd: null pointer");
   if (n == 0) return HGB_OK;
-  const size_t smem = (size_t)(3 * f * ((r | 1) + 1)) * sizeof(float);
-  HGB_REQUIRE(smem <= 48 * 1024, "painn_message_fwd: hidden_dim %d too large for the filter staging", f);
-  const int cpl = f <= 32 ? 1 : 2;
-  int group = 32;
-  if (f < 32) { group = 1; while (group < f) group <<= 1; }
+  const int cpl = painn_cpl(f), group = painn_group(f);
   dim3 grid(hgb_grid_for(n, WPB * (32 / group), HGB_NUM_SMS * 8), (f + group * cpl - 1) / (group * cpl));
   cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(C, E, G) painn_message_fwd_kernel<C, E, G><<<grid, WPB * 32, smem, st>>>(phi, s, v, rowptr, perm, src, dir, rbfc, fc, wf, bf, efilt, n, f, r, s_out, v_out)
-#define LAUNCH_G(E)                                                  \
-  switch (group) {                                                   \
-    case 1: LAUNCH(1, E, 1); break;                                  \
-    case 2: LAUNCH(1, E, 2); break;                                  \
-    case 4: LAUNCH(1, E, 4); break;                                  \
-    case 8: LAUNCH(1, E, 8); break;                                  \
-    case 16: LAUNCH(1, E, 16); break;                                \
-    default: if (cpl == 1) LAUNCH(1, E, 32); else LAUNCH(2, E, 32);  \
+#define LAUNCH(C, E, G, R) painn_message_fwd_kernel<C, E, G, R><<<grid, WPB * 32, 0, st>>>(phi, s, v, rowptr, perm, nbr, epack, wf, bf, efilt, n, f, r, s_out, v_out)
+#define LAUNCH_R(C, E, G) do { if (r <= 5) LAUNCH(C, E, G, 5); else LAUNCH(C, E, G, 8); } while (0)
+#define LAUNCH_G(E)                                                        \
+  switch (group) {                                                         \
+    case 1: LAUNCH_R(1, E, 1); break;                                      \
+    case 2: LAUNCH_R(1, E, 2); break;                                      \
+    case 4: LAUNCH_R(1, E, 4); break;                                      \
+    case 8: LAUNCH_R(1, E, 8); break;                                      \
+    case 16: LAUNCH_R(1, E, 16); break;                                    \
+    default: if (cpl == 1) LAUNCH_R(1, E, 32); else LAUNCH_R(2, E, 32);    \
   }
   if (efilt) { LAUNCH_G(true) } else { LAUNCH_G(false) }
 #undef LAUNCH_G
+#undef LAUNCH_R
 #undef LAUNCH
   HGB_LAUNCH_CHECK("painn_message_fwd");
   return HGB_OK;
@@ -126,167 +154,158 @@ extern "C" int hgb_painn_message_fwd(const float* phi, const float* s, const flo
 
 // ---- backward ----------------------------------------------------------------------------------------
 // workspace layout: part[gridDim.x][3f][r+1]  (column r holds the bias gradient)
-template <int CPL, bool HAS_EF, bool NEED_EDGE, int GROUP>
+template <int CPL, bool HAS_EF, bool NEED_EDGE, int GROUP, int RT>
 __global__ void __launch_bounds__(WPB * 32)
 painn_message_bwd_kernel(const float* __restrict__ gs_out, const float* __restrict__ gv_out, const float* __restrict__ phi,
                          const float* __restrict__ v, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm,
-                         const int32_t* __restrict__ agg, const float* __restrict__ dir, const float* __restrict__ rbfc,
-                         const float* __restrict__ fc, const float* __restrict__ wf, const float* __restrict__ bf,
-                         const float* __restrict__ efilt, int n, int f, int r, float* __restrict__ gphi, float* __restrict__ gv,
-                         float* __restrict__ part, float* __restrict__ g_dir, float* __restrict__ g_rbfc,
-                         float* __restrict__ g_fc, float* __restrict__ g_efilt, int multi_cb) {
-  extern __shared__ float sm[];
-  const int rs = r | 1;
-  float* wfs = sm;
-  float* bfs = sm + 3 * f * rs;
-  float* red = bfs + 3 * f;  // [WPB][32]
-  for (int t = threadIdx.x; t < 3 * f * r; t += blockDim.x) wfs[(t / r) * rs + (t % r)] = wf[t];
-  for (int t = threadIdx.x; t < 3 * f; t += blockDim.x) bfs[t] = bf[t];
-  __syncthreads();
+                         const int32_t* __restrict__ nbr, const float* __restrict__ epack, const float* __restrict__ wf,
+                         const float* __restrict__ bf, const float* __restrict__ efilt, int n, int f, int r,
+                         float* __restrict__ gphi, float* __restrict__ gv, float* __restrict__ part, float* __restrict__ g_epack,
+                         float* __restrict__ g_efilt, int multi_cb) {
+  __shared__ float red[WPB * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NPW = 32 / GROUP;
   const int sub = lane % GROUP, nsub = lane / GROUP;
-  const int cbase = blockIdx.y * GROUP * CPL;
-  int ch[CPL];
-  bool ok[CPL];
-#pragma unroll
-  for (int t = 0; t < CPL; ++t) { ch[t] = cbase + sub + GROUP * t; ok[t] = ch[t] < f; if (!ok[t]) ch[t] = 0; }
+  const int c0 = blockIdx.y * GROUP * CPL + sub * CPL;
+  const bool ok = c0 < f;
+  const int cc = ok ? c0 : 0;
   const int f3 = 3 * f;
   const unsigned gmask = GROUP == 32 ? 0xffffffffu : (((1u << GROUP) - 1u) << (nsub * GROUP));
-  float gw[CPL][3][RMAX + 1];
+  float wr[3][CPL][RT + 1], gw[3][CPL][RT + 1];
 #pragma unroll
-  for (int t = 0; t < CPL; ++t)
+  for (int a = 0; a < 3; ++a)
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
+    for (int t = 0; t < CPL; ++t) {
 #pragma unroll
-      for (int q = 0; q <= RMAX; ++q) gw[t][a][q] = 0.f;
-
+      for (int q = 0; q < RT; ++q) { wr[a][t][q] = q < r ? wf[(a * f + cc + t) * r + q] : 0.f; gw[a][t][q] = 0.f; }
+      wr[a][t][RT] = bf[a * f + cc + t];
+      gw[a][t][RT] = 0.f;
+    }
   for (int j = (blockIdx.x * WPB + warp) * NPW + nsub; j < n; j += gridDim.x * WPB * NPW) {
     const int lo = rowptr[j], hi = rowptr[j + 1];
-    float ph[CPL][3], vj[CPL][3], aphi[CPL][3], agv[CPL][3];
+    float ph[3][CPL], vj[3][CPL], aphi[3][CPL], agv[3][CPL];
 #pragma unroll
-    for (int t = 0; t < CPL; ++t)
+    for (int a = 0; a < 3; ++a) {
+      ChanVec<CPL>::ld(phi + (int64_t)j * f3 + a * f + cc, ph[a]);
+      ChanVec<CPL>::ld(v + (int64_t)j * f3 + a * f + cc, vj[a]);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        ph[t][k] = phi[(int64_t)j * f3 + k * f + ch[t]];
-        vj[t][k] = v[(int64_t)j * f3 + k * f + ch[t]];
-        aphi[t][k] = 0.f;
-        agv[t][k] = 0.f;
-      }
+      for (int t = 0; t < CPL; ++t) { aphi[a][t] = 0.f; agv[a][t] = 0.f; }
+    }
     for (int p = lo; p < hi; ++p) {
+      const int i = nbr[p];
       const int e = perm ? perm[p] : p;
-      const int i = agg[e];
-      const float fce = fc[e];
-      const float d0 = dir[3 * (int64_t)e], d1 = dir[3 * (int64_t)e + 1], d2 = dir[3 * (int64_t)e + 2];
-      float rb[RMAX];
+      const float4* ep = reinterpret_cast<const float4*>(epack + (int64_t)e * EPK);
+      const float4 e0 = __ldg(ep), e1 = __ldg(ep + 1), e2 = __ldg(ep + 2);
+      const float rb[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+      const float fce = e2.x, d[3] = {e2.y, e2.z, e2.w};
+      float gsi[CPL], gvi[3][CPL];
+      ChanVec<CPL>::ld(gs_out + (int64_t)i * f + cc, gsi);
 #pragma unroll
-      for (int q = 0; q < RMAX; ++q) rb[q] = q < r ? rbfc[(int64_t)e * r + q] : 0.f;
-      float e_rb[RMAX], e_fc = 0.f, e_d0 = 0.f, e_d1 = 0.f, e_d2 = 0.f;  // per-edge gradients (NEED_EDGE)
+      for (int k = 0; k < 3; ++k) ChanVec<CPL>::ld(gv_out + (int64_t)i * f3 + k * f + cc, gvi[k]);
+      float ef[3][CPL];
+      if (HAS_EF) {
 #pragma unroll
-      for (int q = 0; q < RMAX; ++q) e_rb[q] = 0.f;
+        for (int a = 0; a < 3; ++a) ChanVec<CPL>::ld(efilt + (int64_t)e * f3 + a * f + cc, ef[a]);
+      }
+      float e_rb[RT], e_fc = 0.f, e_d[3] = {0.f, 0.f, 0.f};   // per-edge gradients (NEED_EDGE)
+#pragma unroll
+      for (int q = 0; q < RT; ++q) e_rb[q] = 0.f;
 #pragma unroll
       for (int t = 0; t < CPL; ++t) {
-        const int c = ch[t];
-        float w[3];
-        w[0] = bfs[c] * fce; w[1] = bfs[f + c] * fce; w[2] = bfs[2 * f + c] * fce;
-#pragma unroll
-        for (int q = 0; q < RMAX; ++q)
-          if (q < r) {
-            w[0] = fmaf(wfs[c * rs + q], rb[q], w[0]);
-            w[1] = fmaf(wfs[(f + c) * rs + q], rb[q], w[1]);
-            w[2] = fmaf(wfs[(2 * f + c) * rs + q], rb[q], w[2]);
-          }
-        float ef[3] = {1.f, 1.f, 1.f};
-        if (HAS_EF) {
-#pragma unroll
-          for (int a = 0; a < 3; ++a) ef[a] = efilt[(int64_t)e * f3 + a * f + c];
-        }
-        const float gsi = ok[t] ? __ldg(gs_out + (int64_t)i * f + c) : 0.f;
-        float gvi[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) gvi[k] = ok[t] ? __ldg(gv_out + (int64_t)i * f3 + k * f + c) : 0.f;
-        // gradients w.r.t. the three gate values f = W * ef * phi
-        float gg[3];
-        gg[0] = gvi[0] * vj[t][0] + gvi[1] * vj[t][1] + gvi[2] * vj[t][2];
-        gg[1] = gvi[0] * d0 + gvi[1] * d1 + gvi[2] * d2;
-        gg[2] = gsi;
-        const float gate_v = w[0] * ef[0] * ph[t][0];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) agv[t][k] += gvi[k] * gate_v;
+        const float live = ok ? 1.f : 0.f;       // masked lanes read channel 0 but must contribute nothing
+        float w[3], gg[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-          aphi[t][a] += gg[a] * w[a] * ef[a];
-          const float gwe = gg[a] * ph[t][a];  // gradient w.r.t. (W * ef)
-          if (HAS_EF && ok[t]) g_efilt[(int64_t)e * f3 + a * f + c] = gwe * w[a];
-          const float gW = gwe * ef[a];        // gradient w.r.t. the raw filter W[a, c]
+          float acc = wr[a][t][RT] * fce;
 #pragma unroll
-          for (int q = 0; q < RMAX; ++q)
-            if (q < r) gw[t][a][q] = fmaf(gW, rb[q], gw[t][a][q]);
-          gw[t][a][RMAX] = fmaf(gW, fce, gw[t][a][RMAX]);
+          for (int q = 0; q < RT; ++q) acc = fmaf(wr[a][t][q], rb[q], acc);
+          w[a] = acc;
+        }
+        const float g0 = gvi[0][t] * live, g1 = gvi[1][t] * live, g2 = gvi[2][t] * live;
+        // gradients w.r.t. the three gate values f_a = W_a * ef_a * phi_a
+        gg[0] = g0 * vj[0][t] + g1 * vj[1][t] + g2 * vj[2][t];
+        gg[1] = g0 * d[0] + g1 * d[1] + g2 * d[2];
+        gg[2] = gsi[t] * live;
+        const float e0f = HAS_EF ? ef[0][t] : 1.f, e1f = HAS_EF ? ef[1][t] : 1.f, e2f = HAS_EF ? ef[2][t] : 1.f;
+        const float efv[3] = {e0f, e1f, e2f};
+        const float gate_v = w[0] * e0f * ph[0][t];
+        agv[0][t] = fmaf(g0, gate_v, agv[0][t]); agv[1][t] = fmaf(g1, gate_v, agv[1][t]); agv[2][t] = fmaf(g2, gate_v, agv[2][t]);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          aphi[a][t] = fmaf(gg[a], w[a] * efv[a], aphi[a][t]);
+          const float gwe = gg[a] * ph[a][t];            // gradient w.r.t. (W * ef)
+          if (HAS_EF && ok) g_efilt[(int64_t)e * f3 + a * f + cc + t] = gwe * w[a];
+          const float gW = gwe * efv[a];                 // gradient w.r.t. the raw filter W[a, c]
+#pragma unroll
+          for (int q = 0; q < RT; ++q) gw[a][t][q] = fmaf(gW, rb[q], gw[a][t][q]);
+          gw[a][t][RT] = fmaf(gW, fce, gw[a][t][RT]);
           if (NEED_EDGE) {
 #pragma unroll
-            for (int q = 0; q < RMAX; ++q)
-              if (q < r) e_rb[q] = fmaf(gW, wfs[(a * f + c) * rs + q], e_rb[q]);
-            e_fc = fmaf(gW, bfs[a * f + c], e_fc);
+            for (int q = 0; q < RT; ++q) e_rb[q] = fmaf(gW, wr[a][t][q], e_rb[q]);
+            e_fc = fmaf(gW, wr[a][t][RT], e_fc);
           }
         }
         if (NEED_EDGE) {
-          const float ge = w[1] * ef[1] * ph[t][1];
-          e_d0 = fmaf(gvi[0], ge, e_d0); e_d1 = fmaf(gvi[1], ge, e_d1); e_d2 = fmaf(gvi[2], ge, e_d2);
+          const float ge = w[1] * e1f * ph[1][t];
+          e_d[0] = fmaf(g0, ge, e_d[0]); e_d[1] = fmaf(g1, ge, e_d[1]); e_d[2] = fmaf(g2, ge, e_d[2]);
         }
       }
       if (NEED_EDGE) {
 #pragma unroll
-        for (int q = 0; q < RMAX; ++q)
-          if (q < r) e_rb[q] = hgb_group_sum<GROUP>(e_rb[q], gmask);
-        e_fc = hgb_group_sum<GROUP>(e_fc, gmask); e_d0 = hgb_group_sum<GROUP>(e_d0, gmask); e_d1 = hgb_group_sum<GROUP>(e_d1, gmask); e_d2 = hgb_group_sum<GROUP>(e_d2, gmask);
+        for (int q = 0; q < RT; ++q) e_rb[q] = hgb_group_sum<GROUP>(e_rb[q], gmask);
+        e_fc = hgb_group_sum<GROUP>(e_fc, gmask);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) e_d[k] = hgb_group_sum<GROUP>(e_d[k], gmask);
         if (sub == 0) {
-          if (multi_cb) {  // several channel blocks contribute to the same edge
+          float* ge = g_epack + (int64_t)e * EPK;
+          if (multi_cb) {   // several channel blocks add into the same (zero-initialised) record
 #pragma unroll
-            for (int q = 0; q < RMAX; ++q)
-              if (q < r) atomicAdd(g_rbfc + (int64_t)e * r + q, e_rb[q]);
-            atomicAdd(g_fc + e, e_fc);
-            atomicAdd(g_dir + 3 * (int64_t)e, e_d0); atomicAdd(g_dir + 3 * (int64_t)e + 1, e_d1); atomicAdd(g_dir + 3 * (int64_t)e + 2, e_d2);
+            for (int q = 0; q < RT; ++q) atomicAdd(ge + q, e_rb[q]);
+            atomicAdd(ge + 8, e_fc);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) atomicAdd(ge + 9 + k, e_d[k]);
           } else {
+            float o[EPK];
 #pragma unroll
-            for (int q = 0; q < RMAX; ++q)
-              if (q < r) g_rbfc[(int64_t)e * r + q] = e_rb[q];
-            g_fc[e] = e_fc;
-            g_dir[3 * (int64_t)e] = e_d0; g_dir[3 * (int64_t)e + 1] = e_d1; g_dir[3 * (int64_t)e + 2] = e_d2;
+            for (int q = 0; q < 8; ++q) o[q] = q < RT ? e_rb[q < RT ? q : 0] : 0.f;
+            o[8] = e_fc; o[9] = e_d[0]; o[10] = e_d[1]; o[11] = e_d[2];
+            float4* gp = reinterpret_cast<float4*>(ge);
+            gp[0] = make_float4(o[0], o[1], o[2], o[3]); gp[1] = make_float4(o[4], o[5], o[6], o[7]); gp[2] = make_float4(o[8], o[9], o[10], o[11]);
           }
         }
       }
     }
+    if (ok) {
 #pragma unroll
-    for (int t = 0; t < CPL; ++t)
-      if (ok[t]) {
-        const int c = ch[t];
+      for (int a = 0; a < 3; ++a) {
+        ChanVec<CPL>::st(gphi + (int64_t)j * f3 + a * f + cc, aphi[a]);
+        float tmp[CPL];
+        ChanVec<CPL>::ld(gv_out + (int64_t)j * f3 + a * f + cc, tmp);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          gphi[(int64_t)j * f3 + k * f + c] = aphi[t][k];
-          gv[(int64_t)j * f3 + k * f + c] = gv_out[(int64_t)j * f3 + k * f + c] + agv[t][k];
-        }
+        for (int t = 0; t < CPL; ++t) tmp[t] += agv[a][t];
+        ChanVec<CPL>::st(gv + (int64_t)j * f3 + a * f + cc, tmp);
       }
+    }
   }
   // block-level reduction of the filter-weight gradients -> part[blockIdx.x]
   float* mypart = part + (int64_t)blockIdx.x * f3 * (r + 1);
 #pragma unroll
-  for (int t = 0; t < CPL; ++t)
+  for (int a = 0; a < 3; ++a)
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
+    for (int t = 0; t < CPL; ++t)
 #pragma unroll
-      for (int q = 0; q <= RMAX; ++q) {
-        if (q < r || q == RMAX) {
+      for (int q = 0; q <= RT; ++q) {
+        if (q < r || q == RT) {                   // uniform across the block
           __syncthreads();
-          red[warp * 32 + lane] = gw[t][a][q];
+          red[warp * 32 + lane] = gw[a][t][q];
           __syncthreads();
-          if (warp == 0 && lane < GROUP) {     // lanes with the same `sub` own the same channel
+          if (warp == 0 && lane < GROUP) {        // lanes with the same `sub` own the same channel
             float acc = 0.f;
 #pragma unroll
             for (int w8 = 0; w8 < WPB; ++w8)
 #pragma unroll
               for (int g = 0; g < NPW; ++g) acc += red[w8 * 32 + lane + GROUP * g];
-            if (ok[t]) mypart[(a * f + ch[t]) * (r + 1) + (q == RMAX ? r : q)] = acc;
+            if (ok) mypart[(a * f + cc + t) * (r + 1) + (q == RT ? r : q)] = acc;
           }
         }
       }
@@ -294,15 +313,23 @@ painn_message_bwd_kernel(const float* __restrict__ gs_out, const float* __restri
 
 __global__ void painn_wgrad_reduce_kernel(const float* __restrict__ part, int nblocks, int f3, int r,
                                           float* __restrict__ gwf, float* __restrict__ gbf) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= f3 * (r + 1)) return;
+  __shared__ float red[8][33];
+  const int cnt = f3 * (r + 1);
+  const int t = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
-  for (int b = 0; b < nblocks; ++b) acc += part[(int64_t)b * f3 * (r + 1) + t];
-  const int row = t / (r + 1), q = t % (r + 1);
-  if (q == r) gbf[row] = acc; else gwf[row * r + q] = acc;
+  if (t < cnt)
+    for (int b = threadIdx.y; b < nblocks; b += 8) acc += part[(int64_t)b * cnt + t];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && t < cnt) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) sum += red[w8][threadIdx.x];
+    const int row = t / (r + 1), q = t % (r + 1);
+    if (q == r) gbf[row] = sum; else gwf[row * r + q] = sum;
+  }
 }
 
-static int painn_group(int f) { int g = 32; if (f < 32) { g = 1; while (g < f) g <<= 1; } return g; }
 static int painn_bwd_grid(int n, int f) { return hgb_grid_for(n, WPB * (32 / painn_group(f)), HGB_NUM_SMS * 4); }
 
 extern "C" int64_t hgb_painn_message_bwd_workspace_bytes(int32_t n, int32_t f, int32_t r) {
@@ -310,16 +337,14 @@ extern "C" int64_t hgb_painn_message_bwd_workspace_bytes(int32_t n, int32_t f, i
 }
 
 extern "C" int hgb_painn_message_bwd(const float* gs_out, const float* gv_out, const float* phi, const float* v,
-                                     const int32_t* rowptr_src, const int32_t* perm_src, const int32_t* agg, const float* dir,
-                                     const float* rbfc, const float* fc, const float* wf, const float* bf, const float* efilt,
-                                     int32_t n, int32_t f, int32_t r, float* gphi, float* gv, float* gwf, float* gbf,
-                                     float* g_dir, float* g_rbfc, float* g_fc, float* g_efilt, void* workspace,
+                                     const int32_t* rowptr_src, const int32_t* perm_src, const int32_t* nbr_agg, const float* epack,
+                                     const float* wf, const float* bf, const float* efilt, int32_t n, int32_t f, int32_t r,
+                                     float* gphi, float* gv, float* gwf, float* gbf, float* g_epack, float* g_efilt, void* workspace,
                                      int64_t workspace_bytes, hgb_stream_t stream) {
   HGB_REQUIRE(n >= 0 && f > 0 && r > 0 && r <= RMAX, "painn_message_bwd: need 0 < num_radial <= %d (got %d)", RMAX, r);
-  HGB_REQUIRE(gs_out && gv_out && phi && v && rowptr_src && agg && dir && rbfc && fc && wf && bf && gphi && gv && gwf && gbf && workspace,
+  HGB_REQUIRE(gs_out && gv_out && phi && v && rowptr_src && nbr_agg && epack && wf && bf && gphi && gv && gwf && gbf && workspace,
               "painn_message_bwd: null pointer");
-  const bool need_edge = g_dir != nullptr;
-  HGB_REQUIRE((g_rbfc != nullptr) == need_edge && (g_fc != nullptr) == need_edge, "painn_message_bwd: g_dir/g_rbfc/g_fc must come together");
+  const bool need_edge = g_epack != nullptr;
   HGB_REQUIRE((efilt != nullptr) == (g_efilt != nullptr), "painn_message_bwd: g_efilt iff efilt");
   HGB_REQUIRE(workspace_bytes >= hgb_painn_message_bwd_workspace_bytes(n, f, r), "painn_message_bwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
@@ -329,29 +354,28 @@ extern "C" int hgb_painn_message_bwd(const float* gs_out, const float* gv_out, c
     cudaMemsetAsync(gbf, 0, (size_t)f3 * 4, st);
     return HGB_OK;
   }
-  const size_t smem = (size_t)(f3 * ((r | 1) + 1) + WPB * 32) * sizeof(float);
-  HGB_REQUIRE(smem <= 48 * 1024, "painn_message_bwd: hidden_dim %d too large for the filter staging", f);
-  const int cpl = f <= 32 ? 1 : 2;
-  const int group = painn_group(f);
+  const int cpl = painn_cpl(f), group = painn_group(f);
   const int ncb = (f + group * cpl - 1) / (group * cpl);
   dim3 grid(painn_bwd_grid(n, f), ncb);
   float* part = (float*)workspace;
-#define LAUNCH(C, E, G, W) painn_message_bwd_kernel<C, E, G, W><<<grid, WPB * 32, smem, st>>>(gs_out, gv_out, phi, v, rowptr_src, perm_src, agg, dir, rbfc, fc, wf, bf, efilt, n, f, r, gphi, gv, part, g_dir, g_rbfc, g_fc, g_efilt, ncb > 1)
-#define LAUNCH_G(E, G)                                                     \
-  switch (group) {                                                         \
-    case 1: LAUNCH(1, E, G, 1); break;                                     \
-    case 2: LAUNCH(1, E, G, 2); break;                                     \
-    case 4: LAUNCH(1, E, G, 4); break;                                     \
-    case 8: LAUNCH(1, E, G, 8); break;                                     \
-    case 16: LAUNCH(1, E, G, 16); break;                                   \
-    default: if (cpl == 1) LAUNCH(1, E, G, 32); else LAUNCH(2, E, G, 32);  \
+#define LAUNCH(C, E, G, W, R) painn_message_bwd_kernel<C, E, G, W, R><<<grid, WPB * 32, 0, st>>>(gs_out, gv_out, phi, v, rowptr_src, perm_src, nbr_agg, epack, wf, bf, efilt, n, f, r, gphi, gv, part, g_epack, g_efilt, ncb > 1)
+#define LAUNCH_R(C, E, G, W) do { if (r <= 5) LAUNCH(C, E, G, W, 5); else LAUNCH(C, E, G, W, 8); } while (0)
+#define LAUNCH_G(E, G)                                                           \
+  switch (group) {                                                               \
+    case 1: LAUNCH_R(1, E, G, 1); break;                                         \
+    case 2: LAUNCH_R(1, E, G, 2); break;                                         \
+    case 4: LAUNCH_R(1, E, G, 4); break;                                         \
+    case 8: LAUNCH_R(1, E, G, 8); break;                                         \
+    case 16: LAUNCH_R(1, E, G, 16); break;                                       \
+    default: if (cpl == 1) LAUNCH_R(1, E, G, 32); else LAUNCH_R(2, E, G, 32);    \
   }
   if (efilt) { if (need_edge) { LAUNCH_G(true, true) } else { LAUNCH_G(true, false) } }
   else { if (need_edge) { LAUNCH_G(false, true) } else { LAUNCH_G(false, false) } }
 #undef LAUNCH_G
+#undef LAUNCH_R
 #undef LAUNCH
   HGB_LAUNCH_CHECK("painn_message_bwd");
-  painn_wgrad_reduce_kernel<<<(f3 * (r + 1) + 127) / 128, 128, 0, st>>>(part, grid.x, f3, r, gwf, gbf);
+  painn_wgrad_reduce_kernel<<<(f3 * (r + 1) + 31) / 32, dim3(32, 8), 0, st>>>(part, grid.x, f3, r, gwf, gbf);
   HGB_LAUNCH_CHECK("painn_wgrad_reduce");
   return HGB_OK;
 }

@@ -139,7 +139,7 @@ struct LinParams {
 
 constexpr int TILE_M = 128;
 
-__global__ void __launch_bounds__(192, 1) tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const LinParams p) {
+__global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const LinParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int KB = p.kr >> 5;
@@ -154,14 +154,16 @@ __global__ void __launch_bounds__(192, 1) tc_linear_kernel(const __grid_constant
   uint64_t* tfull = empty + S;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sbias = reinterpret_cast<float*>(tmem_holder + 4);   // [NO], 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = (p.m + TILE_M - 1) / TILE_M;
+  for (int i = threadIdx.x; i < NO; i += blockDim.x) sbias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
 
   // ---- one-time setup -------------------------------------------------------------------------------
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_holder, (uint32_t)p.tmem_cols);
@@ -227,8 +229,10 @@ __global__ void __launch_bounds__(192, 1) tc_linear_kernel(const __grid_constant
       }
     }
   } else {
-    // ===== epilogue: warps 2..5, each owns the TMEM lane quarter (warp % 4) =====
+    // ===== epilogue: warps 2..9.  Warp w may only touch TMEM lanes 32*(w%4)..+31; the two warps that share a lane
+    // quarter split the 32-column chunks between them (even / odd chunk index). =====
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t aph = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -236,22 +240,38 @@ __global__ void __launch_bounds__(192, 1) tc_linear_kernel(const __grid_constant
       tc_fence_after();
       const int row = t * TILE_M + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * NO;
-      for (int c0 = 0; c0 < NO; c0 += 32) {
+      for (int c0 = half * 32; c0 < NO; c0 += 64) {
         float v[32];
         tmem_ld32(taddr + c0, v);
         if (row < p.m) {
-          if (p.bias) {
+          const float4* bp = reinterpret_cast<const float4*>(sbias + c0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + c0 + j);
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = bp[j];
+            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
           }
           if (p.z) {
             float4* zp = reinterpret_cast<float4*>(p.z + (int64_t)row * NO + c0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) zp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
-          if (p.act != HGB_ACT_NONE) {
+          switch (p.act) {     // hoisted out of the element loop: one specialised, fully unrolled loop per activation
+            case HGB_ACT_NONE: break;
+            case HGB_ACT_RELU:
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = hgb_act(v[j], p.act, p.act_param);
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              break;
+            case HGB_ACT_SILU:
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
+              break;
+            case HGB_ACT_TANH:
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+              break;
+            default:
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = hgb_act(v[j], p.act, p.act_param);
           }
           float4* yp = reinterpret_cast<float4*>(p.y + (int64_t)row * NO + c0);
 #pragma unroll
@@ -392,19 +412,29 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// 32 outputs x 8 partial-walkers per block; fixed summation order
 __global__ void tc_wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int no, int ko, float* __restrict__ dw,
                                        int64_t lddw, float* __restrict__ db, int accumulate) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float red[8][33];
   const int w = ko + 1;
-  if (i >= no * w) return;
+  const int cnt = no * w;
+  const int i = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
-  for (int b = 0; b < nparts; ++b) acc += part[(size_t)b * no * w + i];
-  const int r = i / w, c = i % w;
-  if (c == ko) {
-    if (db) db[r] = accumulate ? db[r] + acc : acc;
-  } else {
-    float* o = dw + (int64_t)r * lddw + c;
-    *o = accumulate ? *o + acc : acc;
+  if (i < cnt)
+    for (int b = threadIdx.y; b < nparts; b += 8) acc += part[(size_t)b * cnt + i];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < cnt) {
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) t += red[w8][threadIdx.x];
+    const int r = i / w, c = i % w;
+    if (c == ko) {
+      if (db) db[r] = accumulate ? db[r] + t : t;
+    } else {
+      float* o = dw + (int64_t)r * lddw + c;
+      *o = accumulate ? *o + t : t;
+    }
   }
 }
 
@@ -473,7 +503,7 @@ extern "C" int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_
   HGB_REQUIRE(stages >= 2, "tc_linear: weight operand does not fit shared memory (n=%d k=%d)", n_out, k_red);
   p.stages = stages;
   p.tmem_cols = pow2_cols(2 * n_out);
-  const size_t smem = 1024 + b_bytes + stages * a_stage + (2 * stages + 4) * 8 + 16;
+  const size_t smem = 1024 + b_bytes + stages * a_stage + (2 * stages + 4) * 8 + 16 + (size_t)n_out * 4 + 16;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -481,7 +511,7 @@ extern "C" int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_
   }
   const int ntiles = (m + TILE_M - 1) / TILE_M;
   const int grid = ntiles < HGB_NUM_SMS ? ntiles : HGB_NUM_SMS;
-  tc_linear_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tm, p);
+  tc_linear_kernel<<<grid, 320, smem, (cudaStream_t)stream>>>(tm, p);
   HGB_LAUNCH_CHECK("tc_linear");
   return HGB_OK;
 }
@@ -528,7 +558,7 @@ extern "C" int hgb_tc_wgrad(const float* dz, int64_t lddz, const float* x, int64
   tc_wgrad_kernel<<<grid, 192, smem, st>>>(tdz, tx, p);
   HGB_LAUNCH_CHECK("tc_wgrad");
   const int outs = n_out * (k_out + 1);
-  tc_wgrad_reduce_kernel<<<(outs + 127) / 128, 128, 0, st>>>(p.part, grid, n_out, k_out, dw, lddw, db, accumulate);
+  tc_wgrad_reduce_kernel<<<(outs + 31) / 32, dim3(32, 8), 0, st>>>(p.part, grid, n_out, k_out, dw, lddw, db, accumulate);
   HGB_LAUNCH_CHECK("tc_wgrad_reduce");
   return HGB_OK;
 }

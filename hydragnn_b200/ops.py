@@ -78,6 +78,17 @@ class EdgePlan:
         self.by_row = csr_build(ei[0], self.num_nodes)
         self.by_col = csr_build(ei[1], self.num_nodes)
         self.row, self.col = self.by_row.idx, self.by_col.idx
+        self._nbr = {}
+
+    def nbr(self, which):
+        """Neighbour node of every CSR slot: 'row' -> col[by_row.perm] (source of the message summed into row),
+        'col' -> row[by_col.perm]."""
+        if which not in self._nbr:
+            idx, perm = (self.col, self.by_row.perm) if which == "row" else (self.row, self.by_col.perm)
+            out = torch.empty_like(perm)
+            _lib.call("hgb_gather_i32", _p(idx), _p(perm), perm.numel(), _p(out), _stream())
+            self._nbr[which] = out
+        return self._nbr[which]
 
 
 def graph_ptr_from_batch(batch, num_graphs):
@@ -406,28 +417,26 @@ class EdgeGeomFn(torch.autograd.Function):
 
 
 class PainnEdgeEmbedFn(torch.autograd.Function):
-    """len/unit -> (dir = unit/len [quirk Q2], rbf*cutoff, cutoff) (hydragnn/models/PAINNStack.py:239-242,257)."""
+    """len/unit -> one 12-float record per edge {rbf*cutoff (8, zero padded), cutoff, dir = unit/len [quirk Q2]}
+    (hydragnn/models/PAINNStack.py:239-242,257)."""
 
     @staticmethod
     def forward(ctx, unit, ln, num_radial, cutoff):
         e = unit.shape[0]
-        d = torch.empty_like(unit)
-        rbfc = torch.empty(e, num_radial, dtype=unit.dtype, device=unit.device)
-        fc = torch.empty(e, dtype=unit.dtype, device=unit.device)
-        _lib.call("hgb_painn_edge_embed_fwd", _p(unit), _p(ln), e, num_radial, float(cutoff), _p(d), _p(rbfc), _p(fc), _stream())
+        epack = torch.empty(e, 12, dtype=unit.dtype, device=unit.device)
+        _lib.call("hgb_painn_edge_embed_fwd", _p(unit), _p(ln), e, num_radial, float(cutoff), _p(epack), _stream())
         ctx.save_for_backward(unit, ln)
         ctx.r, ctx.cutoff = num_radial, float(cutoff)
-        return d, rbfc, fc
+        return epack
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, g_dir, g_rbfc, g_fc):
+    def backward(ctx, g_epack):
         unit, ln = ctx.saved_tensors
         e = unit.shape[0]
         g_unit = torch.empty_like(unit)
         g_len = torch.empty_like(ln)
-        _lib.call("hgb_painn_edge_embed_bwd", _p(unit), _p(ln), _p(_chk(g_dir)), _p(_chk(g_rbfc)), _p(_chk(g_fc)), e, ctx.r,
-                  ctx.cutoff, _p(g_unit), _p(g_len), _stream())
+        _lib.call("hgb_painn_edge_embed_bwd", _p(unit), _p(ln), _p(_chk(g_epack)), e, ctx.r, ctx.cutoff, _p(g_unit), _p(g_len), _stream())
         return g_unit, g_len, None, None
 
 
@@ -435,42 +444,40 @@ class PainnMessageFn(torch.autograd.Function):
     """Fused PaiNN message (hydragnn/models/PAINNStack.py:239-270): returns (s + ds, v + dv)."""
 
     @staticmethod
-    def forward(ctx, phi, s, v, dirs, rbfc, fc, wf, bf, efilt, plan):
+    def forward(ctx, phi, s, v, epack, wf, bf, efilt, plan):
         n, f = s.shape
-        r = rbfc.shape[1]
+        r = wf.shape[1]
         phi, s, v = _chk(phi), _chk(s), _chk(v)
         s_out, v_out = torch.empty_like(s), torch.empty_like(v)
         agg = plan.by_row     # messages are summed into edge[:,0] = edge_index[0]
-        _lib.call("hgb_painn_message_fwd", _p(phi), _p(s), _p(v), _p(agg.rowptr), _p(agg.perm), _p(plan.col), _p(dirs),
-                  _p(rbfc), _p(fc), _p(_chk(wf)), _p(_chk(bf)), _p(_chk(efilt)), n, f, r, _p(s_out), _p(v_out), _stream())
-        ctx.save_for_backward(phi, v, dirs, rbfc, fc, wf, bf, efilt)
+        _lib.call("hgb_painn_message_fwd", _p(phi), _p(s), _p(v), _p(agg.rowptr), _p(agg.perm), _p(plan.nbr("row")), _p(epack),
+                  _p(_chk(wf)), _p(_chk(bf)), _p(_chk(efilt)), n, f, r, _p(s_out), _p(v_out), _stream())
+        ctx.save_for_backward(phi, v, epack, wf, bf, efilt)
         ctx.plan = plan
         return s_out, v_out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gs_out, gv_out):
-        phi, v, dirs, rbfc, fc, wf, bf, efilt = ctx.saved_tensors
+        phi, v, epack, wf, bf, efilt = ctx.saved_tensors
         plan = ctx.plan
         n, f = gs_out.shape
-        r = rbfc.shape[1]
+        r = wf.shape[1]
         gs_out, gv_out = _chk(gs_out), _chk(gv_out)
-        need_edge = ctx.needs_input_grad[3] or ctx.needs_input_grad[4] or ctx.needs_input_grad[5]
+        need_edge = ctx.needs_input_grad[3]
         gphi, gv = torch.empty_like(phi), torch.empty_like(v)
         gwf, gbf = torch.empty_like(wf), torch.empty_like(bf)
-        ncb = (f + 63) // 64 if f > 32 else 1
-        alloc = torch.zeros if ncb > 1 else torch.empty
-        g_dir = alloc(dirs.shape, dtype=dirs.dtype, device=dirs.device) if need_edge else None
-        g_rbfc = alloc(rbfc.shape, dtype=dirs.dtype, device=dirs.device) if need_edge else None
-        g_fc = alloc(fc.shape, dtype=dirs.dtype, device=dirs.device) if need_edge else None
+        cpl = 2 if (f >= 64 and f % 2 == 0) else 1          # mirrors painn_cpl / painn_group in csrc/hgb_painn.cu
+        multi = f > 32 * cpl                                # several channel blocks accumulate into g_epack
+        g_epack = (torch.zeros_like(epack) if multi else torch.empty_like(epack)) if need_edge else None
         g_ef = torch.empty_like(efilt) if efilt is not None else None
         nbytes = _lib.query("hgb_painn_message_bwd_workspace_bytes", n, f, r)
         ws = _ws(nbytes, phi.device)
         src = plan.by_col     # the gather side: edge[:,1] = edge_index[1]
-        _lib.call("hgb_painn_message_bwd", _p(gs_out), _p(gv_out), _p(phi), _p(v), _p(src.rowptr), _p(src.perm), _p(plan.row),
-                  _p(dirs), _p(rbfc), _p(fc), _p(wf), _p(bf), _p(efilt), n, f, r, _p(gphi), _p(gv), _p(gwf), _p(gbf),
-                  _p(g_dir), _p(g_rbfc), _p(g_fc), _p(g_ef), _p(ws), nbytes, _stream())
-        return gphi, gs_out, gv, g_dir, g_rbfc, g_fc, gwf, gbf, g_ef, None
+        _lib.call("hgb_painn_message_bwd", _p(gs_out), _p(gv_out), _p(phi), _p(v), _p(src.rowptr), _p(src.perm), _p(plan.nbr("col")),
+                  _p(epack), _p(wf), _p(bf), _p(efilt), n, f, r, _p(gphi), _p(gv), _p(gwf), _p(gbf), _p(g_epack), _p(g_ef),
+                  _p(ws), nbytes, _stream())
+        return gphi, gs_out, gv, g_epack, gwf, gbf, g_ef, None
 
 
 def raw_linear(x2, w, b, code=0, param=0.0, want_z=False):

@@ -177,8 +177,7 @@ class PainnMessage(nn.Module):
             return s + SegmentSum.apply(m_s, plan.by_row), v + SegmentSum.apply(m_v, plan.by_row)
         phi = run_mlp(self.scalar_message_mlp, s)
         efilt = run_mlp(self.edge_filter, edge_attr) if edge_attr is not None else None
-        return ops.PainnMessageFn.apply(phi, s, v, geom["dir"], geom["rbfc"], geom["fc"], self.filter_layer.weight,
-                                        self.filter_layer.bias, efilt, plan)
+        return ops.PainnMessageFn.apply(phi, s, v, geom["epack"], self.filter_layer.weight, self.filter_layer.bias, efilt, plan)
 
 
 class PainnUpdate(nn.Module):
@@ -488,8 +487,7 @@ class PAINNStack(Base):
             geom = {"unit": vec / (ln + 1e-9), "len": ln}
         else:
             _, ln, unit = ops.EdgeGeomFn.apply(pos, shifts, plan, 1e-9)      # PAINNStack.py:157-159
-            d, rbfc, fc = ops.PainnEdgeEmbedFn.apply(unit, ln, self.num_radial, self.radius)
-            geom = {"dir": d, "rbfc": rbfc, "fc": fc}
+            geom = {"epack": ops.PainnEdgeEmbedFn.apply(unit, ln, self.num_radial, self.radius)}
         v = torch.zeros(x.shape[0], 3, x.shape[1], dtype=x.dtype, device=x.device)   # PAINNStack.py:190
         return x, v, {"edge_attr": data.edge_attr if self.use_edge_attr else None, "geom": geom}
 

@@ -112,6 +112,8 @@ int64_t hgb_exclusive_scan_workspace_bytes(int64_t n);
 int hgb_csr_build(const int64_t* idx, int64_t e, int32_t n, int32_t* idx32, int32_t* rowptr,
                   int32_t* perm, void* workspace, hgb_stream_t stream);
 int64_t hgb_csr_workspace_bytes(int64_t e, int32_t n);
+/* out[p] = idx[perm[p]]: the neighbour node of every CSR slot */
+int hgb_gather_i32(const int32_t* idx, const int32_t* perm, int64_t e, int32_t* out, hgb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Gather / segmented reductions (mutual adjoints)
@@ -200,42 +202,39 @@ int hgb_edge_geom_fwd(const float* pos, const int32_t* row, const int32_t* col, 
 int hgb_edge_geom_bwd(const float* vec, const float* len, float eps, const float* g_vec_in,
                       const float* g_len, const float* g_unit, int64_t e, float* g_vec,
                       hgb_stream_t stream);
-/* PaiNN edge embedding: len -> dir = unit/len (quirk Q2, PAINNStack.py:257), rbfc [e,r] =
- * sin(n pi d / rc)/d * fcut(d), fc [e] = fcut(d).                                                 */
+/* PaiNN edge embedding: one 48-byte record per edge, epack [e,12] = { sin(n pi d/rc)/d * fcut(d) for n = 1..r
+ * (zero padded to 8), fcut(d), dir = unit/len (quirk Q2, PAINNStack.py:257) }.  r <= 8.                     */
 int hgb_painn_edge_embed_fwd(const float* unit, const float* len, int64_t e, int32_t r, float cutoff,
-                             float* dir, float* rbfc, float* fc, hgb_stream_t stream);
-/* backward of the above: (g_dir, g_rbfc, g_fc) -> (g_unit, g_len)                                 */
-int hgb_painn_edge_embed_bwd(const float* unit, const float* len, const float* g_dir,
-                             const float* g_rbfc, const float* g_fc, int64_t e, int32_t r, float cutoff,
-                             float* g_unit, float* g_len, hgb_stream_t stream);
+                             float* epack, hgb_stream_t stream);
+/* backward of the above: g_epack [e,12] -> (g_unit [e,3], g_len [e])                                       */
+int hgb_painn_edge_embed_bwd(const float* unit, const float* len, const float* g_epack, int64_t e, int32_t r,
+                             float cutoff, float* g_unit, float* g_len, hgb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * PaiNN  (hydragnn/models/PAINNStack.py:194-328)
  * ------------------------------------------------------------------------------------------ */
 
-/* Fused message: for every node i, over its CSR segment (edges with edge[:,0] == i):
- *   W = Wf . rbfc[e] + bf * fc[e] (* efilt[e]);  f = W * phi[src[e]];  (g_v, g_e, m_s) = split(f)
- *   s_out[i] = s[i] + sum m_s;  v_out[i,k] = v[i,k] + sum (v[src,k] * g_v + g_e * dir[e,k])
- * Replaces filter GEMM + 2 gathers + 2 index_add_ (PAINNStack.py:239-270); nothing per-edge is
- * written.  Algorithmic bytes: E*(6F*4 + 2*4 + 4*(R+4)) + 12*N*F*4.
- * phi [n,3f], s [n,f], v [n,3,f], src [e] = edge[:,1], wf [3f,r], bf [3f], efilt [e,3f] or NULL.   */
+/* Fused message: for every node i, over its CSR segment (edges with edge[:,0] == i; nbr [e] holds the source
+ * node edge[:,1] of every CSR slot, perm [e] its edge id):
+ *   W = Wf . rbfc[e] + bf * fc[e] (* efilt[e]);  f = W * phi[nbr];  (g_v, g_e, m_s) = split(f)
+ *   s_out[i] = s[i] + sum m_s;  v_out[i,k] = v[i,k] + sum (v[nbr,k] * g_v + g_e * dir[e,k])
+ * Replaces filter GEMM + 2 gathers + 2 index_add_ (PAINNStack.py:239-270); nothing per-edge is written, no
+ * atomics, summation in ascending edge id.  Algorithmic bytes: E*(6F*4 + 8 + 48) + N*(8F*4 + 4).
+ * phi [n,3f], s [n,f], v [n,3,f], wf [3f,r], bf [3f], efilt [e,3f] or NULL.                                 */
 int hgb_painn_message_fwd(const float* phi, const float* s, const float* v, const int32_t* rowptr,
-                          const int32_t* perm, const int32_t* src, const float* dir, const float* rbfc,
-                          const float* fc, const float* wf, const float* bf, const float* efilt,
-                          int32_t n, int32_t f, int32_t r, float* s_out, float* v_out,
-                          hgb_stream_t stream);
-/* Backward of the fused message, as a segmented reduction over the CSR of edge[:,1] (the gather
- * side).  gs_out [n,f], gv_out [n,3,f] are the incoming gradients; agg [e] = edge[:,0].
- * Outputs: gphi [n,3f]; gv [n,3,f] (= gv_out + gathered part; gs_in == gs_out is the caller's);
- * gwf [3f,r], gbf [3f] (via workspace partials); optional per-edge g_dir [e,3], g_rbfc [e,r],
- * g_fc [e] (all three NULL or all non-NULL) and g_efilt [e,3f] (iff efilt).                        */
+                          const int32_t* perm, const int32_t* nbr, const float* epack, const float* wf,
+                          const float* bf, const float* efilt, int32_t n, int32_t f, int32_t r, float* s_out,
+                          float* v_out, hgb_stream_t stream);
+/* Backward of the fused message, as a segmented reduction over the CSR of edge[:,1] (the gather side);
+ * nbr_agg [e] = edge[:,0] of every slot of that CSR.  gs_out [n,f], gv_out [n,3,f] are the incoming gradients.
+ * Outputs: gphi [n,3f]; gv [n,3,f] (= gv_out + gathered part; gs_in == gs_out is the caller's); gwf [3f,r],
+ * gbf [3f] (via workspace partials); optional g_epack [e,12] (zero-initialised by the caller when f > 64) and
+ * g_efilt [e,3f] (iff efilt).                                                                              */
 int hgb_painn_message_bwd(const float* gs_out, const float* gv_out, const float* phi, const float* v,
-                          const int32_t* rowptr_src, const int32_t* perm_src, const int32_t* agg,
-                          const float* dir, const float* rbfc, const float* fc, const float* wf,
-                          const float* bf, const float* efilt, int32_t n, int32_t f, int32_t r,
-                          float* gphi, float* gv, float* gwf, float* gbf, float* g_dir, float* g_rbfc,
-                          float* g_fc, float* g_efilt, void* workspace, int64_t workspace_bytes,
-                          hgb_stream_t stream);
+                          const int32_t* rowptr_src, const int32_t* perm_src, const int32_t* nbr_agg,
+                          const float* epack, const float* wf, const float* bf, const float* efilt, int32_t n,
+                          int32_t f, int32_t r, float* gphi, float* gv, float* gwf, float* gbf, float* g_epack,
+                          float* g_efilt, void* workspace, int64_t workspace_bytes, hgb_stream_t stream);
 int64_t hgb_painn_message_bwd_workspace_bytes(int32_t n, int32_t f, int32_t r);
 
 /* Update block glue (PAINNStack.py:298-328).  uv, vv [n,3,f] are update_U(v), update_V(v).

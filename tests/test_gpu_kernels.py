@@ -315,7 +315,7 @@ def _painn_setup(g, f, r=5, edge_dim=None, n=60, e=500):
     return pos, ei, msg_o
 
 
-@pytest.mark.parametrize("f,edge_dim", [(1, None), (6, None), (64, None), (96, None), (16, 3)])
+@pytest.mark.parametrize("f,edge_dim", [(1, None), (2, None), (6, None), (32, None), (33, None), (64, None), (96, None), (128, None), (16, 3), (64, 2)])
 def test_painn_message_vs_oracle(f, edge_dim):
     g = gen(100 + f)
     torch.manual_seed(f)
@@ -334,8 +334,8 @@ def test_painn_message_vs_oracle(f, edge_dim):
     # engine (fused)
     pe, se, ve = pos.to(DEV).requires_grad_(True), s.to(DEV).requires_grad_(True), v.to(DEV).requires_grad_(True)
     _, ln, unit = ops.EdgeGeomFn.apply(pe, None, plan, 1e-9)
-    d, rbfc, fc = ops.PainnEdgeEmbedFn.apply(unit, ln, 5, 7.0)
-    s1, v1 = msg_e(se, ve, plan, {"dir": d, "rbfc": rbfc, "fc": fc}, None if ea is None else ea.to(DEV))
+    epack = ops.PainnEdgeEmbedFn.apply(unit, ln, 5, 7.0)
+    s1, v1 = msg_e(se, ve, plan, {"epack": epack}, None if ea is None else ea.to(DEV))
     torch.testing.assert_close(s1.cpu(), so, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(v1.cpu(), vo, rtol=1e-4, atol=1e-5)
     ws, wv = torch.randn(so.shape, generator=g), torch.randn(vo.shape, generator=g)
