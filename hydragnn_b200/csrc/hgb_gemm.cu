@@ -305,33 +305,50 @@ linear_smallk_bwd_kernel(const float* __restrict__ dy, const float* __restrict__
     for (int q = 0; q <= SK_KMAX; ++q) gw[j][q] = 0.f;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(m, r0 + rows_per_block);
-  for (int r = r0 + walker; r < r1; r += 8) {
-    float xr[SK_KMAX], dxp[SK_KMAX];
+  // each walker takes SK_RU rows per trip: their loads / shuffles are independent, which is what hides the latency
+#define SK_RU 4
+  for (int rb = r0 + walker * SK_RU; rb < r1; rb += 8 * SK_RU) {
+    float xr[SK_RU][SK_KMAX], dxp[SK_RU][SK_KMAX];
 #pragma unroll
-    for (int q = 0; q < SK_KMAX; ++q) { xr[q] = q < k ? __ldg(x + (int64_t)r * ldx + q) : 0.f; dxp[q] = 0.f; }
+    for (int u = 0; u < SK_RU; ++u)
+#pragma unroll
+      for (int q = 0; q < SK_KMAX; ++q) {
+        xr[u][q] = (q < k && rb + u < r1) ? __ldg(x + (int64_t)(rb + u) * ldx + q) : 0.f;
+        dxp[u][q] = 0.f;
+      }
 #pragma unroll
     for (int j = 0; j < SK_NPT; ++j) {
       const int c = lane + 32 * j;
       if (c < n) {
-        const int64_t o = (int64_t)r * n + c;
-        float g = dy[o];
-        if (act != HGB_ACT_NONE) g *= hgb_act_grad(y ? y[o] : 0.f, z ? z[o] : 0.f, act, ap);
-        gw[j][SK_KMAX] += g;
+        float g[SK_RU];
 #pragma unroll
-        for (int q = 0; q < SK_KMAX; ++q)
-          if (q < k) {
-            gw[j][q] = fmaf(g, xr[q], gw[j][q]);
-            dxp[q] = fmaf(g, sw[c * k + q], dxp[q]);
-          }
+        for (int u = 0; u < SK_RU; ++u) {
+          const int r = rb + u;
+          const int64_t o = (int64_t)r * n + c;
+          g[u] = r < r1 ? dy[o] : 0.f;
+          if (act != HGB_ACT_NONE && r < r1) g[u] *= hgb_act_grad(y ? y[o] : 0.f, z ? z[o] : 0.f, act, ap);
+        }
+#pragma unroll
+        for (int u = 0; u < SK_RU; ++u) {
+          gw[j][SK_KMAX] += g[u];
+#pragma unroll
+          for (int q = 0; q < SK_KMAX; ++q)
+            if (q < k) {
+              gw[j][q] = fmaf(g[u], xr[u][q], gw[j][q]);
+              dxp[u][q] = fmaf(g[u], sw[c * k + q], dxp[u][q]);
+            }
+        }
       }
     }
     if (dx) {
 #pragma unroll
-      for (int q = 0; q < SK_KMAX; ++q)
-        if (q < k) {
-          const float s = hgb_warp_sum(dxp[q]);
-          if (lane == 0) dx[(int64_t)r * k + q] = s;
-        }
+      for (int u = 0; u < SK_RU; ++u)
+#pragma unroll
+        for (int q = 0; q < SK_KMAX; ++q)
+          if (q < k) {
+            const float s = hgb_warp_sum(dxp[u][q]);
+            if (lane == 0 && rb + u < r1) dx[(int64_t)(rb + u) * k + q] = s;
+          }
     }
   }
   // reduce the 8 row walkers -> part[blockIdx.x][n][k+1]
@@ -435,8 +452,8 @@ linear_tiny_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y
 
 static int smallk_blocks(int m, int* rows_per_block) {
   int rpb = (m + HGB_NUM_SMS * 4 - 1) / (HGB_NUM_SMS * 4);
-  rpb = ((rpb + 7) / 8) * 8;
-  if (rpb < 8) rpb = 8;
+  rpb = ((rpb + 31) / 32) * 32;      // 8 walkers x 4 rows per trip
+  if (rpb < 32) rpb = 32;
   *rows_per_block = rpb;
   return (m + rpb - 1) / rpb;
 }

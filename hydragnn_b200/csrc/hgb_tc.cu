@@ -133,6 +133,7 @@ struct LinParams {
   float act_param;
   float* y;
   float* z;
+  const float* addend;  // optional [m, no]: y = act(a.B^T + bias) + addend  (gradient accumulation without an extra pass)
   int stages;
   int tmem_cols;
 };
@@ -272,6 +273,14 @@ __global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant
             default:
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = hgb_act(v[j], p.act, p.act_param);
+          }
+          if (p.addend) {
+            const float4* ap = reinterpret_cast<const float4*>(p.addend + (int64_t)row * NO + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 a4 = __ldg(ap + j);
+              v[4 * j] += a4.x; v[4 * j + 1] += a4.y; v[4 * j + 2] += a4.z; v[4 * j + 3] += a4.w;
+            }
           }
           float4* yp = reinterpret_cast<float4*>(p.y + (int64_t)row * NO + c0);
 #pragma unroll
@@ -485,7 +494,8 @@ extern "C" int hgb_tc_linear_supported(int32_t m, int32_t n_out, int32_t k_red) 
 
 // y[m, no] = act(a[m, kr] . B^T + bias);  B(r, c) = w[r, c] (trans_b = 0) or w[c, r] (trans_b = 1)
 extern "C" int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_t ldw, int32_t trans_b, const float* bias, int32_t m,
-                             int32_t n_out, int32_t k_red, int32_t act, float act_param, float* y, float* z, hgb_stream_t stream) {
+                             int32_t n_out, int32_t k_red, int32_t act, float act_param, float* y, float* z, const float* addend,
+                             hgb_stream_t stream) {
   HGB_REQUIRE(a && w && y && hgb_tc_linear_supported(m, n_out, k_red), "tc_linear: unsupported shape m=%d n=%d k=%d", m, n_out, k_red);
   HGB_REQUIRE(lda % 4 == 0 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!z || (uintptr_t)z % 16 == 0),
               "tc_linear: operands must be 16-byte aligned with a row stride that is a multiple of 4");
@@ -494,7 +504,7 @@ extern "C" int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_
   if (rc) return rc;
   LinParams p;
   p.m = m; p.kr = k_red; p.no = n_out; p.w = w; p.ldw = ldw; p.trans_b = trans_b; p.bias = bias; p.act = act; p.act_param = act_param;
-  p.y = y; p.z = z;
+  p.y = y; p.z = z; p.addend = addend;
   const int KB = k_red / 32;
   const size_t b_bytes = ((size_t)KB * n_out * 128 + 1023) & ~(size_t)1023;
   const size_t a_stage = (size_t)TILE_M * 128;

@@ -181,12 +181,12 @@ def tc_ok(m, n_out, k_red, *tensors):
     return True
 
 
-def raw_tc_linear(a2, w, trans_b, bias, n_out, k_red, code=0, param=0.0, want_z=False):
+def raw_tc_linear(a2, w, trans_b, bias, n_out, k_red, code=0, param=0.0, want_z=False, addend=None):
     m = a2.shape[0]
     y = torch.empty(m, n_out, dtype=a2.dtype, device=a2.device)
     z = torch.empty_like(y) if want_z else None
     _lib.call("hgb_tc_linear", _p(a2), a2.stride(0), _p(w), w.stride(0), int(trans_b), _p(bias), m, n_out, k_red, code, float(param),
-              _p(y), _p(z), _stream())
+              _p(y), _p(z), _p(addend), _stream())
     return y, z
 
 
@@ -241,15 +241,21 @@ def linear_fwd_dispatch(x2, w, b, code=0, param=0.0, want_z=False):
     return raw_linear(x2, w, b, code, param, want_z)
 
 
-def linear_bwd_dispatch(dz, x2, w, need_x=True, need_w=True, need_b=True):
-    """(dx, dw, db) of y = x2 W^T + b given dz."""
+def linear_bwd_dispatch(dz, x2, w, need_x=True, need_w=True, need_b=True, dx_addend=None):
+    """(dx, dw, db) of y = x2 W^T + b given dz.  ``dx_addend`` (same shape as dx) is accumulated into dx."""
     m, n = dz.shape
     k = x2.shape[1]
     if smallk_ok(n, k):
-        return raw_smallk_bwd(dz, None, None, x2, w, 0, 0.0, need_x, need_w, need_b)
+        dx, dw, db = raw_smallk_bwd(dz, None, None, x2, w, 0, 0.0, need_x, need_w, need_b)
+        return (dx + dx_addend if (dx is not None and dx_addend is not None) else dx), dw, db
     dx = dw = db = None
     if need_x:
-        dx = raw_tc_linear(dz, w, True, None, k, n)[0] if tc_ok(m, k, n, dz) else raw_gemm(dz, w, False, False)
+        if tc_ok(m, k, n, dz, dx_addend):
+            dx = raw_tc_linear(dz, w, True, None, k, n, addend=dx_addend)[0]
+        elif dx_addend is not None:
+            dx = raw_gemm(dz, w, False, False, out=dx_addend.clone(), beta_one=True)
+        else:
+            dx = raw_gemm(dz, w, False, False)
     if need_w or need_b:
         if tc_ok(m, n, k, dz, x2) and k + 16 <= 256:
             dw, db = raw_tc_wgrad(dz, x2, want_bias=need_b)
@@ -540,9 +546,8 @@ class PainnUpdateFn(torch.autograd.Function):
         _lib.call("hgb_painn_update_bwd", _p(gs_out), _p(gv_out), _p(g_mlp_in), _p(a), _p(uv), _p(vv), _p(mlp_in), n, f,
                   int(last), _p(guv), _p(gvv), _p(gs), _p(gv), _stream())
         with tensor_cores(ctx.tc):
-            dv_u, guw, gub = linear_bwd_dispatch(guv, v2, uw)
-            dv_v, gvw, gvb = linear_bwd_dispatch(gvv, v2, vw)
-        gv = gv + dv_u + dv_v
+            gv, guw, gub = linear_bwd_dispatch(guv, v2, uw, dx_addend=gv)      # gv (direct path) + guv U + gvv V, accumulated
+            gv, gvw, gvb = linear_bwd_dispatch(gvv, v2, vw, dx_addend=gv)      # in the dgrad epilogues
         return gs, gv.reshape(n, 3, f), guw, gub, gvw, gvb, gw1, gb1, gw2, gb2, None
 
 

@@ -168,11 +168,12 @@ int64_t hgb_linear_smallk_bwd_workspace_bytes(int32_t m, int32_t n, int32_t k);
  * large-M shapes of the node / edge MLPs: m >= 128, n_out and k_red multiples of 32 and <= 256.  Used under
  * precision="bf16" (TF32 products, fp32 accumulation: tighter than the bf16 autocast of the reference).
  * y[m,n_out] = act(a[m,k_red] . B^T + bias) with B(r,c) = w[r,c] (trans_b = 0: forward, w is [n_out,k_red])
- * or B(r,c) = w[c,r] (trans_b = 1: the data gradient dX = dZ . W, w is [k_red,n_out]).                      */
+ * or B(r,c) = w[c,r] (trans_b = 1: the data gradient dX = dZ . W, w is [k_red,n_out]).  `addend` [m,n_out]
+ * (optional) is added after the activation: gradient accumulation without an extra pass.                     */
 int hgb_tc_linear_supported(int32_t m, int32_t n_out, int32_t k_red);
 int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_t ldw, int32_t trans_b, const float* bias,
                   int32_t m, int32_t n_out, int32_t k_red, int32_t act, float act_param, float* y, float* z,
-                  hgb_stream_t stream);
+                  const float* addend, hgb_stream_t stream);
 /* dw[n_out,k_out] (row stride lddw) (+)= dz[m,n_out]^T . x[m,k_out] and db[n_out] (+)= column sums of dz
  * (db may be NULL) in one pass: both operands are consumed MN-major straight from the row-major tensors, the
  * bias gradient rides along as extra all-ones columns of the B operand.  Deterministic two-stage reduce.      */
