@@ -162,3 +162,38 @@ extern "C" int hgb_pool_bwd(const float* gout, const int32_t* graph_ptr, const i
   HGB_LAUNCH_CHECK("pool_bwd");
   return HGB_OK;
 }
+
+// ---- segmented arg-min / arg-max (PNA aggregators, hydragnn/models/PNAEqStack.py:396-400) ---------------------
+// For every (node, channel): the EDGE id holding the minimum / maximum over the node's CSR segment (first one wins
+// on ties, -1 for an empty segment).  Values and gradients are then plain gathers at those ids.
+__global__ void segment_argminmax_kernel(const float* __restrict__ m, const int32_t* __restrict__ rowptr,
+                                         const int32_t* __restrict__ perm, int n, int c, int lanes, int64_t* __restrict__ amin,
+                                         int64_t* __restrict__ amax) {
+  const int gpb = blockDim.x / lanes;
+  const int sub = threadIdx.x % lanes;
+  for (int row = blockIdx.x * gpb + threadIdx.x / lanes; row < n; row += gridDim.x * gpb) {
+    const int lo = rowptr[row], hi = rowptr[row + 1];
+    for (int ch = sub; ch < c; ch += lanes) {
+      float vmin = INFINITY, vmax = -INFINITY;
+      int64_t imin = -1, imax = -1;
+      for (int p = lo; p < hi; ++p) {
+        const int e = perm ? perm[p] : p;
+        const float v = m[(int64_t)e * c + ch];
+        if (imin < 0 || v < vmin) { vmin = v; imin = e; }
+        if (imax < 0 || v > vmax) { vmax = v; imax = e; }
+      }
+      amin[(int64_t)row * c + ch] = imin;
+      amax[(int64_t)row * c + ch] = imax;
+    }
+  }
+}
+
+extern "C" int hgb_segment_argminmax(const float* m, const int32_t* rowptr, const int32_t* perm, int32_t n, int32_t c,
+                                     int64_t* argmin, int64_t* argmax, hgb_stream_t stream) {
+  HGB_REQUIRE(n >= 0 && c > 0 && rowptr && argmin && argmax, "segment_argminmax: bad arguments");
+  if (n == 0) return HGB_OK;
+  const int lanes = group_lanes(c);
+  segment_argminmax_kernel<<<hgb_grid_for(n, 256 / lanes), 256, 0, (cudaStream_t)stream>>>(m, rowptr, perm, n, c, lanes, argmin, argmax);
+  HGB_LAUNCH_CHECK("segment_argminmax");
+  return HGB_OK;
+}

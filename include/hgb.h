@@ -127,6 +127,11 @@ int hgb_gather_rows(const float* x, const int32_t* idx, int64_t e, int32_t c, fl
  * E*C*4 + E*4 + N*C*4 (SURVEY 8d "scatter primitive").                                          */
 int hgb_segment_sum(const float* m, const int32_t* rowptr, const int32_t* perm, int32_t n, int32_t c,
                     float* out, hgb_stream_t stream);
+/* PNA min / max aggregators (PyG DegreeScalerAggregation, hydragnn/models/PNAEqStack.py:396-400): for every
+ * (segment, channel) the EDGE id of the minimum / maximum (first wins on ties, -1 for an empty segment); the
+ * values and their gradients are gathers at those ids.  argmin / argmax are [n,c] int64.                    */
+int hgb_segment_argminmax(const float* m, const int32_t* rowptr, const int32_t* perm, int32_t n, int32_t c,
+                          int64_t* argmin, int64_t* argmax, hgb_stream_t stream);
 /* graph pooling over sorted `batch` (graph_ptr [g+1]); mode HGB_POOL_*.  argmax [g,c] int32 is
  * written for HGB_POOL_MAX (may be NULL otherwise).  -- PyG global_*_pool, Base.py:147-170.     */
 int hgb_pool_fwd(const float* x, const int32_t* graph_ptr, int32_t g, int32_t c, int32_t mode,

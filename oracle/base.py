@@ -13,6 +13,7 @@ from torch import nn
 from .egnn import EGCL
 from .geometry import edge_vectors_and_lengths, graph_pool
 from .painn import PainnMessage, PainnUpdate
+from . import pnaeq
 
 
 def activation(name):
@@ -61,9 +62,12 @@ class OracleModel(nn.Module):
     def __init__(self, mpnn_type, input_dim, hidden_dim, output_dim, output_type, output_heads,
                  activation_function="relu", loss_function_type="mse", task_weights=None,
                  num_conv_layers=2, num_nodes=None, edge_dim=None, num_radial=None, radius=None,
-                 equivariance=False, graph_pooling="mean", **_unused):
+                 equivariance=False, graph_pooling="mean", pna_deg=None, **_unused):
         super().__init__()
-        if mpnn_type not in ("EGNN", "PAINN"):
+        if mpnn_type == "PNAEq":
+            assert pna_deg is not None, "PNAEq requires degree input."
+            self.deg = pnaeq.sanitize_degree(pna_deg)
+        if mpnn_type not in ("EGNN", "PAINN", "PNAEq"):
             raise ValueError("Unknown mpnn_type: {0}".format(mpnn_type))
         self.mpnn_type, self.input_dim, self.hidden_dim = mpnn_type, input_dim, hidden_dim
         self.head_dims, self.head_type = list(output_dim), list(output_type)
@@ -131,8 +135,12 @@ class OracleModel(nn.Module):
         if self.mpnn_type == "EGNN":
             return _Conv("egnn", [EGCL(fin, fout, self.hidden_dim, edge_attr_dim=self.edge_dim,
                                        equivariant=self.equivariance and not last)])
-        msg = PainnMessage(fin, self.num_radial, self.radius, edge_dim=self.edge_dim)
-        upd = PainnUpdate(fin, last_layer=last)
+        if self.mpnn_type == "PNAEq":                                   # PNAEqStack.get_conv :119-192
+            msg = pnaeq.PainnMessage(fin, self.deg, self.edge_dim, self.num_radial)
+            upd = pnaeq.PainnUpdate(fin, last_layer=last)
+        else:
+            msg = PainnMessage(fin, self.num_radial, self.radius, edge_dim=self.edge_dim)
+            upd = PainnUpdate(fin, last_layer=last)
         s_out = nn.Sequential(nn.Linear(fin, fout), nn.Tanh(), nn.Linear(fout, fout))
         v_out = None if last else nn.Linear(fin, fout)
         return _Conv("painn", [msg, upd, s_out, v_out])
@@ -148,6 +156,18 @@ class OracleModel(nn.Module):
             for conv in self.graph_convs:
                 x, equiv = conv.module_0(x, equiv, ei, eattr, shifts)
                 x = self.activation_function(x)                              # Base.py:726
+        elif self.mpnn_type == "PNAEq":
+            vec, dist = edge_vectors_and_lengths(pos, ei, shifts, normalize=True)    # PNAEqStack.py:202-205
+            rbf = pnaeq.rbf_basis(dist.squeeze(-1), self.num_radial, self.radius)
+            edge = ei.t()
+            v = torch.zeros(x.shape[0], 3, x.shape[1], dtype=x.dtype, device=x.device)
+            for conv in self.graph_convs:
+                x, v = conv.module_0(x, v, edge, rbf, vec, eattr)
+                x, v = conv.module_1(x, v)
+                x = conv.module_2(x)
+                if v is not None:
+                    v = conv.module_3(v)
+                x = self.activation_function(x)
         else:
             diff, dist = edge_vectors_and_lengths(pos, ei, shifts, normalize=True)   # PAINNStack.py:157-159
             edge = ei.t()

@@ -142,6 +142,36 @@ def install_stubs():
     return egcl, painn
 
 
+def install_pnaeq_stubs():
+    """PNAEqStack.py additionally needs PyG's MessagePassing / DegreeScalerAggregation / Linear / resolver.
+    MessagePassing is used only as an nn.Module that stores ``aggr_module``; geom_Linear is nn.Linear with the
+    same parameter names; DegreeScalerAggregation is the restatement in oracle/pnaeq.py (so the golden file pins
+    everything in PNAEqStack.py EXCEPT that third-party aggregator)."""
+    from oracle.pnaeq import DegreeScalerAggregation as OracleDSA
+
+    class MessagePassing(torch.nn.Module):
+        def __init__(self, aggr=None, node_dim=0, **kw):
+            super().__init__()
+            if aggr is not None:
+                self.aggr_module = aggr
+
+    class DSA(OracleDSA):
+        def forward(self, x, index=None, dim_size=None, **kw):
+            return super().forward(x, index, dim_size)
+
+    tg = sys.modules["torch_geometric.nn"]
+    tg.MessagePassing = MessagePassing
+    tg.Linear = torch.nn.Linear
+    _mod("torch_geometric.nn.resolver", activation_resolver=lambda act, **kw: {"tanh": torch.nn.Tanh}[act]())
+    _mod("torch_geometric.nn.dense")
+    _mod("torch_geometric.nn.dense.linear", Linear=torch.nn.Linear)
+    _mod("torch_geometric.nn.aggr")
+    _mod("torch_geometric.nn.aggr.scaler", DegreeScalerAggregation=DSA)
+    sys.modules["torch_geometric.typing"].Adj = object
+    sys.modules["torch_geometric"].nn = tg
+    return _load("hydragnn.models.PNAEqStack", REF + "/hydragnn/models/PNAEqStack.py")
+
+
 def toy_batch(gen, sizes, box, input_dim=1, dtype=torch.float32):
     """A few random molecules + an asymmetric hand-made edge list (every atom keeps its
     3 nearest in-graph neighbours as sources)."""
@@ -256,6 +286,26 @@ def main():
                                          "grads": {n: (g.detach() if g is not None else None)
                                                    for (n, _), g in zip(m.named_parameters(), grads)}}
     torch.save(models, HERE + "/models.pt")
+
+    # ---- PNAEq through the reference's PNAEqStack (third-party DegreeScalerAggregation restated, see stub) ----
+    pna = install_pnaeq_stubs()
+    pmodels = {}
+    for pool, last_deg in (("mean", [0, 0, 0, 30, 0]), ("add", [0, 3, 0, 27, float("inf")])):
+        b = toy_batch(gen, [9, 6, 7, 9], 5.0, input_dim=1)
+        torch.manual_seed(0)
+        m = pna.PNAEqStack("inv_node_feat, equiv_node_feat, edge_index, edge_rbf, edge_vec",
+                           "inv_node_feat, equiv_node_feat, edge_index, edge_rbf, edge_vec", last_deg, None, 6, 5.0,
+                           1, 12, [1], 0, "", "", 0, ["graph"], heads_graph, "relu", "mse", False,
+                           loss_weights=[1.0], freeze_conv=False, num_conv_layers=3, num_nodes=None, graph_pooling=pool)
+        m.eval()
+        pred = m(b)
+        loss, _ = m.loss(pred, b.y, [torch.arange(b.y.shape[0])])
+        grads = torch.autograd.grad(loss, list(m.parameters()), allow_unused=True)
+        pmodels["pnaeq_graph_" + pool] = {"state": m.state_dict(), "inputs": t2d(b), "pred": [p.detach() for p in pred],
+                                          "loss": loss.detach(), "deg": last_deg,
+                                          "grads": {n: (g.detach() if g is not None else None)
+                                                    for (n, _), g in zip(m.named_parameters(), grads)}}
+    torch.save(pmodels, HERE + "/models_pnaeq.pt")
 
     # ---- RadiusGraphPBC numpy post-processing ---------------------------------------------
     glb = {"np": np}

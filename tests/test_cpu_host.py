@@ -11,7 +11,7 @@ import torch
 import hydragnn_b200 as hb
 from hydragnn_b200 import _lib, ops
 from hydragnn_b200.synthetic import ARCH, make_samples
-from test_oracle_golden import MODEL_KW
+from test_oracle_golden import MODEL_KW, PNAEQ_KW
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -61,6 +61,17 @@ def test_create_model_reproduces_reference_initialisation(golden_dir):
         assert list(sd.keys()) == list(g[name]["state"].keys()), name
         for k, v in sd.items():
             assert torch.equal(v, g[name]["state"][k]), (name, k)
+
+
+def test_pnaeq_initialisation_matches_reference(golden_dir):
+    g = torch.load(golden_dir + "/models_pnaeq.pt")
+    for name, c in g.items():
+        sd = hb.create_model(**dict(PNAEQ_KW, graph_pooling=name.split("_")[-1], pna_deg=c["deg"])).state_dict()
+        assert list(sd.keys()) == list(c["state"].keys())
+        for k, v in sd.items():
+            assert torch.equal(v, c["state"][k]), (name, k)
+    with pytest.raises(AssertionError, match="degree"):
+        hb.create_model(**dict(PNAEQ_KW, pna_deg=None))
 
 
 def test_create_model_errors_mirror_reference():

@@ -16,7 +16,7 @@ from hydragnn_b200 import ops  # noqa: E402
 from hydragnn_b200.synthetic import ARCH, make_samples  # noqa: E402
 import oracle  # noqa: E402
 from oracle.workloads import add_edges_cpu  # noqa: E402
-from test_oracle_golden import MODEL_KW  # noqa: E402
+from test_oracle_golden import MODEL_KW, PNAEQ_KW  # noqa: E402
 
 DEV = "cuda"
 
@@ -243,3 +243,45 @@ def test_validate_and_train_loop_api():
         err, terr = hb.train([b.clone()], model, opt, compute_grad_energy=True)
     e1, _ = hb.validate([b.clone()], model, compute_grad_energy=True)
     assert terr.shape == (3,) and float(e1) < float(e0)
+
+
+# ---- PNAEq (row a6) ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["pnaeq_graph_mean", "pnaeq_graph_add"])
+def test_pnaeq_matches_reference_golden(golden_dir, name):
+    c = torch.load(golden_dir + "/models_pnaeq.pt")[name]
+    kw = dict(PNAEQ_KW, graph_pooling=name.split("_")[-1], pna_deg=c["deg"])
+    m = _engine(kw, c["state"]).train()
+    d = _batch(c["inputs"])
+    pred = m(d)
+    assert rel_l2(pred[0].detach().cpu(), c["pred"][0]) < 1e-5
+    loss, _ = m.loss(pred, d.y, [torch.arange(d.y.shape[0], device=DEV)])
+    torch.testing.assert_close(loss.detach().cpu(), c["loss"], rtol=1e-5, atol=1e-6)
+    loss.backward()
+    for n, p in m.named_parameters():
+        ref = c["grads"][n]
+        if ref is not None:
+            torch.testing.assert_close(p.grad.cpu(), ref, rtol=5e-4, atol=1e-6, msg=lambda s, n=n: n + ": " + s)
+
+
+def test_pnaeq_mlip_double_backward_matches_oracle():
+    name, g = "md17_egnn", 12
+    cpu = add_edges_cpu(make_samples(name, g), name)
+    deg = torch.bincount(torch.bincount(cpu.edge_index[1], minlength=cpu.pos.shape[0])).tolist()
+    kw = dict(ARCH[name], mpnn_type="PNAEq", pna_deg=deg, num_radial=6, radius=7.0, hidden_dim=16)
+    om = oracle.base.create_model(**kw)
+    em = hb.create_model(**kw)
+    em.model.load_state_dict(om.model.state_dict())
+    gpu = cpu.clone().to(DEV)
+    gpu._num_graphs = g
+    cpu.pos.requires_grad_(True)
+    gpu.pos.requires_grad_(True)
+    om.train()
+    em.train()
+    lo, to = om.energy_force_loss(om(cpu), cpu)
+    le, te = em.energy_force_loss(em(gpu), gpu)
+    torch.testing.assert_close(le.detach().cpu(), lo.detach(), rtol=1e-5, atol=1e-6)
+    lo.backward()
+    le.backward()
+    for (n, p), q in zip(em.model.named_parameters(), om.model.parameters()):
+        if q.grad is not None:
+            torch.testing.assert_close(p.grad.cpu(), q.grad, rtol=2e-3, atol=1e-6, msg=lambda s, n=n: n + ": " + s)

@@ -134,3 +134,28 @@ def test_pbc_limit_neighbors(golden_dir):
     out = oracle.radius_graph.limit_neighbors(src[keep], dst[keep], length[keep], S[keep], c["k"])
     for a, b in zip(out, c["out"]):
         assert np.array_equal(np.asarray(a), b.numpy())
+
+
+PNAEQ_KW = dict(mpnn_type="PNAEq", input_dim=1, hidden_dim=12, output_dim=[1], output_type=["graph"], output_heads=HEADS_GRAPH,
+                activation_function="relu", num_conv_layers=3, task_weights=[1.0], num_radial=6, radius=5.0)
+
+
+def test_pnaeq_matches_reference_golden(golden_dir):
+    """Everything in PNAEqStack.py is the reference's own code; the PyG DegreeScalerAggregation inside it is the
+    restated one (see tests/golden/make_golden.py)."""
+    g = torch.load(golden_dir + "/models_pnaeq.pt")
+    for name, c in g.items():
+        m = OracleModel(**dict(PNAEQ_KW, graph_pooling=name.split("_")[-1], pna_deg=c["deg"]))
+        assert list(m.state_dict().keys()) == list(c["state"].keys()), name
+        m.load_state_dict(c["state"])
+        d = _data(c["inputs"])
+        pred = m(d)
+        torch.testing.assert_close(pred[0], c["pred"][0], **TOL)
+        loss, _ = m.loss(pred, d.y, [torch.arange(d.y.shape[0])])
+        torch.testing.assert_close(loss, c["loss"], **TOL)
+        grads = torch.autograd.grad(loss, list(m.parameters()), allow_unused=True)
+        for (n, _), gr in zip(m.named_parameters(), grads):
+            ref = c["grads"][n]
+            assert (gr is None) == (ref is None), n
+            if gr is not None:
+                torch.testing.assert_close(gr, ref, rtol=1e-4, atol=1e-6)
