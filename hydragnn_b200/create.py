@@ -85,15 +85,16 @@ def create_model(mpnn_type, input_dim, hidden_dim, output_dim, pe_dim=0, global_
                  force_weight=0.0, use_graph_attr_conditioning=False, graph_attr_conditioning_mode="fuse_pool",
                  graph_pooling="mean", verbosity=0, use_gpu=True):
     torch.manual_seed(0)
-    if global_attn_engine:
-        raise ValueError("b200 engine: global attention (GPS) is not implemented yet; run with global_attn_engine=''")
+    if global_attn_engine and (global_attn_engine != "GPS" or global_attn_type != "multihead"):
+        raise ValueError("b200 engine: only global_attn_engine='GPS' with global_attn_type='multihead' is implemented")
     if use_graph_attr_conditioning:
         raise ValueError("b200 engine: graph_attr conditioning is not implemented yet")
     heads = update_multibranch_heads(output_heads)
     common = dict(input_dim=input_dim, hidden_dim=hidden_dim, output_dim=output_dim, output_type=output_type,
                   config_heads=heads, activation_function_type=activation_function, loss_function_type=loss_function_type,
                   equivariance=equivariance, loss_weights=task_weights, freeze_conv=freeze_conv, initial_bias=initial_bias,
-                  num_conv_layers=num_conv_layers, num_nodes=num_nodes, graph_pooling=graph_pooling)
+                  num_conv_layers=num_conv_layers, num_nodes=num_nodes, graph_pooling=graph_pooling, pe_dim=pe_dim,
+                  global_attn_engine=global_attn_engine, global_attn_type=global_attn_type, global_attn_heads=global_attn_heads)
     if mpnn_type == "EGNN":
         model = EGCLStack(edge_dim, max_neighbours=max_neighbours, **common)
     elif mpnn_type == "PAINN":

@@ -190,8 +190,11 @@ class PNAEqStack(Base):
         else:
             _, ln, unit = ops.EdgeGeomFn.apply(pos, shifts, plan, 1e-9)          # PNAEqStack.py:202-204
         geom = {"rbf": rbf_basis(ln.squeeze(-1), self.num_radial, self.radius), "unit": unit}
+        eattr = data.edge_attr if self.use_edge_attr else None
+        if self.use_global_attn:
+            x, eattr = self._gps_embed(data, higher)
         v = torch.zeros(x.shape[0], 3, x.shape[1], dtype=x.dtype, device=x.device)
-        return x, v, {"edge_attr": data.edge_attr if self.use_edge_attr else None, "geom": geom}
+        return x, v, {"edge_attr": eattr, "geom": geom}
 
     def __str__(self):
         return "PNAEqStack"

@@ -261,8 +261,11 @@ class MLPNode(nn.Module):
 class Base(nn.Module):
     def __init__(self, input_dim, hidden_dim, output_dim, output_type, config_heads, activation_function_type,
                  loss_function_type, equivariance=False, loss_weights=None, freeze_conv=False, initial_bias=None,
-                 num_conv_layers=16, num_nodes=None, graph_pooling="mean"):
+                 num_conv_layers=16, num_nodes=None, graph_pooling="mean", pe_dim=0, global_attn_engine=None,
+                 global_attn_type=None, global_attn_heads=0, dropout=0.25):
         super().__init__()
+        self.pe_dim, self.global_attn_engine, self.global_attn_type = pe_dim, global_attn_engine, global_attn_type
+        self.global_attn_heads, self.dropout, self.global_attn_dropout = global_attn_heads, dropout, dropout
         self.input_dim, self.hidden_dim = input_dim, hidden_dim
         self.num_conv_layers, self.num_nodes = num_conv_layers, num_nodes
         self.head_dims, self.head_type = list(output_dim), list(output_type)
@@ -288,12 +291,29 @@ class Base(nn.Module):
             raise ValueError("Unsupported graph_pooling: " + graph_pooling)
         self.graph_pooling = mode
         self.freeze_conv, self.initial_bias = freeze_conv, initial_bias
-        self.use_global_attn = False
-        self.embed_dim = input_dim
         self.force_higher_order = False   # tests can force the any-order path
         self.graph_convs = nn.ModuleList()
         self.feature_layers = nn.ModuleList()
         self.heads_NN = nn.ModuleList()
+        # global attention: every conv runs at hidden_dim and is wrapped in a GPS layer (Base.py:177-215)
+        if self.global_attn_engine:
+            if self.global_attn_engine != "GPS":
+                raise ValueError("Unsupported global_attn_engine: " + str(self.global_attn_engine))
+            self.use_global_attn = True
+            self.embed_dim = self.edge_embed_dim = hidden_dim
+            self.pos_emb = nn.Linear(self.pe_dim, hidden_dim, bias=False)
+            if self.input_dim:
+                self.node_emb = nn.Linear(self.input_dim, hidden_dim, bias=False)
+                self.node_lin = nn.Linear(2 * hidden_dim, hidden_dim, bias=False)
+            if self.is_edge_model:
+                self.rel_pos_emb = nn.Linear(self.pe_dim, hidden_dim, bias=False)
+                if self.use_edge_attr:
+                    self.edge_emb = nn.Linear(self.edge_dim, hidden_dim, bias=False)
+                    self.edge_lin = nn.Linear(2 * hidden_dim, hidden_dim, bias=False)
+        else:
+            self.use_global_attn = False
+            self.embed_dim = input_dim
+            self.edge_embed_dim = getattr(self, "edge_dim", None)
         self._init_conv()
         if freeze_conv:
             for p in self.graph_convs.parameters():
@@ -309,7 +329,12 @@ class Base(nn.Module):
     def _init_conv(self):
         for i in range(self.num_conv_layers):
             last = i == self.num_conv_layers - 1
-            self.graph_convs.append(self.get_conv(self.embed_dim if i == 0 else self.hidden_dim, self.hidden_dim, last))
+            conv = self.get_conv(self.embed_dim if i == 0 else self.hidden_dim, self.hidden_dim, last, edge_dim=self.edge_embed_dim)
+            if self.use_global_attn:                                           # Base._apply_global_attn :234-247
+                from .gps import GPSConv
+                conv = GPSConv(self.hidden_dim, conv, heads=self.global_attn_heads, dropout=self.global_attn_dropout,
+                               attn_type=self.global_attn_type)
+            self.graph_convs.append(conv)
             self.feature_layers.append(nn.Identity())
 
     def _multihead(self):                                                  # Base.py:590-691
@@ -358,6 +383,19 @@ class Base(nn.Module):
             except Exception:
                 pass
         return plan
+
+    def _gps_embed(self, data, higher):
+        """Node / edge embeddings used when global attention is on (Base.py:477-491): returns (x, edge_attr)."""
+        lin = (lambda m, t: ops.linear_any_order(t, m.weight, None)) if higher else (lambda m, t: ops.linear_act(t, m.weight, None))
+        x = lin(self.pos_emb, data.pe)
+        if self.input_dim:
+            x = lin(self.node_lin, torch.cat((lin(self.node_emb, data.x.float()), x), 1))
+        e = None
+        if self.is_edge_model:
+            e = lin(self.rel_pos_emb, data.rel_pe)
+            if self.use_edge_attr:
+                e = lin(self.edge_lin, torch.cat((lin(self.edge_emb, data.edge_attr), e), 1))
+        return x, e
 
     def _higher_order(self, data):
         pos = data.pos
@@ -454,6 +492,9 @@ class EGCLStack(Base):
 
     def _embedding(self, data, plan, higher):
         shifts = data.edge_shifts                                            # zeros if absent (EGCLStack.py:114-118)
+        if self.use_global_attn:
+            x, e = self._gps_embed(data, higher)
+            return x, data.pos, {"edge_attr": e, "edge_shifts": shifts}
         return data.x, data.pos, {"edge_attr": data.edge_attr if self.use_edge_attr else None, "edge_shifts": shifts}
 
     def __str__(self):
@@ -488,8 +529,11 @@ class PAINNStack(Base):
         else:
             _, ln, unit = ops.EdgeGeomFn.apply(pos, shifts, plan, 1e-9)      # PAINNStack.py:157-159
             geom = {"epack": ops.PainnEdgeEmbedFn.apply(unit, ln, self.num_radial, self.radius)}
+        eattr = data.edge_attr if self.use_edge_attr else None
+        if self.use_global_attn:
+            x, eattr = self._gps_embed(data, higher)
         v = torch.zeros(x.shape[0], 3, x.shape[1], dtype=x.dtype, device=x.device)   # PAINNStack.py:190
-        return x, v, {"edge_attr": data.edge_attr if self.use_edge_attr else None, "geom": geom}
+        return x, v, {"edge_attr": eattr, "geom": geom}
 
     def __str__(self):
         return "PAINNStack"

@@ -264,6 +264,19 @@ int hgb_painn_update_bwd(const float* gs_out, const float* gv_out, const float* 
                          float* gv, hgb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * GPS global attention  (hydragnn/globalAtt/gps.py:126-133; ATen SDPA inside nn.MultiheadAttention)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Dense multi-head self-attention over ONE sequence of n tokens (quirk Q1: the reference never passes
+ * graph_batch, so the whole mini-batch attends to itself).  qkv [n,3f] is the packed in-projection
+ * [q | k | v], head h owns columns h*d..h*d+d-1 (d = f/heads in {1,2,4,8,16,32}); out [n,f]; lse [n,heads]
+ * (log-sum-exp of the scaled scores, kept for the backward).  Flash-style: no [n,n] matrix reaches HBM.    */
+int hgb_mha_fwd(const float* qkv, int32_t n, int32_t f, int32_t heads, float* out, float* lse,
+                hgb_stream_t stream);
+int hgb_mha_bwd(const float* qkv, const float* out, const float* lse, const float* gout, int32_t n, int32_t f,
+                int32_t heads, float* gqkv, hgb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Loss / optimizer (hydragnn/train/train_validate_test.py:736-769, torch.optim.AdamW)
  * ------------------------------------------------------------------------------------------ */
 

@@ -14,6 +14,7 @@ from .egnn import EGCL
 from .geometry import edge_vectors_and_lengths, graph_pool
 from .painn import PainnMessage, PainnUpdate
 from . import pnaeq
+from .gps import GPSConv
 
 
 def activation(name):
@@ -62,8 +63,13 @@ class OracleModel(nn.Module):
     def __init__(self, mpnn_type, input_dim, hidden_dim, output_dim, output_type, output_heads,
                  activation_function="relu", loss_function_type="mse", task_weights=None,
                  num_conv_layers=2, num_nodes=None, edge_dim=None, num_radial=None, radius=None,
-                 equivariance=False, graph_pooling="mean", pna_deg=None, **_unused):
+                 equivariance=False, graph_pooling="mean", pna_deg=None, global_attn_engine=None,
+                 global_attn_type=None, global_attn_heads=0, pe_dim=0, dropout=0.25, **_unused):
         super().__init__()
+        self.use_global_attn = bool(global_attn_engine)
+        if self.use_global_attn and (global_attn_engine != "GPS" or global_attn_type != "multihead"):
+            raise ValueError("oracle supports global_attn_engine='GPS' with global_attn_type='multihead'")
+        self.global_attn_heads, self.pe_dim, self.dropout = global_attn_heads, pe_dim, dropout
         if mpnn_type == "PNAEq":
             assert pna_deg is not None, "PNAEq requires degree input."
             self.deg = pnaeq.sanitize_degree(pna_deg)
@@ -89,12 +95,27 @@ class OracleModel(nn.Module):
         else:
             self.edge_dim = edge_dim                                        # PAINNStack.py:43
         self.use_edge_attr = self.edge_dim is not None and self.edge_dim > 0   # Base.py:135-141
+        if self.use_global_attn:                                               # Base.py:179-215
+            self.embed_dim = self.edge_embed_dim = hidden_dim
+            self.pos_emb = nn.Linear(pe_dim, hidden_dim, bias=False)
+            if input_dim:
+                self.node_emb = nn.Linear(input_dim, hidden_dim, bias=False)
+                self.node_lin = nn.Linear(2 * hidden_dim, hidden_dim, bias=False)
+            self.rel_pos_emb = nn.Linear(pe_dim, hidden_dim, bias=False)
+            if self.use_edge_attr:
+                self.edge_emb = nn.Linear(self.edge_dim, hidden_dim, bias=False)
+                self.edge_lin = nn.Linear(2 * hidden_dim, hidden_dim, bias=False)
+        else:
+            self.embed_dim, self.edge_embed_dim = input_dim, self.edge_dim
 
-        # --- conv stack: first layer at input_dim (Q4), last layer flagged (EGCLStack.py:45-70)
+        # --- conv stack: first layer at embed_dim (= input_dim without GPS, Q4), last layer flagged (EGCLStack.py:45-70)
         self.graph_convs = nn.ModuleList()
         for i in range(num_conv_layers):
             last = i == num_conv_layers - 1
-            self.graph_convs.append(self._get_conv(input_dim if i == 0 else hidden_dim, hidden_dim, last))
+            conv = self._get_conv(self.embed_dim if i == 0 else hidden_dim, hidden_dim, last)
+            if self.use_global_attn:                                           # Base._apply_global_attn :234-247
+                conv = GPSConv(hidden_dim, conv, heads=global_attn_heads, dropout=dropout)
+            self.graph_convs.append(conv)
 
         # --- decoder (Base.py:590-691), single or multi branch
         act = self.activation_function
@@ -132,14 +153,15 @@ class OracleModel(nn.Module):
 
     # EGCLStack.get_conv :72-109 / PAINNStack.get_conv :76-147
     def _get_conv(self, fin, fout, last):
+        ed = self.edge_embed_dim                                        # hidden_dim under GPS, else the stack's edge_dim
         if self.mpnn_type == "EGNN":
-            return _Conv("egnn", [EGCL(fin, fout, self.hidden_dim, edge_attr_dim=self.edge_dim,
+            return _Conv("egnn", [EGCL(fin, fout, self.hidden_dim, edge_attr_dim=ed or self.edge_dim,
                                        equivariant=self.equivariance and not last)])
         if self.mpnn_type == "PNAEq":                                   # PNAEqStack.get_conv :119-192
-            msg = pnaeq.PainnMessage(fin, self.deg, self.edge_dim, self.num_radial)
+            msg = pnaeq.PainnMessage(fin, self.deg, ed, self.num_radial)
             upd = pnaeq.PainnUpdate(fin, last_layer=last)
         else:
-            msg = PainnMessage(fin, self.num_radial, self.radius, edge_dim=self.edge_dim)
+            msg = PainnMessage(fin, self.num_radial, self.radius, edge_dim=ed)
             upd = PainnUpdate(fin, last_layer=last)
         s_out = nn.Sequential(nn.Linear(fin, fout), nn.Tanh(), nn.Linear(fout, fout))
         v_out = None if last else nn.Linear(fin, fout)
@@ -151,33 +173,54 @@ class OracleModel(nn.Module):
         if shifts is None:                                                   # Base.py:466-469
             shifts = torch.zeros(ei.shape[1], 3, dtype=pos.dtype, device=pos.device)
         eattr = data.edge_attr if self.use_edge_attr else None
+        if self.use_global_attn:                                               # Base._embedding :477-491
+            xe = self.pos_emb(data.pe)
+            if self.input_dim:
+                xe = self.node_lin(torch.cat((self.node_emb(x.float()), xe), 1))
+            e = self.rel_pos_emb(data.rel_pe)
+            if self.use_edge_attr:
+                e = self.edge_lin(torch.cat((self.edge_emb(eattr), e), 1))
+            x, eattr = xe, e
+
+        def layer(conv, fn):
+            """run one conv, through GPSConv when global attention is on"""
+            if self.use_global_attn:
+                return lambda x_, q_: conv(x_, q_, lambda a, b: fn(conv.conv, a, b))
+            return lambda x_, q_: fn(conv, x_, q_)
+
         if self.mpnn_type == "EGNN":
             equiv = pos
             for conv in self.graph_convs:
-                x, equiv = conv.module_0(x, equiv, ei, eattr, shifts)
+                x, equiv = layer(conv, lambda c, a, b: c.module_0(a, b, ei, eattr, shifts))(x, equiv)
                 x = self.activation_function(x)                              # Base.py:726
         elif self.mpnn_type == "PNAEq":
             vec, dist = edge_vectors_and_lengths(pos, ei, shifts, normalize=True)    # PNAEqStack.py:202-205
             rbf = pnaeq.rbf_basis(dist.squeeze(-1), self.num_radial, self.radius)
             edge = ei.t()
             v = torch.zeros(x.shape[0], 3, x.shape[1], dtype=x.dtype, device=x.device)
+
+            def pna_conv(c, a, b):
+                a, b2 = c.module_0(a, b, edge, rbf, vec, eattr)
+                a, b3 = c.module_1(a, b2)
+                a = c.module_2(a)
+                return a, (c.module_3(b3) if b3 is not None else b2)
+
             for conv in self.graph_convs:
-                x, v = conv.module_0(x, v, edge, rbf, vec, eattr)
-                x, v = conv.module_1(x, v)
-                x = conv.module_2(x)
-                if v is not None:
-                    v = conv.module_3(v)
+                x, v = layer(conv, pna_conv)(x, v)
                 x = self.activation_function(x)
         else:
             diff, dist = edge_vectors_and_lengths(pos, ei, shifts, normalize=True)   # PAINNStack.py:157-159
             edge = ei.t()
             v = torch.zeros(x.shape[0], 3, x.shape[1], dtype=x.dtype, device=x.device)
+
+            def painn_conv(c, a, b):
+                a, b2 = c.module_0(a, b, edge, diff, dist, eattr)
+                a, b3 = c.module_1(a, b2)
+                a = c.module_2(a)
+                return a, (c.module_3(b3) if b3 is not None else b2)
+
             for conv in self.graph_convs:
-                x, v = conv.module_0(x, v, edge, diff, dist, eattr)
-                x, v = conv.module_1(x, v)
-                x = conv.module_2(x)
-                if v is not None:
-                    v = conv.module_3(v)
+                x, v = layer(conv, painn_conv)(x, v)
                 x = self.activation_function(x)
         batch = getattr(data, "batch", None)
         if batch is None:

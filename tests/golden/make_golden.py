@@ -172,6 +172,24 @@ def install_pnaeq_stubs():
     return _load("hydragnn.models.PNAEqStack", REF + "/hydragnn/models/PNAEqStack.py")
 
 
+def install_gps_stubs():
+    """gps.py needs PyG's PerformerAttention / MessagePassing / reset / resolvers / to_dense_batch.  Only
+    ``to_dense_batch(x, None)`` (-> one sequence with an all-true mask) and the ``batch_norm``
+    normalisation (PyG BatchNorm = a module holding ``.module = BatchNorm1d``) are exercised."""
+    from oracle.gps import PyGBatchNorm
+    _mod("torch_geometric.nn.attention", PerformerAttention=type("PerformerAttention", (), {}))
+    _mod("torch_geometric.nn.conv", MessagePassing=torch.nn.Module)
+    _mod("torch_geometric.nn.inits", reset=lambda m: None)
+    res = sys.modules.get("torch_geometric.nn.resolver") or _mod("torch_geometric.nn.resolver")
+    res.activation_resolver = lambda act, **kw: {"tanh": torch.nn.Tanh, "relu": torch.nn.ReLU}[act]()
+    res.normalization_resolver = lambda norm, channels, **kw: PyGBatchNorm(channels)
+    sys.modules["torch_geometric.typing"].Adj = object
+    _mod("torch_geometric.utils", to_dense_batch=lambda x, batch=None: (x.unsqueeze(0), torch.ones(1, x.shape[0], dtype=torch.bool)))
+    gps = _load("hydragnn.globalAtt.gps", REF + "/hydragnn/globalAtt/gps.py")
+    sys.modules["hydragnn.models.Base"].GPSConv = gps.GPSConv
+    return gps
+
+
 def toy_batch(gen, sizes, box, input_dim=1, dtype=torch.float32):
     """A few random molecules + an asymmetric hand-made edge list (every atom keeps its
     3 nearest in-graph neighbours as sources)."""
@@ -306,6 +324,44 @@ def main():
                                           "grads": {n: (g.detach() if g is not None else None)
                                                     for (n, _), g in zip(m.named_parameters(), grads)}}
     torch.save(pmodels, HERE + "/models_pnaeq.pt")
+
+    # ---- GPS: the reference's own gps.py + Base.py (PyG glue stubbed: BatchNorm wrapper, to_dense_batch, resolvers) ----
+    gps = install_gps_stubs()
+    gmodels = {}
+    for kind in ("EGNN", "PAINN"):
+        b = toy_batch(gen, [9, 6, 7, 9], 5.0, input_dim=2)
+        b.pe = torch.randn(b.x.shape[0], 4, generator=gen)
+        b.rel_pe = (b.pe[b.edge_index[0]] - b.pe[b.edge_index[1]]).abs()       # serialized_dataset_loader.py:186-189
+        torch.manual_seed(0)
+        if kind == "EGNN":
+            m = egcl.EGCLStack("inv_node_feat, equiv_node_feat, edge_index, edge_attr, edge_shifts", "", None,
+                               2, 16, [1], 4, "GPS", "multihead", 4, ["graph"], heads_graph, "relu", "mse", False,
+                               max_neighbours=None, loss_weights=[1.0], freeze_conv=False, initial_bias=None,
+                               num_conv_layers=2, num_nodes=None, graph_pooling="mean")
+        else:
+            m = painn.PAINNStack("inv_node_feat, equiv_node_feat, edge_index, diff, dist",
+                                 "inv_node_feat, equiv_node_feat, edge_index, diff, dist", None, 5, 7.0,
+                                 2, 16, [1], 4, "GPS", "multihead", 4, ["graph"], heads_graph, "relu", "mse", False,
+                                 loss_weights=[1.0], freeze_conv=False, num_conv_layers=2, num_nodes=None, graph_pooling="mean")
+        m.eval()
+        pred_eval = [p.detach() for p in m(b)]
+        # train mode (batch-statistics BatchNorm) with the dropout probabilities of THIS INSTANCE set to zero
+        m.train()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+            if isinstance(mod, gps.GPSConv):
+                mod.dropout = 0.0
+        state = {k: v.clone() for k, v in m.state_dict().items()}
+        pred = m(b)
+        loss, _ = m.loss(pred, b.y, [torch.arange(b.y.shape[0])])
+        grads = torch.autograd.grad(loss, list(m.parameters()), allow_unused=True)
+        gmodels["gps_" + kind.lower()] = {"state": state, "inputs": t2d(b), "pred_eval": pred_eval,
+                                          "pred_train": [p.detach() for p in pred], "loss": loss.detach(),
+                                          "state_after": {k: v.clone() for k, v in m.state_dict().items() if "running" in k},
+                                          "grads": {n: (g.detach() if g is not None else None)
+                                                    for (n, _), g in zip(m.named_parameters(), grads)}}
+    torch.save(gmodels, HERE + "/models_gps.pt")
 
     # ---- RadiusGraphPBC numpy post-processing ---------------------------------------------
     glb = {"np": np}

@@ -11,7 +11,7 @@ import torch
 import hydragnn_b200 as hb
 from hydragnn_b200 import _lib, ops
 from hydragnn_b200.synthetic import ARCH, make_samples
-from test_oracle_golden import MODEL_KW, PNAEQ_KW
+from test_oracle_golden import GPS_KW, MODEL_KW, PNAEQ_KW
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -72,6 +72,17 @@ def test_pnaeq_initialisation_matches_reference(golden_dir):
             assert torch.equal(v, c["state"][k]), (name, k)
     with pytest.raises(AssertionError, match="degree"):
         hb.create_model(**dict(PNAEQ_KW, pna_deg=None))
+
+
+def test_gps_initialisation_matches_reference(golden_dir):
+    g = torch.load(golden_dir + "/models_gps.pt")
+    for name, c in g.items():
+        sd = hb.create_model(**GPS_KW[name]).state_dict()
+        assert list(sd.keys()) == list(c["state"].keys())
+        for k, v in sd.items():
+            assert torch.equal(v, c["state"][k]), (name, k)
+    with pytest.raises(ValueError):
+        hb.create_model(**dict(GPS_KW["gps_egnn"], global_attn_type="performer"))
 
 
 def test_create_model_errors_mirror_reference():

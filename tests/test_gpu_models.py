@@ -16,7 +16,7 @@ from hydragnn_b200 import ops  # noqa: E402
 from hydragnn_b200.synthetic import ARCH, make_samples  # noqa: E402
 import oracle  # noqa: E402
 from oracle.workloads import add_edges_cpu  # noqa: E402
-from test_oracle_golden import MODEL_KW, PNAEQ_KW  # noqa: E402
+from test_oracle_golden import GPS_KW, MODEL_KW, PNAEQ_KW, _zero_dropout  # noqa: E402
 
 DEV = "cuda"
 
@@ -285,3 +285,57 @@ def test_pnaeq_mlip_double_backward_matches_oracle():
     for (n, p), q in zip(em.model.named_parameters(), om.model.parameters()):
         if q.grad is not None:
             torch.testing.assert_close(p.grad.cpu(), q.grad, rtol=2e-3, atol=1e-6, msg=lambda s, n=n: n + ": " + s)
+
+
+# ---- GPS global attention (row a9) ---------------------------------------------------------------------------
+@pytest.mark.parametrize("n,f,heads", [(1, 8, 2), (77, 16, 4), (300, 64, 8), (1000, 64, 2), (129, 32, 32)])
+def test_mha_kernel_matches_torch(n, f, heads):
+    from hydragnn_b200.gps import MhaFn, mha_any_order
+    g = torch.Generator().manual_seed(n + f)
+    qkv = torch.randn(n, 3 * f, generator=g)
+    go = torch.randn(n, f, generator=g)
+    qr = qkv.clone().requires_grad_(True)
+    q, k, v = [t.reshape(n, heads, f // heads).transpose(0, 1) for t in qr.split(f, dim=1)]
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(0, 1).reshape(n, f)
+    gr, = torch.autograd.grad(ref, qr, go)
+    qe = qkv.to(DEV).requires_grad_(True)
+    out = MhaFn.apply(qe, heads)
+    ge, = torch.autograd.grad(out, qe, go.to(DEV))
+    torch.testing.assert_close(out.detach().cpu(), ref.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(ge.cpu(), gr, rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(mha_any_order(qe, heads).detach().cpu(), ref.detach(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["gps_egnn", "gps_painn"])
+def test_gps_matches_reference_golden(golden_dir, name):
+    c = torch.load(golden_dir + "/models_gps.pt")[name]
+    m = _engine(GPS_KW[name], c["state"])
+    m.eval()
+    with torch.no_grad():
+        pred = m(_batch(c["inputs"]))
+    assert rel_l2(pred[0].cpu(), c["pred_eval"][0]) < 1e-5
+    m.train()
+    _zero_dropout(m)
+    d = _batch(c["inputs"])
+    pred = m(d)
+    assert rel_l2(pred[0].detach().cpu(), c["pred_train"][0]) < 1e-4
+    loss, _ = m.loss(pred, d.y, [torch.arange(d.y.shape[0], device=DEV)])
+    torch.testing.assert_close(loss.detach().cpu(), c["loss"], rtol=1e-4, atol=1e-6)
+    loss.backward()
+    for n, p in m.named_parameters():
+        ref = c["grads"][n]
+        if ref is not None:
+            torch.testing.assert_close(p.grad.cpu(), ref, rtol=5e-3, atol=2e-5, msg=lambda s, n=n: n + ": " + s)
+    sd = m.state_dict()
+    for k, v in c["state_after"].items():
+        torch.testing.assert_close(sd[k].cpu(), v, rtol=1e-4, atol=1e-6)
+
+
+def test_gps_any_order_path_equals_fused_path(golden_dir):
+    c = torch.load(golden_dir + "/models_gps.pt")["gps_painn"]
+    m = _engine(GPS_KW["gps_painn"], c["state"]).eval()
+    with torch.no_grad():
+        a = m(_batch(c["inputs"]))[0]
+        m.force_higher_order = True
+        b = m(_batch(c["inputs"]))[0]
+    assert rel_l2(b.cpu(), a.cpu()) < 1e-5

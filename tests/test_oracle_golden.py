@@ -159,3 +159,51 @@ def test_pnaeq_matches_reference_golden(golden_dir):
             assert (gr is None) == (ref is None), n
             if gr is not None:
                 torch.testing.assert_close(gr, ref, rtol=1e-4, atol=1e-6)
+
+
+GPS_KW = {
+    "gps_egnn": dict(mpnn_type="EGNN", input_dim=2, hidden_dim=16, output_dim=[1], output_type=["graph"], output_heads=HEADS_GRAPH,
+                     activation_function="relu", num_conv_layers=2, task_weights=[1.0], global_attn_engine="GPS",
+                     global_attn_type="multihead", global_attn_heads=4, pe_dim=4),
+    "gps_painn": dict(mpnn_type="PAINN", input_dim=2, hidden_dim=16, output_dim=[1], output_type=["graph"], output_heads=HEADS_GRAPH,
+                      activation_function="relu", num_conv_layers=2, task_weights=[1.0], num_radial=5, radius=7.0,
+                      global_attn_engine="GPS", global_attn_type="multihead", global_attn_heads=4, pe_dim=4),
+}
+
+
+def _zero_dropout(m):
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+        if hasattr(mod, "dropout") and isinstance(getattr(mod, "dropout"), float):
+            mod.dropout = 0.0
+
+
+def test_gps_matches_reference_golden(golden_dir):
+    """gps.py + Base.py are the reference's own code (PyG glue stubbed, see make_golden.py): eval-mode forward,
+    and train-mode (batch-statistics BatchNorm, dropout p = 0) forward / loss / gradients / running stats."""
+    g = torch.load(golden_dir + "/models_gps.pt")
+    for name, c in g.items():
+        m = OracleModel(**GPS_KW[name])
+        assert set(m.state_dict().keys()) == set(c["state"].keys()), name
+        m.load_state_dict(c["state"])
+        m.eval()
+        for p, q in zip(m(_data(c["inputs"])), c["pred_eval"]):
+            torch.testing.assert_close(p, q, **TOL)
+        m.train()
+        _zero_dropout(m)
+        d = _data(c["inputs"])
+        pred = m(d)
+        for p, q in zip(pred, c["pred_train"]):
+            torch.testing.assert_close(p, q, rtol=1e-4, atol=1e-5)
+        loss, _ = m.loss(pred, d.y, [torch.arange(d.y.shape[0])])
+        torch.testing.assert_close(loss, c["loss"], rtol=1e-4, atol=1e-6)
+        grads = torch.autograd.grad(loss, list(m.parameters()), allow_unused=True)
+        for (n, _), gr in zip(m.named_parameters(), grads):
+            ref = c["grads"][n]
+            assert (gr is None) == (ref is None), n
+            if gr is not None:
+                torch.testing.assert_close(gr, ref, rtol=2e-3, atol=1e-5)
+        sd = m.state_dict()
+        for k, v in c["state_after"].items():
+            torch.testing.assert_close(sd[k], v, rtol=1e-4, atol=1e-6)
