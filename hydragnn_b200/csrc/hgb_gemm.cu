@@ -287,77 +287,70 @@ __global__ void linear_smallk_fwd_kernel(const float* __restrict__ x, int64_t ld
   }
 }
 
-// one pass over (dy, y|z, x): dz = dy * act'(.), dx[m,k] = dz . W, partial dW / db per block
+// one pass over (dy, y|z, x): dz = dy * act'(.), dx[m,k] = dz . W, partial dW / db per block.
+// KT = compile-time bound on k (1,2,4,8), NPT = outputs per lane (n <= 32*NPT): only the needed work is generated.
+#define SK_RU 4   // rows per walker trip: independent loads / shuffles hide the latency
+template <int KT, int NPT>
 __global__ void __launch_bounds__(256)
 linear_smallk_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ z,
                          const float* __restrict__ x, int64_t ldx, const float* __restrict__ w, int64_t ldw, int m, int n, int k,
                          int act, float ap, int rows_per_block, float* __restrict__ dx, float* __restrict__ part) {
-  extern __shared__ float sm[];  // w [n][k], then the reduction scratch [8][32]
-  float* sw = sm;
-  float* red = sm + n * k;
-  for (int i = threadIdx.y * 32 + threadIdx.x; i < n * k; i += 256) sw[i] = w[(int64_t)(i / k) * ldw + (i % k)];
-  __syncthreads();
+  __shared__ float red[8 * 32];
   const int lane = threadIdx.x, walker = threadIdx.y;
-  float gw[SK_NPT][SK_KMAX + 1];
+  float wr[NPT][KT], gw[NPT][KT + 1];
 #pragma unroll
-  for (int j = 0; j < SK_NPT; ++j)
+  for (int j = 0; j < NPT; ++j) {
+    const int c = lane + 32 * j;
 #pragma unroll
-    for (int q = 0; q <= SK_KMAX; ++q) gw[j][q] = 0.f;
+    for (int q = 0; q < KT; ++q) { wr[j][q] = (c < n && q < k) ? w[(int64_t)c * ldw + q] : 0.f; gw[j][q] = 0.f; }
+    gw[j][KT] = 0.f;
+  }
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(m, r0 + rows_per_block);
-  // each walker takes SK_RU rows per trip: their loads / shuffles are independent, which is what hides the latency
-#define SK_RU 4
   for (int rb = r0 + walker * SK_RU; rb < r1; rb += 8 * SK_RU) {
-    float xr[SK_RU][SK_KMAX], dxp[SK_RU][SK_KMAX];
+    float xr[SK_RU][KT], dxp[SK_RU][KT], g[SK_RU][NPT];
+#pragma unroll
+    for (int u = 0; u < SK_RU; ++u) {
+      const int r = rb + u;
+      const bool live = r < r1;
+#pragma unroll
+      for (int q = 0; q < KT; ++q) { xr[u][q] = (live && q < k) ? __ldg(x + (int64_t)r * ldx + q) : 0.f; dxp[u][q] = 0.f; }
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) {
+        const int c = lane + 32 * j;
+        const int64_t o = (int64_t)r * n + c;
+        g[u][j] = (live && c < n) ? __ldg(dy + o) : 0.f;
+        if (act != HGB_ACT_NONE && live && c < n) g[u][j] *= hgb_act_grad(y ? __ldg(y + o) : 0.f, z ? __ldg(z + o) : 0.f, act, ap);
+      }
+    }
 #pragma unroll
     for (int u = 0; u < SK_RU; ++u)
 #pragma unroll
-      for (int q = 0; q < SK_KMAX; ++q) {
-        xr[u][q] = (q < k && rb + u < r1) ? __ldg(x + (int64_t)(rb + u) * ldx + q) : 0.f;
-        dxp[u][q] = 0.f;
-      }
+      for (int j = 0; j < NPT; ++j) {
+        gw[j][KT] += g[u][j];
 #pragma unroll
-    for (int j = 0; j < SK_NPT; ++j) {
-      const int c = lane + 32 * j;
-      if (c < n) {
-        float g[SK_RU];
-#pragma unroll
-        for (int u = 0; u < SK_RU; ++u) {
-          const int r = rb + u;
-          const int64_t o = (int64_t)r * n + c;
-          g[u] = r < r1 ? dy[o] : 0.f;
-          if (act != HGB_ACT_NONE && r < r1) g[u] *= hgb_act_grad(y ? y[o] : 0.f, z ? z[o] : 0.f, act, ap);
-        }
-#pragma unroll
-        for (int u = 0; u < SK_RU; ++u) {
-          gw[j][SK_KMAX] += g[u];
-#pragma unroll
-          for (int q = 0; q < SK_KMAX; ++q)
-            if (q < k) {
-              gw[j][q] = fmaf(g[u], xr[u][q], gw[j][q]);
-              dxp[u][q] = fmaf(g[u], sw[c * k + q], dxp[u][q]);
-            }
+        for (int q = 0; q < KT; ++q) {
+          gw[j][q] = fmaf(g[u][j], xr[u][q], gw[j][q]);
+          dxp[u][q] = fmaf(g[u][j], wr[j][q], dxp[u][q]);
         }
       }
-    }
     if (dx) {
 #pragma unroll
       for (int u = 0; u < SK_RU; ++u)
 #pragma unroll
-        for (int q = 0; q < SK_KMAX; ++q)
-          if (q < k) {
-            const float s = hgb_warp_sum(dxp[u][q]);
-            if (lane == 0 && rb + u < r1) dx[(int64_t)(rb + u) * k + q] = s;
-          }
+        for (int q = 0; q < KT; ++q) {
+          const float sum = hgb_warp_sum(dxp[u][q]);
+          if (lane == 0 && q < k && rb + u < r1) dx[(int64_t)(rb + u) * k + q] = sum;
+        }
     }
   }
   // reduce the 8 row walkers -> part[blockIdx.x][n][k+1]
   float* mypart = part + (int64_t)blockIdx.x * n * (k + 1);
 #pragma unroll
-  for (int j = 0; j < SK_NPT; ++j)
+  for (int j = 0; j < NPT; ++j)
 #pragma unroll
-    for (int q = 0; q <= SK_KMAX; ++q) {
-      if ((q < k || q == SK_KMAX) && 32 * j < n) {   // uniform across the block
+    for (int q = 0; q <= KT; ++q) {
+      if (q < k || q == KT) {   // uniform across the block
         __syncthreads();
         red[walker * 32 + lane] = gw[j][q];
         __syncthreads();
@@ -366,7 +359,7 @@ linear_smallk_bwd_kernel(const float* __restrict__ dy, const float* __restrict__
 #pragma unroll
           for (int w8 = 0; w8 < 8; ++w8) acc += red[w8 * 32 + lane];
           const int c = lane + 32 * j;
-          if (c < n) mypart[c * (k + 1) + (q == SK_KMAX ? k : q)] = acc;
+          if (c < n) mypart[c * (k + 1) + (q == KT ? k : q)] = acc;
         }
       }
     }
@@ -379,8 +372,16 @@ __global__ void linear_smallk_reduce_kernel(const float* __restrict__ part, int 
   const int cnt = n * (k + 1);
   const int i = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
-  if (i < cnt)
-    for (int b = threadIdx.y; b < nblocks; b += 8) acc += part[(int64_t)b * cnt + i];
+  if (i < cnt) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four independent load chains
+    int b = threadIdx.y;
+    for (; b + 24 < nblocks; b += 32) {
+      a0 += part[(size_t)b * cnt + i]; a1 += part[(size_t)(b + 8) * cnt + i];
+      a2 += part[(size_t)(b + 16) * cnt + i]; a3 += part[(size_t)(b + 24) * cnt + i];
+    }
+    for (; b < nblocks; b += 8) a0 += part[(size_t)b * cnt + i];
+    acc = (a0 + a1) + (a2 + a3);
+  }
   red[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0 && i < cnt) {
@@ -452,7 +453,7 @@ linear_tiny_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y
 
 static int smallk_blocks(int m, int* rows_per_block) {
   int rpb = (m + HGB_NUM_SMS * 4 - 1) / (HGB_NUM_SMS * 4);
-  rpb = ((rpb + 31) / 32) * 32;      // 8 walkers x 4 rows per trip
+  rpb = ((rpb + 31) / 32) * 32;      // 8 walkers x 4 rows per trip (also a multiple of the tiny kernel's needs)
   if (rpb < 32) rpb = 32;
   *rows_per_block = rpb;
   return (m + rpb - 1) / rpb;
@@ -494,8 +495,13 @@ extern "C" int hgb_linear_smallk_bwd(const float* dy, const float* y, const floa
   if (n <= SK_NMAX) {
     linear_tiny_bwd_kernel<<<nb, 256, 0, st>>>(dy, y, z, x, ldx, w, ldw, m, n, k, act, act_param, rpb, dx, (float*)workspace);
   } else {
-    linear_smallk_bwd_kernel<<<nb, dim3(32, 8), (size_t)(n * k + 256) * 4, st>>>(dy, y, z, x, ldx, w, ldw, m, n, k, act, act_param, rpb, dx,
-                                                                               (float*)workspace);
+    const int kt = k <= 1 ? 1 : (k <= 2 ? 2 : (k <= 4 ? 4 : 8));
+    const int npt = n <= 32 ? 1 : (n <= 64 ? 2 : (n <= 128 ? 4 : 8));
+#define SK_LAUNCH(KT_, NPT_) linear_smallk_bwd_kernel<KT_, NPT_><<<nb, dim3(32, 8), 0, st>>>(dy, y, z, x, ldx, w, ldw, m, n, k, act, act_param, rpb, dx, (float*)workspace)
+#define SK_LAUNCH_N(KT_) do { if (npt == 1) SK_LAUNCH(KT_, 1); else if (npt == 2) SK_LAUNCH(KT_, 2); else if (npt == 4) SK_LAUNCH(KT_, 4); else SK_LAUNCH(KT_, 8); } while (0)
+    if (kt == 1) SK_LAUNCH_N(1); else if (kt == 2) SK_LAUNCH_N(2); else if (kt == 4) SK_LAUNCH_N(4); else SK_LAUNCH_N(8);
+#undef SK_LAUNCH_N
+#undef SK_LAUNCH
   }
   HGB_LAUNCH_CHECK("linear_smallk_bwd");
   linear_smallk_reduce_kernel<<<(n * (k + 1) + 31) / 32, dim3(32, 8), 0, st>>>((const float*)workspace, nb, n, k, dw, lddw, db);

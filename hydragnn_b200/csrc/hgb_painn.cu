@@ -317,8 +317,16 @@ __global__ void painn_wgrad_reduce_kernel(const float* __restrict__ part, int nb
   const int cnt = f3 * (r + 1);
   const int t = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
-  if (t < cnt)
-    for (int b = threadIdx.y; b < nblocks; b += 8) acc += part[(int64_t)b * cnt + t];
+  if (t < cnt) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four independent load chains
+    int b = threadIdx.y;
+    for (; b + 24 < nblocks; b += 32) {
+      a0 += part[(size_t)b * cnt + t]; a1 += part[(size_t)(b + 8) * cnt + t];
+      a2 += part[(size_t)(b + 16) * cnt + t]; a3 += part[(size_t)(b + 24) * cnt + t];
+    }
+    for (; b < nblocks; b += 8) a0 += part[(size_t)b * cnt + t];
+    acc = (a0 + a1) + (a2 + a3);
+  }
   red[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0 && t < cnt) {

@@ -62,6 +62,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       : "memory");
 }
 
+// smem tile -> global through the TMA engine (hardware-coalesced, clips rows/cols outside the tensor)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(smem_u32(smem_src)), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* holder, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(holder)), "r"(cols));
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -140,7 +150,8 @@ struct LinParams {
 
 constexpr int TILE_M = 128;
 
-__global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const LinParams p) {
+__global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_y,
+                                                           const __grid_constant__ CUtensorMap tmap_z, const LinParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int KB = p.kr >> 5;
@@ -150,7 +161,8 @@ __global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant
   uint8_t* sB = smem;
   uint8_t* sA = smem + ((b_bytes + 1023) & ~1023u);
   const int S = p.stages;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sA + (size_t)S * a_stage);
+  uint8_t* sOut = sA + (size_t)S * a_stage;                   // 8 epilogue warps x 2 staging tiles x 4 KB (1024-aligned)
+  uint64_t* full = reinterpret_cast<uint64_t*>(sOut + 8 * 2 * 4096);
   uint64_t* empty = full + S;
   uint64_t* tfull = empty + S;
   uint64_t* tempty = tfull + 2;
@@ -241,50 +253,62 @@ __global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant
       tc_fence_after();
       const int row = t * TILE_M + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * NO;
+      uint8_t* stz = sOut + (size_t)(warp - 2) * 8192;          // this warp's staging tiles: [0] pre-activation, [1] output
+      uint8_t* sty = stz + 4096;
+      const int row0 = t * TILE_M + q * 32;
       for (int c0 = half * 32; c0 < NO; c0 += 64) {
         float v[32];
         tmem_ld32(taddr + c0, v);
-        if (row < p.m) {
+        {
           const float4* bp = reinterpret_cast<const float4*>(sbias + c0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b4 = bp[j];
             v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
           }
-          if (p.z) {
-            float4* zp = reinterpret_cast<float4*>(p.z + (int64_t)row * NO + c0);
+        }
+        if (lane == 0) tma_store_wait_read();                 // the previous chunk's stores have finished reading the tiles
+        __syncwarp();
+        if (p.z) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) zp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < 8; ++j)   // SWIZZLE_128B tile: 16-byte chunk j of row `lane` lives at chunk j ^ (lane & 7)
+            *reinterpret_cast<float4*>(stz + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        switch (p.act) {     // hoisted out of the element loop: one specialised, fully unrolled loop per activation
+          case HGB_ACT_NONE: break;
+          case HGB_ACT_RELU:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            break;
+          case HGB_ACT_SILU:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
+            break;
+          case HGB_ACT_TANH:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+            break;
+          default:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = hgb_act(v[j], p.act, p.act_param);
+        }
+        if (p.addend && row < p.m) {
+          const float4* ap = reinterpret_cast<const float4*>(p.addend + (int64_t)row * NO + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 a4 = __ldg(ap + j);
+            v[4 * j] += a4.x; v[4 * j + 1] += a4.y; v[4 * j + 2] += a4.z; v[4 * j + 3] += a4.w;
           }
-          switch (p.act) {     // hoisted out of the element loop: one specialised, fully unrolled loop per activation
-            case HGB_ACT_NONE: break;
-            case HGB_ACT_RELU:
+        }
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-              break;
-            case HGB_ACT_SILU:
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
-              break;
-            case HGB_ACT_TANH:
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-              break;
-            default:
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = hgb_act(v[j], p.act, p.act_param);
-          }
-          if (p.addend) {
-            const float4* ap = reinterpret_cast<const float4*>(p.addend + (int64_t)row * NO + c0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 a4 = __ldg(ap + j);
-              v[4 * j] += a4.x; v[4 * j + 1] += a4.y; v[4 * j + 2] += a4.z; v[4 * j + 3] += a4.w;
-            }
-          }
-          float4* yp = reinterpret_cast<float4*>(p.y + (int64_t)row * NO + c0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(sty + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.z) tma_store_2d(&tmap_z, stz, c0, row0);
+          tma_store_2d(&tmap_y, sty, c0, row0);
+          tma_store_commit();
         }
       }
       tc_fence_before();
@@ -292,6 +316,7 @@ __global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant
       if (lane == 0) mbar_arrive(tempty + acc);
       if (++acc == 2) { acc = 0; aph ^= 1; }
     }
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -429,8 +454,16 @@ __global__ void tc_wgrad_reduce_kernel(const float* __restrict__ part, int npart
   const int cnt = no * w;
   const int i = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
-  if (i < cnt)
-    for (int b = threadIdx.y; b < nparts; b += 8) acc += part[(size_t)b * cnt + i];
+  if (i < cnt) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four independent load chains
+    int b = threadIdx.y;
+    for (; b + 24 < nparts; b += 32) {
+      a0 += part[(size_t)b * cnt + i]; a1 += part[(size_t)(b + 8) * cnt + i];
+      a2 += part[(size_t)(b + 16) * cnt + i]; a3 += part[(size_t)(b + 24) * cnt + i];
+    }
+    for (; b < nparts; b += 8) a0 += part[(size_t)b * cnt + i];
+    acc = (a0 + a1) + (a2 + a3);
+  }
   red[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0 && i < cnt) {
@@ -499,8 +532,12 @@ extern "C" int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_
   HGB_REQUIRE(a && w && y && hgb_tc_linear_supported(m, n_out, k_red), "tc_linear: unsupported shape m=%d n=%d k=%d", m, n_out, k_red);
   HGB_REQUIRE(lda % 4 == 0 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!z || (uintptr_t)z % 16 == 0),
               "tc_linear: operands must be 16-byte aligned with a row stride that is a multiple of 4");
-  CUtensorMap tm;
+  CUtensorMap tm, tmy, tmz;
   int rc = make_tmap(&tm, a, m, k_red, lda, TILE_M);
+  if (rc) return rc;
+  rc = make_tmap(&tmy, y, m, n_out, n_out, 32);
+  if (rc) return rc;
+  rc = make_tmap(&tmz, z ? z : y, m, n_out, n_out, 32);
   if (rc) return rc;
   LinParams p;
   p.m = m; p.kr = k_red; p.no = n_out; p.w = w; p.ldw = ldw; p.trans_b = trans_b; p.bias = bias; p.act = act; p.act_param = act_param;
@@ -508,12 +545,12 @@ extern "C" int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_
   const int KB = k_red / 32;
   const size_t b_bytes = ((size_t)KB * n_out * 128 + 1023) & ~(size_t)1023;
   const size_t a_stage = (size_t)TILE_M * 128;
-  int stages = (int)((200 * 1024 - b_bytes) / a_stage);
-  if (stages > 8) stages = 8;
+  int stages = (int)((224 * 1024 - 2048 - 65536 - b_bytes - (size_t)n_out * 4) / a_stage);
+  if (stages > 6) stages = 6;
   HGB_REQUIRE(stages >= 2, "tc_linear: weight operand does not fit shared memory (n=%d k=%d)", n_out, k_red);
   p.stages = stages;
   p.tmem_cols = pow2_cols(2 * n_out);
-  const size_t smem = 1024 + b_bytes + stages * a_stage + (2 * stages + 4) * 8 + 16 + (size_t)n_out * 4 + 16;
+  const size_t smem = 1024 + b_bytes + stages * a_stage + 65536 + (2 * stages + 4) * 8 + 16 + (size_t)n_out * 4 + 16;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -521,7 +558,7 @@ extern "C" int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_
   }
   const int ntiles = (m + TILE_M - 1) / TILE_M;
   const int grid = ntiles < HGB_NUM_SMS ? ntiles : HGB_NUM_SMS;
-  tc_linear_kernel<<<grid, 320, smem, (cudaStream_t)stream>>>(tm, p);
+  tc_linear_kernel<<<grid, 320, smem, (cudaStream_t)stream>>>(tm, tmy, tmz, p);
   HGB_LAUNCH_CHECK("tc_linear");
   return HGB_OK;
 }
