@@ -120,6 +120,151 @@ painn_message_fwd_kernel(const float* __restrict__ phi, const float* __restrict_
   }
 }
 
+// ---- tiled variant (F % 64 == 0): the block stages the phi / v rows of a tile of TN consecutive nodes in shared
+// memory with two bulk async copies (cp.async.bulk, mbarrier-completed, double buffered) and the warps then gather
+// neighbour rows from shared memory.  Batched molecular graphs keep all neighbours of a node within a few rows of
+// it, so almost every gather becomes an ~30-cycle shared-memory read instead of an ~800-cycle global one; the rare
+// neighbour outside the tile (a graph straddling a tile edge, or a large graph) falls back to a global load.
+__device__ __forceinline__ uint32_t pm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pm_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pm_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void pm_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pm_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pm_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(pm_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void pm_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(pm_smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(pm_smem_u32(bar))
+               : "memory");
+}
+
+#define TWPB 16   // warps per block in the tiled kernels (2 blocks / SM -> 32 warps hide the index / edge-record loads)
+template <bool HAS_EF, int RT>
+__global__ void __launch_bounds__(TWPB * 32, 2)
+painn_message_fwd_tiled_kernel(const float* __restrict__ phi, const float* __restrict__ s, const float* __restrict__ v,
+                               const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm,
+                               const int32_t* __restrict__ nbr, const float* __restrict__ epack, const float* __restrict__ wf,
+                               const float* __restrict__ bf, const float* __restrict__ efilt, int n, int f, int r, int tn,
+                               float* __restrict__ s_out, float* __restrict__ v_out) {
+  extern __shared__ __align__(128) uint8_t pm_smem[];
+  const int f3 = 3 * f;
+  const uint32_t tile_bytes = (uint32_t)tn * f3 * 4;
+  float* sphi[2] = {reinterpret_cast<float*>(pm_smem), reinterpret_cast<float*>(pm_smem + 2 * (size_t)tile_bytes)};
+  float* sv[2] = {reinterpret_cast<float*>(pm_smem + tile_bytes), reinterpret_cast<float*>(pm_smem + 3 * (size_t)tile_bytes)};
+  uint64_t* full = reinterpret_cast<uint64_t*>(pm_smem + 4 * (size_t)tile_bytes);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ntiles = (n + tn - 1) / tn;
+  if (threadIdx.x == 0) {
+    pm_mbar_init(full, 1);
+    pm_mbar_init(full + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int t, int buf) {   // thread 0: two bulk copies for tile t
+    const int n0 = t * tn;
+    const uint32_t bytes = (uint32_t)(min(n, n0 + tn) - n0) * f3 * 4;
+    pm_mbar_expect_tx(full + buf, 2 * bytes);
+    pm_bulk_g2s(sphi[buf], phi + (int64_t)n0 * f3, bytes, full + buf);
+    pm_bulk_g2s(sv[buf], v + (int64_t)n0 * f3, bytes, full + buf);
+  };
+  if (threadIdx.x == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  const int ncb = f >> 6;   // 64-channel blocks
+  int it = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int tnext = t + gridDim.x;
+    if (threadIdx.x == 0 && tnext < ntiles) issue(tnext, buf ^ 1);   // buffer buf^1 was released by the barrier ending the previous tile
+    pm_mbar_wait(full + buf, (it >> 1) & 1);
+    const int n0 = t * tn, n1 = min(n, n0 + tn);
+    const float* tphi = sphi[buf];
+    const float* tv = sv[buf];
+    for (int cb = 0; cb < ncb; ++cb) {
+      const int cc = cb * 64 + lane * 2;
+      float wr[3][2][RT + 1];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int tt = 0; tt < 2; ++tt) {
+#pragma unroll
+          for (int q = 0; q < RT; ++q) wr[a][tt][q] = q < r ? __ldg(wf + (a * f + cc + tt) * r + q) : 0.f;
+          wr[a][tt][RT] = __ldg(bf + a * f + cc + tt);
+        }
+      for (int i = n0 + warp; i < n1; i += TWPB) {
+        const int lo = rowptr[i], hi = rowptr[i + 1];
+        float as[2] = {0.f, 0.f}, av[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+        for (int p = lo; p < hi; ++p) {
+          const int j = nbr[p];
+          const int e = perm ? perm[p] : p;
+          const float4* ep = reinterpret_cast<const float4*>(epack + (int64_t)e * EPK);
+          const float4 e0 = __ldg(ep), e1 = __ldg(ep + 1), e2 = __ldg(ep + 2);
+          const float rb[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+          const float fce = e2.x, d[3] = {e2.y, e2.z, e2.w};
+          float pv[3][2], vv[3][2];
+          if (j >= n0 && j < n1) {          // warp-uniform: the common case, rows already on chip
+            const float* ph = tphi + (size_t)(j - n0) * f3 + cc;
+            const float* vj = tv + (size_t)(j - n0) * f3 + cc;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+              const float2 x2 = *reinterpret_cast<const float2*>(ph + a * f), y2 = *reinterpret_cast<const float2*>(vj + a * f);
+              pv[a][0] = x2.x; pv[a][1] = x2.y; vv[a][0] = y2.x; vv[a][1] = y2.y;
+            }
+          } else {
+            const float* ph = phi + (int64_t)j * f3 + cc;
+            const float* vj = v + (int64_t)j * f3 + cc;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { ChanVec<2>::ld(ph + a * f, pv[a]); ChanVec<2>::ld(vj + a * f, vv[a]); }
+          }
+          float ef[3][2];
+          if (HAS_EF) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) ChanVec<2>::ld(efilt + (int64_t)e * f3 + a * f + cc, ef[a]);
+          }
+#pragma unroll
+          for (int tt = 0; tt < 2; ++tt) {
+            float w[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+              float acc = wr[a][tt][RT] * fce;
+#pragma unroll
+              for (int q = 0; q < RT; ++q) acc = fmaf(wr[a][tt][q], rb[q], acc);
+              w[a] = HAS_EF ? acc * ef[a][tt] : acc;
+            }
+            const float gv = w[0] * pv[0][tt], ge = w[1] * pv[1][tt];
+            as[tt] = fmaf(w[2], pv[2][tt], as[tt]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) av[k][tt] += vv[k][tt] * gv + ge * d[k];
+          }
+        }
+        // residual: the node's own rows are in the tile as well
+        float so[2], tmp[2];
+        ChanVec<2>::ld(s + (int64_t)i * f + cc, so);
+        so[0] += as[0]; so[1] += as[1];
+        ChanVec<2>::st(s_out + (int64_t)i * f + cc, so);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float2 own = *reinterpret_cast<const float2*>(tv + (size_t)(i - n0) * f3 + k * f + cc);
+          tmp[0] = own.x + av[k][0]; tmp[1] = own.y + av[k][1];
+          ChanVec<2>::st(v_out + (int64_t)i * f3 + k * f + cc, tmp);
+        }
+      }
+    }
+    __syncthreads();   // everyone is done with buffer `buf` before it is refilled
+  }
+}
+
 static int painn_group(int f) { int g = 32; if (f < 32) { g = 1; while (g < f) g <<= 1; } return g; }
 static int painn_cpl(int f) { return (f >= 64 && f % 2 == 0) ? 2 : 1; }
 
@@ -130,9 +275,31 @@ extern "C" int hgb_painn_message_fwd(const float* phi, const float* s, const flo
   HGB_REQUIRE(n >= 0 && f > 0 && r > 0 && r <= RMAX, "painn_message_fwd: need 0 < num_radial <= %d (got %d)", RMAX, r);
   HGB_REQUIRE(phi && s && v && rowptr && nbr && epack && wf && bf && s_out && v_out, "painn_message_fwd: null pointer");
   if (n == 0) return HGB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (f % 64 == 0 && f <= 256 && n >= 256 && ((uintptr_t)phi % 16 == 0) && ((uintptr_t)v % 16 == 0)) {
+    // tiled path: two double-buffered [tn x 3f] fp32 tiles
+    int tn = (int)((100 * 1024) / ((size_t)4 * 3 * f * 4));   // two blocks per SM
+    if (tn > 32) tn = 32;
+    const size_t smem = (size_t)4 * tn * 3 * f * 4 + 64;
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(painn_message_fwd_tiled_kernel<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(painn_message_fwd_tiled_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(painn_message_fwd_tiled_kernel<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(painn_message_fwd_tiled_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      attr_done = true;
+    }
+    const int ntiles = (n + tn - 1) / tn;
+    const int g1 = ntiles < 2 * HGB_NUM_SMS ? ntiles : 2 * HGB_NUM_SMS;
+#define LAUNCH_T(E, R) painn_message_fwd_tiled_kernel<E, R><<<g1, TWPB * 32, smem, st>>>(phi, s, v, rowptr, perm, nbr, epack, wf, bf, efilt, n, f, r, tn, s_out, v_out)
+    if (efilt) { if (r <= 5) LAUNCH_T(true, 5); else LAUNCH_T(true, 8); }
+    else { if (r <= 5) LAUNCH_T(false, 5); else LAUNCH_T(false, 8); }
+#undef LAUNCH_T
+    HGB_LAUNCH_CHECK("painn_message_fwd_tiled");
+    return HGB_OK;
+  }
   const int cpl = painn_cpl(f), group = painn_group(f);
   dim3 grid(hgb_grid_for(n, WPB * (32 / group), HGB_NUM_SMS * 8), (f + group * cpl - 1) / (group * cpl));
-  cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(C, E, G, R) painn_message_fwd_kernel<C, E, G, R><<<grid, WPB * 32, 0, st>>>(phi, s, v, rowptr, perm, nbr, epack, wf, bf, efilt, n, f, r, s_out, v_out)
 #define LAUNCH_R(C, E, G) do { if (r <= 5) LAUNCH(C, E, G, 5); else LAUNCH(C, E, G, 8); } while (0)
 #define LAUNCH_G(E)                                                        \

@@ -353,6 +353,41 @@ def test_painn_message_vs_oracle(f, edge_dim):
     torch.testing.assert_close(v2.cpu(), vo, rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("f,n", [(64, 3000), (128, 700)])
+def test_painn_message_tiled_path_vs_oracle(f, n):
+    """n >= 256 and F % 64 == 0 selects the shared-memory-tiled kernels: mostly-local edges (on-chip gathers) plus
+    some long-range ones (global fallback), in a non-sorted edge order."""
+    g = gen(300 + f)
+    torch.manual_seed(f)
+    pos = torch.randn(n, 3, generator=g) * 2
+    src = torch.arange(n).repeat_interleave(6)
+    dst = (src + torch.randint(-8, 9, (src.numel(),), generator=g)).clamp(0, n - 1)
+    far = torch.randint(0, n, (2, n // 2), generator=g)
+    ei = torch.cat([torch.stack([dst, src]), far], dim=1)
+    ei = ei[:, ei[0] != ei[1]]
+    ei = ei[:, torch.randperm(ei.shape[1], generator=g)]
+    msg_o = oracle.painn.PainnMessage(f, 5, 7.0, None)
+    from hydragnn_b200.stacks import PainnMessage
+    msg_e = PainnMessage(f, 5, 7.0, None).to(DEV)
+    msg_e.load_state_dict(msg_o.state_dict())
+    s, v = torch.randn(n, f, generator=g), torch.randn(n, 3, f, generator=g)
+    plan = ops.EdgePlan(ei.to(DEV), n)
+    pr, sr, vr = pos.clone().requires_grad_(True), s.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    diff, dist = oracle.geometry.edge_vectors_and_lengths(pr, ei, None, normalize=True)
+    so, vo = msg_o(sr, vr, ei.t(), diff, dist, None)
+    pe, se, ve = pos.to(DEV).requires_grad_(True), s.to(DEV).requires_grad_(True), v.to(DEV).requires_grad_(True)
+    _, ln, unit = ops.EdgeGeomFn.apply(pe, None, plan, 1e-9)
+    epack = ops.PainnEdgeEmbedFn.apply(unit, ln, 5, 7.0)
+    s1, v1 = msg_e(se, ve, plan, {"epack": epack}, None)
+    torch.testing.assert_close(s1.cpu(), so, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(v1.cpu(), vo, rtol=1e-4, atol=1e-5)
+    ws, wv = torch.randn(so.shape, generator=g), torch.randn(vo.shape, generator=g)
+    gr = torch.autograd.grad((so * ws).sum() + (vo * wv).sum(), [pr, sr, vr] + list(msg_o.parameters()))
+    ge = torch.autograd.grad((s1 * ws.to(DEV)).sum() + (v1 * wv.to(DEV)).sum(), [pe, se, ve] + list(msg_e.parameters()))
+    for a, b in zip(ge, gr):
+        torch.testing.assert_close(a.cpu(), b, rtol=5e-4, atol=5e-4)
+
+
 @pytest.mark.parametrize("f,last", [(1, False), (6, False), (64, False), (64, True), (7, True)])
 def test_painn_update_vs_oracle(f, last):
     g = gen(200 + f)
