@@ -344,6 +344,7 @@ def painn_message_roofline(m, d, ops, dev):
     with torch.no_grad():
         _, ln, unit = ops.EdgeGeomFn.apply(d.pos.detach(), None, plan, 1e-9)
         epack = ops.PainnEdgeEmbedFn.apply(unit, ln, r, m.radius)
+        rec = ops.painn_edge_records(epack, plan, "row")
         s = torch.randn(n, f, device=dev)
         v = torch.randn(n, 3, f, device=dev)
         phi = torch.randn(n, 3 * f, device=dev)
@@ -354,7 +355,7 @@ def painn_message_roofline(m, d, ops, dev):
             flush.zero_()
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0.record()
-            ops.PainnMessageFn.apply(phi, s, v, epack, msg.filter_layer.weight, msg.filter_layer.bias, None, plan)
+            ops.PainnMessageFn.apply(phi, s, v, epack, msg.filter_layer.weight, msg.filter_layer.bias, None, plan, rec)
             t1.record()
             torch.cuda.synchronize()
             if it >= 3:

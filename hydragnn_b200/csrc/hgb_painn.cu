@@ -120,6 +120,31 @@ painn_message_fwd_kernel(const float* __restrict__ phi, const float* __restrict_
   }
 }
 
+// ---- CSR-ordered edge records ---------------------------------------------------------------------------------
+// rec [E,16] (64 B, slot p of a CSR view): { epack[perm[p]] (12 floats), neighbour node (int bits), edge id (int bits),
+// 0, 0 }.  A node's records are contiguous, carry the gather index themselves and are read with four broadcast 16-byte
+// loads: no index -> index -> payload dependency chain is left in the message kernels.
+#define REC 16
+__global__ void painn_edge_records_kernel(const float* __restrict__ epack, const int32_t* __restrict__ perm,
+                                          const int32_t* __restrict__ nbr, int64_t e, float* __restrict__ rec) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < e; p += (int64_t)gridDim.x * blockDim.x) {
+    const int ed = perm ? perm[p] : (int)p;
+    const float4* src = reinterpret_cast<const float4*>(epack + (int64_t)ed * EPK);
+    float4* dst = reinterpret_cast<float4*>(rec + p * REC);
+    dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2);
+    dst[3] = make_float4(__int_as_float(nbr[p]), __int_as_float(ed), 0.f, 0.f);
+  }
+}
+
+extern "C" int hgb_painn_edge_records(const float* epack, const int32_t* perm, const int32_t* nbr, int64_t e, float* rec,
+                                      hgb_stream_t stream) {
+  if (e == 0) return HGB_OK;
+  HGB_REQUIRE(epack && nbr && rec, "painn_edge_records: null pointer");
+  painn_edge_records_kernel<<<hgb_grid_for(e, 256), 256, 0, (cudaStream_t)stream>>>(epack, perm, nbr, e, rec);
+  HGB_LAUNCH_CHECK("painn_edge_records");
+  return HGB_OK;
+}
+
 // ---- tiled variant (F % 64 == 0): the block stages the phi / v rows of a tile of TN consecutive nodes in shared
 // memory with two bulk async copies (cp.async.bulk, mbarrier-completed, double buffered) and the warps then gather
 // neighbour rows from shared memory.  Batched molecular graphs keep all neighbours of a node within a few rows of
@@ -151,12 +176,11 @@ __device__ __forceinline__ void pm_bulk_g2s(void* dst, const void* src, uint32_t
                : "memory");
 }
 
-#define TWPB 16   // warps per block in the tiled kernels (2 blocks / SM -> 32 warps hide the index / edge-record loads)
+#define TWPB 12   // warps per block in the tiled kernels: 2 blocks / SM -> 24 warps at <= 85 registers (no spills)
 template <bool HAS_EF, int RT>
 __global__ void __launch_bounds__(TWPB * 32, 2)
 painn_message_fwd_tiled_kernel(const float* __restrict__ phi, const float* __restrict__ s, const float* __restrict__ v,
-                               const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm,
-                               const int32_t* __restrict__ nbr, const float* __restrict__ epack, const float* __restrict__ wf,
+                               const int32_t* __restrict__ rowptr, const float* __restrict__ rec, const float* __restrict__ wf,
                                const float* __restrict__ bf, const float* __restrict__ efilt, int n, int f, int r, int tn,
                                float* __restrict__ s_out, float* __restrict__ v_out) {
   extern __shared__ __align__(128) uint8_t pm_smem[];
@@ -206,12 +230,13 @@ painn_message_fwd_tiled_kernel(const float* __restrict__ phi, const float* __res
         const int lo = rowptr[i], hi = rowptr[i + 1];
         float as[2] = {0.f, 0.f}, av[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
         for (int p = lo; p < hi; ++p) {
-          const int j = nbr[p];
-          const int e = perm ? perm[p] : p;
-          const float4* ep = reinterpret_cast<const float4*>(epack + (int64_t)e * EPK);
-          const float4 e0 = __ldg(ep), e1 = __ldg(ep + 1), e2 = __ldg(ep + 2);
+          const float4* ep = reinterpret_cast<const float4*>(rec + (int64_t)p * REC);
+          const float4 e0 = __ldg(ep), e1 = __ldg(ep + 1), e2 = __ldg(ep + 2), e3 = __ldg(ep + 3);
           const float rb[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
           const float fce = e2.x, d[3] = {e2.y, e2.z, e2.w};
+          const int j = __float_as_int(e3.x);
+          const int e = __float_as_int(e3.y);
+          (void)e;
           float pv[3][2], vv[3][2];
           if (j >= n0 && j < n1) {          // warp-uniform: the common case, rows already on chip
             const float* ph = tphi + (size_t)(j - n0) * f3 + cc;
@@ -269,17 +294,19 @@ static int painn_group(int f) { int g = 32; if (f < 32) { g = 1; while (g < f) g
 static int painn_cpl(int f) { return (f >= 64 && f % 2 == 0) ? 2 : 1; }
 
 extern "C" int hgb_painn_message_fwd(const float* phi, const float* s, const float* v, const int32_t* rowptr,
-                                     const int32_t* perm, const int32_t* nbr, const float* epack, const float* wf, const float* bf,
-                                     const float* efilt, int32_t n, int32_t f, int32_t r, float* s_out, float* v_out,
+                                     const int32_t* perm, const int32_t* nbr, const float* epack, const float* rec, const float* wf,
+                                     const float* bf, const float* efilt, int32_t n, int32_t f, int32_t r, float* s_out, float* v_out,
                                      hgb_stream_t stream) {
   HGB_REQUIRE(n >= 0 && f > 0 && r > 0 && r <= RMAX, "painn_message_fwd: need 0 < num_radial <= %d (got %d)", RMAX, r);
   HGB_REQUIRE(phi && s && v && rowptr && nbr && epack && wf && bf && s_out && v_out, "painn_message_fwd: null pointer");
   if (n == 0) return HGB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (f % 64 == 0 && f <= 256 && n >= 256 && ((uintptr_t)phi % 16 == 0) && ((uintptr_t)v % 16 == 0)) {
+  if (rec && f % 64 == 0 && f <= 256 && n >= 256 && ((uintptr_t)phi % 16 == 0) && ((uintptr_t)v % 16 == 0)) {
     // tiled path: two double-buffered [tn x 3f] fp32 tiles
-    int tn = (int)((100 * 1024) / ((size_t)4 * 3 * f * 4));   // two blocks per SM
-    if (tn > 32) tn = 32;
+    int tn = (int)((110 * 1024) / ((size_t)4 * 3 * f * 4));   // two blocks per SM
+    tn = (tn / TWPB) * TWPB;                                   // whole nodes per warp
+    if (tn > 3 * TWPB) tn = 3 * TWPB;
+    if (tn < TWPB) tn = TWPB;
     const size_t smem = (size_t)4 * tn * 3 * f * 4 + 64;
     static bool attr_done = false;
     if (!attr_done) {
@@ -291,7 +318,7 @@ extern "C" int hgb_painn_message_fwd(const float* phi, const float* s, const flo
     }
     const int ntiles = (n + tn - 1) / tn;
     const int g1 = ntiles < 2 * HGB_NUM_SMS ? ntiles : 2 * HGB_NUM_SMS;
-#define LAUNCH_T(E, R) painn_message_fwd_tiled_kernel<E, R><<<g1, TWPB * 32, smem, st>>>(phi, s, v, rowptr, perm, nbr, epack, wf, bf, efilt, n, f, r, tn, s_out, v_out)
+#define LAUNCH_T(E, R) painn_message_fwd_tiled_kernel<E, R><<<g1, TWPB * 32, smem, st>>>(phi, s, v, rowptr, rec, wf, bf, efilt, n, f, r, tn, s_out, v_out)
     if (efilt) { if (r <= 5) LAUNCH_T(true, 5); else LAUNCH_T(true, 8); }
     else { if (r <= 5) LAUNCH_T(false, 5); else LAUNCH_T(false, 8); }
 #undef LAUNCH_T
@@ -478,6 +505,192 @@ painn_message_bwd_kernel(const float* __restrict__ gs_out, const float* __restri
       }
 }
 
+// ---- tiled backward (F % 64 == 0): the incoming gradients gs_out / gv_out of a tile of consecutive nodes are staged in
+// shared memory (bulk async copies, double buffered); the warp that owns source node j gathers the gradient rows of the
+// nodes it sent messages to from shared memory.  rec is the by-col CSR record array (neighbour = aggregating node).
+template <bool HAS_EF, bool NEED_EDGE, int RT>
+__global__ void __launch_bounds__(WPB * 32, 2)
+painn_message_bwd_tiled_kernel(const float* __restrict__ gs_out, const float* __restrict__ gv_out, const float* __restrict__ phi,
+                               const float* __restrict__ v, const int32_t* __restrict__ rowptr, const float* __restrict__ rec,
+                               const float* __restrict__ wf, const float* __restrict__ bf, const float* __restrict__ efilt, int n,
+                               int f, int r, int tn, float* __restrict__ gphi, float* __restrict__ gv, float* __restrict__ part,
+                               float* __restrict__ g_epack, float* __restrict__ g_efilt, int multi_cb) {
+  extern __shared__ __align__(128) uint8_t pm_smem[];
+  const int f3 = 3 * f;
+  const uint32_t gs_bytes = (uint32_t)tn * f * 4, gv_bytes = (uint32_t)tn * f3 * 4;
+  float* sgs[2] = {reinterpret_cast<float*>(pm_smem), reinterpret_cast<float*>(pm_smem + (size_t)gs_bytes + gv_bytes)};
+  float* sgv[2] = {reinterpret_cast<float*>(pm_smem + gs_bytes), reinterpret_cast<float*>(pm_smem + 2 * (size_t)gs_bytes + gv_bytes)};
+  uint64_t* full = reinterpret_cast<uint64_t*>(pm_smem + 2 * ((size_t)gs_bytes + gv_bytes));
+  float* red = reinterpret_cast<float*>(full + 2);   // [WPB * 32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ntiles = (n + tn - 1) / tn;
+  if (threadIdx.x == 0) {
+    pm_mbar_init(full, 1);
+    pm_mbar_init(full + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int t, int buf) {
+    const int n0 = t * tn;
+    const uint32_t rows = (uint32_t)(min(n, n0 + tn) - n0);
+    pm_mbar_expect_tx(full + buf, rows * (uint32_t)(f + f3) * 4);
+    pm_bulk_g2s(sgs[buf], gs_out + (int64_t)n0 * f, rows * f * 4, full + buf);
+    pm_bulk_g2s(sgv[buf], gv_out + (int64_t)n0 * f3, rows * f3 * 4, full + buf);
+  };
+  if (threadIdx.x == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  const int cb = blockIdx.y;                 // 64-channel block
+  const int cc = cb * 64 + lane * 2;
+  float wr[3][2][RT + 1], gw[3][2][RT + 1];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+#pragma unroll
+      for (int q = 0; q < RT; ++q) { wr[a][t][q] = q < r ? wf[(a * f + cc + t) * r + q] : 0.f; gw[a][t][q] = 0.f; }
+      wr[a][t][RT] = bf[a * f + cc + t];
+      gw[a][t][RT] = 0.f;
+    }
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int tnext = tile + gridDim.x;
+    if (threadIdx.x == 0 && tnext < ntiles) issue(tnext, buf ^ 1);
+    pm_mbar_wait(full + buf, (it >> 1) & 1);
+    const int n0 = tile * tn, n1 = min(n, n0 + tn);
+    const float* tgs = sgs[buf];
+    const float* tgv = sgv[buf];
+    for (int j = n0 + warp; j < n1; j += WPB) {
+      const int lo = rowptr[j], hi = rowptr[j + 1];
+      float ph[3][2], vj[3][2], aphi[3][2], agv[3][2];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        ChanVec<2>::ld(phi + (int64_t)j * f3 + a * f + cc, ph[a]);
+        ChanVec<2>::ld(v + (int64_t)j * f3 + a * f + cc, vj[a]);
+        aphi[a][0] = aphi[a][1] = 0.f; agv[a][0] = agv[a][1] = 0.f;
+      }
+      for (int p = lo; p < hi; ++p) {
+        const float4* ep = reinterpret_cast<const float4*>(rec + (int64_t)p * REC);
+        const float4 e0 = __ldg(ep), e1 = __ldg(ep + 1), e2 = __ldg(ep + 2), e3 = __ldg(ep + 3);
+        const float rb[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+        const float fce = e2.x, d[3] = {e2.y, e2.z, e2.w};
+        const int i = __float_as_int(e3.x);
+        const int e = __float_as_int(e3.y);
+        float gsi[2], gvi[3][2];
+        if (i >= n0 && i < n1) {
+          const float2 g2 = *reinterpret_cast<const float2*>(tgs + (size_t)(i - n0) * f + cc);
+          gsi[0] = g2.x; gsi[1] = g2.y;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const float2 h2 = *reinterpret_cast<const float2*>(tgv + (size_t)(i - n0) * f3 + k * f + cc);
+            gvi[k][0] = h2.x; gvi[k][1] = h2.y;
+          }
+        } else {
+          ChanVec<2>::ld(gs_out + (int64_t)i * f + cc, gsi);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) ChanVec<2>::ld(gv_out + (int64_t)i * f3 + k * f + cc, gvi[k]);
+        }
+        float ef[3][2];
+        if (HAS_EF) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) ChanVec<2>::ld(efilt + (int64_t)e * f3 + a * f + cc, ef[a]);
+        }
+        float e_rb[RT], e_fc = 0.f, e_d[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < RT; ++q) e_rb[q] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          float w[3], gg[3];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            float acc = wr[a][t][RT] * fce;
+#pragma unroll
+            for (int q = 0; q < RT; ++q) acc = fmaf(wr[a][t][q], rb[q], acc);
+            w[a] = acc;
+          }
+          const float g0 = gvi[0][t], g1 = gvi[1][t], g2 = gvi[2][t];
+          gg[0] = g0 * vj[0][t] + g1 * vj[1][t] + g2 * vj[2][t];
+          gg[1] = g0 * d[0] + g1 * d[1] + g2 * d[2];
+          gg[2] = gsi[t];
+          const float efv[3] = {HAS_EF ? ef[0][t] : 1.f, HAS_EF ? ef[1][t] : 1.f, HAS_EF ? ef[2][t] : 1.f};
+          const float gate_v = w[0] * efv[0] * ph[0][t];
+          agv[0][t] = fmaf(g0, gate_v, agv[0][t]); agv[1][t] = fmaf(g1, gate_v, agv[1][t]); agv[2][t] = fmaf(g2, gate_v, agv[2][t]);
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            aphi[a][t] = fmaf(gg[a], w[a] * efv[a], aphi[a][t]);
+            const float gwe = gg[a] * ph[a][t];
+            if (HAS_EF) g_efilt[(int64_t)e * f3 + a * f + cc + t] = gwe * w[a];
+            const float gW = gwe * efv[a];
+#pragma unroll
+            for (int q = 0; q < RT; ++q) gw[a][t][q] = fmaf(gW, rb[q], gw[a][t][q]);
+            gw[a][t][RT] = fmaf(gW, fce, gw[a][t][RT]);
+            if (NEED_EDGE) {
+#pragma unroll
+              for (int q = 0; q < RT; ++q) e_rb[q] = fmaf(gW, wr[a][t][q], e_rb[q]);
+              e_fc = fmaf(gW, wr[a][t][RT], e_fc);
+            }
+          }
+          if (NEED_EDGE) {
+            const float ge = w[1] * efv[1] * ph[1][t];
+            e_d[0] = fmaf(g0, ge, e_d[0]); e_d[1] = fmaf(g1, ge, e_d[1]); e_d[2] = fmaf(g2, ge, e_d[2]);
+          }
+        }
+        if (NEED_EDGE) {
+#pragma unroll
+          for (int q = 0; q < RT; ++q) e_rb[q] = hgb_warp_sum(e_rb[q]);
+          e_fc = hgb_warp_sum(e_fc);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) e_d[k] = hgb_warp_sum(e_d[k]);
+          if (lane == 0) {
+            float* ge = g_epack + (int64_t)e * EPK;
+            if (multi_cb) {
+#pragma unroll
+              for (int q = 0; q < RT; ++q) atomicAdd(ge + q, e_rb[q]);
+              atomicAdd(ge + 8, e_fc);
+#pragma unroll
+              for (int k = 0; k < 3; ++k) atomicAdd(ge + 9 + k, e_d[k]);
+            } else {
+              float o[EPK];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) o[q] = q < RT ? e_rb[q < RT ? q : 0] : 0.f;
+              o[8] = e_fc; o[9] = e_d[0]; o[10] = e_d[1]; o[11] = e_d[2];
+              float4* gp = reinterpret_cast<float4*>(ge);
+              gp[0] = make_float4(o[0], o[1], o[2], o[3]); gp[1] = make_float4(o[4], o[5], o[6], o[7]); gp[2] = make_float4(o[8], o[9], o[10], o[11]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        ChanVec<2>::st(gphi + (int64_t)j * f3 + a * f + cc, aphi[a]);
+        const float2 own = *reinterpret_cast<const float2*>(tgv + (size_t)(j - n0) * f3 + a * f + cc);
+        float tmp[2] = {own.x + agv[a][0], own.y + agv[a][1]};
+        ChanVec<2>::st(gv + (int64_t)j * f3 + a * f + cc, tmp);
+      }
+    }
+    __syncthreads();
+  }
+  // block-level reduction of the filter-weight gradients -> part[blockIdx.x]
+  float* mypart = part + (int64_t)blockIdx.x * f3 * (r + 1);
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int q = 0; q <= RT; ++q) {
+        if (q < r || q == RT) {
+          __syncthreads();
+          red[warp * 32 + lane] = gw[a][t][q];
+          __syncthreads();
+          if (warp == 0) {
+            float acc = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < WPB; ++w8) acc += red[w8 * 32 + lane];
+            mypart[(a * f + cc + t) * (r + 1) + (q == RT ? r : q)] = acc;
+          }
+        }
+      }
+}
+
 __global__ void painn_wgrad_reduce_kernel(const float* __restrict__ part, int nblocks, int f3, int r,
                                           float* __restrict__ gwf, float* __restrict__ gbf) {
   __shared__ float red[8][33];
@@ -513,7 +726,7 @@ extern "C" int64_t hgb_painn_message_bwd_workspace_bytes(int32_t n, int32_t f, i
 
 extern "C" int hgb_painn_message_bwd(const float* gs_out, const float* gv_out, const float* phi, const float* v,
                                      const int32_t* rowptr_src, const int32_t* perm_src, const int32_t* nbr_agg, const float* epack,
-                                     const float* wf, const float* bf, const float* efilt, int32_t n, int32_t f, int32_t r,
+                                     const float* rec, const float* wf, const float* bf, const float* efilt, int32_t n, int32_t f, int32_t r,
                                      float* gphi, float* gv, float* gwf, float* gbf, float* g_epack, float* g_efilt, void* workspace,
                                      int64_t workspace_bytes, hgb_stream_t stream) {
   HGB_REQUIRE(n >= 0 && f > 0 && r > 0 && r <= RMAX, "painn_message_bwd: need 0 < num_radial <= %d (got %d)", RMAX, r);
@@ -529,10 +742,38 @@ extern "C" int hgb_painn_message_bwd(const float* gs_out, const float* gv_out, c
     cudaMemsetAsync(gbf, 0, (size_t)f3 * 4, st);
     return HGB_OK;
   }
+  float* part = (float*)workspace;
+  if (rec && f % 64 == 0 && f <= 256 && n >= 256 && ((uintptr_t)gs_out % 16 == 0) && ((uintptr_t)gv_out % 16 == 0)) {
+    const int tn = 32;
+    const size_t smem = (size_t)2 * tn * 4 * f * 4 + 16 + WPB * 32 * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+#define SETA(E, G, R) cudaFuncSetAttribute(painn_message_bwd_tiled_kernel<E, G, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+      SETA(false, false, 5); SETA(false, true, 5); SETA(true, false, 5); SETA(true, true, 5);
+      SETA(false, false, 8); SETA(false, true, 8); SETA(true, false, 8); SETA(true, true, 8);
+#undef SETA
+      attr_done = true;
+    }
+    const int ntiles = (n + tn - 1) / tn;
+    int gx = painn_bwd_grid(n, f);            // the workspace is sized for this many partials
+    if (gx > ntiles) gx = ntiles;
+    if (gx > 2 * HGB_NUM_SMS) gx = 2 * HGB_NUM_SMS;
+    const int ncb2 = f / 64;
+    dim3 grid2(gx, ncb2);
+#define LAUNCH_T(E, G, R) painn_message_bwd_tiled_kernel<E, G, R><<<grid2, WPB * 32, smem, st>>>(gs_out, gv_out, phi, v, rowptr_src, rec, wf, bf, efilt, n, f, r, tn, gphi, gv, part, g_epack, g_efilt, ncb2 > 1)
+#define LAUNCH_TR(E, G) do { if (r <= 5) LAUNCH_T(E, G, 5); else LAUNCH_T(E, G, 8); } while (0)
+    if (efilt) { if (need_edge) LAUNCH_TR(true, true); else LAUNCH_TR(true, false); }
+    else { if (need_edge) LAUNCH_TR(false, true); else LAUNCH_TR(false, false); }
+#undef LAUNCH_TR
+#undef LAUNCH_T
+    HGB_LAUNCH_CHECK("painn_message_bwd_tiled");
+    painn_wgrad_reduce_kernel<<<(f3 * (r + 1) + 31) / 32, dim3(32, 8), 0, st>>>(part, gx, f3, r, gwf, gbf);
+    HGB_LAUNCH_CHECK("painn_wgrad_reduce");
+    return HGB_OK;
+  }
   const int cpl = painn_cpl(f), group = painn_group(f);
   const int ncb = (f + group * cpl - 1) / (group * cpl);
   dim3 grid(painn_bwd_grid(n, f), ncb);
-  float* part = (float*)workspace;
 #define LAUNCH(C, E, G, W, R) painn_message_bwd_kernel<C, E, G, W, R><<<grid, WPB * 32, 0, st>>>(gs_out, gv_out, phi, v, rowptr_src, perm_src, nbr_agg, epack, wf, bf, efilt, n, f, r, gphi, gv, part, g_epack, g_efilt, ncb > 1)
 #define LAUNCH_R(C, E, G, W) do { if (r <= 5) LAUNCH(C, E, G, W, 5); else LAUNCH(C, E, G, W, 8); } while (0)
 #define LAUNCH_G(E, G)                                                           \

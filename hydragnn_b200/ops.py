@@ -450,16 +450,16 @@ class PainnMessageFn(torch.autograd.Function):
     """Fused PaiNN message (hydragnn/models/PAINNStack.py:239-270): returns (s + ds, v + dv)."""
 
     @staticmethod
-    def forward(ctx, phi, s, v, epack, wf, bf, efilt, plan):
+    def forward(ctx, phi, s, v, epack, wf, bf, efilt, plan, rec_row=None):
         n, f = s.shape
         r = wf.shape[1]
         phi, s, v = _chk(phi), _chk(s), _chk(v)
         s_out, v_out = torch.empty_like(s), torch.empty_like(v)
         agg = plan.by_row     # messages are summed into edge[:,0] = edge_index[0]
         _lib.call("hgb_painn_message_fwd", _p(phi), _p(s), _p(v), _p(agg.rowptr), _p(agg.perm), _p(plan.nbr("row")), _p(epack),
-                  _p(_chk(wf)), _p(_chk(bf)), _p(_chk(efilt)), n, f, r, _p(s_out), _p(v_out), _stream())
+                  _p(rec_row), _p(_chk(wf)), _p(_chk(bf)), _p(_chk(efilt)), n, f, r, _p(s_out), _p(v_out), _stream())
         ctx.save_for_backward(phi, v, epack, wf, bf, efilt)
-        ctx.plan = plan
+        ctx.plan, ctx.use_rec = plan, rec_row is not None
         return s_out, v_out
 
     @staticmethod
@@ -480,10 +480,26 @@ class PainnMessageFn(torch.autograd.Function):
         nbytes = _lib.query("hgb_painn_message_bwd_workspace_bytes", n, f, r)
         ws = _ws(nbytes, phi.device)
         src = plan.by_col     # the gather side: edge[:,1] = edge_index[1]
+        rec_col = None
+        if ctx.use_rec:       # by-col records: built once per batch (cached on the plan, keyed by the epack buffer)
+            cache = plan.__dict__.setdefault("_rec_col", {})
+            key = epack.data_ptr()
+            if key not in cache:
+                cache.clear()
+                cache[key] = painn_edge_records(epack, plan, "col")
+            rec_col = cache[key]
         _lib.call("hgb_painn_message_bwd", _p(gs_out), _p(gv_out), _p(phi), _p(v), _p(src.rowptr), _p(src.perm), _p(plan.nbr("col")),
-                  _p(epack), _p(wf), _p(bf), _p(efilt), n, f, r, _p(gphi), _p(gv), _p(gwf), _p(gbf), _p(g_epack), _p(g_ef),
+                  _p(epack), _p(rec_col), _p(wf), _p(bf), _p(efilt), n, f, r, _p(gphi), _p(gv), _p(gwf), _p(gbf), _p(g_epack), _p(g_ef),
                   _p(ws), nbytes, _stream())
-        return gphi, gs_out, gv, g_epack, gwf, gbf, g_ef, None
+        return gphi, gs_out, gv, g_epack, gwf, gbf, g_ef, None, None
+
+
+def painn_edge_records(epack, plan, which):
+    """CSR-ordered 64-byte edge records for the tiled message kernels (built once per batch, shared by all layers)."""
+    csr = plan.by_row if which == "row" else plan.by_col
+    rec = torch.empty(plan.num_edges, 16, dtype=epack.dtype, device=epack.device)
+    _lib.call("hgb_painn_edge_records", _p(epack.detach()), _p(csr.perm), _p(plan.nbr(which)), plan.num_edges, _p(rec), _stream())
+    return rec
 
 
 def raw_linear(x2, w, b, code=0, param=0.0, want_z=False):

@@ -177,7 +177,10 @@ class PainnMessage(nn.Module):
             return s + SegmentSum.apply(m_s, plan.by_row), v + SegmentSum.apply(m_v, plan.by_row)
         phi = run_mlp(self.scalar_message_mlp, s)
         efilt = run_mlp(self.edge_filter, edge_attr) if edge_attr is not None else None
-        return ops.PainnMessageFn.apply(phi, s, v, geom["epack"], self.filter_layer.weight, self.filter_layer.bias, efilt, plan)
+        if "rec_row" not in geom and self.node_size % 64 == 0:      # built once per batch, reused by every layer
+            geom["rec_row"] = ops.painn_edge_records(geom["epack"], plan, "row")
+        return ops.PainnMessageFn.apply(phi, s, v, geom["epack"], self.filter_layer.weight, self.filter_layer.bias, efilt, plan,
+                                        geom.get("rec_row"))
 
 
 class PainnUpdate(nn.Module):

@@ -228,17 +228,23 @@ int hgb_painn_edge_embed_bwd(const float* unit, const float* len, const float* g
  * atomics, summation in ascending edge id.  Algorithmic bytes: E*(6F*4 + 8 + 48) + N*(8F*4 + 4).
  * phi [n,3f], s [n,f], v [n,3,f], wf [3f,r], bf [3f], efilt [e,3f] or NULL.                                 */
 int hgb_painn_message_fwd(const float* phi, const float* s, const float* v, const int32_t* rowptr,
-                          const int32_t* perm, const int32_t* nbr, const float* epack, const float* wf,
-                          const float* bf, const float* efilt, int32_t n, int32_t f, int32_t r, float* s_out,
-                          float* v_out, hgb_stream_t stream);
+                          const int32_t* perm, const int32_t* nbr, const float* epack, const float* rec,
+                          const float* wf, const float* bf, const float* efilt, int32_t n, int32_t f, int32_t r,
+                          float* s_out, float* v_out, hgb_stream_t stream);
+/* CSR-ordered 64-byte edge records rec [e,16] = { epack[perm[p]] (12), nbr[p] (int bits), perm[p] (int bits), 0, 0 }:
+ * a node's records are contiguous and carry the gather index.  When `rec` is passed to hgb_painn_message_fwd and
+ * f % 64 == 0, the shared-memory-tiled kernel is used: the phi / v rows of 32 consecutive nodes are staged with
+ * cp.async.bulk (double buffered) and neighbour rows are gathered from shared memory.                          */
+int hgb_painn_edge_records(const float* epack, const int32_t* perm, const int32_t* nbr, int64_t e, float* rec,
+                           hgb_stream_t stream);
 /* Backward of the fused message, as a segmented reduction over the CSR of edge[:,1] (the gather side);
  * nbr_agg [e] = edge[:,0] of every slot of that CSR.  gs_out [n,f], gv_out [n,3,f] are the incoming gradients.
  * Outputs: gphi [n,3f]; gv [n,3,f] (= gv_out + gathered part; gs_in == gs_out is the caller's); gwf [3f,r],
  * gbf [3f] (via workspace partials); optional g_epack [e,12] (zero-initialised by the caller when f > 64) and
- * g_efilt [e,3f] (iff efilt).                                                                              */
+ * g_efilt [e,3f] (iff efilt).  `rec` (optional): by-col CSR edge records -> shared-memory-tiled kernel.       */
 int hgb_painn_message_bwd(const float* gs_out, const float* gv_out, const float* phi, const float* v,
                           const int32_t* rowptr_src, const int32_t* perm_src, const int32_t* nbr_agg,
-                          const float* epack, const float* wf, const float* bf, const float* efilt, int32_t n,
+                          const float* epack, const float* rec, const float* wf, const float* bf, const float* efilt, int32_t n,
                           int32_t f, int32_t r, float* gphi, float* gv, float* gwf, float* gbf, float* g_epack,
                           float* g_efilt, void* workspace, int64_t workspace_bytes, hgb_stream_t stream);
 int64_t hgb_painn_message_bwd_workspace_bytes(int32_t n, int32_t f, int32_t r);

@@ -33,9 +33,11 @@ epack = ops.PainnEdgeEmbedFn.apply(unit, ln, r, 7.0)
 s, v, phi = torch.randn(n, f, device=dev), torch.randn(n, 3, f, device=dev), torch.randn(n, 3 * f, device=dev)
 wf, bf = torch.randn(3 * f, r, device=dev), torch.randn(3 * f, device=dev)
 out = {}
-out["painn_message_fwd F=64 (ms)"] = timeit(lambda: ops.PainnMessageFn.apply(phi, s, v, epack, wf, bf, None, plan))
+rec = ops.painn_edge_records(epack, plan, "row")
+out["painn_message_fwd F=64 (ms)"] = timeit(lambda: ops.PainnMessageFn.apply(phi, s, v, epack, wf, bf, None, plan, rec))
+out["painn_edge_records (ms)"] = timeit(lambda: ops.painn_edge_records(epack, plan, "row"))
 sr, vr, pr = s.clone().requires_grad_(True), v.clone().requires_grad_(True), phi.clone().requires_grad_(True)
-so, vo = ops.PainnMessageFn.apply(pr, sr, vr, epack, wf.requires_grad_(True), bf.requires_grad_(True), None, plan)
+so, vo = ops.PainnMessageFn.apply(pr, sr, vr, epack, wf.requires_grad_(True), bf.requires_grad_(True), None, plan, rec)
 gs, gv = torch.randn_like(so), torch.randn_like(vo)
 out["painn_message_bwd F=64 (ms)"] = timeit(lambda: torch.autograd.grad((so, vo), (pr, sr, vr, wf, bf), (gs, gv), retain_graph=True))
 alg_f = e * (6 * f * 4 + 8 + 48) + n * (8 * f * 4 + 4)
