@@ -154,6 +154,9 @@ __device__ __forceinline__ uint32_t pm_smem_u32(const void* p) { return (uint32_
 __device__ __forceinline__ void pm_mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pm_smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void pm_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pm_smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void pm_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pm_smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -176,7 +179,19 @@ __device__ __forceinline__ void pm_bulk_g2s(void* dst, const void* src, uint32_t
                : "memory");
 }
 
-#define TWPB 12   // warps per block in the tiled kernels: 2 blocks / SM -> 24 warps at <= 85 registers (no spills)
+#define TWPB 10   // warps per block in the tiled kernels: 2 blocks / SM -> 24 warps at <= 85 registers (no spills)
+__device__ __forceinline__ void pm_cp_async16(void* smem, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void pm_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void pm_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void pm_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// lanes 0..: touch the 128-byte lines of [base, base + bytes)
+__device__ __forceinline__ void pm_prefetch_range(const void* base, int bytes, int lane) {
+  const char* b = reinterpret_cast<const char*>(base);
+  if (lane * 128 < bytes) pm_prefetch_l1(b + lane * 128);
+}
+
 template <bool HAS_EF, int RT>
 __global__ void __launch_bounds__(TWPB * 32, 2)
 painn_message_fwd_tiled_kernel(const float* __restrict__ phi, const float* __restrict__ s, const float* __restrict__ v,
@@ -189,15 +204,21 @@ painn_message_fwd_tiled_kernel(const float* __restrict__ phi, const float* __res
   float* sphi[2] = {reinterpret_cast<float*>(pm_smem), reinterpret_cast<float*>(pm_smem + 2 * (size_t)tile_bytes)};
   float* sv[2] = {reinterpret_cast<float*>(pm_smem + tile_bytes), reinterpret_cast<float*>(pm_smem + 3 * (size_t)tile_bytes)};
   uint64_t* full = reinterpret_cast<uint64_t*>(pm_smem + 4 * (size_t)tile_bytes);
+  uint64_t* empty = full + 2;
+  // per warp: 2 x (8 edge records [32 float4] + the node's s row slice [16 float4])
+  float4* scr = reinterpret_cast<float4*>(full + 4) + (threadIdx.x >> 5) * 96;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ntiles = (n + tn - 1) / tn;
+  const int ncb = f >> 6;   // 64-channel blocks
   if (threadIdx.x == 0) {
     pm_mbar_init(full, 1);
     pm_mbar_init(full + 1, 1);
+    pm_mbar_init(empty, TWPB);
+    pm_mbar_init(empty + 1, TWPB);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  auto issue = [&](int t, int buf) {   // thread 0: two bulk copies for tile t
+  auto issue = [&](int t, int buf) {   // one thread: two bulk copies for tile t
     const int n0 = t * tn;
     const uint32_t bytes = (uint32_t)(min(n, n0 + tn) - n0) * f3 * 4;
     pm_mbar_expect_tx(full + buf, 2 * bytes);
@@ -205,12 +226,41 @@ painn_message_fwd_tiled_kernel(const float* __restrict__ phi, const float* __res
     pm_bulk_g2s(sv[buf], v + (int64_t)n0 * f3, bytes, full + buf);
   };
   if (threadIdx.x == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
-  const int ncb = f >> 6;   // 64-channel blocks
+  // The warp's work sequence: nodes n0 + warp, + TWPB, ... of (tile, channel block 0), then channel block 1, ..., then the
+  // block's next tile.  While one node is processed, the records and the s row of the next one travel global -> scratch
+  // with cp.async and the row pointers of the one after that are fetched into registers.
+  const float4* rec4 = reinterpret_cast<const float4*>(rec);
+  auto succ = [&](int i, int& tile, int& cb) {
+    int in = i + TWPB;
+    if (in < min(n, tile * tn + tn)) return in;
+    if (++cb == ncb) { cb = 0; tile += (int)gridDim.x; }
+    in = tile * tn + warp;
+    return (tile < ntiles && in < min(n, tile * tn + tn)) ? in : -1;
+  };
+  auto stage = [&](int in, int cbn, int lo_n, int hi_n, float4* dst) {
+    if (lane < 4 * min(8, hi_n - lo_n)) pm_cp_async16(dst + lane, rec4 + (int64_t)lo_n * 4 + lane);
+    if (lane < 16) pm_cp_async16(dst + 32 + lane, s + (int64_t)in * f + cbn * 64 + lane * 4);
+  };
+  int lo = 0, hi = 0, sb = 0, lo_n = 0, hi_n = 0, in = -1, tile_n = blockIdx.x, cb_n = 0;
+  {
+    const int i0 = blockIdx.x * tn + warp;
+    if ((int)blockIdx.x < ntiles && i0 < min(n, (int)blockIdx.x * tn + tn)) {
+      lo = rowptr[i0]; hi = rowptr[i0 + 1];
+      stage(i0, 0, lo, hi, scr);
+      in = succ(i0, tile_n, cb_n);
+      if (in >= 0) { lo_n = rowptr[in]; hi_n = rowptr[in + 1]; }
+    }
+    pm_cp_async_commit();
+  }
   int it = 0;
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
     const int buf = it & 1;
     const int tnext = t + gridDim.x;
-    if (threadIdx.x == 0 && tnext < ntiles) issue(tnext, buf ^ 1);   // buffer buf^1 was released by the barrier ending the previous tile
+    if (warp == 0 && tnext < ntiles) {       // refill the other buffer once every warp has released it (tile it-1)
+      if (it >= 1) pm_mbar_wait(empty + (buf ^ 1), ((it - 1) >> 1) & 1);
+      if (lane == 0) issue(tnext, buf ^ 1);
+      __syncwarp();
+    }
     pm_mbar_wait(full + buf, (it >> 1) & 1);
     const int n0 = t * tn, n1 = min(n, n0 + tn);
     const float* tphi = sphi[buf];
@@ -227,11 +277,26 @@ painn_message_fwd_tiled_kernel(const float* __restrict__ phi, const float* __res
           wr[a][tt][RT] = __ldg(bf + a * f + cc + tt);
         }
       for (int i = n0 + warp; i < n1; i += TWPB) {
-        const int lo = rowptr[i], hi = rowptr[i + 1];
+        pm_cp_async_wait_all();
+        __syncwarp();
+        const float4* cur = scr + sb * 48;
+        int inn = -1, lo_nn = 0, hi_nn = 0;
+        if (in >= 0) {
+          stage(in, cb_n, lo_n, hi_n, scr + (sb ^ 1) * 48);
+          inn = succ(in, tile_n, cb_n);
+          if (inn >= 0) { lo_nn = rowptr[inn]; hi_nn = rowptr[inn + 1]; }
+        }
+        pm_cp_async_commit();
         float as[2] = {0.f, 0.f}, av[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
         for (int p = lo; p < hi; ++p) {
-          const float4* ep = reinterpret_cast<const float4*>(rec + (int64_t)p * REC);
-          const float4 e0 = __ldg(ep), e1 = __ldg(ep + 1), e2 = __ldg(ep + 2), e3 = __ldg(ep + 3);
+          float4 e0, e1, e2, e3;
+          if (p - lo < 8) {
+            const float4* ep = cur + (p - lo) * 4;
+            e0 = ep[0]; e1 = ep[1]; e2 = ep[2]; e3 = ep[3];
+          } else {
+            const float4* ep = rec4 + (int64_t)p * 4;
+            e0 = __ldg(ep); e1 = __ldg(ep + 1); e2 = __ldg(ep + 2); e3 = __ldg(ep + 3);
+          }
           const float rb[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
           const float fce = e2.x, d[3] = {e2.y, e2.z, e2.w};
           const int j = __float_as_int(e3.x);
@@ -273,10 +338,9 @@ painn_message_fwd_tiled_kernel(const float* __restrict__ phi, const float* __res
             for (int k = 0; k < 3; ++k) av[k][tt] += vv[k][tt] * gv + ge * d[k];
           }
         }
-        // residual: the node's own rows are in the tile as well
-        float so[2], tmp[2];
-        ChanVec<2>::ld(s + (int64_t)i * f + cc, so);
-        so[0] += as[0]; so[1] += as[1];
+        // residual: the node's own s row comes from the scratch, its v rows from the tile
+        const float2 own_s = *(reinterpret_cast<const float2*>(cur + 32) + lane);
+        float so[2] = {own_s.x + as[0], own_s.y + as[1]}, tmp[2];
         ChanVec<2>::st(s_out + (int64_t)i * f + cc, so);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -284,9 +348,12 @@ painn_message_fwd_tiled_kernel(const float* __restrict__ phi, const float* __res
           tmp[0] = own.x + av[k][0]; tmp[1] = own.y + av[k][1];
           ChanVec<2>::st(v_out + (int64_t)i * f3 + k * f + cc, tmp);
         }
+        lo = lo_n; hi = hi_n; sb ^= 1;
+        in = inn; lo_n = lo_nn; hi_n = hi_nn;
       }
     }
-    __syncthreads();   // everyone is done with buffer `buf` before it is refilled
+    __syncwarp();
+    if (lane == 0) pm_mbar_arrive(empty + buf);   // this warp no longer reads buffer `buf`
   }
 }
 
@@ -301,13 +368,13 @@ extern "C" int hgb_painn_message_fwd(const float* phi, const float* s, const flo
   HGB_REQUIRE(phi && s && v && rowptr && nbr && epack && wf && bf && s_out && v_out, "painn_message_fwd: null pointer");
   if (n == 0) return HGB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (rec && f % 64 == 0 && f <= 256 && n >= 256 && ((uintptr_t)phi % 16 == 0) && ((uintptr_t)v % 16 == 0)) {
+  if (rec && f % 64 == 0 && f <= 256 && n >= 256 && (((uintptr_t)phi | (uintptr_t)v | (uintptr_t)s | (uintptr_t)rec) % 16 == 0)) {
     // tiled path: two double-buffered [tn x 3f] fp32 tiles
-    int tn = (int)((110 * 1024) / ((size_t)4 * 3 * f * 4));   // two blocks per SM
+    int tn = (int)((110 * 1024 - TWPB * 1536 - 64) / ((size_t)4 * 3 * f * 4));   // two blocks per SM
     tn = (tn / TWPB) * TWPB;                                   // whole nodes per warp
     if (tn > 3 * TWPB) tn = 3 * TWPB;
     if (tn < TWPB) tn = TWPB;
-    const size_t smem = (size_t)4 * tn * 3 * f * 4 + 64;
+    const size_t smem = (size_t)4 * tn * 3 * f * 4 + 64 + TWPB * 1536;
     static bool attr_done = false;
     if (!attr_done) {
       cudaFuncSetAttribute(painn_message_fwd_tiled_kernel<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -521,12 +588,16 @@ painn_message_bwd_tiled_kernel(const float* __restrict__ gs_out, const float* __
   float* sgs[2] = {reinterpret_cast<float*>(pm_smem), reinterpret_cast<float*>(pm_smem + (size_t)gs_bytes + gv_bytes)};
   float* sgv[2] = {reinterpret_cast<float*>(pm_smem + gs_bytes), reinterpret_cast<float*>(pm_smem + 2 * (size_t)gs_bytes + gv_bytes)};
   uint64_t* full = reinterpret_cast<uint64_t*>(pm_smem + 2 * ((size_t)gs_bytes + gv_bytes));
-  float* red = reinterpret_cast<float*>(full + 2);   // [WPB * 32]
+  uint64_t* empty = full + 2;
+  float* red = reinterpret_cast<float*>(full + 4);   // [WPB * 32]
+  float4* scr = reinterpret_cast<float4*>(red + WPB * 32) + (threadIdx.x >> 5) * 256;   // per warp: 2 x (8 edge records + phi/v rows of one node)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ntiles = (n + tn - 1) / tn;
   if (threadIdx.x == 0) {
     pm_mbar_init(full, 1);
     pm_mbar_init(full + 1, 1);
+    pm_mbar_init(empty, WPB);
+    pm_mbar_init(empty + 1, WPB);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -550,27 +621,80 @@ painn_message_bwd_tiled_kernel(const float* __restrict__ gs_out, const float* __
       wr[a][t][RT] = bf[a * f + cc + t];
       gw[a][t][RT] = 0.f;
     }
+  // software pipeline over the warp's nodes: while node j is processed, the first 8 records and the phi / v rows of the
+  // warp's next node (possibly in the block's next tile) travel global -> per-warp scratch with cp.async (no registers).
+  const float4* rec4 = reinterpret_cast<const float4*>(rec);
+  auto stage = [&](int jn, int lo_n, int hi_n, float4* dst) {
+    if (lane < 4 * min(8, hi_n - lo_n)) pm_cp_async16(dst + lane, rec4 + (int64_t)lo_n * 4 + lane);
+    const float* pj = phi + (int64_t)jn * f3 + cb * 64;
+    const float* vjp = v + (int64_t)jn * f3 + cb * 64;
+    pm_cp_async16(dst + 32 + lane, pj + (lane >> 4) * f + (lane & 15) * 4);
+    pm_cp_async16(dst + 80 + lane, vjp + (lane >> 4) * f + (lane & 15) * 4);
+    if (lane < 16) {
+      pm_cp_async16(dst + 64 + lane, pj + 2 * f + lane * 4);
+      pm_cp_async16(dst + 112 + lane, vjp + 2 * f + lane * 4);
+    }
+  };
+  // the warp's node sequence: n0 + warp, + WPB, ... inside a tile, then the same in the block's next tile
+  auto succ = [&](int j, int& tile) {
+    int jn = j + WPB;
+    if (jn < min(n, tile * tn + tn)) return jn;
+    tile += (int)gridDim.x;
+    jn = tile * tn + warp;
+    return (tile < ntiles && jn < min(n, tile * tn + tn)) ? jn : -1;
+  };
+  int lo = 0, hi = 0, sb = 0, lo_n = 0, hi_n = 0, jn = -1, tile_n = blockIdx.x;
+  {
+    const int j0 = blockIdx.x * tn + warp;
+    if ((int)blockIdx.x < ntiles && j0 < min(n, (int)blockIdx.x * tn + tn)) {
+      lo = rowptr[j0]; hi = rowptr[j0 + 1];
+      stage(j0, lo, hi, scr);
+      jn = succ(j0, tile_n);
+      if (jn >= 0) { lo_n = rowptr[jn]; hi_n = rowptr[jn + 1]; }
+    }
+    pm_cp_async_commit();
+  }
   int it = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int buf = it & 1;
     const int tnext = tile + gridDim.x;
-    if (threadIdx.x == 0 && tnext < ntiles) issue(tnext, buf ^ 1);
+    if (warp == 0 && tnext < ntiles) {       // refill the other buffer once every warp has released it (tile it-1)
+      if (it >= 1) pm_mbar_wait(empty + (buf ^ 1), ((it - 1) >> 1) & 1);
+      if (lane == 0) issue(tnext, buf ^ 1);
+      __syncwarp();
+    }
     pm_mbar_wait(full + buf, (it >> 1) & 1);
     const int n0 = tile * tn, n1 = min(n, n0 + tn);
     const float* tgs = sgs[buf];
     const float* tgv = sgv[buf];
     for (int j = n0 + warp; j < n1; j += WPB) {
-      const int lo = rowptr[j], hi = rowptr[j + 1];
+      pm_cp_async_wait_all();
+      __syncwarp();
+      const float4* cur = scr + sb * 128;
+      int jnn = -1, lo_nn = 0, hi_nn = 0;
+      if (jn >= 0) {                       // next node: stage it; node after next: fetch its row pointers
+        stage(jn, lo_n, hi_n, scr + (sb ^ 1) * 128);
+        jnn = succ(jn, tile_n);
+        if (jnn >= 0) { lo_nn = rowptr[jnn]; hi_nn = rowptr[jnn + 1]; }
+      }
+      pm_cp_async_commit();
       float ph[3][2], vj[3][2], aphi[3][2], agv[3][2];
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        ChanVec<2>::ld(phi + (int64_t)j * f3 + a * f + cc, ph[a]);
-        ChanVec<2>::ld(v + (int64_t)j * f3 + a * f + cc, vj[a]);
+        const float2 p2 = *(reinterpret_cast<const float2*>(cur + 32 + a * 16) + lane);
+        const float2 v2 = *(reinterpret_cast<const float2*>(cur + 80 + a * 16) + lane);
+        ph[a][0] = p2.x; ph[a][1] = p2.y; vj[a][0] = v2.x; vj[a][1] = v2.y;
         aphi[a][0] = aphi[a][1] = 0.f; agv[a][0] = agv[a][1] = 0.f;
       }
       for (int p = lo; p < hi; ++p) {
-        const float4* ep = reinterpret_cast<const float4*>(rec + (int64_t)p * REC);
-        const float4 e0 = __ldg(ep), e1 = __ldg(ep + 1), e2 = __ldg(ep + 2), e3 = __ldg(ep + 3);
+        float4 e0, e1, e2, e3;
+        if (p - lo < 8) {
+          const float4* ep = cur + (p - lo) * 4;
+          e0 = ep[0]; e1 = ep[1]; e2 = ep[2]; e3 = ep[3];
+        } else {
+          const float4* ep = rec4 + (int64_t)p * 4;
+          e0 = __ldg(ep); e1 = __ldg(ep + 1); e2 = __ldg(ep + 2); e3 = __ldg(ep + 3);
+        }
         const float rb[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
         const float fce = e2.x, d[3] = {e2.y, e2.z, e2.w};
         const int i = __float_as_int(e3.x);
@@ -666,8 +790,11 @@ painn_message_bwd_tiled_kernel(const float* __restrict__ gs_out, const float* __
         float tmp[2] = {own.x + agv[a][0], own.y + agv[a][1]};
         ChanVec<2>::st(gv + (int64_t)j * f3 + a * f + cc, tmp);
       }
+      lo = lo_n; hi = hi_n; sb ^= 1;
+      jn = jnn; lo_n = lo_nn; hi_n = hi_nn;
     }
-    __syncthreads();
+    __syncwarp();
+    if (lane == 0) pm_mbar_arrive(empty + buf);   // this warp no longer reads buffer `buf`
   }
   // block-level reduction of the filter-weight gradients -> part[blockIdx.x]
   float* mypart = part + (int64_t)blockIdx.x * f3 * (r + 1);
@@ -743,9 +870,9 @@ extern "C" int hgb_painn_message_bwd(const float* gs_out, const float* gv_out, c
     return HGB_OK;
   }
   float* part = (float*)workspace;
-  if (rec && f % 64 == 0 && f <= 256 && n >= 256 && ((uintptr_t)gs_out % 16 == 0) && ((uintptr_t)gv_out % 16 == 0)) {
+  if (rec && f % 64 == 0 && f <= 256 && n >= 256 && (((uintptr_t)gs_out | (uintptr_t)gv_out | (uintptr_t)phi | (uintptr_t)v | (uintptr_t)rec) % 16 == 0)) {
     const int tn = 32;
-    const size_t smem = (size_t)2 * tn * 4 * f * 4 + 16 + WPB * 32 * 4;
+    const size_t smem = (size_t)2 * tn * 4 * f * 4 + 32 + WPB * 32 * 4 + WPB * 4096;
     static bool attr_done = false;
     if (!attr_done) {
 #define SETA(E, G, R) cudaFuncSetAttribute(painn_message_bwd_tiled_kernel<E, G, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)

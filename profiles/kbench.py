@@ -40,6 +40,10 @@ sr, vr, pr = s.clone().requires_grad_(True), v.clone().requires_grad_(True), phi
 so, vo = ops.PainnMessageFn.apply(pr, sr, vr, epack, wf.requires_grad_(True), bf.requires_grad_(True), None, plan, rec)
 gs, gv = torch.randn_like(so), torch.randn_like(vo)
 out["painn_message_bwd F=64 (ms)"] = timeit(lambda: torch.autograd.grad((so, vo), (pr, sr, vr, wf, bf), (gs, gv), retain_graph=True))
+so2, vo2 = ops.PainnMessageFn.apply(pr, sr, vr, epack, wf, bf, None, plan, None)
+out["painn_message_bwd generic F=64 (ms)"] = timeit(lambda: torch.autograd.grad((so2, vo2), (pr, sr, vr, wf, bf), (gs, gv), retain_graph=True))
+if os.environ.get("KBENCH_ONLY") == "painn":
+    print(json.dumps(out, indent=1)); sys.exit(0)
 alg_f = e * (6 * f * 4 + 8 + 48) + n * (8 * f * 4 + 4)
 out["painn_message_fwd GB/s algorithmic"] = alg_f / out["painn_message_fwd F=64 (ms)"] / 1e6
 for (m, k, nn_) in [(n, 64, 64), (n, 64, 192), (3 * n, 64, 64), (n, 128, 64), (n, 192, 64)]:
