@@ -180,6 +180,11 @@ __device__ __forceinline__ void pm_bulk_g2s(void* dst, const void* src, uint32_t
 }
 
 #define TWPB 10   // warps per block in the tiled kernels: 2 blocks / SM -> 24 warps at <= 85 registers (no spills)
+__device__ __forceinline__ float2 pm_lds_f2(uint32_t addr) {   // explicit shared-space load (a generic pointer would compile to LD.E)
+  float2 r;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
+  return r;
+}
 __device__ __forceinline__ void pm_cp_async16(void* smem, const void* g) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
 }
@@ -192,13 +197,14 @@ __device__ __forceinline__ void pm_prefetch_range(const void* base, int bytes, i
   if (lane * 128 < bytes) pm_prefetch_l1(b + lane * 128);
 }
 
-template <bool HAS_EF, int RT>
+template <bool HAS_EF, int RT, int FT>
 __global__ void __launch_bounds__(TWPB * 32, 2)
 painn_message_fwd_tiled_kernel(const float* __restrict__ phi, const float* __restrict__ s, const float* __restrict__ v,
                                const int32_t* __restrict__ rowptr, const float* __restrict__ rec, const float* __restrict__ wf,
-                               const float* __restrict__ bf, const float* __restrict__ efilt, int n, int f, int r, int tn,
+                               const float* __restrict__ bf, const float* __restrict__ efilt, int n, int f_rt, int r, int tn,
                                float* __restrict__ s_out, float* __restrict__ v_out) {
   extern __shared__ __align__(128) uint8_t pm_smem[];
+  const int f = FT ? FT : f_rt;   // FT = 64: strides become immediates
   const int f3 = 3 * f;
   const uint32_t tile_bytes = (uint32_t)tn * f3 * 4;
   float* sphi[2] = {reinterpret_cast<float*>(pm_smem), reinterpret_cast<float*>(pm_smem + 2 * (size_t)tile_bytes)};
@@ -263,8 +269,8 @@ painn_message_fwd_tiled_kernel(const float* __restrict__ phi, const float* __res
     }
     pm_mbar_wait(full + buf, (it >> 1) & 1);
     const int n0 = t * tn, n1 = min(n, n0 + tn);
-    const float* tphi = sphi[buf];
     const float* tv = sv[buf];
+    const uint32_t tphi_u = pm_smem_u32(sphi[buf]), tv_u = pm_smem_u32(sv[buf]);
     for (int cb = 0; cb < ncb; ++cb) {
       const int cc = cb * 64 + lane * 2;
       float wr[3][2][RT + 1];
@@ -304,11 +310,10 @@ painn_message_fwd_tiled_kernel(const float* __restrict__ phi, const float* __res
           (void)e;
           float pv[3][2], vv[3][2];
           if (j >= n0 && j < n1) {          // warp-uniform: the common case, rows already on chip
-            const float* ph = tphi + (size_t)(j - n0) * f3 + cc;
-            const float* vj = tv + (size_t)(j - n0) * f3 + cc;
+            const uint32_t off = (uint32_t)((j - n0) * f3 + cc) * 4u;
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-              const float2 x2 = *reinterpret_cast<const float2*>(ph + a * f), y2 = *reinterpret_cast<const float2*>(vj + a * f);
+              const float2 x2 = pm_lds_f2(tphi_u + off + a * f * 4), y2 = pm_lds_f2(tv_u + off + a * f * 4);
               pv[a][0] = x2.x; pv[a][1] = x2.y; vv[a][0] = y2.x; vv[a][1] = y2.y;
             }
           } else {
@@ -335,7 +340,7 @@ painn_message_fwd_tiled_kernel(const float* __restrict__ phi, const float* __res
             const float gv = w[0] * pv[0][tt], ge = w[1] * pv[1][tt];
             as[tt] = fmaf(w[2], pv[2][tt], as[tt]);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) av[k][tt] += vv[k][tt] * gv + ge * d[k];
+            for (int k = 0; k < 3; ++k) av[k][tt] = fmaf(ge, d[k], fmaf(vv[k][tt], gv, av[k][tt]));
           }
         }
         // residual: the node's own s row comes from the scratch, its v rows from the tile
@@ -377,18 +382,20 @@ extern "C" int hgb_painn_message_fwd(const float* phi, const float* s, const flo
     const size_t smem = (size_t)4 * tn * 3 * f * 4 + 64 + TWPB * 1536;
     static bool attr_done = false;
     if (!attr_done) {
-      cudaFuncSetAttribute(painn_message_fwd_tiled_kernel<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      cudaFuncSetAttribute(painn_message_fwd_tiled_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      cudaFuncSetAttribute(painn_message_fwd_tiled_kernel<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      cudaFuncSetAttribute(painn_message_fwd_tiled_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+#define SETA(E, R) cudaFuncSetAttribute(painn_message_fwd_tiled_kernel<E, R, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+                   cudaFuncSetAttribute(painn_message_fwd_tiled_kernel<E, R, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+      SETA(false, 5); SETA(false, 8); SETA(true, 5); SETA(true, 8);
+#undef SETA
       attr_done = true;
     }
     const int ntiles = (n + tn - 1) / tn;
     const int g1 = ntiles < 2 * HGB_NUM_SMS ? ntiles : 2 * HGB_NUM_SMS;
-#define LAUNCH_T(E, R) painn_message_fwd_tiled_kernel<E, R><<<g1, TWPB * 32, smem, st>>>(phi, s, v, rowptr, rec, wf, bf, efilt, n, f, r, tn, s_out, v_out)
+#define LAUNCH_F(E, R, F) painn_message_fwd_tiled_kernel<E, R, F><<<g1, TWPB * 32, smem, st>>>(phi, s, v, rowptr, rec, wf, bf, efilt, n, f, r, tn, s_out, v_out)
+#define LAUNCH_T(E, R) do { if (f == 64) LAUNCH_F(E, R, 64); else LAUNCH_F(E, R, 0); } while (0)
     if (efilt) { if (r <= 5) LAUNCH_T(true, 5); else LAUNCH_T(true, 8); }
     else { if (r <= 5) LAUNCH_T(false, 5); else LAUNCH_T(false, 8); }
 #undef LAUNCH_T
+#undef LAUNCH_F
     HGB_LAUNCH_CHECK("painn_message_fwd_tiled");
     return HGB_OK;
   }
@@ -575,14 +582,15 @@ painn_message_bwd_kernel(const float* __restrict__ gs_out, const float* __restri
 // ---- tiled backward (F % 64 == 0): the incoming gradients gs_out / gv_out of a tile of consecutive nodes are staged in
 // shared memory (bulk async copies, double buffered); the warp that owns source node j gathers the gradient rows of the
 // nodes it sent messages to from shared memory.  rec is the by-col CSR record array (neighbour = aggregating node).
-template <bool HAS_EF, bool NEED_EDGE, int RT>
+template <bool HAS_EF, bool NEED_EDGE, int RT, int FT>
 __global__ void __launch_bounds__(WPB * 32, 2)
 painn_message_bwd_tiled_kernel(const float* __restrict__ gs_out, const float* __restrict__ gv_out, const float* __restrict__ phi,
                                const float* __restrict__ v, const int32_t* __restrict__ rowptr, const float* __restrict__ rec,
                                const float* __restrict__ wf, const float* __restrict__ bf, const float* __restrict__ efilt, int n,
-                               int f, int r, int tn, float* __restrict__ gphi, float* __restrict__ gv, float* __restrict__ part,
+                               int f_rt, int r, int tn, float* __restrict__ gphi, float* __restrict__ gv, float* __restrict__ part,
                                float* __restrict__ g_epack, float* __restrict__ g_efilt, int multi_cb) {
   extern __shared__ __align__(128) uint8_t pm_smem[];
+  const int f = FT ? FT : f_rt;
   const int f3 = 3 * f;
   const uint32_t gs_bytes = (uint32_t)tn * f * 4, gv_bytes = (uint32_t)tn * f3 * 4;
   float* sgs[2] = {reinterpret_cast<float*>(pm_smem), reinterpret_cast<float*>(pm_smem + (size_t)gs_bytes + gv_bytes)};
@@ -665,8 +673,8 @@ painn_message_bwd_tiled_kernel(const float* __restrict__ gs_out, const float* __
     }
     pm_mbar_wait(full + buf, (it >> 1) & 1);
     const int n0 = tile * tn, n1 = min(n, n0 + tn);
-    const float* tgs = sgs[buf];
     const float* tgv = sgv[buf];
+    const uint32_t tgs_u = pm_smem_u32(sgs[buf]), tgv_u = pm_smem_u32(sgv[buf]);
     for (int j = n0 + warp; j < n1; j += WPB) {
       pm_cp_async_wait_all();
       __syncwarp();
@@ -701,11 +709,12 @@ painn_message_bwd_tiled_kernel(const float* __restrict__ gs_out, const float* __
         const int e = __float_as_int(e3.y);
         float gsi[2], gvi[3][2];
         if (i >= n0 && i < n1) {
-          const float2 g2 = *reinterpret_cast<const float2*>(tgs + (size_t)(i - n0) * f + cc);
+          const float2 g2 = pm_lds_f2(tgs_u + (uint32_t)((i - n0) * f + cc) * 4u);
           gsi[0] = g2.x; gsi[1] = g2.y;
+          const uint32_t off = (uint32_t)((i - n0) * f3 + cc) * 4u;
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
-            const float2 h2 = *reinterpret_cast<const float2*>(tgv + (size_t)(i - n0) * f3 + k * f + cc);
+            const float2 h2 = pm_lds_f2(tgv_u + off + k * f * 4);
             gvi[k][0] = h2.x; gvi[k][1] = h2.y;
           }
         } else {
@@ -875,7 +884,8 @@ extern "C" int hgb_painn_message_bwd(const float* gs_out, const float* gv_out, c
     const size_t smem = (size_t)2 * tn * 4 * f * 4 + 32 + WPB * 32 * 4 + WPB * 4096;
     static bool attr_done = false;
     if (!attr_done) {
-#define SETA(E, G, R) cudaFuncSetAttribute(painn_message_bwd_tiled_kernel<E, G, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+#define SETA(E, G, R) cudaFuncSetAttribute(painn_message_bwd_tiled_kernel<E, G, R, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+                      cudaFuncSetAttribute(painn_message_bwd_tiled_kernel<E, G, R, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
       SETA(false, false, 5); SETA(false, true, 5); SETA(true, false, 5); SETA(true, true, 5);
       SETA(false, false, 8); SETA(false, true, 8); SETA(true, false, 8); SETA(true, true, 8);
 #undef SETA
@@ -887,7 +897,8 @@ extern "C" int hgb_painn_message_bwd(const float* gs_out, const float* gv_out, c
     if (gx > 2 * HGB_NUM_SMS) gx = 2 * HGB_NUM_SMS;
     const int ncb2 = f / 64;
     dim3 grid2(gx, ncb2);
-#define LAUNCH_T(E, G, R) painn_message_bwd_tiled_kernel<E, G, R><<<grid2, WPB * 32, smem, st>>>(gs_out, gv_out, phi, v, rowptr_src, rec, wf, bf, efilt, n, f, r, tn, gphi, gv, part, g_epack, g_efilt, ncb2 > 1)
+#define LAUNCH_F(E, G, R, F) painn_message_bwd_tiled_kernel<E, G, R, F><<<grid2, WPB * 32, smem, st>>>(gs_out, gv_out, phi, v, rowptr_src, rec, wf, bf, efilt, n, f, r, tn, gphi, gv, part, g_epack, g_efilt, ncb2 > 1)
+#define LAUNCH_T(E, G, R) do { if (f == 64) LAUNCH_F(E, G, R, 64); else LAUNCH_F(E, G, R, 0); } while (0)
 #define LAUNCH_TR(E, G) do { if (r <= 5) LAUNCH_T(E, G, 5); else LAUNCH_T(E, G, 8); } while (0)
     if (efilt) { if (need_edge) LAUNCH_TR(true, true); else LAUNCH_TR(true, false); }
     else { if (need_edge) LAUNCH_TR(false, true); else LAUNCH_TR(false, false); }
