@@ -332,8 +332,13 @@ def run_engine(args):
 
 
 def painn_message_roofline(m, d, ops, dev):
-    """CUDA-event timing of hgb_painn_message_fwd alone on the real layer-2 inputs (F = hidden_dim), L2 flushed
-    between launches.  Algorithmic bytes: E*(6F*4 + 8 + 48) + N*(8F*4 + 4)."""
+    """CUDA-event timing of hgb_painn_message_fwd (the segmented-scatter kernel of SURVEY.md 8d) alone on the real layer-2
+    shapes (F = hidden_dim), L2 flushed between launches.
+
+    `achieved` uses the COMPULSORY bytes of the shared-memory-tiled kernel ("roofline bytes"): every tensor
+    crosses HBM once -- N*(3F phi + 3F v + F s read, F s_out + 3F v_out written)*4 + E*64 (edge records) + (N+1)*4.
+    `survey_formula` is SURVEY.md 8(d)'s scatter figure, which charges every edge its own gathered rows
+    (E*(6F*4 + 8 + 48) + N*(8F*4 + 4)); with the gathers served from shared memory it exceeds the HBM peak."""
     hbm, src = peaks()
     from hydragnn_b200.stacks import Base
     plan = Base.plan_for(d)
@@ -361,11 +366,20 @@ def painn_message_roofline(m, d, ops, dev):
             if it >= 3:
                 ts.append(t0.elapsed_time(t1))
     ms = sum(ts) / len(ts)
-    alg = e * (6 * f * 4 + 8 + 48) + n * (8 * f * 4 + 4)
+    alg = n * 11 * f * 4 + e * 64 + (n + 1) * 4
+    survey = e * (6 * f * 4 + 8 + 48) + n * (8 * f * 4 + 4)
     ach = alg / (ms * 1e-3) / 1e9
-    return {"kernel": "painn_message_fwd_kernel<2,false,32,5>", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
-            "frac": ach / hbm, "traffic": None, "peak_source": src + " (burst copy figure; kernel timed alone, L2 flushed)",
-            "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms}
+    return {"kernel": "painn_message_fwd_tiled_kernel<false,5,64>", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
+            "frac": ach / hbm, "traffic": NCU_TRAFFIC_BYTES if (n, e, f) == NCU_TRAFFIC_SHAPE else None,
+            "traffic_source": "profiles/r01_ncu_painn_message_v3_details.csv (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+            "peak_source": src + " (burst copy figure; kernel timed alone, L2 flushed)",
+            "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms,
+            "survey_formula": {"bytes_per_launch": survey, "achieved": survey / (ms * 1e-3) / 1e9, "frac": survey / (ms * 1e-3) / 1e9 / hbm}}
+
+
+# measured once with `ncu --set full` on the bench shapes (N, E, F): 317.0 MB read + 123.7 MB written
+NCU_TRAFFIC_SHAPE = (147456, 786432, 64)
+NCU_TRAFFIC_BYTES = 440675072
 
 
 if __name__ == "__main__":

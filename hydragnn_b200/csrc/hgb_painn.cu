@@ -207,8 +207,10 @@ painn_message_fwd_tiled_kernel(const float* __restrict__ phi, const float* __res
   const int f = FT ? FT : f_rt;   // FT = 64: strides become immediates
   const int f3 = 3 * f;
   const uint32_t tile_bytes = (uint32_t)tn * f3 * 4;
-  float* sphi[2] = {reinterpret_cast<float*>(pm_smem), reinterpret_cast<float*>(pm_smem + 2 * (size_t)tile_bytes)};
-  float* sv[2] = {reinterpret_cast<float*>(pm_smem + tile_bytes), reinterpret_cast<float*>(pm_smem + 3 * (size_t)tile_bytes)};
+  // buffer b: phi tile at pm_smem + 2 b tile_bytes, v tile right behind it (pointer arithmetic, not an indexed array:
+  // a dynamically indexed pointer array would live in local memory)
+  auto sphi = [&](int b) { return reinterpret_cast<float*>(pm_smem + (size_t)(2 * b) * tile_bytes); };
+  auto sv = [&](int b) { return reinterpret_cast<float*>(pm_smem + (size_t)(2 * b + 1) * tile_bytes); };
   uint64_t* full = reinterpret_cast<uint64_t*>(pm_smem + 4 * (size_t)tile_bytes);
   uint64_t* empty = full + 2;
   // per warp: 2 x (8 edge records [32 float4] + the node's s row slice [16 float4])
@@ -228,8 +230,8 @@ painn_message_fwd_tiled_kernel(const float* __restrict__ phi, const float* __res
     const int n0 = t * tn;
     const uint32_t bytes = (uint32_t)(min(n, n0 + tn) - n0) * f3 * 4;
     pm_mbar_expect_tx(full + buf, 2 * bytes);
-    pm_bulk_g2s(sphi[buf], phi + (int64_t)n0 * f3, bytes, full + buf);
-    pm_bulk_g2s(sv[buf], v + (int64_t)n0 * f3, bytes, full + buf);
+    pm_bulk_g2s(sphi(buf), phi + (int64_t)n0 * f3, bytes, full + buf);
+    pm_bulk_g2s(sv(buf), v + (int64_t)n0 * f3, bytes, full + buf);
   };
   if (threadIdx.x == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
   // The warp's work sequence: nodes n0 + warp, + TWPB, ... of (tile, channel block 0), then channel block 1, ..., then the
@@ -269,8 +271,8 @@ painn_message_fwd_tiled_kernel(const float* __restrict__ phi, const float* __res
     }
     pm_mbar_wait(full + buf, (it >> 1) & 1);
     const int n0 = t * tn, n1 = min(n, n0 + tn);
-    const float* tv = sv[buf];
-    const uint32_t tphi_u = pm_smem_u32(sphi[buf]), tv_u = pm_smem_u32(sv[buf]);
+    const float* tv = sv(buf);
+    const uint32_t tphi_u = pm_smem_u32(sphi(buf)), tv_u = pm_smem_u32(sv(buf));
     for (int cb = 0; cb < ncb; ++cb) {
       const int cc = cb * 64 + lane * 2;
       float wr[3][2][RT + 1];
@@ -593,8 +595,8 @@ painn_message_bwd_tiled_kernel(const float* __restrict__ gs_out, const float* __
   const int f = FT ? FT : f_rt;
   const int f3 = 3 * f;
   const uint32_t gs_bytes = (uint32_t)tn * f * 4, gv_bytes = (uint32_t)tn * f3 * 4;
-  float* sgs[2] = {reinterpret_cast<float*>(pm_smem), reinterpret_cast<float*>(pm_smem + (size_t)gs_bytes + gv_bytes)};
-  float* sgv[2] = {reinterpret_cast<float*>(pm_smem + gs_bytes), reinterpret_cast<float*>(pm_smem + 2 * (size_t)gs_bytes + gv_bytes)};
+  auto sgs = [&](int b) { return reinterpret_cast<float*>(pm_smem + (size_t)b * (gs_bytes + gv_bytes)); };
+  auto sgv = [&](int b) { return reinterpret_cast<float*>(pm_smem + (size_t)b * (gs_bytes + gv_bytes) + gs_bytes); };
   uint64_t* full = reinterpret_cast<uint64_t*>(pm_smem + 2 * ((size_t)gs_bytes + gv_bytes));
   uint64_t* empty = full + 2;
   float* red = reinterpret_cast<float*>(full + 4);   // [WPB * 32]
@@ -613,8 +615,8 @@ painn_message_bwd_tiled_kernel(const float* __restrict__ gs_out, const float* __
     const int n0 = t * tn;
     const uint32_t rows = (uint32_t)(min(n, n0 + tn) - n0);
     pm_mbar_expect_tx(full + buf, rows * (uint32_t)(f + f3) * 4);
-    pm_bulk_g2s(sgs[buf], gs_out + (int64_t)n0 * f, rows * f * 4, full + buf);
-    pm_bulk_g2s(sgv[buf], gv_out + (int64_t)n0 * f3, rows * f3 * 4, full + buf);
+    pm_bulk_g2s(sgs(buf), gs_out + (int64_t)n0 * f, rows * f * 4, full + buf);
+    pm_bulk_g2s(sgv(buf), gv_out + (int64_t)n0 * f3, rows * f3 * 4, full + buf);
   };
   if (threadIdx.x == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
   const int cb = blockIdx.y;                 // 64-channel block
@@ -673,8 +675,8 @@ painn_message_bwd_tiled_kernel(const float* __restrict__ gs_out, const float* __
     }
     pm_mbar_wait(full + buf, (it >> 1) & 1);
     const int n0 = tile * tn, n1 = min(n, n0 + tn);
-    const float* tgv = sgv[buf];
-    const uint32_t tgs_u = pm_smem_u32(sgs[buf]), tgv_u = pm_smem_u32(sgv[buf]);
+    const float* tgv = sgv(buf);
+    const uint32_t tgs_u = pm_smem_u32(sgs(buf)), tgv_u = pm_smem_u32(sgv(buf));
     for (int j = n0 + warp; j < n1; j += WPB) {
       pm_cp_async_wait_all();
       __syncwarp();
