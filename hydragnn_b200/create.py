@@ -13,7 +13,7 @@ from torch import nn
 from . import ops
 from .stacks import EGCLStack, PAINNStack
 
-SUPPORTED = ("EGNN", "PAINN", "PNAEq")
+SUPPORTED = ("EGNN", "PAINN", "PNAEq", "MACE")
 
 
 def get_device(use_gpu=True):
@@ -103,6 +103,19 @@ def create_model(mpnn_type, input_dim, hidden_dim, output_dim, pe_dim=0, global_
         assert pna_deg is not None, "PNAEq requires degree input."
         from .pnaeq import PNAEqStack
         model = PNAEqStack(pna_deg, edge_dim, num_radial, radius, **common)
+    elif mpnn_type == "MACE":
+        assert radius is not None, "MACE requires radius input."
+        assert num_radial is not None, "MACE requires num_radial input."
+        assert max_ell is not None, "MACE requires max_ell input."
+        assert node_max_ell is not None, "MACE requires node_max_ell input."
+        assert max_ell >= 1, "MACE requires max_ell >= 1."
+        assert node_max_ell >= 1, "MACE requires node_max_ell >= 1."
+        from .mace import MACEStack
+        model = MACEStack(radius, radial_type, distance_transform, num_radial, edge_dim, max_ell, node_max_ell, avg_num_neighbors,
+                          envelope_exponent, correlation, input_dim, hidden_dim, output_dim, output_type, heads,
+                          activation_function, loss_function_type, loss_weights=task_weights, freeze_conv=freeze_conv,
+                          initial_bias=initial_bias, num_conv_layers=num_conv_layers, num_nodes=num_nodes,
+                          graph_pooling=graph_pooling, global_attn_engine=global_attn_engine)
     else:
         raise ValueError("Unknown mpnn_type: {0}".format(mpnn_type))
     if enable_interatomic_potential:

@@ -85,6 +85,32 @@ def test_gps_initialisation_matches_reference(golden_dir):
         hb.create_model(**dict(GPS_KW["gps_egnn"], global_attn_type="performer"))
 
 
+def test_mace_initialisation_matches_oracle_and_tables_agree():
+    """No reference-generated golden exists for MACE (e3nn is not installable): the engine's construction order / RNG
+    consumption is pinned to the oracle's restatement, and the engine's coupling tables to the oracle's."""
+    from oracle import e3 as oe3, mace as omace
+    from hydragnn_b200 import e3 as pe3
+    from test_oracle_mace import MACE_KW
+    for extra in ({}, {"max_ell": 3, "node_max_ell": 2, "correlation": 3, "hidden_dim": 4, "num_conv_layers": 3}):
+        kw = dict(MACE_KW, **extra)
+        torch.manual_seed(0)
+        so = omace.MACEOracle(**kw).state_dict()
+        se = hb.create_model(mpnn_type="MACE", use_gpu=False, **kw).state_dict()
+        assert list(so.keys()) == list(se.keys())
+        for k in so:
+            assert so[k].shape == se[k].shape and torch.allclose(so[k].float(), se[k].float(), atol=1e-6), k
+    for a in [(1, 1, 0), (1, 2, 3), (2, 2, 2), (3, 2, 1), (3, 3, 2)]:
+        assert torch.allclose(pe3.w3j(*a), oe3.wigner_3j(*a), atol=1e-14)
+    coupling = oe3.Irreps("1x0e+1x1o+1x2e")
+    for l, nu in [(0, 1), (0, 2), (1, 2), (0, 3), (1, 3), (2, 2)]:
+        assert torch.allclose(pe3.u_matrix(2, l, nu), omace.u_matrix_real(coupling, "%d%s" % (l, "eo"[l % 2]), nu), atol=1e-12)
+    v = torch.randn(20, 3, dtype=torch.float64)
+    assert torch.allclose(pe3.spherical_harmonics_cl(3, torch.nn.functional.normalize(v, dim=-1)), oe3.spherical_harmonics(3, v), atol=1e-12)
+    assert pe3.tp_paths(1, 2, 2) == [(0, 0, 0), (1, 1, 0), (0, 1, 1), (1, 0, 1), (1, 2, 1), (0, 2, 2), (1, 1, 2)]
+    with pytest.raises(AssertionError, match="max_ell"):
+        hb.create_model(mpnn_type="MACE", use_gpu=False, **dict(MACE_KW, max_ell=None))
+
+
 def test_create_model_errors_mirror_reference():
     with pytest.raises(ValueError, match="Unknown mpnn_type"):
         hb.create_model(**dict(MODEL_KW["egnn_mlip"], mpnn_type="GIN"))
