@@ -109,6 +109,18 @@ class Interaction(nn.Module):
         aug = torch.cat([radial, gather(down, plan.by_row), gather(down, plan.by_col)], dim=1)
         tpw = self.conv_tp_weights(aug, higher)                                      # [E, n_paths * F]
         e = tpw.shape[0]
+        if not higher and ops.mace_tp_supported(self.lmax_in, self.lmax_sh, f):
+            # fused: coupling, path weights and the scatter over receivers in one kernel; mji [E, F (L+1)^2] never exists
+            packed = ops.MaceTpScatterFn.apply(torch.cat(up, dim=1), sh, tpw, plan, self.lmax_in, self.lmax_sh)
+            n, msgs, off = up[0].shape[0], [], 0
+            for l3 in range(self.lmax_sh + 1):
+                n_p = sum(1 for p in self.paths if p[2] == l3)
+                if n_p:
+                    size = n * (2 * l3 + 1) * n_p * f
+                    msgs.append(packed.narrow(0, off, size).view(n, 2 * l3 + 1, n_p * f))
+                    off += size
+            out = self.linear(msgs, higher)
+            return [o / self.avg for o in out], sc
         up_s = [gather(u.reshape(u.shape[0], -1), plan.by_row).reshape(e, u.shape[1], f) for u in up]
         per_l = [[] for _ in range(self.lmax_sh + 1)]
         for k, (l1, l2, l3) in enumerate(self.paths):
@@ -192,7 +204,15 @@ class Product(nn.Module):
 
     def forward(self, msgs, sc, zcsr, higher=False):
         x = torch.cat(msgs, dim=1)
-        out = self.linear(self.symmetric_contractions(x, zcsr), higher)
+        cons = self.symmetric_contractions.contractions
+        lin, lout = int(round(math.sqrt(x.shape[1]))) - 1, len(cons) - 1
+        if not higher and ops.mace_sc_supported(lin, lout, cons[0].correlation):
+            wall = torch.cat([w for c in cons for w in (c.weights_max, c.weights[0])], dim=1)       # [118, KTOT, F]
+            y = ops.MaceSymContractFn.apply(x, wall, zcsr, lin, lout)
+            contracted = [y[:, l * l:(l + 1) ** 2, :] for l in range(lout + 1)]
+        else:
+            contracted = self.symmetric_contractions(x, zcsr)
+        out = self.linear(contracted, higher)
         return [a + b for a, b in zip(out, sc)]
 
 

@@ -609,6 +609,81 @@ class LossFn(torch.autograd.Function):
         return gpred * g, None, None
 
 
+# =====================================================================================================
+# MACE: fused tensor-product + scatter, symmetric contraction (first-order blocks)
+# =====================================================================================================
+def mace_tp_supported(lin, lsh, f):
+    return 0 <= lin <= 2 and 1 <= lsh <= 3 and lin <= lsh and f % 32 == 0
+
+
+class MaceTpScatterFn(torch.autograd.Function):
+    """conv_tp + scatter-sum over receivers in one kernel (blocks.py:390-395).  up [N, S_in, F], sh [E, S_sh], tpw [E, P F];
+    returns the packed message buffer (per output degree l3 a [N, 2l3+1, n_paths(l3) F] block)."""
+
+    @staticmethod
+    def forward(ctx, up, sh, tpw, plan, lin, lsh):
+        up, sh, tpw = _chk(up.contiguous()), _chk(sh.contiguous()), _chk(tpw.contiguous())
+        n, f = up.shape[0], up.shape[2]
+        nacc = _lib.query("hgb_mace_tp_num_acc", lin, lsh)
+        out = torch.empty(nacc * n * f, dtype=up.dtype, device=up.device)
+        csr = plan.by_col
+        _lib.call("hgb_mace_tp_scatter_fwd", _p(up), _p(sh), _p(tpw), _p(csr.rowptr), _p(csr.perm), _p(plan.nbr("col")), n, f, lin, lsh,
+                  sh.shape[1], _p(out), _stream())
+        ctx.save_for_backward(up, sh, tpw)
+        ctx.plan, ctx.cfg = plan, (lin, lsh)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        up, sh, tpw = ctx.saved_tensors
+        plan, (lin, lsh) = ctx.plan, ctx.cfg
+        n, s_in, f = up.shape
+        e = tpw.shape[0]
+        g = _chk(g.contiguous())
+        g_tpw = torch.empty_like(tpw)
+        g_up_e = torch.empty(e, s_in * f, dtype=up.dtype, device=up.device)
+        g_sh = torch.zeros_like(sh) if ctx.needs_input_grad[1] else None
+        csr = plan.by_col
+        _lib.call("hgb_mace_tp_scatter_bwd", _p(g), _p(up), _p(sh), _p(tpw), _p(csr.rowptr), _p(csr.perm), _p(plan.nbr("col")), n, f, lin,
+                  lsh, sh.shape[1], _p(g_tpw), _p(g_up_e), _p(g_sh), _stream())
+        g_up = raw_segment_sum(g_up_e, plan.by_row.rowptr, plan.by_row.perm, n).reshape(n, s_in, f) if ctx.needs_input_grad[0] else None
+        return g_up, g_sh, g_tpw, None, None, None
+
+
+def mace_sc_supported(lin, lout, correlation):
+    return correlation == 2 and 1 <= lin <= 3 and 0 <= lout <= 2 and lout <= lin
+
+
+class MaceSymContractFn(torch.autograd.Function):
+    """SymmetricContraction, correlation 2, all output degrees at once.  x [N, S, F], wall [118, KTOT, F], zcsr: CSR of the
+    element index."""
+
+    @staticmethod
+    def forward(ctx, x, wall, zcsr, lin, lout):
+        x, wall = _chk(x.contiguous()), _chk(wall.contiguous())
+        n, _, f = x.shape
+        assert wall.shape[1] == _lib.query("hgb_mace_symcontract_num_weights", lin, lout)
+        out = torch.empty(n, (lout + 1) ** 2, f, dtype=x.dtype, device=x.device)
+        _lib.call("hgb_mace_symcontract_fwd", _p(x), _p(wall), _p(zcsr.idx), n, f, lin, lout, _p(out), _stream())
+        ctx.save_for_backward(x, wall)
+        ctx.zcsr, ctx.cfg = zcsr, (lin, lout)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, wall = ctx.saved_tensors
+        zcsr, (lin, lout) = ctx.zcsr, ctx.cfg
+        n, _, f = x.shape
+        gx = torch.empty_like(x)
+        gw_node = torch.empty(n, wall.shape[1] * f, dtype=x.dtype, device=x.device)
+        _lib.call("hgb_mace_symcontract_bwd", _p(_chk(g.contiguous())), _p(x), _p(wall), _p(zcsr.idx), n, f, lin, lout, _p(gx), _p(gw_node),
+                  _stream())
+        gwall = raw_segment_sum(gw_node, zcsr.rowptr, zcsr.perm, zcsr.n).reshape(wall.shape)
+        return gx, gwall, None, None, None
+
+
 def adamw_step(p, g, m, v, step_dev, lr, beta1, beta2, eps, weight_decay, grad_scale=1.0):
     _lib.call("hgb_adamw_step", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
               float(weight_decay), float(grad_scale), _p(step_dev), _stream())

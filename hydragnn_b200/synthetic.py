@@ -14,6 +14,8 @@ WORKLOADS = {
     "qm9_painn": dict(n=9, rho=0.10, species=[1, 6, 7, 8, 9], radius=7.0, max_neighbours=5),
     "md17_egnn": dict(n=21, rho=0.08, species=[6] * 9 + [1] * 8 + [8] * 4, radius=7.0, max_neighbours=5, fixed_species=True),
     "lj_egnn": dict(n=27, lattice=3.8, radius=5.0, max_neighbours=5, pbc=True),
+    # SURVEY C4 (open-catalyst-like): 80 atoms in a periodic cubic cell at 0.05 / A^3, Z ~ U{1..83}, r = 6 A, all neighbours
+    "oc20_mace": dict(n=80, rho=0.05, species=list(range(1, 84)), radius=6.0, max_neighbours=128, pbc_box=True, two_heads=True),
 }
 
 ARCH = {
@@ -29,6 +31,14 @@ ARCH = {
                       output_heads={"node": {"num_headlayers": 2, "dim_headlayers": [60, 20], "type": "mlp"}},
                       activation_function="relu", loss_function_type="mse", enable_interatomic_potential=True,
                       energy_weight=1.0, energy_peratom_weight=1.0, force_weight=1.0),
+    # MACE knobs of tests/test_forces_equivariant.py:318-327, heads of multidataset/gfm_multitasking.json
+    "oc20_mace": dict(mpnn_type="MACE", input_dim=1, hidden_dim=64, num_conv_layers=2, num_radial=8, radius=6.0,
+                      max_neighbours=128, max_ell=2, node_max_ell=1, correlation=2, envelope_exponent=5, radial_type="bessel",
+                      avg_num_neighbors=45.0, output_dim=[1, 3], output_type=["graph", "node"], task_weights=[1.0, 1.0],
+                      output_heads={"graph": {"num_sharedlayers": 2, "dim_sharedlayers": 50, "num_headlayers": 2,
+                                              "dim_headlayers": [50, 25]},
+                                    "node": {"num_headlayers": 2, "dim_headlayers": [200, 200], "type": "mlp"}},
+                      activation_function="relu", loss_function_type="mae", graph_pooling="mean"),
     # examples/LennardJones/LJ.json with mpnn_type EGNN, 2 layers
     "lj_egnn": dict(mpnn_type="EGNN", input_dim=1, hidden_dim=32, num_conv_layers=2, radius=5.0, max_neighbours=5,
                     output_dim=[1], output_type=["node"], task_weights=[1.0],
@@ -80,6 +90,13 @@ def make_samples(name, num_graphs, seed=1234, with_edges=None):
     out.y = torch.randn(num_graphs, 1, generator=gen)
     out.energy = torch.randn(num_graphs, generator=gen)
     out.forces = torch.randn(num_graphs * n, 3, generator=gen)
+    if w.get("two_heads"):                                  # y = per graph [energy, forces...] with y_loc offsets
+        out.y = torch.cat([out.y, out.forces.reshape(num_graphs, 3 * n)], dim=1).reshape(-1, 1).contiguous()
+        out.y_loc = torch.tensor([[0, 1, 1 + 3 * n]]).expand(num_graphs, 3).contiguous()
+    if w.get("pbc_box"):
+        L = (n / w["rho"]) ** (1.0 / 3.0)
+        out.cell = (torch.eye(3) * L)[None].expand(num_graphs, 3, 3).contiguous()
+        out.pbc = torch.ones(num_graphs, 3, dtype=torch.bool)
     if w.get("pbc"):
         L = 3 * w["lattice"]
         out.cell = (torch.eye(3) * L)[None].expand(num_graphs, 3, 3).contiguous()

@@ -297,6 +297,37 @@ int hgb_adamw_step(float* p, const float* g, float* m, float* v, int64_t count, 
                    float beta2, float eps, float weight_decay, float grad_scale, float* step_dev,
                    hgb_stream_t stream);
 
+/* ---- MACE (hydragnn/utils/model/mace_utils/modules/blocks.py:369-402, symmetric_contraction.py:92-242) ------------------
+ * Features are channel-last: [N, spherical index, F].  lmax_in <= 2, 1 <= lmax_sh <= 3, lmax_in <= lmax_sh, F % 32 == 0.
+ * Path order / coupling constants = tp_out_irreps_with_instructions (irreps_tools.py:15-44) with e3nn's real Wigner 3j.   */
+
+/* number of accumulator rows (sum over output degrees l3 of n_paths(l3) * (2 l3 + 1)); -1 if unsupported.               */
+int hgb_mace_tp_num_acc(int32_t lmax_in, int32_t lmax_sh);
+
+/* conv_tp (o3.TensorProduct "uvu", blocks.py:320-327,390) fused with scatter(..., receiver, "sum") (:393-395).
+ * up [N,(lmax_in+1)^2,F], sh [E, sh_ld] (first (lmax_sh+1)^2 columns), tpw [E, n_paths*F]; (rowptr, perm, snd): CSR of the
+ * receivers with the edge id and the sender of every slot.  out: packed, per output degree l3 a [N, 2l3+1, n_paths(l3)*F]
+ * block starting at float offset N*F*acc_base(l3).                                                                      */
+int hgb_mace_tp_scatter_fwd(const float* up, const float* sh, const float* tpw, const int32_t* rowptr, const int32_t* perm,
+                            const int32_t* snd, int32_t n, int32_t f, int32_t lmax_in, int32_t lmax_sh, int32_t sh_ld, float* out,
+                            hgb_stream_t stream);
+
+/* backward: g_tpw [E, n_paths*F], g_up_edge [E,(lmax_in+1)^2,F] (per-edge sender gradients; reduce per sender with
+ * hgb_segment_sum), g_sh [E, sh_ld] or NULL (must be zero-filled by the caller when F/64 > 1).                          */
+int hgb_mace_tp_scatter_bwd(const float* g_out, const float* up, const float* sh, const float* tpw, const int32_t* rowptr,
+                            const int32_t* perm, const int32_t* snd, int32_t n, int32_t f, int32_t lmax_in, int32_t lmax_sh,
+                            int32_t sh_ld, float* g_tpw, float* g_up_edge, float* g_sh, hgb_stream_t stream);
+
+/* SymmetricContraction with correlation 2 (symmetric_contraction.py:131-239): weight rows per output degree L are
+ * [weights_max (P2(L)), weights.0 (P1(L))], concatenated over L: wall [118, KTOT, F]; z [N] element index (0-based);
+ * x [N,(lmax_in+1)^2,F] -> out [N,(lmax_out+1)^2,F].                                                                    */
+int hgb_mace_symcontract_num_weights(int32_t lmax_in, int32_t lmax_out);
+int hgb_mace_symcontract_fwd(const float* x, const float* wall, const int32_t* z, int32_t n, int32_t f, int32_t lmax_in,
+                             int32_t lmax_out, float* out, hgb_stream_t stream);
+/* gx [N,(lmax_in+1)^2,F]; gw_node [N,KTOT,F] (per-node weight gradients; reduce per element with hgb_segment_sum).       */
+int hgb_mace_symcontract_bwd(const float* g_out, const float* x, const float* wall, const int32_t* z, int32_t n, int32_t f,
+                             int32_t lmax_in, int32_t lmax_out, float* gx, float* gw_node, hgb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,7 +37,7 @@ def _to_dev(d, pos_grad=False):
     return g
 
 
-@pytest.mark.parametrize("variant", ["default", "ell3_corr3", "one_layer", "gaussian_add"])
+@pytest.mark.parametrize("variant", ["default", "ell3_corr3", "one_layer", "gaussian_add", "fused32", "fused64_ell3", "fused32_ell1"])
 def test_mace_forward_and_gradients_match_oracle(variant):
     kw = dict(MACE_KW)
     if variant == "ell3_corr3":
@@ -46,6 +46,12 @@ def test_mace_forward_and_gradients_match_oracle(variant):
         kw.update(num_conv_layers=1)
     elif variant == "gaussian_add":
         kw.update(radial_type="gaussian", graph_pooling="add", num_conv_layers=3, activation_function="sigmoid")
+    elif variant == "fused32":            # channel counts % 32 == 0 take the fused tensor-product / contraction kernels
+        kw.update(hidden_dim=32)
+    elif variant == "fused64_ell3":
+        kw.update(hidden_dim=64, max_ell=3, node_max_ell=2, num_conv_layers=3)
+    elif variant == "fused32_ell1":
+        kw.update(hidden_dim=32, max_ell=1, node_max_ell=1)
     o, e = _pair(kw)
     gen = torch.Generator().manual_seed(11)
     d = mace_batch(gen, sizes=(7, 9, 5))
