@@ -143,7 +143,8 @@ struct LinParams {
   float act_param;
   float* y;
   float* z;
-  const float* addend;  // optional [m, no]: y = act(a.B^T + bias) + addend  (gradient accumulation without an extra pass)
+  const float* addend;  // optional [m, no] (row stride ldy): y = act(a.B^T + bias) + addend  (gradient accumulation without an extra pass)
+  int64_t ldy;          // row stride of y / z / addend (>= no: column chunks of a wider matrix)
   int stages;
   int tmem_cols;
 };
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant
             for (int j = 0; j < 32; ++j) v[j] = hgb_act(v[j], p.act, p.act_param);
         }
         if (p.addend && row < p.m) {
-          const float4* ap = reinterpret_cast<const float4*>(p.addend + (int64_t)row * NO + c0);
+          const float4* ap = reinterpret_cast<const float4*>(p.addend + (int64_t)row * p.ldy + c0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 a4 = __ldg(ap + j);
@@ -523,25 +524,28 @@ bool shape_ok(int kr, int no) { return kr >= 32 && kr <= 256 && kr % 32 == 0 && 
 
 }  // namespace
 
-extern "C" int hgb_tc_linear_supported(int32_t m, int32_t n_out, int32_t k_red) { return (m >= 128 && shape_ok(k_red, n_out)) ? 1 : 0; }
+// wide operands are cut into <= 256-column / <= 256-deep pieces (see hgb_tc_linear below)
+static bool wide_ok(int kr, int no) { return kr >= 32 && kr <= 1024 && kr % 32 == 0 && no >= 32 && no <= 1024 && no % 32 == 0; }
 
-// y[m, no] = act(a[m, kr] . B^T + bias);  B(r, c) = w[r, c] (trans_b = 0) or w[c, r] (trans_b = 1)
-extern "C" int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_t ldw, int32_t trans_b, const float* bias, int32_t m,
-                             int32_t n_out, int32_t k_red, int32_t act, float act_param, float* y, float* z, const float* addend,
-                             hgb_stream_t stream) {
-  HGB_REQUIRE(a && w && y && hgb_tc_linear_supported(m, n_out, k_red), "tc_linear: unsupported shape m=%d n=%d k=%d", m, n_out, k_red);
-  HGB_REQUIRE(lda % 4 == 0 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!z || (uintptr_t)z % 16 == 0),
+extern "C" int hgb_tc_linear_supported(int32_t m, int32_t n_out, int32_t k_red) { return (m >= 128 && wide_ok(k_red, n_out)) ? 1 : 0; }
+
+// one (<= 256) x (<= 256) piece: y[m, no] = act(a[m, kr] . B^T + bias) + addend, y / z / addend with row stride ldy
+static int tc_linear_piece(const float* a, int64_t lda, const float* w, int64_t ldw, int32_t trans_b, const float* bias, int32_t m,
+                           int32_t n_out, int32_t k_red, int32_t act, float act_param, float* y, float* z, const float* addend,
+                           int64_t ldy, hgb_stream_t stream) {
+  HGB_REQUIRE(a && w && y && m >= 128 && shape_ok(k_red, n_out), "tc_linear: unsupported shape m=%d n=%d k=%d", m, n_out, k_red);
+  HGB_REQUIRE(lda % 4 == 0 && ldy % 4 == 0 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!z || (uintptr_t)z % 16 == 0),
               "tc_linear: operands must be 16-byte aligned with a row stride that is a multiple of 4");
   CUtensorMap tm, tmy, tmz;
   int rc = make_tmap(&tm, a, m, k_red, lda, TILE_M);
   if (rc) return rc;
-  rc = make_tmap(&tmy, y, m, n_out, n_out, 32);
+  rc = make_tmap(&tmy, y, m, n_out, ldy, 32);
   if (rc) return rc;
-  rc = make_tmap(&tmz, z ? z : y, m, n_out, n_out, 32);
+  rc = make_tmap(&tmz, z ? z : y, m, n_out, ldy, 32);
   if (rc) return rc;
   LinParams p;
   p.m = m; p.kr = k_red; p.no = n_out; p.w = w; p.ldw = ldw; p.trans_b = trans_b; p.bias = bias; p.act = act; p.act_param = act_param;
-  p.y = y; p.z = z; p.addend = addend;
+  p.y = y; p.z = z; p.addend = addend; p.ldy = ldy;
   const int KB = k_red / 32;
   const size_t b_bytes = ((size_t)KB * n_out * 128 + 1023) & ~(size_t)1023;
   const size_t a_stage = (size_t)TILE_M * 128;
@@ -563,13 +567,36 @@ extern "C" int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_
   return HGB_OK;
 }
 
+// y[m, no] = act(a[m, kr] . B^T + bias) + addend;  B(r, c) = w[r, c] (trans_b = 0) or w[c, r] (trans_b = 1).
+// no > 256: independent column pieces.  kr > 256: the pieces of the reduction accumulate through `addend` (linear layers
+// only: an activation or a saved pre-activation needs the whole sum first).
+extern "C" int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_t ldw, int32_t trans_b, const float* bias, int32_t m,
+                             int32_t n_out, int32_t k_red, int32_t act, float act_param, float* y, float* z, const float* addend,
+                             hgb_stream_t stream) {
+  HGB_REQUIRE(a && w && y && hgb_tc_linear_supported(m, n_out, k_red), "tc_linear: unsupported shape m=%d n=%d k=%d", m, n_out, k_red);
+  HGB_REQUIRE(k_red <= 256 || (act == HGB_ACT_NONE && !z), "tc_linear: reduction length %d > 256 needs a plain linear layer", k_red);
+  for (int c0 = 0; c0 < n_out; c0 += 256) {
+    const int nc = n_out - c0 < 256 ? n_out - c0 : 256;
+    for (int k0 = 0; k0 < k_red; k0 += 256) {
+      const int kc = k_red - k0 < 256 ? k_red - k0 : 256;
+      // B piece: rows = output columns c0.., columns = reduction k0..
+      const float* wp = trans_b ? w + (int64_t)k0 * ldw + c0 : w + (int64_t)c0 * ldw + k0;
+      const float* add = k0 == 0 ? (addend ? addend + c0 : nullptr) : y + c0;
+      int rc = tc_linear_piece(a + k0, lda, wp, ldw, trans_b, (bias && k0 == 0) ? bias + c0 : nullptr, m, nc, kc, act, act_param, y + c0,
+                               z ? z + c0 : nullptr, add, n_out, stream);
+      if (rc) return rc;
+    }
+  }
+  return HGB_OK;
+}
+
 extern "C" int64_t hgb_tc_wgrad_workspace_bytes(int32_t n_out, int32_t k_out) { return (int64_t)HGB_NUM_SMS * n_out * (k_out + 1) * 4; }
 
 // dw[no, ko] (row stride lddw) (+)= dz[m, no]^T x[m, ko];  db[no] (+)= column sums of dz (db may be NULL)
 extern "C" int hgb_tc_wgrad(const float* dz, int64_t lddz, const float* x, int64_t ldx, int32_t m, int32_t n_out, int32_t k_out,
                             float* dw, int64_t lddw, float* db, int32_t accumulate, void* workspace, int64_t workspace_bytes,
                             hgb_stream_t stream) {
-  HGB_REQUIRE(dz && x && dw && workspace && hgb_tc_linear_supported(m, n_out, k_out) && k_out + 16 <= 256,
+  HGB_REQUIRE(dz && x && dw && workspace && m >= 128 && shape_ok(k_out, n_out) && k_out + 16 <= 256,
               "tc_wgrad: unsupported shape m=%d n=%d k=%d", m, n_out, k_out);
   HGB_REQUIRE(lddz % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)dz % 16 == 0) && ((uintptr_t)x % 16 == 0), "tc_wgrad: operands must be 16-byte aligned");
   HGB_REQUIRE(workspace_bytes >= hgb_tc_wgrad_workspace_bytes(n_out, k_out), "tc_wgrad: workspace too small");

@@ -69,10 +69,20 @@ class RadialMLP(nn.Module):
             layer.weight = nn.Parameter(torch.randn(a, b))
             self.add_module("layer%d" % i, layer)
 
-    def forward(self, x, higher=False):
+    def forward_split(self, radial, down, plan, higher=False):
+        """Same network on the input [radial | down[sender] | down[receiver]] without building it: the first layer is
+        linear in the three blocks, so the two node blocks are multiplied per NODE and gathered per edge afterwards."""
+        r, f = radial.shape[1], down.shape[1]
+        w0 = self.layer0.weight / math.sqrt(self.hs[0])
+        h = _lin(radial, w0[:r].t(), higher)
+        h = h + ops.GatherRows.apply(_lin(down, w0[r:r + f].t(), higher), plan.by_row)
+        h = h + ops.GatherRows.apply(_lin(down, w0[r + f:].t(), higher), plan.by_col)
+        return self.forward(torch.nn.functional.silu(h), higher, first=1)
+
+    def forward(self, x, higher=False, first=0):
         cst = e3.silu_second_moment_constant()
         nl = len(self.hs) - 1
-        for i in range(nl):
+        for i in range(first, nl):
             w = getattr(self, "layer%d" % i).weight
             scale = (cst if i > 0 else 1.0) / math.sqrt(self.hs[i])
             x = _lin(x, (w * scale).t(), higher, "silu" if i < nl - 1 else None)
@@ -106,8 +116,7 @@ class Interaction(nn.Module):
         up = self.linear_up(xs, higher)
         down = self.linear_down(xs, higher)[0].reshape(-1, f)
         gather = ops.GatherRows.apply
-        aug = torch.cat([radial, gather(down, plan.by_row), gather(down, plan.by_col)], dim=1)
-        tpw = self.conv_tp_weights(aug, higher)                                      # [E, n_paths * F]
+        tpw = self.conv_tp_weights.forward_split(radial, down, plan, higher)         # [E, n_paths * F]
         e = tpw.shape[0]
         if not higher and ops.mace_tp_supported(self.lmax_in, self.lmax_sh, f):
             # fused: coupling, path weights and the scatter over receivers in one kernel; mji [E, F (L+1)^2] never exists

@@ -44,6 +44,22 @@ def test_tc_dgrad_and_wgrad(m, n, k):
     assert torch.equal(dw, dw2) and torch.equal(db, db2)          # deterministic
 
 
+@pytest.mark.parametrize("m,k,n", [(3000, 64, 448), (2000, 192, 512), (1500, 64, 288)])
+def test_tc_wide_shapes_are_cut_into_pieces(m, k, n):
+    """n_out > 256 -> column pieces; reduction > 256 (the dgrad of a wide layer) -> pieces accumulated through `addend`."""
+    g = torch.Generator().manual_seed(m + k + n)
+    x, w, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) * 0.2, torch.randn(n, generator=g)
+    y, z = ops.raw_tc_linear(x.to(DEV), w.to(DEV), False, b.to(DEV), n, k, ops.ACT_CODES["silu"], 0.0, want_z=True)
+    ref_z = x.double() @ w.double().t() + b.double()
+    assert rel(z, ref_z) < 2e-3 and rel(y, torch.nn.functional.silu(ref_z)) < 2e-3
+    dz = torch.randn(m, n, generator=g)
+    add = torch.randn(m, k, generator=g)
+    dx, _ = ops.raw_tc_linear(dz.to(DEV), w.to(DEV), True, None, k, n, addend=add.to(DEV))
+    assert rel(dx, dz.double() @ w.double() + add.double()) < 2e-3
+    dw, db = ops.raw_tc_wgrad(dz.to(DEV), x.to(DEV), want_bias=True)
+    assert rel(dw, dz.double().t() @ x.double()) < 2e-3 and rel(db, dz.double().sum(0)) < 2e-3
+
+
 def test_linear_act_autograd_on_tensor_cores():
     g = torch.Generator().manual_seed(5)
     x, w, b = torch.randn(3000, 64, generator=g), torch.randn(192, 64, generator=g) * 0.2, torch.randn(192, generator=g)
