@@ -575,8 +575,12 @@ extern "C" int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_
                              hgb_stream_t stream) {
   HGB_REQUIRE(a && w && y && hgb_tc_linear_supported(m, n_out, k_red), "tc_linear: unsupported shape m=%d n=%d k=%d", m, n_out, k_red);
   HGB_REQUIRE(k_red <= 256 || (act == HGB_ACT_NONE && !z), "tc_linear: reduction length %d > 256 needs a plain linear layer", k_red);
-  for (int c0 = 0; c0 < n_out; c0 += 256) {
-    const int nc = n_out - c0 < 256 ? n_out - c0 : 256;
+  // piece sizes: the B piece (kc x nc fp32) stays resident in shared memory next to >= 2 A stages and the epilogue tiles
+  const int kc_max = k_red < 256 ? k_red : 256;
+  int nc_max = (int)((122 * 1024) / (4 * (size_t)kc_max) / 32) * 32;
+  if (nc_max > 256) nc_max = 256;
+  for (int c0 = 0; c0 < n_out; c0 += nc_max) {
+    const int nc = n_out - c0 < nc_max ? n_out - c0 : nc_max;
     for (int k0 = 0; k0 < k_red; k0 += 256) {
       const int kc = k_red - k0 < 256 ? k_red - k0 : 256;
       // B piece: rows = output columns c0.., columns = reduction k0..

@@ -197,8 +197,9 @@ def raw_tc_wgrad(dz, x2, want_bias=True, dw=None, db=None, accumulate=False):
         dw = torch.empty(n_out, k_out, dtype=dz.dtype, device=dz.device)
     if want_bias and db is None:
         db = torch.empty(n_out, dtype=dz.dtype, device=dz.device)
-    for c0 in range(0, n_out, 256):                 # output-feature pieces (independent rows of dw)
-        nc = min(256, n_out - c0)
+    piece = 256 if k_out <= 96 else 128             # two pipeline stages of (dz piece + x) must fit shared memory
+    for c0 in range(0, n_out, piece):               # output-feature pieces (independent rows of dw)
+        nc = min(piece, n_out - c0)
         nbytes = _lib.query("hgb_tc_wgrad_workspace_bytes", nc, k_out)
         ws = _ws(nbytes, dz.device)
         _lib.call("hgb_tc_wgrad", _p(dz[:, c0:]), dz.stride(0), _p(x2), x2.stride(0), m, nc, k_out, _p(dw[c0:]), dw.stride(0),
