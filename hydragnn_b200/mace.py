@@ -453,7 +453,7 @@ class MACEStack(nn.Module):
             raise RuntimeError("b200 engine kernels are fp32 (bf16 via autocast-style GEMMs); got " + str(data.x.dtype))
         assert data.pos is not None, "MACE requires node positions (data.pos) to be set."
         higher = self._higher_order(data)
-        if getattr(self, "precision", "fp32") == "bf16" and not higher and not ops._TC["enabled"]:
+        if getattr(self, "precision", "fp32") == "bf16" and not ops._TC["enabled"]:
             with ops.tensor_cores(True):
                 return self.forward(data)
         plan = Base.plan_for(data)

@@ -309,27 +309,38 @@ class SegmentSum(torch.autograd.Function):
 
 
 class MatMul(torch.autograd.Function):
-    """``op(a) @ op(b)`` (2-D).  d/da and d/db are MatMuls again, so this is closed under autograd."""
+    """``op(a) @ op(b)`` (2-D).  d/da and d/db are MatMuls again, so this is closed under autograd.  Under
+    ``tensor_cores(True)`` (precision="bf16") the three shapes a training step produces -- x Wᵀ, g W and gᵀ x -- run on the
+    tcgen05 TF32 kernels; the flag travels with the node so that (double) backward passes outside the context keep it."""
 
     @staticmethod
     def forward(ctx, a, b, ta, tb):
         ctx.save_for_backward(a, b)
-        ctx.ta, ctx.tb = ta, tb
-        return raw_gemm(_row_major_2d(a), _row_major_2d(b), ta, tb)
+        ctx.ta, ctx.tb, ctx.tc = ta, tb, _TC["enabled"]
+        a2, b2 = _row_major_2d(a), _row_major_2d(b)
+        if ctx.tc:
+            if not ta and tb and tc_ok(a2.shape[0], b2.shape[0], a2.shape[1], a2, b2):         # [m,k] x [n,k]^T
+                return raw_tc_linear(a2, b2, False, None, b2.shape[0], a2.shape[1])[0]
+            if not ta and not tb and tc_ok(a2.shape[0], b2.shape[1], a2.shape[1], a2, b2):     # [m,n] x [n,k]
+                return raw_tc_linear(a2, b2, True, None, b2.shape[1], a2.shape[1])[0]
+            if ta and not tb and tc_ok(a2.shape[0], a2.shape[1], b2.shape[1], a2, b2) and b2.shape[1] + 16 <= 256:
+                return raw_tc_wgrad(a2, b2, want_bias=False)[0]                                    # [m,n]^T x [m,k]
+        return raw_gemm(a2, b2, ta, tb)
 
     @staticmethod
     def backward(ctx, g):
         a, b = ctx.saved_tensors
         ta, tb = ctx.ta, ctx.tb
         ga = gb = None
-        if ctx.needs_input_grad[0]:
-            #  C = A B     : gA = G B^T      C = A^T B   : gA = B G^T
-            #  C = A B^T   : gA = G B        C = A^T B^T : gA = B^T G^T
-            ga = MatMul.apply(b, g, tb, True) if ta else MatMul.apply(g, b, False, not tb)
-        if ctx.needs_input_grad[1]:
-            #  C = A B     : gB = A^T G      C = A B^T   : gB = G^T A
-            #  C = A^T B   : gB = A G        C = A^T B^T : gB = G^T A^T
-            gb = MatMul.apply(g, a, True, ta) if tb else MatMul.apply(a, g, not ta, False)
+        with tensor_cores(ctx.tc):
+            if ctx.needs_input_grad[0]:
+                #  C = A B     : gA = G B^T      C = A^T B   : gA = B G^T
+                #  C = A B^T   : gA = G B        C = A^T B^T : gA = B^T G^T
+                ga = MatMul.apply(b, g, tb, True) if ta else MatMul.apply(g, b, False, not tb)
+            if ctx.needs_input_grad[1]:
+                #  C = A B     : gB = A^T G      C = A B^T   : gB = G^T A
+                #  C = A^T B   : gB = A G        C = A^T B^T : gB = G^T A^T
+                gb = MatMul.apply(g, a, True, ta) if tb else MatMul.apply(a, g, not ta, False)
         return ga, gb, None, None
 
 

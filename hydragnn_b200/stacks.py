@@ -132,10 +132,16 @@ class E_GCL(nn.Module):
             coord_diff = vec / (radial + 1.0)
         else:
             _, radial, coord_diff = ops.EdgeGeomFn.apply(coord, edge_shifts, plan, 1.0)
-        feats = [GatherRows.apply(x, plan.by_row), GatherRows.apply(x, plan.by_col), radial]
+        # edge_mlp (:245-250).  Its first Linear acts on [x_row | x_col | radial | edge_attr]; it is linear in the blocks,
+        # so the two node blocks are multiplied per NODE (N rows instead of E) and gathered per edge afterwards.
+        lin0, fin = self.edge_mlp[0], x.shape[1]
+        w0 = lin0.weight
+        lin = ops.linear_any_order if higher_order else ops.linear_act
+        h = GatherRows.apply(lin(x, w0[:, :fin], None), plan.by_row) + GatherRows.apply(lin(x, w0[:, fin:2 * fin], None), plan.by_col)
+        h = h + radial * w0[:, 2 * fin] + lin0.bias
         if edge_attr is not None:
-            feats.append(edge_attr)
-        m = run_mlp(self.edge_mlp, torch.cat(feats, dim=1), higher_order)           # :245-250
+            h = h + lin(edge_attr, w0[:, 2 * fin + 1:], None)
+        m = run_mlp(self.edge_mlp[2:], self.edge_mlp[1](h), higher_order)
         if self.equivariant:                                                         # :268-276
             trans = torch.clamp(coord_diff * run_mlp(self.coord_mlp, m, higher_order), min=-100, max=100)
             cnt = (plan.by_row.rowptr[1:] - plan.by_row.rowptr[:-1]).clamp(min=1).to(trans.dtype)
@@ -410,7 +416,7 @@ class Base(nn.Module):
         if x.dtype != torch.float32:
             raise RuntimeError("b200 engine kernels are fp32 (bf16 via autocast-style GEMMs); got " + str(x.dtype))
         higher = self._higher_order(data)
-        if getattr(self, "precision", "fp32") == "bf16" and not higher and not ops._TC["enabled"]:
+        if getattr(self, "precision", "fp32") == "bf16" and not ops._TC["enabled"]:
             with ops.tensor_cores(True):       # large-M Linears on tcgen05 (TF32 in, fp32 accumulate)
                 return self.forward(data)
         plan = self.plan_for(data)

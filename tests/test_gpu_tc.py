@@ -96,3 +96,26 @@ def test_qm9_painn_bf16_mode_close_to_fp32_and_trains():
     opt = hb.FlatAdamW(model, lr=1e-3)
     losses = [float(hb.train_step(model, opt, b)[0]) for _ in range(20)]
     assert losses[-1] < losses[0]
+
+
+def test_mlip_double_backward_on_tensor_cores_close_to_fp32():
+    """precision="bf16" also covers the any-order (MLIP) path: MatMul and its (double) backward run on the TF32 kernels."""
+    name, G = "md17_egnn", 64
+    b = make_samples(name, G).to(DEV)
+    b._num_graphs = G
+    b = hb.get_radius_graph(7.0, 5)(b)
+    m32 = hb.create_model(**ARCH[name])
+    mtc = hb.set_precision(hb.create_model(**ARCH[name]), "bf16")
+    out = []
+    for m in (m32, mtc):
+        m.train()
+        d = b.clone()
+        d.pos.requires_grad_(True)
+        before = hb._lib.launch_count()
+        loss, tasks = m.energy_force_loss(m(d), d)
+        loss.backward()
+        out.append((float(loss), [p.grad.clone() for p in m.parameters()]))
+    assert abs(out[1][0] - out[0][0]) <= 2e-2 * abs(out[0][0])
+    num = sum(float((p - q).double().pow(2).sum()) for p, q in zip(out[1][1], out[0][1]))
+    den = sum(float(q.double().pow(2).sum()) for q in out[0][1])
+    assert (num / den) ** 0.5 < 3e-2
