@@ -249,19 +249,29 @@ class PainnConv(nn.Module):
 
 
 class MLPNode(nn.Module):
-    """Shared node-level MLP head, ``node_type == 'mlp'`` (hydragnn/models/Base.py:912-964)."""
+    """Node-level MLP head (hydragnn/models/Base.py:912-979): one shared MLP (``node_type == 'mlp'``) or one MLP per node
+    position (``'mlp_per_node'``: graphs of exactly ``num_nodes`` atoms, node i of every graph goes through ``mlp[i]``)."""
 
-    def __init__(self, input_dim, output_dim, hidden_dim_node, activation):
+    def __init__(self, input_dim, output_dim, hidden_dim_node, activation, num_mlp=1, num_nodes=None):
         super().__init__()
-        dims = [input_dim] + list(hidden_dim_node)
-        layers = []
-        for d0, d1 in zip(dims[:-1], dims[1:]):
-            layers += [nn.Linear(d0, d1), activation]
-        layers.append(nn.Linear(dims[-1], output_dim))
-        self.mlp = nn.ModuleList([nn.Sequential(*layers)])
+        self.num_nodes, self.output_dim = num_nodes, output_dim
+        self.mlp = nn.ModuleList()
+        for _ in range(num_mlp):
+            dims = [input_dim] + list(hidden_dim_node)
+            layers = []
+            for d0, d1 in zip(dims[:-1], dims[1:]):
+                layers += [nn.Linear(d0, d1), activation]
+            layers.append(nn.Linear(dims[-1], output_dim))
+            self.mlp.append(nn.Sequential(*layers))
 
     def forward(self, x, higher_order=False):
-        return run_mlp(self.mlp[0], x, higher_order)
+        if self.num_nodes is None:
+            return run_mlp(self.mlp[0], x, higher_order)
+        k = self.num_nodes
+        if x.shape[0] % k:
+            raise ValueError("mlp_per_node needs graphs of exactly num_nodes = %d atoms" % k)
+        xs = x.reshape(-1, k, x.shape[1])
+        return torch.stack([run_mlp(self.mlp[i], xs[:, i, :].contiguous(), higher_order) for i in range(k)], dim=1).reshape(x.shape[0], -1)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -304,6 +314,8 @@ class Base(nn.Module):
         self.graph_convs = nn.ModuleList()
         self.feature_layers = nn.ModuleList()
         self.heads_NN = nn.ModuleList()
+        self.convs_node_hidden, self.batch_norms_node_hidden = nn.ModuleDict(), nn.ModuleDict()      # Base.py:88-91
+        self.convs_node_output, self.batch_norms_node_output = nn.ModuleDict(), nn.ModuleDict()
         # global attention: every conv runs at hidden_dim and is wrapped in a GPS layer (Base.py:177-215)
         if self.global_attn_engine:
             if self.global_attn_engine != "GPS":
@@ -358,6 +370,9 @@ class Base(nn.Module):
                 for _ in range(a["num_sharedlayers"] - 1):
                     layers += [nn.Linear(a["dim_sharedlayers"], a["dim_sharedlayers"]), act]
                 self.graph_shared[br["type"]] = nn.Sequential(*layers)
+        if "node" in self.config_heads:
+            self._init_node_conv()
+        inode = 0
         for ih in range(self.num_heads):
             head = nn.ModuleDict()
             if self.head_type[ih] == "graph":
@@ -372,12 +387,54 @@ class Base(nn.Module):
             elif self.head_type[ih] == "node":
                 for br in self.config_heads["node"]:
                     a = br["architecture"]
-                    if a["type"] != "mlp":
-                        raise ValueError("b200 engine: node heads of type %r are not supported yet (use 'mlp')" % (a["type"],))
-                    head[br["type"]] = MLPNode(self.hidden_dim, self.head_dims[ih], a["dim_headlayers"], act)
+                    if a["type"] in ("mlp", "mlp_per_node"):                            # Base.py:648-664
+                        per_node = a["type"] == "mlp_per_node"
+                        if per_node:
+                            assert self.num_nodes is not None, "num_nodes must be provided for mlp_per_node; use 'mlp' for variable-size graphs"
+                        head[br["type"]] = MLPNode(self.hidden_dim, self.head_dims[ih], a["dim_headlayers"], act,
+                                                   num_mlp=self.num_nodes if per_node else 1, num_nodes=self.num_nodes if per_node else None)
+                    elif a["type"] == "conv":                                            # :665-680, the same modules listed again
+                        key, mods = br["type"], nn.ModuleList()
+                        for conv, bn in zip(self.convs_node_hidden[key], self.batch_norms_node_hidden[key]):
+                            mods.append(conv)
+                            mods.append(bn)
+                        mods.append(self.convs_node_output[key][inode])
+                        mods.append(self.batch_norms_node_output[key][inode])
+                        head[key] = mods
+                        inode += 1
+                    else:
+                        raise ValueError("Unknown head NN structure for node features" + str(a["type"]) +
+                                         "; currently only support 'mlp', 'mlp_per_node' or 'conv'")
             else:
                 raise ValueError("Unknown head type" + str(self.head_type[ih]) + "; currently only support 'graph' or 'node'")
             self.heads_NN.append(head)
+
+    def _init_node_conv(self):
+        """Base._init_node_conv (:508-588): conv-type node heads; the hidden convolutions are shared between the heads."""
+        from .gps import PyGBatchNorm
+        cfgs = self.config_heads["node"]
+        if any(br["architecture"]["type"] != "conv" for br in cfgs):
+            return
+        node_heads = [i for i, t in enumerate(self.head_type) if t == "node"]
+        if not node_heads:
+            return
+        if self.use_global_attn or len(cfgs) > 1:
+            raise ValueError("b200 engine: conv-type node heads are implemented for one branch and without global attention")
+        for br in cfgs:
+            a = br["architecture"]
+            hid = a["dim_headlayers"]
+            ch, bh, co, bo = nn.ModuleList(), nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+            ch.append(self.get_conv(self.hidden_dim, hid[0], last_layer=False))
+            bh.append(PyGBatchNorm(hid[0]))
+            for k in range(a["num_headlayers"] - 1):
+                ch.append(self.get_conv(hid[k], hid[k + 1], last_layer=False))
+                bh.append(PyGBatchNorm(hid[k + 1]))
+            for ih in node_heads:
+                co.append(self.get_conv(hid[-1], self.head_dims[ih], last_layer=True))
+                bo.append(PyGBatchNorm(self.head_dims[ih]))
+            key = br["type"]
+            self.convs_node_hidden[key], self.batch_norms_node_hidden[key] = ch, bh
+            self.convs_node_output[key], self.batch_norms_node_output[key] = co, bo
 
     # -- per-batch preparation -----------------------------------------------------------------------
     @staticmethod
@@ -446,6 +503,13 @@ class Base(nn.Module):
                 if kind == "graph":
                     h = run_mlp(self.graph_shared["branch-0"], x_graph, higher)
                     outputs.append(run_mlp(head["branch-0"], h, higher)[:, :hd])
+                elif isinstance(head["branch-0"], nn.ModuleList):                 # conv-type node head (Base.py:800-810)
+                    a, b = x, equiv
+                    mods = head["branch-0"]
+                    for conv, bn in zip(mods[0::2], mods[1::2]):
+                        a, b = conv(inv_node_feat=a, equiv_node_feat=b, plan=plan, higher_order=higher, **conv_args)
+                        a = self.activation_function(bn(a))
+                    outputs.append(a[:, :hd])
                 else:
                     outputs.append(head["branch-0"](x, higher)[:, :hd])
                 continue

@@ -120,6 +120,8 @@ class OracleModel(nn.Module):
         # --- decoder (Base.py:590-691), single or multi branch
         act = self.activation_function
         self.heads_NN = nn.ModuleList()          # registered before graph_shared, as in Base.__init__:83
+        self.convs_node_hidden, self.batch_norms_node_hidden = nn.ModuleDict(), nn.ModuleDict()       # Base.py:88-91
+        self.convs_node_output, self.batch_norms_node_output = nn.ModuleDict(), nn.ModuleDict()
         self.graph_shared = nn.ModuleDict()
         self.num_branches = 1
         if "graph" in self.config_heads:
@@ -130,6 +132,9 @@ class OracleModel(nn.Module):
                 for _ in range(a["num_sharedlayers"] - 1):
                     layers += [nn.Linear(a["dim_sharedlayers"], a["dim_sharedlayers"]), act]
                 self.graph_shared[br["type"]] = nn.Sequential(*layers)
+        if "node" in self.config_heads:
+            self._init_node_conv(num_nodes)
+        inode = 0
         for ih in range(self.num_heads):
             head = nn.ModuleDict()
             if self.head_type[ih] == "graph":
@@ -144,12 +149,51 @@ class OracleModel(nn.Module):
             elif self.head_type[ih] == "node":
                 for br in self.config_heads["node"]:
                     a = br["architecture"]
-                    if a["type"] != "mlp":
-                        raise ValueError("oracle supports node heads of type 'mlp' only")
-                    head[br["type"]] = _MLPNode(hidden_dim, self.head_dims[ih], a["dim_headlayers"], act)
+                    if a["type"] in ("mlp", "mlp_per_node"):                       # Base.py:648-664
+                        per_node = a["type"] == "mlp_per_node"
+                        if per_node:
+                            assert num_nodes is not None, "num_nodes must be provided for mlp_per_node; use 'mlp' for variable-size graphs"
+                        head[br["type"]] = _MLPNode(hidden_dim, self.head_dims[ih], a["dim_headlayers"], act,
+                                                    num_mlp=num_nodes if per_node else 1, num_nodes=num_nodes if per_node else None)
+                    elif a["type"] == "conv":                                       # Base.py:665-680: the SAME modules, listed again
+                        key, mods = br["type"], nn.ModuleList()
+                        for conv, bn in zip(self.convs_node_hidden[key], self.batch_norms_node_hidden[key]):
+                            mods.append(conv)
+                            mods.append(bn)
+                        mods.append(self.convs_node_output[key][inode])
+                        mods.append(self.batch_norms_node_output[key][inode])
+                        head[key] = mods
+                        inode += 1
+                    else:
+                        raise ValueError("Unknown head NN structure for node features" + a["type"])
             else:
                 raise ValueError("Unknown head type" + str(self.head_type[ih]))
             self.heads_NN.append(head)
+
+    def _init_node_conv(self, num_nodes):
+        """Base._init_node_conv (:508-588): conv-type node heads share their hidden convolutions between heads."""
+        from .gps import PyGBatchNorm
+        cfgs = self.config_heads["node"]
+        if any(br["architecture"]["type"] != "conv" for br in cfgs):
+            return
+        node_heads = [i for i, t in enumerate(self.head_type) if t == "node"]
+        if not node_heads:
+            return
+        for br in cfgs:
+            a = br["architecture"]
+            hid = a["dim_headlayers"]
+            ch, bh, co, bo = nn.ModuleList(), nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+            ch.append(self._get_conv(self.hidden_dim, hid[0], False))
+            bh.append(PyGBatchNorm(hid[0]))
+            for k in range(a["num_headlayers"] - 1):
+                ch.append(self._get_conv(hid[k], hid[k + 1], False))
+                bh.append(PyGBatchNorm(hid[k + 1]))
+            for ih in node_heads:
+                co.append(self._get_conv(hid[-1], self.head_dims[ih], True))
+                bo.append(PyGBatchNorm(self.head_dims[ih]))
+            key = br["type"]
+            self.convs_node_hidden[key], self.batch_norms_node_hidden[key] = ch, bh
+            self.convs_node_output[key], self.batch_norms_node_output[key] = co, bo
 
     # EGCLStack.get_conv :72-109 / PAINNStack.get_conv :76-147
     def _get_conv(self, fin, fout, last):
@@ -190,8 +234,9 @@ class OracleModel(nn.Module):
 
         if self.mpnn_type == "EGNN":
             equiv = pos
+            run_conv = lambda c, a, b: c.module_0(a, b, ei, eattr, shifts)
             for conv in self.graph_convs:
-                x, equiv = layer(conv, lambda c, a, b: c.module_0(a, b, ei, eattr, shifts))(x, equiv)
+                x, equiv = layer(conv, run_conv)(x, equiv)
                 x = self.activation_function(x)                              # Base.py:726
         elif self.mpnn_type == "PNAEq":
             vec, dist = edge_vectors_and_lengths(pos, ei, shifts, normalize=True)    # PNAEqStack.py:202-205
@@ -205,9 +250,11 @@ class OracleModel(nn.Module):
                 a = c.module_2(a)
                 return a, (c.module_3(b3) if b3 is not None else b2)
 
+            run_conv = pna_conv
             for conv in self.graph_convs:
                 x, v = layer(conv, pna_conv)(x, v)
                 x = self.activation_function(x)
+            equiv = v
         else:
             diff, dist = edge_vectors_and_lengths(pos, ei, shifts, normalize=True)   # PAINNStack.py:157-159
             edge = ei.t()
@@ -219,9 +266,11 @@ class OracleModel(nn.Module):
                 a = c.module_2(a)
                 return a, (c.module_3(b3) if b3 is not None else b2)
 
+            run_conv = painn_conv
             for conv in self.graph_convs:
                 x, v = layer(conv, painn_conv)(x, v)
                 x = self.activation_function(x)
+            equiv = v
         batch = getattr(data, "batch", None)
         if batch is None:
             batch = torch.zeros(x.shape[0], dtype=torch.long, device=x.device)
@@ -233,8 +282,15 @@ class OracleModel(nn.Module):
             if self.num_branches == 1:
                 if kind == "graph":
                     outs.append(head["branch-0"](self.graph_shared["branch-0"](xg))[:, :hd])
+                elif isinstance(head["branch-0"], nn.ModuleList):          # conv-type node head (Base.py:800-810)
+                    a, b = x, equiv
+                    mods = head["branch-0"]
+                    for conv, bn in zip(mods[0::2], mods[1::2]):
+                        a, b = run_conv(conv, a, b)
+                        a = self.activation_function(bn(a))
+                    outs.append(a[:, :hd])
                 else:
-                    outs.append(head["branch-0"](x)[:, :hd])
+                    outs.append(head["branch-0"](x, batch)[:, :hd])
                 continue
             # multi-branch masking (Base.py:770-780, 816-840)
             ids = ds[:, 0]
@@ -248,7 +304,9 @@ class OracleModel(nn.Module):
                 out = x.new_zeros(x.shape[0], hd)
                 for b in ids.unique():
                     m = (ids == b)[batch]
-                    out[m] = head["branch-%d" % int(b)](x[m])[:, :hd]
+                    if isinstance(head["branch-%d" % int(b)], nn.ModuleList):
+                        raise ValueError("oracle: conv-type node heads with several branches are not restated")
+                    out[m] = head["branch-%d" % int(b)](x[m], batch[m])[:, :hd]
             outs.append(out)
         return outs
 
@@ -264,19 +322,28 @@ class OracleModel(nn.Module):
 
 
 class _MLPNode(nn.Module):
-    """``MLPNode`` with ``node_type == 'mlp'`` (Base.py:912-964)."""
+    """``MLPNode`` (Base.py:912-979): one shared MLP ('mlp') or one MLP per node position ('mlp_per_node', graphs of exactly
+    ``num_nodes`` atoms: node i of every graph goes through ``mlp[i]``)."""
 
-    def __init__(self, fin, fout, hidden, act):
+    def __init__(self, fin, fout, hidden, act, num_mlp=1, num_nodes=None):
         super().__init__()
-        dims = [fin] + list(hidden)
-        layers = []
-        for d0, d1 in zip(dims[:-1], dims[1:]):
-            layers += [nn.Linear(d0, d1), act]
-        layers.append(nn.Linear(dims[-1], fout))
-        self.mlp = nn.ModuleList([nn.Sequential(*layers)])
+        self.num_nodes, self.fout = num_nodes, fout
+        self.mlp = nn.ModuleList()
+        for _ in range(num_mlp):
+            dims = [fin] + list(hidden)
+            layers = []
+            for d0, d1 in zip(dims[:-1], dims[1:]):
+                layers += [nn.Linear(d0, d1), act]
+            layers.append(nn.Linear(dims[-1], fout))
+            self.mlp.append(nn.Sequential(*layers))
 
-    def forward(self, x):
-        return self.mlp[0](x)
+    def forward(self, x, batch=None):
+        if self.num_nodes is None:
+            return self.mlp[0](x)
+        outs = x.new_zeros(x.shape[0], self.fout)
+        for i in range(self.num_nodes):
+            outs[i::self.num_nodes] = self.mlp[i](x[i::self.num_nodes])
+        return outs
 
 
 def create_model(**kw):

@@ -377,6 +377,36 @@ def main():
     lim = glb["_limit_neighbors"](None, *a, 6)
     torch.save({"in": [torch.from_numpy(np.asarray(t)) for t in (src, dst, length, S)],
                 "k": 6, "out": [torch.from_numpy(np.asarray(t)) for t in lim]}, HERE + "/pbc_limit.pt")
+    # ---- node heads of type 'mlp_per_node' and 'conv' (Base.py:508-588, 648-680, 800-810, 912-979) -------------------
+    # own generator so that the files above stay byte-identical; PyG BatchNorm naming (a module holding `.module`)
+    from oracle.gps import PyGBatchNorm
+    sys.modules["hydragnn.models.Base"].BatchNorm = PyGBatchNorm
+    gen2 = torch.Generator().manual_seed(4321)
+    hmodels = {}
+    heads_pernode = {"node": [{"type": "branch-0", "architecture": {"num_headlayers": 2, "dim_headlayers": [7, 5], "type": "mlp_per_node"}}]}
+    heads_conv = {"node": [{"type": "branch-0", "architecture": {"num_headlayers": 2, "dim_headlayers": [10, 6], "type": "conv"}}]}
+    for name in ("egnn_mlp_per_node", "egnn_conv_head", "painn_conv_head"):
+        b = toy_batch(gen2, [6, 6, 6] if name == "egnn_mlp_per_node" else [7, 5, 8], 4.0, input_dim=1)
+        b.y = torch.randn(b.x.shape[0], 2, generator=gen2)
+        torch.manual_seed(0)
+        if name.startswith("egnn"):
+            m = egcl.EGCLStack("inv_node_feat, equiv_node_feat, edge_index, edge_attr, edge_shifts", "", None,
+                               1, 12, [2], 0, "", "", 0, ["node"], heads_pernode if name == "egnn_mlp_per_node" else heads_conv,
+                               "relu", "mse", False, max_neighbours=None, loss_weights=[1.0], freeze_conv=False, initial_bias=None,
+                               num_conv_layers=2, num_nodes=6 if name == "egnn_mlp_per_node" else None, graph_pooling="mean")
+        else:
+            m = painn.PAINNStack("inv_node_feat, equiv_node_feat, edge_index, diff, dist",
+                                 "inv_node_feat, equiv_node_feat, edge_index, diff, dist", None, 5, 7.0,
+                                 1, 12, [2], 0, "", "", 0, ["node"], heads_conv, "relu", "mse", False,
+                                 loss_weights=[1.0], freeze_conv=False, num_conv_layers=2, num_nodes=None, graph_pooling="mean")
+        m.train()                                      # batch-statistics BatchNorm in the conv heads
+        state = {k: v.clone() for k, v in m.state_dict().items()}
+        pred = m(b)
+        loss, _ = m.loss(pred, b.y, [torch.arange(b.y.shape[0])])
+        grads = torch.autograd.grad(loss, list(m.parameters()), allow_unused=True)
+        hmodels[name] = {"state": state, "inputs": t2d(b), "pred": [p.detach() for p in pred], "loss": loss.detach(),
+                         "grads": {n: (g.detach() if g is not None else None) for (n, _), g in zip(m.named_parameters(), grads)}}
+    torch.save(hmodels, HERE + "/models_heads.pt")
     print("golden vectors written to", HERE)
 
 

@@ -11,7 +11,7 @@ import torch
 import hydragnn_b200 as hb
 from hydragnn_b200 import _lib, ops
 from hydragnn_b200.synthetic import ARCH, make_samples
-from test_oracle_golden import GPS_KW, MODEL_KW, PNAEQ_KW
+from test_oracle_golden import GPS_KW, HEAD_KW, MODEL_KW, PNAEQ_KW
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -109,6 +109,17 @@ def test_mace_initialisation_matches_oracle_and_tables_agree():
     assert pe3.tp_paths(1, 2, 2) == [(0, 0, 0), (1, 1, 0), (0, 1, 1), (1, 0, 1), (1, 2, 1), (0, 2, 2), (1, 1, 2)]
     with pytest.raises(AssertionError, match="max_ell"):
         hb.create_model(mpnn_type="MACE", use_gpu=False, **dict(MACE_KW, max_ell=None))
+
+
+def test_node_head_variants_initialisation_matches_reference(golden_dir):
+    g = torch.load(golden_dir + "/models_heads.pt")
+    for name, kw in HEAD_KW.items():
+        sd = hb.create_model(use_gpu=False, **kw).state_dict()
+        assert list(sd.keys()) == list(g[name]["state"].keys()), name
+        for k, v in sd.items():
+            assert torch.equal(v, g[name]["state"][k]), (name, k)
+    with pytest.raises(AssertionError, match="num_nodes"):
+        hb.create_model(use_gpu=False, **dict(HEAD_KW["egnn_mlp_per_node"], num_nodes=None))
 
 
 def test_create_model_errors_mirror_reference():

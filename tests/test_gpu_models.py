@@ -16,7 +16,7 @@ from hydragnn_b200 import ops  # noqa: E402
 from hydragnn_b200.synthetic import ARCH, make_samples  # noqa: E402
 import oracle  # noqa: E402
 from oracle.workloads import add_edges_cpu  # noqa: E402
-from test_oracle_golden import GPS_KW, MODEL_KW, PNAEQ_KW, _zero_dropout  # noqa: E402
+from test_oracle_golden import GPS_KW, HEAD_KW, MODEL_KW, PNAEQ_KW, _zero_dropout  # noqa: E402
 
 DEV = "cuda"
 
@@ -339,3 +339,23 @@ def test_gps_any_order_path_equals_fused_path(golden_dir):
         m.force_higher_order = True
         b = m(_batch(c["inputs"]))[0]
     assert rel_l2(b.cpu(), a.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("name", list(HEAD_KW))
+def test_node_heads_mlp_per_node_and_conv_match_reference_golden(golden_dir, name):
+    c = torch.load(golden_dir + "/models_heads.pt")[name]
+    m = _engine(HEAD_KW[name], c["state"])
+    m.train()
+    d = _batch(c["inputs"])
+    pred = m(d)
+    assert rel_l2(pred[0].cpu(), c["pred"][0]) < 1e-5
+    loss, _ = m.loss(pred, d.y, [torch.arange(d.y.shape[0], device=DEV)])
+    assert abs(float(loss) - float(c["loss"])) < 1e-5 * max(1.0, abs(float(c["loss"])))
+    loss.backward()
+    gmax = max(float(v.abs().max()) for v in c["grads"].values() if v is not None)
+    for n, p in m.named_parameters():
+        ref = c["grads"][n]
+        if ref is None:
+            continue
+        # biases in front of a BatchNorm have an exactly-zero gradient: compare on the scale of the whole gradient
+        assert torch.allclose(p.grad.cpu(), ref, rtol=1e-3, atol=1e-4 * gmax), (name, n)

@@ -207,3 +207,39 @@ def test_gps_matches_reference_golden(golden_dir):
         sd = m.state_dict()
         for k, v in c["state_after"].items():
             torch.testing.assert_close(sd[k], v, rtol=1e-4, atol=1e-6)
+
+
+HEADS_PERNODE = {"node": {"num_headlayers": 2, "dim_headlayers": [7, 5], "type": "mlp_per_node"}}
+HEADS_CONV = {"node": {"num_headlayers": 2, "dim_headlayers": [10, 6], "type": "conv"}}
+HEAD_KW = {
+    "egnn_mlp_per_node": dict(mpnn_type="EGNN", input_dim=1, hidden_dim=12, output_dim=[2], output_type=["node"], output_heads=HEADS_PERNODE,
+                              activation_function="relu", num_conv_layers=2, task_weights=[1.0], num_nodes=6),
+    "egnn_conv_head": dict(mpnn_type="EGNN", input_dim=1, hidden_dim=12, output_dim=[2], output_type=["node"], output_heads=HEADS_CONV,
+                           activation_function="relu", num_conv_layers=2, task_weights=[1.0]),
+    "painn_conv_head": dict(mpnn_type="PAINN", input_dim=1, hidden_dim=12, output_dim=[2], output_type=["node"], output_heads=HEADS_CONV,
+                            activation_function="relu", num_conv_layers=2, task_weights=[1.0], num_radial=5, radius=7.0),
+}
+
+
+def test_node_heads_mlp_per_node_and_conv_match_reference_golden(golden_dir):
+    """`mlp_per_node` and `conv` node heads (Base.py:508-588, 648-680, 800-810, 912-979) through the reference's own Base."""
+    g = torch.load(golden_dir + "/models_heads.pt")
+    for name, kw in HEAD_KW.items():
+        c = g[name]
+        torch.manual_seed(0)
+        m = OracleModel(**kw)
+        assert list(m.state_dict().keys()) == list(c["state"].keys()), name
+        for k, v in m.state_dict().items():                       # same construction order => same seeded initialisation
+            assert torch.equal(v, c["state"][k]), (name, k)
+        m.train()
+        d = _data(c["inputs"])
+        pred = m(d)
+        torch.testing.assert_close(pred[0], c["pred"][0], **TOL)
+        loss, _ = m.loss(pred, d.y, [torch.arange(d.y.shape[0])])
+        torch.testing.assert_close(loss, c["loss"], **TOL)
+        grads = torch.autograd.grad(loss, list(m.parameters()), allow_unused=True)
+        for (n, _), gr in zip(m.named_parameters(), grads):
+            ref = c["grads"][n]
+            assert (gr is None) == (ref is None), (name, n)
+            if gr is not None:
+                torch.testing.assert_close(gr, ref, rtol=1e-4, atol=1e-5)      # biases in front of a BatchNorm: exact gradient 0, fp noise
