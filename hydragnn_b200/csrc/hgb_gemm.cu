@@ -287,6 +287,37 @@ __global__ void linear_smallk_fwd_kernel(const float* __restrict__ x, int64_t ld
   }
 }
 
+// n % 4 == 0: a thread owns four consecutive output columns of a row (16-byte stores), its weights live in registers, rows are
+// walked with a 2-D block (x: column group, y: row) -- no index division, no shared memory.
+template <int KT>
+__global__ void linear_smallk_fwd_vec4_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w, int64_t ldw,
+                                              const float* __restrict__ b, int m, int n, int k, int act, float ap,
+                                              float* __restrict__ y, float* __restrict__ z) {
+  const int c0 = threadIdx.x * 4;
+  float wr[4][KT], bias[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    bias[j] = b ? b[c0 + j] : 0.f;
+#pragma unroll
+    for (int q = 0; q < KT; ++q) wr[j][q] = q < k ? w[(int64_t)(c0 + j) * ldw + q] : 0.f;
+  }
+  for (int r = blockIdx.x * blockDim.y + threadIdx.y; r < m; r += gridDim.x * blockDim.y) {
+    float xr[KT];
+#pragma unroll
+    for (int q = 0; q < KT; ++q) xr[q] = q < k ? __ldg(x + (int64_t)r * ldx + q) : 0.f;
+    float acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[j] = bias[j];
+#pragma unroll
+      for (int q = 0; q < KT; ++q) acc[j] = fmaf(xr[q], wr[j][q], acc[j]);
+    }
+    const int64_t o = (int64_t)r * n + c0;
+    if (z) *reinterpret_cast<float4*>(z + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(y + o) = make_float4(hgb_act(acc[0], act, ap), hgb_act(acc[1], act, ap), hgb_act(acc[2], act, ap), hgb_act(acc[3], act, ap));
+  }
+}
+
 // one pass over (dy, y|z, x): dz = dy * act'(.), dx[m,k] = dz . W, partial dW / db per block.
 // KT = compile-time bound on k (1,2,4,8), NPT = outputs per lane (n <= 32*NPT): only the needed work is generated.
 #define SK_RU 4   // rows per walker trip: independent loads / shuffles hide the latency
@@ -466,6 +497,17 @@ extern "C" int hgb_linear_smallk_fwd(const float* x, int64_t ldx, const float* w
   HGB_REQUIRE(x && w && y && m >= 0 && hgb_linear_smallk_supported(n, k), "linear_smallk_fwd: unsupported shape n=%d k=%d", n, k);
   if (m == 0) return HGB_OK;
   const int64_t total = (int64_t)m * n;
+  if (n % 4 == 0 && n >= 16 && ((uintptr_t)y % 16 == 0) && (!z || (uintptr_t)z % 16 == 0)) {
+    const int cg = n / 4;                                   // <= 64 column groups
+    dim3 block(cg, 256 / cg > 0 ? 256 / cg : 1);
+    const int grid = hgb_grid_for(m, block.y, HGB_NUM_SMS * 8);
+    cudaStream_t st = (cudaStream_t)stream;
+#define SKV(KT_) linear_smallk_fwd_vec4_kernel<KT_><<<grid, block, 0, st>>>(x, ldx, w, ldw, b, m, n, k, act, act_param, y, z)
+    if (k <= 1) SKV(1); else if (k <= 2) SKV(2); else if (k <= 4) SKV(4); else SKV(8);
+#undef SKV
+    HGB_LAUNCH_CHECK("linear_smallk_fwd");
+    return HGB_OK;
+  }
   linear_smallk_fwd_kernel<<<hgb_grid_for(total, 256), 256, (size_t)(n * k + n) * 4, (cudaStream_t)stream>>>(x, ldx, w, ldw, b, total, n, k,
                                                                                                        act, act_param, y, z);
   HGB_LAUNCH_CHECK("linear_smallk_fwd");
