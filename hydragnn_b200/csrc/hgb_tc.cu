@@ -181,22 +181,6 @@ __global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_holder, (uint32_t)p.tmem_cols);
-  // stage the weight operand (generic-proxy stores, then make them visible to the async proxy)
-  {
-    const int total = NO * p.kr;
-    if (!p.trans_b) {
-      for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int r = i / p.kr, c = i - r * p.kr;
-        *reinterpret_cast<float*>(sB + kmajor_sw128_off(r, c, NO)) = __ldg(p.w + (int64_t)r * p.ldw + c);
-      }
-    } else {
-      for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int c = i / NO, r = i - c * NO;  // r fastest: w[c, r] is contiguous in r
-        *reinterpret_cast<float*>(sB + kmajor_sw128_off(r, c, NO)) = __ldg(p.w + (int64_t)c * p.ldw + r);
-      }
-    }
-    fence_proxy_async();
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -217,7 +201,9 @@ __global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant
         }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer =====  (waits until warps 2..9 have staged the weight operand; the TMA producer does not)
+    asm volatile("bar.sync 1, 288;" ::: "memory");
+    tc_fence_after();
     if (lane == 0) {
       int s = 0, acc = 0;
       uint32_t ph = 0, aph = 0;
@@ -243,7 +229,39 @@ __global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant
       }
     }
   } else {
-    // ===== epilogue: warps 2..9.  Warp w may only touch TMEM lanes 32*(w%4)..+31; the two warps that share a lane
+    // ===== warps 2..9: first stage the weight operand into its K-major SWIZZLE_128B layout (generic-proxy stores made
+    // visible to the async proxy), release the MMA warp, then run the epilogue =====
+    {
+      const int total = NO * p.kr;
+      constexpr int SU = 8;   // independent loads in flight per thread: the staging is latency-, not bandwidth-limited
+      for (int base = threadIdx.x - 64; base < total; base += 256 * SU) {
+        float val[SU];
+        uint32_t off[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+          const int i = base + u * 256;
+          val[u] = 0.f;
+          off[u] = 0xffffffffu;
+          if (i < total) {
+            if (!p.trans_b) {
+              const int r = i / p.kr, c = i - r * p.kr;
+              off[u] = kmajor_sw128_off(r, c, NO);
+              val[u] = __ldg(p.w + (int64_t)r * p.ldw + c);
+            } else {
+              const int c = i / NO, r = i - c * NO;  // r fastest: w[c, r] is contiguous in r
+              off[u] = kmajor_sw128_off(r, c, NO);
+              val[u] = __ldg(p.w + (int64_t)c * p.ldw + r);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < SU; ++u)
+          if (off[u] != 0xffffffffu) *reinterpret_cast<float*>(sB + off[u]) = val[u];
+      }
+      fence_proxy_async();
+    }
+    asm volatile("bar.arrive 1, 288;" ::: "memory");
+    // ===== epilogue.  Warp w may only touch TMEM lanes 32*(w%4)..+31; the two warps that share a lane
     // quarter split the 32-column chunks between them (even / odd chunk index). =====
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
