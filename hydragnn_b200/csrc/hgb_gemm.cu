@@ -102,7 +102,7 @@ static int pick_splits(int m, int n, int k) {
   const int tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
   if (tiles >= HGB_NUM_SMS || k < 4096) return 1;
   int s = (HGB_NUM_SMS * 4 + tiles - 1) / tiles;
-  const int maxs = (k + 255) / 256;
+  const int maxs = (k + 63) / 64;
   if (s > maxs) s = maxs;
   return s < 1 ? 1 : s;
 }
@@ -534,8 +534,13 @@ extern "C" int hgb_linear_smallk_bwd(const float* dy, const float* y, const floa
   }
   int rpb;
   const int nb = smallk_blocks(m, &rpb);
+  int nb_used = nb;
   if (n <= SK_NMAX) {
-    linear_tiny_bwd_kernel<<<nb, 256, 0, st>>>(dy, y, z, x, ldx, w, ldw, m, n, k, act, act_param, rpb, dx, (float*)workspace);
+    // thread-per-row kernel: the per-block reduction (n (k+1) block-wide sums) dominates unless a thread owns several rows
+    int rpb_t = (m + HGB_NUM_SMS * 2 - 1) / (HGB_NUM_SMS * 2);
+    rpb_t = ((rpb_t + 255) / 256) * 256;
+    nb_used = (m + rpb_t - 1) / rpb_t;          // <= nb: the workspace is sized for nb partials
+    linear_tiny_bwd_kernel<<<nb_used, 256, 0, st>>>(dy, y, z, x, ldx, w, ldw, m, n, k, act, act_param, rpb_t, dx, (float*)workspace);
   } else {
     const int kt = k <= 1 ? 1 : (k <= 2 ? 2 : (k <= 4 ? 4 : 8));
     const int npt = n <= 32 ? 1 : (n <= 64 ? 2 : (n <= 128 ? 4 : 8));
@@ -546,7 +551,7 @@ extern "C" int hgb_linear_smallk_bwd(const float* dy, const float* y, const floa
 #undef SK_LAUNCH
   }
   HGB_LAUNCH_CHECK("linear_smallk_bwd");
-  linear_smallk_reduce_kernel<<<(n * (k + 1) + 31) / 32, dim3(32, 8), 0, st>>>((const float*)workspace, nb, n, k, dw, lddw, db);
+  linear_smallk_reduce_kernel<<<(n * (k + 1) + 31) / 32, dim3(32, 8), 0, st>>>((const float*)workspace, nb_used, n, k, dw, lddw, db);
   HGB_LAUNCH_CHECK("linear_smallk_reduce");
   return HGB_OK;
 }
