@@ -66,6 +66,7 @@ __device__ __forceinline__ float hgb_act(float x, int act, float p) {
 __device__ __forceinline__ float hgb_act_grad(float y, float z, int act, float p) {
   switch (act) {
     case HGB_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case HGB_ACT_DERIV: return z;   // the tensor already holds the derivative
     case HGB_ACT_SILU: { float s = hgb_sigmoid(z); return s * (1.f + z * (1.f - s)); }
     case HGB_ACT_TANH: return 1.f - y * y;
     case HGB_ACT_SIGMOID: return y * (1.f - y);

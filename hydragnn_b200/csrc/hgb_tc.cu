@@ -145,6 +145,9 @@ struct LinParams {
   float* z;
   const float* addend;  // optional [m, no] (row stride ldy): y = act(a.B^T + bias) + addend  (gradient accumulation without an extra pass)
   int64_t ldy;          // row stride of y / z / addend (>= no: column chunks of a wider matrix)
+  const float* gsrc;    // optional [m, no] (row stride ldy): the result is multiplied by act'(gsrc), i.e. this GEMM is the dgrad of a
+  int gact;             //   layer whose INPUT was act(.): gsrc = saved pre-activation (SiLU) or activation output (others)
+  int z_deriv;          // forward with a SiLU and z != NULL: z receives silu'(pre-activation) instead of the pre-activation
   int stages;
   int tmem_cols;
 };
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant
         }
         if (lane == 0) tma_store_wait_read();                 // the previous chunk's stores have finished reading the tiles
         __syncwarp();
-        if (p.z) {
+        if (p.z && !(p.z_deriv && p.act == HGB_ACT_SILU)) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)   // SWIZZLE_128B tile: 16-byte chunk j of row `lane` lives at chunk j ^ (lane & 7)
             *reinterpret_cast<float4*>(stz + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -300,8 +303,21 @@ __global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             break;
           case HGB_ACT_SILU:
+            if (p.z && p.z_deriv) {   // z receives silu'(pre) = s + y (1 - s): the backward then needs one multiply per element
+              float d[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
+              for (int j = 0; j < 32; ++j) {
+                const float sg = __fdividef(1.f, 1.f + __expf(-v[j]));
+                v[j] *= sg;
+                d[j] = fmaf(v[j], 1.f - sg, sg);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(stz + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
+            }
             break;
           case HGB_ACT_TANH:
 #pragma unroll
@@ -317,6 +333,21 @@ __global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant
           for (int j = 0; j < 8; ++j) {
             const float4 a4 = __ldg(ap + j);
             v[4 * j] += a4.x; v[4 * j + 1] += a4.y; v[4 * j + 2] += a4.z; v[4 * j + 3] += a4.w;
+          }
+        }
+        if (p.gsrc && row < p.m) {
+          const float4* gp = reinterpret_cast<const float4*>(p.gsrc + (int64_t)row * p.ldy + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 g4 = __ldg(gp + j);
+            if (p.gact == HGB_ACT_DERIV) {          // gsrc already holds act'(.)
+              v[4 * j] *= g4.x; v[4 * j + 1] *= g4.y; v[4 * j + 2] *= g4.z; v[4 * j + 3] *= g4.w;
+            } else {
+              v[4 * j] *= hgb_act_grad(g4.x, g4.x, p.gact, p.act_param);
+              v[4 * j + 1] *= hgb_act_grad(g4.y, g4.y, p.gact, p.act_param);
+              v[4 * j + 2] *= hgb_act_grad(g4.z, g4.z, p.gact, p.act_param);
+              v[4 * j + 3] *= hgb_act_grad(g4.w, g4.w, p.gact, p.act_param);
+            }
           }
         }
 #pragma unroll
@@ -550,7 +581,7 @@ extern "C" int hgb_tc_linear_supported(int32_t m, int32_t n_out, int32_t k_red) 
 // one (<= 256) x (<= 256) piece: y[m, no] = act(a[m, kr] . B^T + bias) + addend, y / z / addend with row stride ldy
 static int tc_linear_piece(const float* a, int64_t lda, const float* w, int64_t ldw, int32_t trans_b, const float* bias, int32_t m,
                            int32_t n_out, int32_t k_red, int32_t act, float act_param, float* y, float* z, const float* addend,
-                           int64_t ldy, hgb_stream_t stream) {
+                           const float* gsrc, int32_t gact, int64_t ldy, hgb_stream_t stream) {
   HGB_REQUIRE(a && w && y && m >= 128 && shape_ok(k_red, n_out), "tc_linear: unsupported shape m=%d n=%d k=%d", m, n_out, k_red);
   HGB_REQUIRE(lda % 4 == 0 && ldy % 4 == 0 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!z || (uintptr_t)z % 16 == 0),
               "tc_linear: operands must be 16-byte aligned with a row stride that is a multiple of 4");
@@ -563,7 +594,7 @@ static int tc_linear_piece(const float* a, int64_t lda, const float* w, int64_t 
   if (rc) return rc;
   LinParams p;
   p.m = m; p.kr = k_red; p.no = n_out; p.w = w; p.ldw = ldw; p.trans_b = trans_b; p.bias = bias; p.act = act; p.act_param = act_param;
-  p.y = y; p.z = z; p.addend = addend; p.ldy = ldy;
+  p.y = y; p.z = z; p.addend = addend; p.ldy = ldy; p.gsrc = gsrc; p.gact = gact; p.z_deriv = (!gsrc && gact == HGB_ACT_DERIV) ? 1 : 0;
   const int KB = k_red / 32;
   const size_t b_bytes = ((size_t)KB * n_out * 128 + 1023) & ~(size_t)1023;
   const size_t a_stage = (size_t)TILE_M * 128;
@@ -590,9 +621,9 @@ static int tc_linear_piece(const float* a, int64_t lda, const float* w, int64_t 
 // only: an activation or a saved pre-activation needs the whole sum first).
 extern "C" int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_t ldw, int32_t trans_b, const float* bias, int32_t m,
                              int32_t n_out, int32_t k_red, int32_t act, float act_param, float* y, float* z, const float* addend,
-                             hgb_stream_t stream) {
+                             const float* gsrc, int32_t gact, hgb_stream_t stream) {
   HGB_REQUIRE(a && w && y && hgb_tc_linear_supported(m, n_out, k_red), "tc_linear: unsupported shape m=%d n=%d k=%d", m, n_out, k_red);
-  HGB_REQUIRE(k_red <= 256 || (act == HGB_ACT_NONE && !z), "tc_linear: reduction length %d > 256 needs a plain linear layer", k_red);
+  HGB_REQUIRE(k_red <= 256 || (act == HGB_ACT_NONE && !z && !gsrc), "tc_linear: reduction length %d > 256 needs a plain linear layer", k_red);
   // piece sizes: the B piece (kc x nc fp32) stays resident in shared memory next to >= 2 A stages and the epilogue tiles
   const int kc_max = k_red < 256 ? k_red : 256;
   int nc_max = (int)((122 * 1024) / (4 * (size_t)kc_max) / 32) * 32;
@@ -605,7 +636,7 @@ extern "C" int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_
       const float* wp = trans_b ? w + (int64_t)k0 * ldw + c0 : w + (int64_t)c0 * ldw + k0;
       const float* add = k0 == 0 ? (addend ? addend + c0 : nullptr) : y + c0;
       int rc = tc_linear_piece(a + k0, lda, wp, ldw, trans_b, (bias && k0 == 0) ? bias + c0 : nullptr, m, nc, kc, act, act_param, y + c0,
-                               z ? z + c0 : nullptr, add, n_out, stream);
+                               z ? z + c0 : nullptr, add, gsrc ? gsrc + c0 : nullptr, gact, n_out, stream);
       if (rc) return rc;
     }
   }

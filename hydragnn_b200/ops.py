@@ -181,12 +181,12 @@ def tc_ok(m, n_out, k_red, *tensors):
     return True
 
 
-def raw_tc_linear(a2, w, trans_b, bias, n_out, k_red, code=0, param=0.0, want_z=False, addend=None):
+def raw_tc_linear(a2, w, trans_b, bias, n_out, k_red, code=0, param=0.0, want_z=False, addend=None, gsrc=None, gact=0):
     m = a2.shape[0]
     y = torch.empty(m, n_out, dtype=a2.dtype, device=a2.device)
     z = torch.empty_like(y) if want_z else None
     _lib.call("hgb_tc_linear", _p(a2), a2.stride(0), _p(w), w.stride(0), int(trans_b), _p(bias), m, n_out, k_red, code, float(param),
-              _p(y), _p(z), _p(addend), _stream())
+              _p(y), _p(z), _p(addend), _p(gsrc), int(gact), _stream())
     return y, z
 
 
@@ -233,32 +233,51 @@ def raw_smallk_bwd(dy, y, z, x2, w, code=0, param=0.0, need_x=True, need_w=True,
     return dx, dw, db
 
 
+ACT_DERIV = 100   # HGB_ACT_DERIV: "the tensor already holds act'(.)"
+
+
 def linear_fwd_dispatch(x2, w, b, code=0, param=0.0, want_z=False):
     """y = act(x2 W^T + b) on the tensor-core kernel when the shape qualifies, else the exact-fp32 kernel."""
+    return linear_fwd_dispatch_ex(x2, w, b, code, param, want_z)[:2]
+
+
+def linear_fwd_dispatch_ex(x2, w, b, code=0, param=0.0, want_z=False, z_deriv=False):
+    """-> (y, z, z_is_derivative).  With ``z_deriv`` a SiLU layer on the tensor-core path stores silu'(pre-activation) in z
+    (computed next to the activation itself), so that its backward is a plain multiply."""
     m, k = x2.shape
     n = w.shape[0]
     if smallk_ok(n, k):
-        return raw_smallk_fwd(x2, w, b, code, param, want_z)
+        return raw_smallk_fwd(x2, w, b, code, param, want_z) + (False,)
     if tc_ok(m, n, k, x2):
-        return raw_tc_linear(x2, w, False, b, n, k, code, param, want_z)
-    return raw_linear(x2, w, b, code, param, want_z)
+        deriv = bool(z_deriv and want_z and code == ACT_CODES["silu"])
+        return raw_tc_linear(x2, w, False, b, n, k, code, param, want_z, gact=ACT_DERIV if deriv else 0) + (deriv,)
+    return raw_linear(x2, w, b, code, param, want_z) + (False,)
 
 
-def linear_bwd_dispatch(dz, x2, w, need_x=True, need_w=True, need_b=True, dx_addend=None):
-    """(dx, dw, db) of y = x2 W^T + b given dz.  ``dx_addend`` (same shape as dx) is accumulated into dx."""
+def linear_bwd_dispatch(dz, x2, w, need_x=True, need_w=True, need_b=True, dx_addend=None, dx_gsrc=None, dx_gact=0, dx_gparam=0.0):
+    """(dx, dw, db) of y = x2 W^T + b given dz.  ``dx_addend`` (same shape as dx) is accumulated into dx.  With ``dx_gsrc``
+    the layer's input was act(.) and dx is returned already multiplied by act'(dx_gsrc) (SiLU: pre-activation, else output):
+    on the tensor-core path that happens in the dgrad epilogue."""
     m, n = dz.shape
     k = x2.shape[1]
+
+    def through_act(dx):
+        if dx is None or dx_gsrc is None:
+            return dx
+        silu = dx_gact in (ACT_CODES["silu"], ACT_DERIV)
+        return raw_act_bwd(dx, None if silu else dx_gsrc, dx_gsrc if silu else None, dx_gact, dx_gparam)
+
     if smallk_ok(n, k):
         dx, dw, db = raw_smallk_bwd(dz, None, None, x2, w, 0, 0.0, need_x, need_w, need_b)
-        return (dx + dx_addend if (dx is not None and dx_addend is not None) else dx), dw, db
+        return through_act(dx + dx_addend if (dx is not None and dx_addend is not None) else dx), dw, db
     dx = dw = db = None
     if need_x:
-        if tc_ok(m, k, n, dz, dx_addend):
-            dx = raw_tc_linear(dz, w, True, None, k, n, addend=dx_addend)[0]
+        if tc_ok(m, k, n, dz, dx_addend, dx_gsrc):
+            dx = raw_tc_linear(dz, w, True, None, k, n, param=dx_gparam, addend=dx_addend, gsrc=dx_gsrc, gact=dx_gact)[0]
         elif dx_addend is not None:
-            dx = raw_gemm(dz, w, False, False, out=dx_addend.clone(), beta_one=True)
+            dx = through_act(raw_gemm(dz, w, False, False, out=dx_addend.clone(), beta_one=True))
         else:
-            dx = raw_gemm(dz, w, False, False)
+            dx = through_act(raw_gemm(dz, w, False, False))
     if need_w or need_b:
         if tc_ok(m, n, k, dz, x2) and k + 16 <= 256:
             dw, db = raw_tc_wgrad(dz, x2, want_bias=need_b)
@@ -399,6 +418,45 @@ class LinearAct(torch.autograd.Function):
 
 def linear_act(x, weight, bias=None, act=None, act_param=0.0):
     return LinearAct.apply(x, weight, bias, act, act_param)
+
+
+class Mlp2Fn(torch.autograd.Function):
+    """``act2(act1(x W1^T + b1) W2^T + b2)`` as one node: in the backward the gradient through act1 is applied in the epilogue of
+    the second layer's data-gradient GEMM (no separate activation-backward pass over the hidden tensor)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, act1, p1, w2, b2, act2, p2):
+        shp = x.shape
+        x2 = _row_major_2d(x)
+        w1 = w1 if w1.stride(1) == 1 else w1.contiguous()
+        w2 = w2 if w2.stride(1) == 1 else w2.contiguous()
+        c1, c2 = ACT_CODES[act1], ACT_CODES[act2]
+        silu = ACT_CODES["silu"]
+        h, z1, deriv = linear_fwd_dispatch_ex(x2, w1, _chk(b1), c1, p1, want_z=(c1 == silu), z_deriv=True)
+        y, z2 = linear_fwd_dispatch(h, w2, _chk(b2), c2, p2, want_z=(c2 == silu))
+        ctx.save_for_backward(x2, w1, w2, h, z1, y if c2 not in (0, silu) else None, z2)
+        ctx.cfg = (ACT_DERIV if deriv else c1, float(p1), c2, float(p2), shp, b1 is not None, b2 is not None)
+        ctx.tc = _TC["enabled"]
+        return y.reshape(shp[:-1] + (w2.shape[0],))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x2, w1, w2, h, z1, y, z2 = ctx.saved_tensors
+        c1, p1, c2, p2, shp, has_b1, has_b2 = ctx.cfg
+        m = x2.shape[0]
+        gy2 = _chk(gy.reshape(m, w2.shape[0]))
+        dz2 = raw_act_bwd(gy2, y, z2, c2, p2) if c2 != 0 else gy2
+        with tensor_cores(ctx.tc):
+            dz1, gw2, gb2 = linear_bwd_dispatch(dz2, h, w2, True, ctx.needs_input_grad[5], has_b2 and ctx.needs_input_grad[6],
+                                                dx_gsrc=(z1 if c1 in (ACT_CODES["silu"], ACT_DERIV) else h), dx_gact=c1, dx_gparam=p1)
+            gx, gw1, gb1 = linear_bwd_dispatch(dz1, x2, w1, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                               has_b1 and ctx.needs_input_grad[2])
+        return (gx.reshape(shp) if gx is not None else None), gw1, gb1, None, None, gw2, gb2, None, None
+
+
+def mlp2(x, w1, b1, act1, p1, w2, b2, act2=None, p2=0.0):
+    return Mlp2Fn.apply(x, w1, b1, act1, p1, w2, b2, act2, p2)
 
 
 class EdgeGeomFn(torch.autograd.Function):
@@ -545,8 +603,9 @@ class PainnUpdateFn(torch.autograd.Function):
         vv, _ = linear_fwd_dispatch(v2, vw, vb)
         mlp_in = torch.empty(n, 2 * f, dtype=s.dtype, device=s.device)
         _lib.call("hgb_painn_update_pre_fwd", _p(vv), _p(s), n, f, _p(mlp_in), _stream())
-        h, z1 = linear_fwd_dispatch(mlp_in, w1, b1, ACT_CODES["silu"], 0.0, want_z=True)
+        h, z1, deriv = linear_fwd_dispatch_ex(mlp_in, w1, b1, ACT_CODES["silu"], 0.0, want_z=True, z_deriv=True)
         a, _ = linear_fwd_dispatch(h, w2, b2)
+        ctx.z1_code = ACT_DERIV if deriv else ACT_CODES["silu"]
         s_out = torch.empty_like(s)
         v_out = None if last else torch.empty_like(v)
         _lib.call("hgb_painn_update_post_fwd", _p(a), _p(uv), _p(vv), _p(s), _p(v), n, f, int(last), _p(s_out), _p(v_out), _stream())
@@ -568,8 +627,7 @@ class PainnUpdateFn(torch.autograd.Function):
         ga = torch.empty_like(a)
         _lib.call("hgb_painn_update_post_bwd_a", _p(gs_out), _p(gv_out), _p(uv), _p(vv), n, f, int(last), _p(ga), _stream())
         with tensor_cores(ctx.tc):
-            gh, gw2, gb2 = linear_bwd_dispatch(ga, h, w2)
-            gz1 = raw_act_bwd(gh, None, z1, ACT_CODES["silu"])
+            gz1, gw2, gb2 = linear_bwd_dispatch(ga, h, w2, dx_gsrc=z1, dx_gact=ctx.z1_code)     # dgrad through the SiLU
             g_mlp_in, gw1, gb1 = linear_bwd_dispatch(gz1, mlp_in, w1)
         guv, gvv = torch.empty_like(uv), torch.empty_like(vv)
         gs, gv = torch.empty_like(gs_out), torch.empty_like(v2)

@@ -90,6 +90,14 @@ def run_mlp(seq, x, higher_order=False):
         m = mods[i]
         if isinstance(m, nn.Linear):
             code = _act_code(mods[i + 1]) if i + 1 < len(mods) else None
+            if (not higher_order and code is not None and i + 2 < len(mods) and isinstance(mods[i + 2], nn.Linear)):
+                # Linear - act - Linear (- act): one autograd node, activation gradient folded into a GEMM epilogue
+                m2 = mods[i + 2]
+                code2 = _act_code(mods[i + 3]) if i + 3 < len(mods) else None
+                x = ops.mlp2(x, m.weight, m.bias, code[0], code[1], m2.weight, m2.bias, code2[0] if code2 else None,
+                             code2[1] if code2 else 0.0)
+                i += 4 if code2 is not None else 3
+                continue
             if higher_order:
                 x = ops.linear_any_order(x, m.weight, m.bias)
             elif code is not None:

@@ -32,6 +32,7 @@ typedef void* hgb_stream_t; /* cudaStream_t */
 #define HGB_ECAPACITY (-3)
 
 /* activation codes (hydragnn/utils/model/model.py:30-46 plus the ones hard-wired in the stacks) */
+#define HGB_ACT_DERIV 100 /* not an activation: "the tensor already holds act'(.)" (hgb_tc_linear, hgb_act_bwd) */
 #define HGB_ACT_NONE 0
 #define HGB_ACT_RELU 1
 #define HGB_ACT_SILU 2
@@ -174,11 +175,16 @@ int64_t hgb_linear_smallk_bwd_workspace_bytes(int32_t m, int32_t n, int32_t k);
  * precision="bf16" (TF32 products, fp32 accumulation: tighter than the bf16 autocast of the reference).
  * y[m,n_out] = act(a[m,k_red] . B^T + bias) with B(r,c) = w[r,c] (trans_b = 0: forward, w is [n_out,k_red])
  * or B(r,c) = w[c,r] (trans_b = 1: the data gradient dX = dZ . W, w is [k_red,n_out]).  `addend` [m,n_out]
- * (optional) is added after the activation: gradient accumulation without an extra pass.                     */
+ * (optional) is added after the activation: gradient accumulation without an extra pass.  `gsrc` [m,n_out]
+ * (optional): the result is multiplied by act'(gsrc) with activation code `gact` -- the GEMM is then the data
+ * gradient THROUGH the activation that produced this layer's input (gsrc = its saved pre-activation for SiLU,
+ * its output for the others; gact = HGB_ACT_DERIV: gsrc already holds act'), which removes the separate
+ * activation-backward pass.  Forward calls with gsrc = NULL, gact = HGB_ACT_DERIV, act = SiLU and z != NULL store
+ * silu'(pre-activation) in z instead of the pre-activation.  n_out, k_red up to 1024 are cut into <= 256 pieces.                                                                     */
 int hgb_tc_linear_supported(int32_t m, int32_t n_out, int32_t k_red);
 int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_t ldw, int32_t trans_b, const float* bias,
                   int32_t m, int32_t n_out, int32_t k_red, int32_t act, float act_param, float* y, float* z,
-                  const float* addend, hgb_stream_t stream);
+                  const float* addend, const float* gsrc, int32_t gact, hgb_stream_t stream);
 /* dw[n_out,k_out] (row stride lddw) (+)= dz[m,n_out]^T . x[m,k_out] and db[n_out] (+)= column sums of dz
  * (db may be NULL) in one pass: both operands are consumed MN-major straight from the row-major tensors, the
  * bias gradient rides along as extra all-ones columns of the B operand.  Deterministic two-stage reduce.      */
