@@ -938,28 +938,28 @@ extern "C" int hgb_painn_message_bwd(const float* gs_out, const float* gv_out, c
 
 // ---- update block glue --------------------------------------------------------------------------------
 __global__ void painn_update_pre_fwd_kernel(const float* __restrict__ vv, const float* __restrict__ s, int64_t nf, int f,
-                                            float* __restrict__ mlp_in) {
+                                            int64_t ld, float* __restrict__ mlp_in) {
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nf; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = t / f;
     const int c = (int)(t % f);
-    const float a = vv[i * 3 * f + c], b = vv[i * 3 * f + f + c], d = vv[i * 3 * f + 2 * f + c];
+    const float a = vv[(i * 3) * ld + c], b = vv[(i * 3 + 1) * ld + c], d = vv[(i * 3 + 2) * ld + c];
     mlp_in[i * 2 * f + c] = sqrtf(a * a + b * b + d * d);
     mlp_in[i * 2 * f + f + c] = s[t];
   }
 }
 
-extern "C" int hgb_painn_update_pre_fwd(const float* vv, const float* s, int32_t n, int32_t f, float* mlp_in, hgb_stream_t stream) {
+extern "C" int hgb_painn_update_pre_fwd(const float* vv, int64_t ld, const float* s, int32_t n, int32_t f, float* mlp_in, hgb_stream_t stream) {
   HGB_REQUIRE(n >= 0 && f > 0 && vv && s && mlp_in, "painn_update_pre_fwd: bad arguments");
   if (n == 0) return HGB_OK;
   const int64_t nf = (int64_t)n * f;
-  painn_update_pre_fwd_kernel<<<hgb_grid_for(nf, 256), 256, 0, (cudaStream_t)stream>>>(vv, s, nf, f, mlp_in);
+  painn_update_pre_fwd_kernel<<<hgb_grid_for(nf, 256), 256, 0, (cudaStream_t)stream>>>(vv, s, nf, f, ld, mlp_in);
   HGB_LAUNCH_CHECK("painn_update_pre_fwd");
   return HGB_OK;
 }
 
 __global__ void painn_update_post_fwd_kernel(const float* __restrict__ a, const float* __restrict__ uv,
                                              const float* __restrict__ vv, const float* __restrict__ s,
-                                             const float* __restrict__ v, int64_t nf, int f, int last, float* __restrict__ s_out,
+                                             const float* __restrict__ v, int64_t nf, int f, int64_t ld, int last, float* __restrict__ s_out,
                                              float* __restrict__ v_out) {
   const int na = last ? 2 : 3;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nf; t += (int64_t)gridDim.x * blockDim.x) {
@@ -969,22 +969,22 @@ __global__ void painn_update_post_fwd_kernel(const float* __restrict__ a, const 
     const float a_sv = ai[(na - 2) * f + c], a_ss = ai[(na - 1) * f + c];
     float inner = 0.f;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) inner += uv[i * 3 * f + k * f + c] * vv[i * 3 * f + k * f + c];
+    for (int k = 0; k < 3; ++k) inner += uv[(i * 3 + k) * ld + c] * vv[(i * 3 + k) * ld + c];
     s_out[t] = s[t] + a_sv * inner + a_ss;
     if (!last) {
       const float a_vv = ai[c];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) v_out[i * 3 * f + k * f + c] = v[i * 3 * f + k * f + c] + a_vv * uv[i * 3 * f + k * f + c];
+      for (int k = 0; k < 3; ++k) v_out[i * 3 * f + k * f + c] = v[i * 3 * f + k * f + c] + a_vv * uv[(i * 3 + k) * ld + c];
     }
   }
 }
 
-extern "C" int hgb_painn_update_post_fwd(const float* a, const float* uv, const float* vv, const float* s, const float* v,
+extern "C" int hgb_painn_update_post_fwd(const float* a, const float* uv, const float* vv, int64_t ld, const float* s, const float* v,
                                          int32_t n, int32_t f, int32_t last, float* s_out, float* v_out, hgb_stream_t stream) {
   HGB_REQUIRE(n >= 0 && f > 0 && a && uv && vv && s && s_out && (last || (v && v_out)), "painn_update_post_fwd: bad arguments");
   if (n == 0) return HGB_OK;
   const int64_t nf = (int64_t)n * f;
-  painn_update_post_fwd_kernel<<<hgb_grid_for(nf, 256), 256, 0, (cudaStream_t)stream>>>(a, uv, vv, s, v, nf, f, last, s_out, v_out);
+  painn_update_post_fwd_kernel<<<hgb_grid_for(nf, 256), 256, 0, (cudaStream_t)stream>>>(a, uv, vv, s, v, nf, f, ld, last, s_out, v_out);
   HGB_LAUNCH_CHECK("painn_update_post_fwd");
   return HGB_OK;
 }
@@ -992,7 +992,7 @@ extern "C" int hgb_painn_update_post_fwd(const float* a, const float* uv, const 
 // ga = gradient w.r.t. the update_mlp output a (needed first: it feeds the MLP backward)
 __global__ void painn_update_post_bwd_a_kernel(const float* __restrict__ gs_out, const float* __restrict__ gv_out,
                                                const float* __restrict__ uv, const float* __restrict__ vv, int64_t nf, int f,
-                                               int last, float* __restrict__ ga) {
+                                               int64_t ld, int last, float* __restrict__ ga) {
   const int na = last ? 2 : 3;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nf; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = t / f;
@@ -1000,8 +1000,8 @@ __global__ void painn_update_post_bwd_a_kernel(const float* __restrict__ gs_out,
     float inner = 0.f, gdot = 0.f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const float u = uv[i * 3 * f + k * f + c];
-      inner += u * vv[i * 3 * f + k * f + c];
+      const float u = uv[(i * 3 + k) * ld + c];
+      inner += u * vv[(i * 3 + k) * ld + c];
       if (!last) gdot += gv_out[i * 3 * f + k * f + c] * u;
     }
     float* gi = ga + i * na * f;
@@ -1012,12 +1012,12 @@ __global__ void painn_update_post_bwd_a_kernel(const float* __restrict__ gs_out,
   }
 }
 
-extern "C" int hgb_painn_update_post_bwd_a(const float* gs_out, const float* gv_out, const float* uv, const float* vv, int32_t n,
+extern "C" int hgb_painn_update_post_bwd_a(const float* gs_out, const float* gv_out, const float* uv, const float* vv, int64_t ld, int32_t n,
                                            int32_t f, int32_t last, float* ga, hgb_stream_t stream) {
   HGB_REQUIRE(n >= 0 && f > 0 && gs_out && uv && vv && ga && (last || gv_out), "painn_update_post_bwd_a: bad arguments");
   if (n == 0) return HGB_OK;
   const int64_t nf = (int64_t)n * f;
-  painn_update_post_bwd_a_kernel<<<hgb_grid_for(nf, 256), 256, 0, (cudaStream_t)stream>>>(gs_out, gv_out, uv, vv, nf, f, last, ga);
+  painn_update_post_bwd_a_kernel<<<hgb_grid_for(nf, 256), 256, 0, (cudaStream_t)stream>>>(gs_out, gv_out, uv, vv, nf, f, ld, last, ga);
   HGB_LAUNCH_CHECK("painn_update_post_bwd_a");
   return HGB_OK;
 }
@@ -1026,7 +1026,7 @@ extern "C" int hgb_painn_update_post_bwd_a(const float* gs_out, const float* gv_
 __global__ void painn_update_bwd_kernel(const float* __restrict__ gs_out, const float* __restrict__ gv_out,
                                         const float* __restrict__ g_mlp_in, const float* __restrict__ a,
                                         const float* __restrict__ uv, const float* __restrict__ vv,
-                                        const float* __restrict__ mlp_in, int64_t nf, int f, int last, float* __restrict__ guv,
+                                        const float* __restrict__ mlp_in, int64_t nf, int f, int64_t ld, int last, float* __restrict__ guv,
                                         float* __restrict__ gvv, float* __restrict__ gs, float* __restrict__ gv) {
   const int na = last ? 2 : 3;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nf; t += (int64_t)gridDim.x * blockDim.x) {
@@ -1042,25 +1042,25 @@ __global__ void painn_update_bwd_kernel(const float* __restrict__ gs_out, const 
     gs[t] = g + g_mlp_in[i * 2 * f + f + c];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const int64_t o = i * 3 * f + k * f + c;
-      const float u = uv[o], w = vv[o];
+      const int64_t o = i * 3 * f + k * f + c, op = (i * 3 + k) * ld + c;
+      const float u = uv[op], w = vv[op];
       const float gvo = last ? 0.f : gv_out[o];
-      guv[o] = gvo * a_vv + g * a_sv * w;
-      gvv[o] = g * a_sv * u + gn_over * w;
-      if (gv) gv[o] = gvo;   // direct path v -> v_out (the U / V linear backward adds the rest)
+      guv[op] = gvo * a_vv + g * a_sv * w;
+      gvv[op] = g * a_sv * u + gn_over * w;
+      if (gv) gv[o] = gvo;   // optional copy of the direct path v -> v_out (callers may pass gv_out itself as the dgrad addend)
     }
   }
 }
 
 extern "C" int hgb_painn_update_bwd(const float* gs_out, const float* gv_out, const float* g_mlp_in, const float* a,
-                                    const float* uv, const float* vv, const float* mlp_in, int32_t n, int32_t f, int32_t last,
+                                    const float* uv, const float* vv, int64_t ld, const float* mlp_in, int32_t n, int32_t f, int32_t last,
                                     float* guv, float* gvv, float* gs, float* gv, hgb_stream_t stream) {
   HGB_REQUIRE(n >= 0 && f > 0 && gs_out && g_mlp_in && a && uv && vv && mlp_in && guv && gvv && gs && (last || gv_out),
               "painn_update_bwd: bad arguments");
   if (n == 0) return HGB_OK;
   const int64_t nf = (int64_t)n * f;
   painn_update_bwd_kernel<<<hgb_grid_for(nf, 256), 256, 0, (cudaStream_t)stream>>>(gs_out, gv_out, g_mlp_in, a, uv, vv, mlp_in,
-                                                                                 nf, f, last, guv, gvv, gs, gv);
+                                                                                 nf, f, ld, last, guv, gvv, gs, gv);
   HGB_LAUNCH_CHECK("painn_update_bwd");
   return HGB_OK;
 }

@@ -591,25 +591,28 @@ def raw_act_bwd(dy, y, z, code, param=0.0):
 
 class PainnUpdateFn(torch.autograd.Function):
     """The whole PaiNN update block (hydragnn/models/PAINNStack.py:298-328) with one hand-written
-    backward: U/V linears, |Vv|, update_mlp (Linear-SiLU-Linear) and the gated residuals."""
+    backward: U/V linears, |Vv|, update_mlp (Linear-SiLU-Linear) and the gated residuals.
+    update_U and update_V read the same input, so they run as ONE GEMM against the stacked weights [U; V]
+    (output [3n, 2f]: uv = left half, vv = right half); the backward is one dgrad and one wgrad for both."""
 
     @staticmethod
     def forward(ctx, s, v, uw, ub, vw, vb, w1, b1, w2, b2, last):
         n, f = s.shape
         s, v = _chk(s), _chk(v)
-        uw, ub, vw, vb, w1, b1, w2, b2 = [_chk(t) for t in (uw, ub, vw, vb, w1, b1, w2, b2)]
+        w1, b1, w2, b2 = [_chk(t) for t in (w1, b1, w2, b2)]
         v2 = v.reshape(3 * n, f)
-        uv, _ = linear_fwd_dispatch(v2, uw, ub)
-        vv, _ = linear_fwd_dispatch(v2, vw, vb)
+        wuv, buv = torch.cat([uw, vw], dim=0).contiguous(), torch.cat([ub, vb], dim=0).contiguous()
+        y_uv, _ = linear_fwd_dispatch(v2, wuv, buv)                                  # [3n, 2f]
+        uv, vv, ld = y_uv, y_uv[:, f:], 2 * f
         mlp_in = torch.empty(n, 2 * f, dtype=s.dtype, device=s.device)
-        _lib.call("hgb_painn_update_pre_fwd", _p(vv), _p(s), n, f, _p(mlp_in), _stream())
+        _lib.call("hgb_painn_update_pre_fwd", _p(vv), ld, _p(s), n, f, _p(mlp_in), _stream())
         h, z1, deriv = linear_fwd_dispatch_ex(mlp_in, w1, b1, ACT_CODES["silu"], 0.0, want_z=True, z_deriv=True)
         a, _ = linear_fwd_dispatch(h, w2, b2)
         ctx.z1_code = ACT_DERIV if deriv else ACT_CODES["silu"]
         s_out = torch.empty_like(s)
         v_out = None if last else torch.empty_like(v)
-        _lib.call("hgb_painn_update_post_fwd", _p(a), _p(uv), _p(vv), _p(s), _p(v), n, f, int(last), _p(s_out), _p(v_out), _stream())
-        ctx.save_for_backward(v2, uv, vv, mlp_in, z1, h, a, uw, vw, w1, w2)
+        _lib.call("hgb_painn_update_post_fwd", _p(a), _p(uv), _p(vv), ld, _p(s), _p(v), n, f, int(last), _p(s_out), _p(v_out), _stream())
+        ctx.save_for_backward(v2, y_uv, mlp_in, z1, h, a, wuv, w1, w2)
         ctx.last = bool(last)
         ctx.tc = _TC["enabled"]
         if last:
@@ -619,24 +622,26 @@ class PainnUpdateFn(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, gs_out, gv_out):
-        v2, uv, vv, mlp_in, z1, h, a, uw, vw, w1, w2 = ctx.saved_tensors
+        v2, y_uv, mlp_in, z1, h, a, wuv, w1, w2 = ctx.saved_tensors
         last = ctx.last
         n, f = gs_out.shape
+        ld = 2 * f
+        uv, vv = y_uv, y_uv[:, f:]
         gs_out = _chk(gs_out)
-        gv_out = None if last else _chk(gv_out)
+        gv_out = None if last else _chk(gv_out.contiguous())
         ga = torch.empty_like(a)
-        _lib.call("hgb_painn_update_post_bwd_a", _p(gs_out), _p(gv_out), _p(uv), _p(vv), n, f, int(last), _p(ga), _stream())
+        _lib.call("hgb_painn_update_post_bwd_a", _p(gs_out), _p(gv_out), _p(uv), _p(vv), ld, n, f, int(last), _p(ga), _stream())
         with tensor_cores(ctx.tc):
             gz1, gw2, gb2 = linear_bwd_dispatch(ga, h, w2, dx_gsrc=z1, dx_gact=ctx.z1_code)     # dgrad through the SiLU
             g_mlp_in, gw1, gb1 = linear_bwd_dispatch(gz1, mlp_in, w1)
-        guv, gvv = torch.empty_like(uv), torch.empty_like(vv)
-        gs, gv = torch.empty_like(gs_out), torch.empty_like(v2)
-        _lib.call("hgb_painn_update_bwd", _p(gs_out), _p(gv_out), _p(g_mlp_in), _p(a), _p(uv), _p(vv), _p(mlp_in), n, f,
-                  int(last), _p(guv), _p(gvv), _p(gs), _p(gv), _stream())
+        g_uv = torch.empty_like(y_uv)                                                # [3n, 2f] = [guv | gvv]
+        gs = torch.empty_like(gs_out)
+        _lib.call("hgb_painn_update_bwd", _p(gs_out), _p(gv_out), _p(g_mlp_in), _p(a), _p(uv), _p(vv), ld, _p(mlp_in), n, f,
+                  int(last), _p(g_uv), _p(g_uv[:, f:]), _p(gs), None, _stream())
         with tensor_cores(ctx.tc):
-            gv, guw, gub = linear_bwd_dispatch(guv, v2, uw, dx_addend=gv)      # gv (direct path) + guv U + gvv V, accumulated
-            gv, gvw, gvb = linear_bwd_dispatch(gvv, v2, vw, dx_addend=gv)      # in the dgrad epilogues
-        return gs, gv.reshape(n, 3, f), guw, gub, gvw, gvb, gw1, gb1, gw2, gb2, None
+            # gv = gv_out (direct path, added in the dgrad epilogue) + [guv | gvv] [U; V]
+            gv, gwuv, gbuv = linear_bwd_dispatch(g_uv, v2, wuv, dx_addend=None if last else gv_out.reshape(3 * n, f))
+        return gs, gv.reshape(n, 3, f), gwuv[:f], gbuv[:f], gwuv[f:], gbuv[f:], gw1, gb1, gw2, gb2, None
 
 
 class PoolFn(torch.autograd.Function):

@@ -255,23 +255,26 @@ int hgb_painn_message_bwd(const float* gs_out, const float* gv_out, const float*
                           float* g_efilt, void* workspace, int64_t workspace_bytes, hgb_stream_t stream);
 int64_t hgb_painn_message_bwd_workspace_bytes(int32_t n, int32_t f, int32_t r);
 
-/* Update block glue (PAINNStack.py:298-328).  uv, vv [n,3,f] are update_U(v), update_V(v).
+/* Update block glue (PAINNStack.py:298-328).  uv, vv are update_U(v), update_V(v) as [3n, f] matrices with row
+ * stride `ld` (ld = f: two separate tensors; ld = 2f: the two halves of ONE [3n, 2f] matrix produced by a single
+ * GEMM against the stacked weights [U; V]); guv / gvv use the same stride.
  * pre:  mlp_in [n,2f] = [ |vv| over the 3 components , s ]                                        */
-int hgb_painn_update_pre_fwd(const float* vv, const float* s, int32_t n, int32_t f, float* mlp_in,
+int hgb_painn_update_pre_fwd(const float* vv, int64_t ld, const float* s, int32_t n, int32_t f, float* mlp_in,
                              hgb_stream_t stream);
 /* post: a [n,(2|3)f] from update_mlp.  s_out = s + a_sv * sum_k(uv*vv) + a_ss;
  *       v_out = v + a_vv * uv (skipped when last != 0: a = (a_sv, a_ss), v_out may be NULL)        */
-int hgb_painn_update_post_fwd(const float* a, const float* uv, const float* vv, const float* s,
+int hgb_painn_update_post_fwd(const float* a, const float* uv, const float* vv, int64_t ld, const float* s,
                               const float* v, int32_t n, int32_t f, int32_t last, float* s_out,
                               float* v_out, hgb_stream_t stream);
 /* backward of pre+post in one pass.  Inputs: gs_out, gv_out (NULL when last), g_mlp_in [n,2f]
  * (gradient that came back through update_mlp), a, uv, vv, mlp_in.  Outputs: ga [n,(2|3)f] is
- * produced by *_post_bwd_a (needed before the MLP backward can run), then the rest.                */
+ * produced by *_post_bwd_a (needed before the MLP backward can run), then the rest; gv (optional)
+ * receives a copy of gv_out (the direct path), callers may instead hand gv_out to the dgrad as addend.  */
 int hgb_painn_update_post_bwd_a(const float* gs_out, const float* gv_out, const float* uv,
-                                const float* vv, int32_t n, int32_t f, int32_t last, float* ga,
+                                const float* vv, int64_t ld, int32_t n, int32_t f, int32_t last, float* ga,
                                 hgb_stream_t stream);
 int hgb_painn_update_bwd(const float* gs_out, const float* gv_out, const float* g_mlp_in,
-                         const float* a, const float* uv, const float* vv, const float* mlp_in,
+                         const float* a, const float* uv, const float* vv, int64_t ld, const float* mlp_in,
                          int32_t n, int32_t f, int32_t last, float* guv, float* gvv, float* gs,
                          float* gv, hgb_stream_t stream);
 
