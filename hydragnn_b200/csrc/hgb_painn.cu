@@ -856,7 +856,8 @@ __global__ void painn_wgrad_reduce_kernel(const float* __restrict__ part, int nb
   }
 }
 
-static int painn_bwd_grid(int n, int f) { return hgb_grid_for(n, WPB * (32 / painn_group(f)), HGB_NUM_SMS * 4); }
+// narrow layers: the per-block reduction of the filter-weight gradient dominates, so fewer / longer-lived blocks
+static int painn_bwd_grid(int n, int f) { return hgb_grid_for(n, WPB * (32 / painn_group(f)), HGB_NUM_SMS * (f < 32 ? 2 : 4)); }
 
 extern "C" int64_t hgb_painn_message_bwd_workspace_bytes(int32_t n, int32_t f, int32_t r) {
   return (int64_t)painn_bwd_grid(n, f) * 3 * f * (r + 1) * 4;
