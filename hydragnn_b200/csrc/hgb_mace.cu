@@ -22,6 +22,48 @@ __device__ __forceinline__ void mace_load_edge(const float* __restrict__ up, con
     for (int t = 0; t < CPL; ++t) w[k][t] = __ldg(tpw + (e * T::NPATH + k) * f + c + t);
 }
 
+// ---- per-warp asynchronous staging of one edge's operands (path weights, sender rows, harmonics) ------------------------------
+__device__ __forceinline__ void mace_cp16(void* smem, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void mace_cp4(void* smem, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void mace_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void mace_cp_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <class T, int CPL>
+struct MaceStage {
+  static constexpr int CH = 32 * CPL;                                   // channels handled per pass
+  static constexpr int FLOATS = (T::NPATH + T::S_IN) * CH + 16;         // w rows | up rows | harmonics (padded)
+  // buffer layout (floats): [0, NPATH*CH) path weights, [NPATH*CH, (NPATH+S_IN)*CH) sender rows, then S_SH harmonics
+  __device__ __forceinline__ static void issue(float* buf, const float* __restrict__ up, const float* __restrict__ sh,
+                                               const float* __restrict__ tpw, int64_t e, int j, int f, int c0, int sh_ld, int lane) {
+    constexpr int Q = CH / 4;                                           // 16-byte pieces per row
+    const float* wsrc = tpw + e * T::NPATH * f + c0;
+#pragma unroll
+    for (int idx = lane; idx < T::NPATH * Q; idx += 32) mace_cp16(buf + idx * 4, wsrc + (int64_t)(idx / Q) * f + (idx % Q) * 4);
+    const float* usrc = up + (int64_t)j * T::S_IN * f + c0;
+    float* ub = buf + T::NPATH * CH;
+#pragma unroll
+    for (int idx = lane; idx < T::S_IN * Q; idx += 32) mace_cp16(ub + idx * 4, usrc + (int64_t)(idx / Q) * f + (idx % Q) * 4);
+    if (lane < T::S_SH) mace_cp4(buf + (T::NPATH + T::S_IN) * CH + lane, sh + e * sh_ld + lane);
+  }
+  __device__ __forceinline__ static void read(const float* buf, int lane, float (&y)[T::S_SH], float (&u)[T::S_IN][CPL],
+                                              float (&w)[T::NPATH][CPL]) {
+#pragma unroll
+    for (int k = 0; k < T::NPATH; ++k)
+#pragma unroll
+      for (int t = 0; t < CPL; ++t) w[k][t] = buf[k * CH + lane * CPL + t];
+#pragma unroll
+    for (int s = 0; s < T::S_IN; ++s)
+#pragma unroll
+      for (int t = 0; t < CPL; ++t) u[s][t] = buf[(T::NPATH + s) * CH + lane * CPL + t];
+#pragma unroll
+    for (int s = 0; s < T::S_SH; ++s) y[s] = buf[(T::NPATH + T::S_IN) * CH + s];
+  }
+};
+
 // float offset of accumulator row r of node i inside the packed output (segments per output degree)
 template <class T>
 __device__ __forceinline__ int64_t mace_row_offset(int r, int i, int n, int f) {
@@ -39,6 +81,9 @@ mace_tp_scatter_fwd_kernel(const float* __restrict__ up, const float* __restrict
                            const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm, const int32_t* __restrict__ snd, int n,
                            int f, int sh_ld, float* __restrict__ out) {
   using T = MaceTP<LIN, LSH>;
+  using ST = MaceStage<T, CPL>;
+  extern __shared__ __align__(16) float mace_smem[];
+  float* sbuf = mace_smem + (threadIdx.x >> 5) * 2 * ST::FLOATS;       // this warp's two edge buffers
   const int lane = threadIdx.x & 31;
   const int ncb = f / (32 * CPL);
   for (int i = blockIdx.x * MWPB + (threadIdx.x >> 5); i < n; i += gridDim.x * MWPB) {
@@ -50,14 +95,20 @@ mace_tp_scatter_fwd_kernel(const float* __restrict__ up, const float* __restrict
       for (int r = 0; r < T::NACC; ++r)
 #pragma unroll
         for (int t = 0; t < CPL; ++t) acc[r][t] = 0.f;
+      if (lo < hi) ST::issue(sbuf, up, sh, tpw, perm[lo], snd[lo], f, cb * ST::CH, sh_ld, lane);
+      mace_cp_commit();
+      int cur = 0;
       for (int p = lo; p < hi; ++p) {
-        const int e = perm[p], j = snd[p];
+        mace_cp_wait();
+        __syncwarp();
+        if (p + 1 < hi) ST::issue(sbuf + (cur ^ 1) * ST::FLOATS, up, sh, tpw, perm[p + 1], snd[p + 1], f, cb * ST::CH, sh_ld, lane);
+        mace_cp_commit();
         float y[T::S_SH], u[T::S_IN][CPL], w[T::NPATH][CPL];
-#pragma unroll
-        for (int s = 0; s < T::S_SH; ++s) y[s] = __ldg(sh + (int64_t)e * sh_ld + s);
-        mace_load_edge<T, CPL>(up, tpw, e, j, f, c, u, w);
+        ST::read(sbuf + cur * ST::FLOATS, lane, y, u, w);
         T::template fwd<CPL>(y, u, w, acc);
+        cur ^= 1;
       }
+      __syncwarp();
 #pragma unroll
       for (int r = 0; r < T::NACC; ++r)
 #pragma unroll
@@ -75,6 +126,9 @@ mace_tp_scatter_bwd_kernel(const float* __restrict__ gout, const float* __restri
                            const int32_t* __restrict__ snd, int n, int f, int sh_ld, float* __restrict__ g_tpw,
                            float* __restrict__ g_up_edge, float* __restrict__ g_sh, int multi_cb) {
   using T = MaceTP<LIN, LSH>;
+  using ST = MaceStage<T, CPL>;
+  extern __shared__ __align__(16) float mace_smem[];
+  float* sbuf = mace_smem + (threadIdx.x >> 5) * 2 * ST::FLOATS;
   const int lane = threadIdx.x & 31;
   const int ncb = f / (32 * CPL);
   for (int i = blockIdx.x * MWPB + (threadIdx.x >> 5); i < n; i += gridDim.x * MWPB) {
@@ -87,12 +141,20 @@ mace_tp_scatter_bwd_kernel(const float* __restrict__ gout, const float* __restri
       for (int r = 0; r < T::NACC; ++r)
 #pragma unroll
         for (int t = 0; t < CPL; ++t) g[r][t] = __ldg(gout + mace_row_offset<T>(r, i, n, f) + c + t);
+      ST::issue(sbuf, up, sh, tpw, perm[lo], snd[lo], f, cb * ST::CH, sh_ld, lane);
+      mace_cp_commit();
+      int cur = 0;
       for (int p = lo; p < hi; ++p) {
-        const int e = perm[p], j = snd[p];
+        const int e = perm[p];
+        mace_cp_wait();
+        __syncwarp();
+        if (p + 1 < hi) ST::issue(sbuf + (cur ^ 1) * ST::FLOATS, up, sh, tpw, perm[p + 1], snd[p + 1], f, cb * ST::CH, sh_ld, lane);
+        mace_cp_commit();
         float y[T::S_SH], u[T::S_IN][CPL], w[T::NPATH][CPL], gw[T::NPATH][CPL], gy[T::S_SH], gu[T::S_IN][CPL];
+        ST::read(sbuf + cur * ST::FLOATS, lane, y, u, w);
+        cur ^= 1;
 #pragma unroll
-        for (int s = 0; s < T::S_SH; ++s) { y[s] = __ldg(sh + (int64_t)e * sh_ld + s); gy[s] = 0.f; }
-        mace_load_edge<T, CPL>(up, tpw, e, j, f, c, u, w);
+        for (int s = 0; s < T::S_SH; ++s) gy[s] = 0.f;
 #pragma unroll
         for (int s = 0; s < T::S_IN; ++s)
 #pragma unroll
@@ -118,6 +180,7 @@ mace_tp_scatter_bwd_kernel(const float* __restrict__ gout, const float* __restri
           }
         }
       }
+      __syncwarp();
     }
   }
 }
@@ -157,9 +220,9 @@ extern "C" int hgb_mace_tp_scatter_fwd(const float* up, const float* sh, const f
   const int grid = hgb_grid_for(n, MWPB, HGB_NUM_SMS * 16);
   MACE_TP_DISPATCH(lin, lsh, {
     if (f % 64 == 0 && MaceTP<LIN, LSH>::NACC <= 40)
-      mace_tp_scatter_fwd_kernel<LIN, LSH, 2><<<grid, MWPB * 32, 0, st>>>(up, sh, tpw, rowptr, perm, snd, n, f, sh_ld, out);
+      mace_tp_scatter_fwd_kernel<LIN, LSH, 2><<<grid, MWPB * 32, MWPB * 2 * MaceStage<MaceTP<LIN, LSH>, 2>::FLOATS * 4, st>>>(up, sh, tpw, rowptr, perm, snd, n, f, sh_ld, out);
     else
-      mace_tp_scatter_fwd_kernel<LIN, LSH, 1><<<grid, MWPB * 32, 0, st>>>(up, sh, tpw, rowptr, perm, snd, n, f, sh_ld, out);
+      mace_tp_scatter_fwd_kernel<LIN, LSH, 1><<<grid, MWPB * 32, MWPB * 2 * MaceStage<MaceTP<LIN, LSH>, 1>::FLOATS * 4, st>>>(up, sh, tpw, rowptr, perm, snd, n, f, sh_ld, out);
   });
   HGB_LAUNCH_CHECK("mace_tp_scatter_fwd");
   return HGB_OK;
@@ -174,7 +237,7 @@ extern "C" int hgb_mace_tp_scatter_bwd(const float* g_out, const float* up, cons
   if (n == 0) return HGB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = hgb_grid_for(n, MWPB, HGB_NUM_SMS * 16);
-#define LAUNCH_B(C, Y) mace_tp_scatter_bwd_kernel<LIN, LSH, C, Y><<<grid, MWPB * 32, 0, st>>>(g_out, up, sh, tpw, rowptr, perm, snd, n, f, sh_ld, g_tpw, g_up_edge, g_sh, ncb > 1)
+#define LAUNCH_B(C, Y) mace_tp_scatter_bwd_kernel<LIN, LSH, C, Y><<<grid, MWPB * 32, MWPB * 2 * MaceStage<MaceTP<LIN, LSH>, C>::FLOATS * 4, st>>>(g_out, up, sh, tpw, rowptr, perm, snd, n, f, sh_ld, g_tpw, g_up_edge, g_sh, ncb > 1)
   MACE_TP_DISPATCH(lin, lsh, {
     const bool two = f % 64 == 0 && MaceTP<LIN, LSH>::NACC <= 24;
     const int ncb = f / (32 * (two ? 2 : 1));
