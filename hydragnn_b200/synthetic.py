@@ -14,6 +14,8 @@ WORKLOADS = {
     "qm9_painn": dict(n=9, rho=0.10, species=[1, 6, 7, 8, 9], radius=7.0, max_neighbours=5),
     "md17_egnn": dict(n=21, rho=0.08, species=[6] * 9 + [1] * 8 + [8] * 4, radius=7.0, max_neighbours=5, fixed_species=True),
     "lj_egnn": dict(n=27, lattice=3.8, radius=5.0, max_neighbours=5, pbc=True),
+    # SURVEY C5 in miniature (multibranch GFM shape): 40-atom clusters, r = 5, k = 20, positional encodings for GPS
+    "gfm_pnaeq": dict(n=40, rho=0.06, species=list(range(1, 84)), radius=5.0, max_neighbours=20, pe_dim=6),
     # SURVEY C4 (open-catalyst-like): 80 atoms in a periodic cubic cell at 0.05 / A^3, Z ~ U{1..83}, r = 6 A, all neighbours
     "oc20_mace": dict(n=80, rho=0.05, species=list(range(1, 84)), radius=6.0, max_neighbours=128, pbc_box=True, two_heads=True),
 }
@@ -31,6 +33,13 @@ ARCH = {
                       output_heads={"node": {"num_headlayers": 2, "dim_headlayers": [60, 20], "type": "mlp"}},
                       activation_function="relu", loss_function_type="mse", enable_interatomic_potential=True,
                       energy_weight=1.0, energy_peratom_weight=1.0, force_weight=1.0),
+    # PNAEq + GPS (examples/multibranch/multibranch_GFM260.json knobs, GPS knobs of qm9.json); pna_deg is filled in
+    # from the batch (degree histogram) by the caller
+    "gfm_pnaeq": dict(mpnn_type="PNAEq", input_dim=1, hidden_dim=64, num_conv_layers=3, num_radial=6, radius=5.0, max_neighbours=20,
+                      global_attn_engine="GPS", global_attn_type="multihead", global_attn_heads=8, pe_dim=6,
+                      output_dim=[1], output_type=["graph"], task_weights=[1.0],
+                      output_heads={"graph": {"num_sharedlayers": 2, "dim_sharedlayers": 50, "num_headlayers": 2, "dim_headlayers": [50, 25]}},
+                      activation_function="relu", loss_function_type="mse", graph_pooling="mean"),
     # MACE knobs of tests/test_forces_equivariant.py:318-327, heads of multidataset/gfm_multitasking.json
     "oc20_mace": dict(mpnn_type="MACE", input_dim=1, hidden_dim=64, num_conv_layers=2, num_radial=8, radius=6.0,
                       max_neighbours=128, max_ell=2, node_max_ell=1, correlation=2, envelope_exponent=5, radial_type="bessel",
@@ -90,6 +99,8 @@ def make_samples(name, num_graphs, seed=1234, with_edges=None):
     out.y = torch.randn(num_graphs, 1, generator=gen)
     out.energy = torch.randn(num_graphs, generator=gen)
     out.forces = torch.randn(num_graphs * n, 3, generator=gen)
+    if w.get("pe_dim"):
+        out.pe = torch.randn(num_graphs * n, w["pe_dim"], generator=gen)
     if w.get("two_heads"):                                  # y = per graph [energy, forces...] with y_loc offsets
         out.y = torch.cat([out.y, out.forces.reshape(num_graphs, 3 * n)], dim=1).reshape(-1, 1).contiguous()
         out.y_loc = torch.tensor([[0, 1, 1 + 3 * n]]).expand(num_graphs, 3).contiguous()

@@ -18,6 +18,11 @@ n, e = b.pos.shape[0], b.edge_index.shape[1]
 kw = dict(ARCH[name])
 if kw["mpnn_type"] == "MACE":
     kw["avg_num_neighbors"] = e / n
+if kw["mpnn_type"] == "PNAEq":
+    deg = torch.bincount(b.edge_index[1], minlength=n)
+    kw["pna_deg"] = torch.bincount(deg).tolist()
+if kw.get("global_attn_engine"):
+    b.rel_pe = (b.pe[b.edge_index[0]] - b.pe[b.edge_index[1]]).abs()      # serialized_dataset_loader.py:186-189
 mlip = bool(kw.get("enable_interatomic_potential"))
 model = hb.get_distributed_model(hb.set_precision(hb.create_model(**kw), prec))
 opt = hb.FlatAdamW(model, lr=1e-3)
