@@ -197,3 +197,82 @@ extern "C" int hgb_segment_argminmax(const float* m, const int32_t* rowptr, cons
   HGB_LAUNCH_CHECK("segment_argminmax");
   return HGB_OK;
 }
+
+// ---- PNA aggregation: mean | min | max | std of every CSR segment in ONE pass (PNAEqStack.py:396-400; PyG 2.6.1
+// MeanAggregation / MinAggregation / MaxAggregation / StdAggregation).  out [n, 4c]; amin / amax [n, c] hold the EDGE id
+// of the first minimum / maximum (-1 for an empty segment) for the backward.  std = sqrt(clamp(E[x^2] - E[x]^2, 1e-5)),
+// reported as 0 where it equals sqrt(1e-5) (PyG masks the clamped entries).
+#define PNA_EPS 1e-5f
+__global__ void pna_aggregate_fwd_kernel(const float* __restrict__ m, const int32_t* __restrict__ rowptr,
+                                         const int32_t* __restrict__ perm, int n, int c, int lanes, float* __restrict__ out,
+                                         int32_t* __restrict__ amin, int32_t* __restrict__ amax) {
+  const int gpb = blockDim.x / lanes;
+  const int sub = threadIdx.x % lanes;
+  for (int row = blockIdx.x * gpb + threadIdx.x / lanes; row < n; row += gridDim.x * gpb) {
+    const int lo = rowptr[row], hi = rowptr[row + 1];
+    const float inv = 1.f / (float)max(hi - lo, 1);
+    for (int ch = sub; ch < c; ch += lanes) {
+      float s1 = 0.f, s2 = 0.f, vmin = 0.f, vmax = 0.f;
+      int imin = -1, imax = -1;
+      for (int p = lo; p < hi; ++p) {
+        const int e = perm ? perm[p] : p;
+        const float v = __ldg(m + (int64_t)e * c + ch);
+        s1 += v;
+        s2 = fmaf(v, v, s2);
+        if (imin < 0 || v < vmin) { vmin = v; imin = e; }
+        if (imax < 0 || v > vmax) { vmax = v; imax = e; }
+      }
+      const float mean = s1 * inv;
+      float sd = sqrtf(fmaxf(s2 * inv - mean * mean, PNA_EPS));
+      if (sd <= sqrtf(PNA_EPS)) sd = 0.f;
+      float* o = out + (int64_t)row * 4 * c;
+      o[ch] = mean;
+      o[c + ch] = vmin;
+      o[2 * c + ch] = vmax;
+      o[3 * c + ch] = sd;
+      amin[(int64_t)row * c + ch] = imin;
+      amax[(int64_t)row * c + ch] = imax;
+    }
+  }
+}
+
+// g_m[e, ch] = g_mean/cnt + [e == amin] g_min + [e == amax] g_max + g_std (m - mean) / (cnt std)
+__global__ void pna_aggregate_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ m, const float* __restrict__ out,
+                                         const int32_t* __restrict__ idx, const int32_t* __restrict__ rowptr,
+                                         const int32_t* __restrict__ amin, const int32_t* __restrict__ amax, int64_t total, int c,
+                                         float* __restrict__ gm) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int e = (int)(t / c);
+    const int ch = (int)(t - (int64_t)e * c);
+    const int i = idx[e];
+    const float inv = 1.f / (float)max(rowptr[i + 1] - rowptr[i], 1);
+    const float* g = gout + (int64_t)i * 4 * c;
+    const float* o = out + (int64_t)i * 4 * c;
+    float acc = g[ch] * inv;
+    if (amin[(int64_t)i * c + ch] == e) acc += g[c + ch];
+    if (amax[(int64_t)i * c + ch] == e) acc += g[2 * c + ch];
+    const float sd = o[3 * c + ch];
+    if (sd > 0.f) acc = fmaf(g[3 * c + ch] * inv / sd, m[t] - o[ch], acc);
+    gm[t] = acc;
+  }
+}
+
+extern "C" int hgb_pna_aggregate_fwd(const float* m, const int32_t* rowptr, const int32_t* perm, int32_t n, int32_t c, float* out,
+                                     int32_t* argmin, int32_t* argmax, hgb_stream_t stream) {
+  HGB_REQUIRE(n >= 0 && c > 0 && rowptr && out && argmin && argmax, "pna_aggregate_fwd: bad arguments");
+  if (n == 0) return HGB_OK;
+  const int lanes = group_lanes(c);
+  pna_aggregate_fwd_kernel<<<hgb_grid_for(n, 256 / lanes), 256, 0, (cudaStream_t)stream>>>(m, rowptr, perm, n, c, lanes, out, argmin, argmax);
+  HGB_LAUNCH_CHECK("pna_aggregate_fwd");
+  return HGB_OK;
+}
+
+extern "C" int hgb_pna_aggregate_bwd(const float* g_out, const float* m, const float* out, const int32_t* idx, const int32_t* rowptr,
+                                     const int32_t* argmin, const int32_t* argmax, int64_t e, int32_t c, float* g_m, hgb_stream_t stream) {
+  HGB_REQUIRE(e >= 0 && c > 0 && g_out && out && idx && rowptr && argmin && argmax && g_m, "pna_aggregate_bwd: bad arguments");
+  if (e == 0) return HGB_OK;
+  HGB_REQUIRE(m, "pna_aggregate_bwd: null messages");
+  pna_aggregate_bwd_kernel<<<hgb_grid_for(e * c, 256), 256, 0, (cudaStream_t)stream>>>(g_out, m, out, idx, rowptr, argmin, argmax, e * c, c, g_m);
+  HGB_LAUNCH_CHECK("pna_aggregate_bwd");
+  return HGB_OK;
+}

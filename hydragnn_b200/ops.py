@@ -686,6 +686,32 @@ class LossFn(torch.autograd.Function):
         return gpred * g, None, None
 
 
+class PnaAggregateFn(torch.autograd.Function):
+    """[mean | min | max | std] of every CSR segment in one pass (the four PNA aggregators of PNAEqStack.py:396-400)."""
+
+    @staticmethod
+    def forward(ctx, m, csr):
+        m = _chk(m.contiguous())
+        n, c = csr.n, m.shape[1]
+        out = torch.empty(n, 4 * c, dtype=m.dtype, device=m.device)
+        amin = torch.empty(n, c, dtype=torch.int32, device=m.device)
+        amax = torch.empty_like(amin)
+        _lib.call("hgb_pna_aggregate_fwd", _p(m), _p(csr.rowptr), _p(csr.perm), n, c, _p(out), _p(amin), _p(amax), _stream())
+        ctx.save_for_backward(m, out, amin, amax)
+        ctx.csr = csr
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        m, out, amin, amax = ctx.saved_tensors
+        csr = ctx.csr
+        gm = torch.empty_like(m)
+        _lib.call("hgb_pna_aggregate_bwd", _p(_chk(g.contiguous())), _p(m), _p(out), _p(csr.idx), _p(csr.rowptr), _p(amin), _p(amax),
+                  m.shape[0], m.shape[1], _p(gm), _stream())
+        return gm, None
+
+
 # =====================================================================================================
 # MACE: fused tensor-product + scatter, symmetric contraction (first-order blocks)
 # =====================================================================================================

@@ -46,6 +46,25 @@ class DegreeScalerAggregation(nn.Module):
         self.register_buffer("avg_deg_lin", torch.tensor(float((bins * d).sum()) / n))
         self.register_buffer("avg_deg_log", torch.tensor(float(((bins + 1).log() * d).sum()) / n))
 
+    def scaler_factors(self, csr):
+        """[N, num_scalers] per-node factors of the degree scalers (PyG DegreeScalerAggregation.forward)."""
+        deg = (csr.rowptr[1:] - csr.rowptr[:-1]).to(torch.float32).clamp(min=1)
+        cols = []
+        for s in self.scaler:
+            if s == "identity":
+                cols.append(torch.ones_like(deg))
+            elif s == "amplification":
+                cols.append(torch.log(deg + 1) / self.avg_deg_log)
+            elif s == "attenuation":
+                cols.append(self.avg_deg_log / torch.log(deg + 1))
+            elif s == "linear":
+                cols.append(deg / self.avg_deg_lin)
+            elif s == "inverse_linear":
+                cols.append(self.avg_deg_lin / deg)
+            else:
+                raise ValueError("unsupported scaler " + str(s))
+        return torch.stack(cols, dim=1)
+
     def forward(self, x, csr):
         n, c = csr.n, x.shape[1]
         x = x.contiguous()
@@ -110,15 +129,31 @@ class PainnMessage(nn.Module):
         rbf, vec = geom["rbf"], geom["unit"]
         F = self.node_size
         src, dst = plan.by_row, plan.by_col                          # src = edge_index[0], dst = edge_index[1] (:341)
-        feats = [GatherRows.apply(x, src), GatherRows.apply(x, dst), run_mlp(self.rbf_emb, rbf, higher_order)]
+        lin = ops.linear_any_order if higher_order else ops.linear_act
+        # pre_nn (:352-357) on [x_src | x_dst | rbf_emb | edge_enc]: linear in the blocks -> the two node blocks are multiplied
+        # per NODE (N rows instead of E) and gathered per edge afterwards
+        pre = self.pre_nns[0][0]
+        w0 = pre.weight
+        m = GatherRows.apply(lin(x, w0[:, :F], None), src) + GatherRows.apply(lin(x, w0[:, F:2 * F], None), dst)
+        m = m + lin(run_mlp(self.rbf_emb, rbf, higher_order), w0[:, 2 * F:3 * F], pre.bias)
         if edge_attr is not None:
-            feats.append(run_mlp(nn.Sequential(self.edge_encoder), edge_attr, higher_order))
-        m = run_mlp(self.pre_nns[0], torch.cat(feats, dim=-1), higher_order)
+            m = m + lin(run_mlp(nn.Sequential(self.edge_encoder), edge_attr, higher_order), w0[:, 3 * F:], None)
         f = run_mlp(self.scalar_message_mlp, m, higher_order) * run_mlp(nn.Sequential(self.rbf_lin), rbf, higher_order)
         g_v, g_e, m_s = torch.split(f, F, dim=-1)
         m_v = GatherRows.apply(v, dst) * g_v.unsqueeze(1) + g_e.unsqueeze(1) * vec.unsqueeze(-1)
-        agg = self.aggr_module(m_s, src)                              # :396-400
-        dx = run_mlp(self.post_nns[0], torch.cat([x, agg], dim=-1), higher_order)
+        am = self.aggr_module
+        if not higher_order and am.aggr == ["mean", "min", "max", "std"]:
+            # fused: the four aggregators in one pass; the degree scalers are per-node factors, so
+            #   post_nn([x | s_1 A | ... | s_5 A]) = x W_x^T + b + sum_k s_k (A W_k^T):  the 20F-wide tensor is never built
+            agg4 = ops.PnaAggregateFn.apply(m_s.contiguous(), src)                   # [N, 4F]
+            post = self.post_nns[0][0]
+            ns = len(am.scaler)
+            wk = post.weight[:, F:].reshape(F, ns, 4 * F).permute(1, 0, 2).reshape(ns * F, 4 * F)
+            bk = ops.linear_act(agg4, wk, None).reshape(-1, ns, F)                    # [N, 5, F]
+            dx = ops.linear_act(x, post.weight[:, :F], post.bias) + (bk * am.scaler_factors(src)[:, :, None]).sum(dim=1)
+        else:
+            agg = am(m_s, src)                                        # :396-400
+            dx = run_mlp(self.post_nns[0], torch.cat([x, agg], dim=-1), higher_order)
         dv = SegmentSum.apply(m_v.contiguous(), src)
         return x + dx, v + dv
 

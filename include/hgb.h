@@ -306,6 +306,14 @@ int hgb_adamw_step(float* p, const float* g, float* m, float* v, int64_t count, 
                    float beta2, float eps, float weight_decay, float grad_scale, float* step_dev,
                    hgb_stream_t stream);
 
+/* PNA aggregation (hydragnn/models/PNAEqStack.py:396-400; torch_geometric 2.6.1 DegreeScalerAggregation with aggregators
+ * mean, min, max, std): one pass per CSR segment.  m [e,c] -> out [n,4c] = [mean | min | max | std]; argmin / argmax [n,c]
+ * = edge id of the first extremum (-1: empty segment).  Backward: g_m [e,c] from g_out [n,4c]; idx [e] = segment of every edge. */
+int hgb_pna_aggregate_fwd(const float* m, const int32_t* rowptr, const int32_t* perm, int32_t n, int32_t c, float* out,
+                          int32_t* argmin, int32_t* argmax, hgb_stream_t stream);
+int hgb_pna_aggregate_bwd(const float* g_out, const float* m, const float* out, const int32_t* idx, const int32_t* rowptr,
+                          const int32_t* argmin, const int32_t* argmax, int64_t e, int32_t c, float* g_m, hgb_stream_t stream);
+
 /* ---- MACE (hydragnn/utils/model/mace_utils/modules/blocks.py:369-402, symmetric_contraction.py:92-242) ------------------
  * Features are channel-last: [N, spherical index, F].  lmax_in <= 2, 1 <= lmax_sh <= 3, lmax_in <= lmax_sh, F % 32 == 0.
  * Path order / coupling constants = tp_out_irreps_with_instructions (irreps_tools.py:15-44) with e3nn's real Wigner 3j.   */
