@@ -2,13 +2,16 @@
 // hydragnn/globalAtt/gps.py:126-133 with quirk Q1: the whole mini-batch is ONE sequence).
 //
 // Head dims on this path are tiny (hidden 64 / 8 heads = 8), so attention here is exp/FMA-bound SIMT work, not a
-// tensor-core GEMM: one thread owns one (query, head) row with q, the output accumulator and the online-softmax
-// state in registers; K/V tiles of the same head are staged in shared memory and broadcast to the block.
+// tensor-core GEMM: four lanes share one (query, head) row (each walks every 4th key, partial online-softmax states
+// combined with shuffles), q, the output accumulator and the softmax state live in registers; K/V tiles of the same head are staged in shared memory and broadcast to the block.
 // No [N,N] matrix ever reaches HBM (flash-style), forward saves only the log-sum-exp per (query, head).
 #include "hgb_common.cuh"
 
 #define ATT_TK 64    // keys per shared-memory tile
-#define ATT_TQ 128   // queries (threads) per block
+#define ATT_TQ 128   // threads per block
+#define ATT_KS 4     // lanes that share one (row, head): each walks every 4th key of a tile; combined with shuffles.
+#define ATT_QPB (ATT_TQ / ATT_KS)   // rows per block.  (Sequences here are a few thousand atoms: one thread per row would
+                                    // leave most of the 148 SMs idle and serialise the whole key loop in one dependency chain.)
 
 // qkv [n, 3f]: row = [ q (f) | k (f) | v (f) ], head h owns columns h*D .. h*D+D-1 of each part
 template <int D>
@@ -16,7 +19,8 @@ __global__ void __launch_bounds__(ATT_TQ) mha_fwd_kernel(const float* __restrict
                                                          float* __restrict__ out, float* __restrict__ lse) {
   __shared__ float sk[ATT_TK][D], sv[ATT_TK][D];
   const int h = blockIdx.y, nh = gridDim.y;
-  const int i = blockIdx.x * ATT_TQ + threadIdx.x;
+  const int ks = threadIdx.x & (ATT_KS - 1);
+  const int i = blockIdx.x * ATT_QPB + (threadIdx.x >> 2);
   const int f3 = 3 * f;
   float q[D], o[D];
   float m = -INFINITY, l = 0.f;
@@ -32,7 +36,7 @@ __global__ void __launch_bounds__(ATT_TQ) mha_fwd_kernel(const float* __restrict
     }
     __syncthreads();
     const int jn = min(ATT_TK, n - j0);
-    for (int jj = 0; jj < jn; ++jj) {
+    for (int jj = ks; jj < jn; jj += ATT_KS) {
       float s = 0.f;
 #pragma unroll
       for (int d = 0; d < D; ++d) s = fmaf(q[d], sk[jj][d], s);
@@ -49,7 +53,18 @@ __global__ void __launch_bounds__(ATT_TQ) mha_fwd_kernel(const float* __restrict
       for (int d = 0; d < D; ++d) o[d] = fmaf(p, sv[jj][d], o[d]);
     }
   }
-  if (i < n) {
+  // combine the ATT_KS partial softmax states of this row
+#pragma unroll
+  for (int off = 1; off < ATT_KS; off <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, off), l2 = __shfl_xor_sync(0xffffffffu, l, off);
+    const float mn = fmaxf(m, m2);
+    const float c1 = m == -INFINITY ? 0.f : __expf(m - mn), c2 = m2 == -INFINITY ? 0.f : __expf(m2 - mn);
+    l = l * c1 + l2 * c2;
+#pragma unroll
+    for (int d = 0; d < D; ++d) o[d] = o[d] * c1 + __shfl_xor_sync(0xffffffffu, o[d], off) * c2;
+    m = mn;
+  }
+  if (i < n && ks == 0) {
     const float inv = 1.f / l;
 #pragma unroll
     for (int d = 0; d < D; ++d) out[(int64_t)i * f + h * D + d] = o[d] * inv;
@@ -57,14 +72,15 @@ __global__ void __launch_bounds__(ATT_TQ) mha_fwd_kernel(const float* __restrict
   }
 }
 
-// dq: thread per (query, head).  delta_i = dO_i . O_i
+// dq: ATT_KS lanes per (query, head).  delta_i = dO_i . O_i
 template <int D>
 __global__ void __launch_bounds__(ATT_TQ) mha_bwd_q_kernel(const float* __restrict__ qkv, const float* __restrict__ out,
                                                            const float* __restrict__ lse, const float* __restrict__ gout, int n, int f,
                                                            float scale, float* __restrict__ gqkv) {
   __shared__ float sk[ATT_TK][D], sv[ATT_TK][D];
   const int h = blockIdx.y, nh = gridDim.y;
-  const int i = blockIdx.x * ATT_TQ + threadIdx.x;
+  const int ks = threadIdx.x & (ATT_KS - 1);
+  const int i = blockIdx.x * ATT_QPB + (threadIdx.x >> 2);
   const int f3 = 3 * f;
   float q[D], go[D], dq[D];
   float delta = 0.f, li = 0.f;
@@ -86,7 +102,7 @@ __global__ void __launch_bounds__(ATT_TQ) mha_bwd_q_kernel(const float* __restri
     }
     __syncthreads();
     const int jn = min(ATT_TK, n - j0);
-    for (int jj = 0; jj < jn; ++jj) {
+    for (int jj = ks; jj < jn; jj += ATT_KS) {
       float s = 0.f, dp = 0.f;
 #pragma unroll
       for (int d = 0; d < D; ++d) { s = fmaf(q[d], sk[jj][d], s); dp = fmaf(go[d], sv[jj][d], dp); }
@@ -95,20 +111,25 @@ __global__ void __launch_bounds__(ATT_TQ) mha_bwd_q_kernel(const float* __restri
       for (int d = 0; d < D; ++d) dq[d] = fmaf(ds, sk[jj][d], dq[d]);
     }
   }
-  if (i < n) {
+#pragma unroll
+  for (int off = 1; off < ATT_KS; off <<= 1)
+#pragma unroll
+    for (int d = 0; d < D; ++d) dq[d] += __shfl_xor_sync(0xffffffffu, dq[d], off);
+  if (i < n && ks == 0) {
 #pragma unroll
     for (int d = 0; d < D; ++d) gqkv[(int64_t)i * f3 + h * D + d] = dq[d] * scale;
   }
 }
 
-// dk, dv: thread per (key, head); tiles of (q, dO, lse, delta) staged in shared memory
+// dk, dv: ATT_KS lanes per (key, head); tiles of (q, dO, lse, delta) staged in shared memory
 template <int D>
 __global__ void __launch_bounds__(ATT_TQ) mha_bwd_kv_kernel(const float* __restrict__ qkv, const float* __restrict__ out,
                                                             const float* __restrict__ lse, const float* __restrict__ gout, int n, int f,
                                                             float scale, float* __restrict__ gqkv) {
   __shared__ float sq[ATT_TK][D], sg[ATT_TK][D], sl[ATT_TK], sd[ATT_TK];
   const int h = blockIdx.y, nh = gridDim.y;
-  const int j = blockIdx.x * ATT_TQ + threadIdx.x;
+  const int ks = threadIdx.x & (ATT_KS - 1);
+  const int j = blockIdx.x * ATT_QPB + (threadIdx.x >> 2);
   const int f3 = 3 * f;
   float k[D], v[D], dk[D], dv[D];
 #pragma unroll
@@ -134,7 +155,7 @@ __global__ void __launch_bounds__(ATT_TQ) mha_bwd_kv_kernel(const float* __restr
       sl[ii] = i < n ? lse[(int64_t)i * nh + h] : INFINITY;   // exp(s - inf) = 0 for padded queries
     }
     __syncthreads();
-    for (int ii = 0; ii < ATT_TK; ++ii) {
+    for (int ii = ks; ii < ATT_TK; ii += ATT_KS) {
       float s = 0.f, dp = 0.f;
 #pragma unroll
       for (int d = 0; d < D; ++d) { s = fmaf(sq[ii][d], k[d], s); dp = fmaf(sg[ii][d], v[d], dp); }
@@ -144,7 +165,14 @@ __global__ void __launch_bounds__(ATT_TQ) mha_bwd_kv_kernel(const float* __restr
       for (int d = 0; d < D; ++d) { dv[d] = fmaf(p, sg[ii][d], dv[d]); dk[d] = fmaf(ds, sq[ii][d], dk[d]); }
     }
   }
-  if (j < n) {
+#pragma unroll
+  for (int off = 1; off < ATT_KS; off <<= 1)
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      dk[d] += __shfl_xor_sync(0xffffffffu, dk[d], off);
+      dv[d] += __shfl_xor_sync(0xffffffffu, dv[d], off);
+    }
+  if (j < n && ks == 0) {
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       gqkv[(int64_t)j * f3 + f + h * D + d] = dk[d];          // sq already carries the 1/sqrt(D) scale
@@ -169,7 +197,7 @@ extern "C" int hgb_mha_fwd(const float* qkv, int32_t n, int32_t f, int32_t heads
   if (n == 0) return HGB_OK;
   const int d = f / heads;
   const float scale = 1.f / sqrtf((float)d);
-  dim3 grid((n + ATT_TQ - 1) / ATT_TQ, heads);
+  dim3 grid((n + ATT_QPB - 1) / ATT_QPB, heads);
   cudaStream_t st = (cudaStream_t)stream;
   ATT_DISPATCH(mha_fwd_kernel, qkv, n, f, scale, out, lse)
   HGB_LAUNCH_CHECK("mha_fwd");
@@ -182,7 +210,7 @@ extern "C" int hgb_mha_bwd(const float* qkv, const float* out, const float* lse,
   if (n == 0) return HGB_OK;
   const int d = f / heads;
   const float scale = 1.f / sqrtf((float)d);
-  dim3 grid((n + ATT_TQ - 1) / ATT_TQ, heads);
+  dim3 grid((n + ATT_QPB - 1) / ATT_QPB, heads);
   cudaStream_t st = (cudaStream_t)stream;
   ATT_DISPATCH(mha_bwd_q_kernel, qkv, out, lse, gout, n, f, scale, gqkv)
   HGB_LAUNCH_CHECK("mha_bwd_q");
