@@ -371,15 +371,15 @@ def painn_message_roofline(m, d, ops, dev):
     ach = alg / (ms * 1e-3) / 1e9
     return {"kernel": "painn_message_fwd_tiled_kernel<false,5,64>", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
             "frac": ach / hbm, "traffic": NCU_TRAFFIC_BYTES if (n, e, f) == NCU_TRAFFIC_SHAPE else None,
-            "traffic_source": "profiles/r01_ncu_painn_message_v3_details.csv (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+            "traffic_source": "profiles/r01_ncu_painn_message_final_details.csv (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
             "peak_source": src + " (burst copy figure; kernel timed alone, L2 flushed)",
             "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms,
             "survey_formula": {"bytes_per_launch": survey, "achieved": survey / (ms * 1e-3) / 1e9, "frac": survey / (ms * 1e-3) / 1e9 / hbm}}
 
 
-# measured once with `ncu --set full` on the bench shapes (N, E, F): 317.0 MB read + 123.7 MB written
+# measured once with `ncu --set full` on the bench shapes (N, E, F): 315.2 MB read + 120.7 MB written
 NCU_TRAFFIC_SHAPE = (147456, 786432, 64)
-NCU_TRAFFIC_BYTES = 440675072
+NCU_TRAFFIC_BYTES = 435925760
 
 
 if __name__ == "__main__":
