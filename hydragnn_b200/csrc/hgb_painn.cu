@@ -883,8 +883,13 @@ extern "C" int hgb_painn_message_bwd(const float* gs_out, const float* gv_out, c
   }
   float* part = (float*)workspace;
   if (rec && f % 64 == 0 && f <= 256 && n >= 256 && (((uintptr_t)gs_out | (uintptr_t)gv_out | (uintptr_t)phi | (uintptr_t)v | (uintptr_t)rec) % 16 == 0)) {
-    const int tn = 32;
-    const size_t smem = (size_t)2 * tn * 4 * f * 4 + 32 + WPB * 32 * 4 + WPB * 4096;
+    // two double-buffered [tn x 4f] fp32 tiles + per-warp scratch; two blocks per SM
+    const size_t fixed = 32 + WPB * 32 * 4 + WPB * 4096;
+    int tn = (int)((110 * 1024 - fixed) / ((size_t)2 * 4 * f * 4));
+    tn = (tn / WPB) * WPB;                                   // whole nodes per warp
+    if (tn > 32) tn = 32;
+    if (tn < WPB) tn = WPB;
+    const size_t smem = (size_t)2 * tn * 4 * f * 4 + fixed;
     static bool attr_done = false;
     if (!attr_done) {
 #define SETA(E, G, R) cudaFuncSetAttribute(painn_message_bwd_tiled_kernel<E, G, R, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \

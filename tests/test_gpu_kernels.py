@@ -353,7 +353,7 @@ def test_painn_message_vs_oracle(f, edge_dim):
     torch.testing.assert_close(v2.cpu(), vo, rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("f,n", [(64, 3000), (128, 700)])
+@pytest.mark.parametrize("f,n", [(64, 3000), (128, 700), (64, 257), (64, 20011), (128, 9001), (192, 1500), (256, 520)])
 def test_painn_message_tiled_path_vs_oracle(f, n):
     """n >= 256 and F % 64 == 0 selects the shared-memory-tiled kernels: mostly-local edges (on-chip gathers) plus
     some long-range ones (global fallback), in a non-sorted edge order."""
