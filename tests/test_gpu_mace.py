@@ -37,7 +37,7 @@ def _to_dev(d, pos_grad=False):
     return g
 
 
-@pytest.mark.parametrize("variant", ["default", "ell3_corr3", "one_layer", "gaussian_add", "fused32", "fused64_ell3", "fused32_ell1"])
+@pytest.mark.parametrize("variant", ["default", "ell3_corr3", "one_layer", "gaussian_add", "fused32", "fused64_ell3", "fused32_ell1", "fused128"])
 def test_mace_forward_and_gradients_match_oracle(variant):
     kw = dict(MACE_KW)
     if variant == "ell3_corr3":
@@ -50,6 +50,8 @@ def test_mace_forward_and_gradients_match_oracle(variant):
         kw.update(hidden_dim=32)
     elif variant == "fused64_ell3":
         kw.update(hidden_dim=64, max_ell=3, node_max_ell=2, num_conv_layers=3)
+    elif variant == "fused128":            # two channel blocks per node in the tensor-product kernel
+        kw.update(hidden_dim=128)
     elif variant == "fused32_ell1":
         kw.update(hidden_dim=32, max_ell=1, node_max_ell=1)
     o, e = _pair(kw)
