@@ -437,3 +437,34 @@ def test_loss_and_adamw_match_torch():
     assert float(step) == 5.0
     mae = ops.LossFn.apply(pe, tgt.to(DEV), 1)
     torch.testing.assert_close(mae.cpu(), (pe.cpu() - tgt).abs().mean(), **TOL)
+
+
+@pytest.mark.parametrize("n,e,c", [(50, 400, 12), (300, 5000, 64), (7, 3, 5)])
+def test_pna_aggregate_kernel_vs_torch(n, e, c):
+    """mean | min | max | std per segment (with empty segments) and its backward against plain torch."""
+    g = gen(n + e + c)
+    idx = torch.randint(0, n, (e,), generator=g)
+    idx[idx == 3] = 4                                     # segment 3 stays empty
+    m = torch.randn(e, c, generator=g)
+    csr = ops.csr_build(idx.to(DEV), n)
+    me = m.to(DEV).requires_grad_(True)
+    out = ops.PnaAggregateFn.apply(me, csr)
+    mr = m.double().requires_grad_(True)
+    ref = torch.zeros(n, 4 * c, dtype=torch.float64)
+    rows = []
+    for i in range(n):
+        seg = mr[idx == i]
+        if seg.shape[0] == 0:
+            rows.append(torch.zeros(4 * c, dtype=torch.float64))
+            continue
+        mean = seg.mean(0)
+        var = (seg * seg).mean(0) - mean * mean
+        sd = var.clamp(min=1e-5).sqrt()
+        sd = sd.masked_fill(sd <= 1e-5 ** 0.5, 0.0)
+        rows.append(torch.cat([mean, seg.min(0).values, seg.max(0).values, sd]))
+    ref = torch.stack(rows)
+    torch.testing.assert_close(out.cpu().double(), ref.detach(), rtol=1e-4, atol=1e-5)
+    w = torch.randn(n, 4 * c, generator=g)
+    ge, = torch.autograd.grad((out * w.to(DEV)).sum(), me)
+    gr, = torch.autograd.grad((ref * w.double()).sum(), mr)
+    torch.testing.assert_close(ge.cpu().double(), gr, rtol=1e-3, atol=1e-4)
