@@ -9,7 +9,7 @@ Public surface (mirrors the slice of ``hydragnn`` that sits on the per-step hot 
 
 The CUDA library is loaded lazily on first use; importing the package works on a CPU-only host.
 """
-from .data import Batch, Data  # noqa: F401
+from .data import Batch, Data, collate_to_device  # noqa: F401
 from .create import create_model, create_model_config, get_device, set_precision  # noqa: F401
 from .radius import (get_radius_graph, get_radius_graph_config, get_radius_graph_pbc,  # noqa: F401
                      get_radius_graph_pbc_config, RadiusGraph, RadiusGraphPBC)

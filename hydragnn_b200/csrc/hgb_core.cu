@@ -189,3 +189,46 @@ extern "C" int hgb_gather_i32(const int32_t* idx, const int32_t* perm, int64_t e
   HGB_LAUNCH_CHECK("gather_i32");
   return HGB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// device-side collate (replaces the index bookkeeping of PyG Batch.from_data_list, hydragnn/preprocess/load_data.py:157-164):
+// batch[i] = graph of node i, and edge_index with per-graph node offsets added, both from [G+1] offset vectors.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ptr_search(const int32_t* __restrict__ ptr, int g, int64_t i) {   // largest k with ptr[k] <= i
+  int lo = 0, hi = g;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (ptr[mid] <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void collate_batch_vector_kernel(const int32_t* __restrict__ ptr, int g, int64_t n, int64_t* __restrict__ batch) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) batch[i] = ptr_search(ptr, g, i);
+}
+
+__global__ void collate_offset_edges_kernel(const int64_t* __restrict__ local, const int32_t* __restrict__ eptr,
+                                            const int32_t* __restrict__ nptr, int g, int64_t e, int64_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t off = nptr[ptr_search(eptr, g, i)];
+    out[i] = local[i] + off;
+    out[e + i] = local[e + i] + off;
+  }
+}
+
+extern "C" int hgb_collate_batch_vector(const int32_t* ptr, int32_t g, int64_t n, int64_t* batch, hgb_stream_t stream) {
+  HGB_REQUIRE(g >= 0 && n >= 0 && ptr && (n == 0 || batch), "collate_batch_vector: bad arguments");
+  if (n == 0) return HGB_OK;
+  collate_batch_vector_kernel<<<hgb_grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(ptr, g, n, batch);
+  HGB_LAUNCH_CHECK("collate_batch_vector");
+  return HGB_OK;
+}
+
+extern "C" int hgb_collate_offset_edges(const int64_t* edge_index_local, const int32_t* edge_ptr, const int32_t* node_ptr, int32_t g,
+                                        int64_t e, int64_t* edge_index, hgb_stream_t stream) {
+  HGB_REQUIRE(g >= 0 && e >= 0 && edge_ptr && node_ptr && (e == 0 || (edge_index_local && edge_index)), "collate_offset_edges: bad arguments");
+  if (e == 0) return HGB_OK;
+  collate_offset_edges_kernel<<<hgb_grid_for(e, 256), 256, 0, (cudaStream_t)stream>>>(edge_index_local, edge_ptr, node_ptr, g, e, edge_index);
+  HGB_LAUNCH_CHECK("collate_offset_edges");
+  return HGB_OK;
+}

@@ -122,3 +122,50 @@ class Batch(Data):
         out.ptr = torch.tensor(offs + [n], dtype=torch.long)
         out._num_graphs = len(samples)
         return out
+
+
+def collate_to_device(samples, device, non_blocking=True):
+    """``Batch.from_data_list(samples).to(device)`` with the index work done on the GPU: every tensor field is
+    packed into ONE pinned staging buffer and copied once; ``ptr`` is a device scan of the node counts, ``batch`` and the
+    node offsets of ``edge_index`` come from two small kernels instead of per-sample Python arithmetic."""
+    from . import _lib, ops
+    device = torch.device(device)
+    out = Batch()
+    g = len(samples)
+    keys = []
+    for s in samples:
+        for k in s.keys():
+            if k not in keys:
+                keys.append(k)
+
+    def staged(parts, dim=0, stack=False):
+        t = torch.stack(parts) if stack else torch.cat(parts, dim=dim)
+        return t.pin_memory().to(device, non_blocking=non_blocking)
+
+    counts = torch.tensor([s.num_nodes for s in samples], dtype=torch.int32)
+    nptr = ops.exclusive_scan(counts.pin_memory().to(device, non_blocking=non_blocking))
+    n = int(counts.sum())
+    for k in keys:
+        vals = [getattr(s, k) for s in samples]
+        if not all(torch.is_tensor(v) for v in vals):
+            out.__dict__[k] = vals
+        elif k == "edge_index":
+            ecnt = torch.tensor([v.shape[1] for v in vals], dtype=torch.int32)
+            eptr = ops.exclusive_scan(ecnt.pin_memory().to(device, non_blocking=non_blocking))
+            local = staged(vals, dim=1).contiguous()
+            e = local.shape[1]
+            ei = torch.empty_like(local)
+            _lib.call("hgb_collate_offset_edges", ops._p(local), ops._p(eptr), ops._p(nptr), g, e, ops._p(ei), ops._stream())
+            out.edge_index = ei
+        elif k == "cell":
+            out.cell = staged([v.reshape(3, 3) for v in vals], stack=True)
+        elif k == "pbc":
+            out.pbc = staged([v.reshape(3) for v in vals], stack=True)
+        elif vals[0].dim() == 0:
+            out.__dict__[k] = staged(vals, stack=True)
+        else:
+            out.__dict__[k] = staged(vals)
+    batch = torch.empty(n, dtype=torch.int64, device=device)
+    _lib.call("hgb_collate_batch_vector", ops._p(nptr), g, n, ops._p(batch), ops._stream())
+    out.batch, out.ptr, out._num_graphs = batch, nptr.to(torch.int64), g
+    return out

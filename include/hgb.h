@@ -306,6 +306,13 @@ int hgb_adamw_step(float* p, const float* g, float* m, float* v, int64_t count, 
                    float beta2, float eps, float weight_decay, float grad_scale, float* step_dev,
                    hgb_stream_t stream);
 
+/* Device-side collate (replaces the index bookkeeping of PyG Batch.from_data_list + move_batch_to_device,
+ * hydragnn/preprocess/load_data.py:157-164, train_validate_test.py:74-84): ptr [g+1] = exclusive scan of the per-graph
+ * node counts.  batch[i] = graph of node i;  edge_index[:, k] = edge_index_local[:, k] + node_ptr[graph of edge k].      */
+int hgb_collate_batch_vector(const int32_t* ptr, int32_t g, int64_t n, int64_t* batch, hgb_stream_t stream);
+int hgb_collate_offset_edges(const int64_t* edge_index_local, const int32_t* edge_ptr, const int32_t* node_ptr, int32_t g,
+                             int64_t e, int64_t* edge_index, hgb_stream_t stream);
+
 /* PNA aggregation (hydragnn/models/PNAEqStack.py:396-400; torch_geometric 2.6.1 DegreeScalerAggregation with aggregators
  * mean, min, max, std): one pass per CSR segment.  m [e,c] -> out [n,4c] = [mean | min | max | std]; argmin / argmax [n,c]
  * = edge id of the first extremum (-1: empty segment).  Backward: g_m [e,c] from g_out [n,4c]; idx [e] = segment of every edge. */

@@ -468,3 +468,20 @@ def test_pna_aggregate_kernel_vs_torch(n, e, c):
     ge, = torch.autograd.grad((out * w.to(DEV)).sum(), me)
     gr, = torch.autograd.grad((ref * w.double()).sum(), mr)
     torch.testing.assert_close(ge.cpu().double(), gr, rtol=1e-3, atol=1e-4)
+
+
+def test_collate_to_device_equals_from_data_list():
+    g = gen(77)
+    samples = []
+    for k in (5, 1, 9, 3):
+        ei = torch.randint(0, k, (2, 3 * k), generator=g)
+        samples.append(hb.Data(x=torch.randn(k, 2, generator=g), pos=torch.randn(k, 3, generator=g), edge_index=ei,
+                               edge_attr=torch.randn(3 * k, 4, generator=g), y=torch.randn(1, 1, generator=g),
+                               energy=torch.randn((), generator=g), cell=torch.randn(3, 3, generator=g),
+                               pbc=torch.tensor([True, False, True])))
+    ref = hb.Batch.from_data_list(samples)
+    out = hb.collate_to_device(samples, DEV)
+    torch.cuda.synchronize()
+    for k in ("x", "pos", "edge_index", "edge_attr", "y", "energy", "cell", "pbc", "batch", "ptr"):
+        assert torch.equal(out[k].cpu(), ref[k]), k
+    assert out.num_graphs == 4
