@@ -1070,3 +1070,145 @@ extern "C" int hgb_painn_update_bwd(const float* gs_out, const float* gv_out, co
   HGB_LAUNCH_CHECK("painn_update_bwd");
   return HGB_OK;
 }
+
+// ---- PaiNN update block at node_size == 1 ----------------------------------------------------------------------------------
+// The reference runs its first PaiNN layer at width input_dim (quirk Q4: 1 for atomic-number inputs).  At that width the
+// whole update block (PAINNStack.py:298-328: U, V, |Vv|, Linear(2,1)-SiLU-Linear(1,2|3), gated residuals) is a few scalar
+// operations per node: one kernel forward, one kernel + a tiny reduce backward, instead of ~14 launches.
+// Parameter pack p[16]: 0 uw, 1 ub, 2 vw, 3 vb, 4 w1[norm], 5 w1[s], 6 b1, 7.. w2[0..na-1], 10.. b2[0..na-1]
+// Gradient pack g[16] uses the same slots.
+struct UpdScalar {
+  float uv[3], vv[3], nrm, z1, h, a[3], inner;
+};
+__device__ __forceinline__ void upd_scalar_eval(const float* __restrict__ p, int na, float s, const float (&v)[3], UpdScalar& r) {
+  float n2 = 0.f;
+  r.inner = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    r.uv[k] = fmaf(p[0], v[k], p[1]);
+    r.vv[k] = fmaf(p[2], v[k], p[3]);
+    n2 = fmaf(r.vv[k], r.vv[k], n2);
+    r.inner = fmaf(r.uv[k], r.vv[k], r.inner);
+  }
+  r.nrm = sqrtf(n2);
+  r.z1 = fmaf(p[4], r.nrm, fmaf(p[5], s, p[6]));
+  r.h = r.z1 * hgb_sigmoid(r.z1);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) r.a[j] = j < na ? fmaf(p[7 + j], r.h, p[10 + j]) : 0.f;
+}
+
+__global__ void painn_update_scalar_fwd_kernel(const float* __restrict__ s, const float* __restrict__ v, const float* __restrict__ pk,
+                                               int n, int last, float* __restrict__ s_out, float* __restrict__ v_out) {
+  __shared__ float p[16];
+  if (threadIdx.x < 16) p[threadIdx.x] = pk[threadIdx.x];
+  __syncthreads();
+  const int na = last ? 2 : 3;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float si = s[i];
+    const float vi[3] = {v[3 * i], v[3 * i + 1], v[3 * i + 2]};
+    UpdScalar r;
+    upd_scalar_eval(p, na, si, vi, r);
+    const float a_sv = r.a[na - 2], a_ss = r.a[na - 1];
+    s_out[i] = si + a_sv * r.inner + a_ss;
+    if (!last) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) v_out[3 * i + k] = fmaf(r.a[0], r.uv[k], vi[k]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+painn_update_scalar_bwd_kernel(const float* __restrict__ gs_out, const float* __restrict__ gv_out, const float* __restrict__ s,
+                               const float* __restrict__ v, const float* __restrict__ pk, int n, int last, float* __restrict__ gs,
+                               float* __restrict__ gv, float* __restrict__ part) {
+  __shared__ float p[16];
+  __shared__ float red[8][16];
+  if (threadIdx.x < 16) p[threadIdx.x] = pk[threadIdx.x];
+  __syncthreads();
+  const int na = last ? 2 : 3;
+  float g[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) g[q] = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float si = s[i];
+    const float vi[3] = {v[3 * i], v[3 * i + 1], v[3 * i + 2]};
+    UpdScalar r;
+    upd_scalar_eval(p, na, si, vi, r);
+    const float go = gs_out[i];
+    float gvo[3] = {0.f, 0.f, 0.f};
+    if (!last) { gvo[0] = gv_out[3 * i]; gvo[1] = gv_out[3 * i + 1]; gvo[2] = gv_out[3 * i + 2]; }
+    const float a_sv = r.a[na - 2], a_vv = last ? 0.f : r.a[0];
+    float ga[3] = {0.f, 0.f, 0.f};
+    ga[na - 1] = go;
+    ga[na - 2] = go * r.inner;
+    if (!last) ga[0] = gvo[0] * r.uv[0] + gvo[1] * r.uv[1] + gvo[2] * r.uv[2];
+    float gh = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      if (j < na) { gh = fmaf(ga[j], p[7 + j], gh); g[7 + j] = fmaf(ga[j], r.h, g[7 + j]); g[10 + j] += ga[j]; }
+    const float sg = hgb_sigmoid(r.z1);
+    const float gz1 = gh * sg * (1.f + r.z1 * (1.f - sg));
+    g[4] = fmaf(gz1, r.nrm, g[4]);
+    g[5] = fmaf(gz1, si, g[5]);
+    g[6] += gz1;
+    gs[i] = go + gz1 * p[5];
+    const float gn_over = r.nrm > 0.f ? gz1 * p[4] / r.nrm : 0.f;
+    const float g_inner = go * a_sv;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float guv = gvo[k] * a_vv + g_inner * r.vv[k];
+      const float gvv = g_inner * r.uv[k] + gn_over * r.vv[k];
+      gv[3 * i + k] = gvo[k] + guv * p[0] + gvv * p[2];
+      g[0] = fmaf(guv, vi[k], g[0]); g[1] += guv;
+      g[2] = fmaf(gvv, vi[k], g[2]); g[3] += gvv;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const float t = hgb_warp_sum(g[q]);
+    if (lane == 0) red[warp][q] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) t += red[w8][threadIdx.x];
+    part[blockIdx.x * 16 + threadIdx.x] = t;
+  }
+}
+
+__global__ void painn_update_scalar_reduce_kernel(const float* __restrict__ part, int nb, float* __restrict__ gp) {
+  if (threadIdx.x < 16) {
+    float t = 0.f;
+    for (int b = 0; b < nb; ++b) t += part[b * 16 + threadIdx.x];
+    gp[threadIdx.x] = t;
+  }
+}
+
+#define UPD_SCALAR_BLOCKS (HGB_NUM_SMS * 2)
+extern "C" int64_t hgb_painn_update_scalar_workspace_bytes(void) { return (int64_t)UPD_SCALAR_BLOCKS * 16 * 4; }
+
+extern "C" int hgb_painn_update_scalar_fwd(const float* s, const float* v, const float* params16, int32_t n, int32_t last, float* s_out,
+                                           float* v_out, hgb_stream_t stream) {
+  HGB_REQUIRE(n >= 0 && s && v && params16 && s_out && (last || v_out), "painn_update_scalar_fwd: bad arguments");
+  if (n == 0) return HGB_OK;
+  painn_update_scalar_fwd_kernel<<<hgb_grid_for(n, 256, HGB_NUM_SMS * 4), 256, 0, (cudaStream_t)stream>>>(s, v, params16, n, last, s_out, v_out);
+  HGB_LAUNCH_CHECK("painn_update_scalar_fwd");
+  return HGB_OK;
+}
+
+extern "C" int hgb_painn_update_scalar_bwd(const float* gs_out, const float* gv_out, const float* s, const float* v, const float* params16,
+                                           int32_t n, int32_t last, float* gs, float* gv, float* gparams16, void* workspace,
+                                           hgb_stream_t stream) {
+  HGB_REQUIRE(n >= 0 && gs_out && s && v && params16 && gs && gv && gparams16 && workspace && (last || gv_out),
+              "painn_update_scalar_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) { cudaMemsetAsync(gparams16, 0, 64, st); return HGB_OK; }
+  const int nb = hgb_grid_for(n, 256, UPD_SCALAR_BLOCKS);
+  painn_update_scalar_bwd_kernel<<<nb, 256, 0, st>>>(gs_out, gv_out, s, v, params16, n, last, gs, gv, (float*)workspace);
+  HGB_LAUNCH_CHECK("painn_update_scalar_bwd");
+  painn_update_scalar_reduce_kernel<<<1, 32, 0, st>>>((const float*)workspace, nb, gparams16);
+  HGB_LAUNCH_CHECK("painn_update_scalar_reduce");
+  return HGB_OK;
+}

@@ -644,6 +644,47 @@ class PainnUpdateFn(torch.autograd.Function):
         return gs, gv.reshape(n, 3, f), gwuv[:f], gbuv[:f], gwuv[f:], gbuv[f:], gw1, gb1, gw2, gb2, None
 
 
+SCALAR_UPDATE = False   # PaiNN update block at node_size == 1 through the one-kernel path (enabled once verified on the GPU)
+
+
+class PainnUpdateScalarFn(torch.autograd.Function):
+    """PaiNN update block at node_size == 1 (the first layer of the reference runs at width input_dim, quirk Q4): the whole
+    block in one kernel forward, one kernel + a 16-value reduce backward (everything is recomputed from s, v)."""
+
+    @staticmethod
+    def forward(ctx, s, v, uw, ub, vw, vb, w1, b1, w2, b2, last):
+        n = s.shape[0]
+        na = 2 if last else 3
+        pad = s.new_zeros(3 - na)
+        pk = torch.cat([uw.reshape(1), ub.reshape(1), vw.reshape(1), vb.reshape(1), w1.reshape(2), b1.reshape(1), w2.reshape(na), pad,
+                        b2.reshape(na), pad, s.new_zeros(3)]).contiguous()
+        s2, v2 = _chk(s.reshape(n).contiguous()), _chk(v.reshape(n, 3).contiguous())
+        s_out = torch.empty_like(s2)
+        v_out = None if last else torch.empty_like(v2)
+        _lib.call("hgb_painn_update_scalar_fwd", _p(s2), _p(v2), _p(pk), n, int(last), _p(s_out), _p(v_out), _stream())
+        ctx.save_for_backward(s2, v2, pk)
+        ctx.last = bool(last)
+        if last:
+            return s_out.reshape(n, 1), s_out.new_zeros(0)
+        return s_out.reshape(n, 1), v_out.reshape(n, 3, 1)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gs_out, gv_out):
+        s2, v2, pk = ctx.saved_tensors
+        n, last = s2.shape[0], ctx.last
+        na = 2 if last else 3
+        gs_out = _chk(gs_out.reshape(n).contiguous())
+        gv_out = None if last else _chk(gv_out.reshape(n, 3).contiguous())
+        gs, gv, gp = torch.empty_like(s2), torch.empty_like(v2), torch.empty(16, dtype=s2.dtype, device=s2.device)
+        nbytes = _lib.query("hgb_painn_update_scalar_workspace_bytes")
+        ws = _ws(nbytes, s2.device)
+        _lib.call("hgb_painn_update_scalar_bwd", _p(gs_out), _p(gv_out), _p(s2), _p(v2), _p(pk), n, int(last), _p(gs), _p(gv), _p(gp),
+                  _p(ws), _stream())
+        return (gs.reshape(n, 1), gv.reshape(n, 3, 1), gp[0:1].reshape(1, 1), gp[1:2], gp[2:3].reshape(1, 1), gp[3:4],
+                gp[4:6].reshape(1, 2), gp[6:7], gp[7:7 + na].reshape(na, 1), gp[10:10 + na], None)
+
+
 class PoolFn(torch.autograd.Function):
     """global_{add,mean,max}_pool over a sorted batch vector (hydragnn/models/Base.py:147-170)."""
 

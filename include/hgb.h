@@ -306,6 +306,17 @@ int hgb_adamw_step(float* p, const float* g, float* m, float* v, int64_t count, 
                    float beta2, float eps, float weight_decay, float grad_scale, float* step_dev,
                    hgb_stream_t stream);
 
+/* PaiNN update block at node_size == 1 (the reference's first layer runs at width input_dim, quirk Q4): the whole block
+ * (PAINNStack.py:298-328) per node in one kernel.  params16 / gparams16 (device, 16 floats): 0 uw, 1 ub, 2 vw, 3 vb,
+ * 4 w1[|Vv|], 5 w1[s], 6 b1, 7..9 w2 rows, 10..12 b2 (rows = (a_vv, a_sv, a_ss), or (a_sv, a_ss) when last != 0).
+ * s [n], v [n,3]; gv receives the complete gradient w.r.t. v (direct path included).                                     */
+int64_t hgb_painn_update_scalar_workspace_bytes(void);
+int hgb_painn_update_scalar_fwd(const float* s, const float* v, const float* params16, int32_t n, int32_t last, float* s_out,
+                                float* v_out, hgb_stream_t stream);
+int hgb_painn_update_scalar_bwd(const float* gs_out, const float* gv_out, const float* s, const float* v, const float* params16,
+                                int32_t n, int32_t last, float* gs, float* gv, float* gparams16, void* workspace,
+                                hgb_stream_t stream);
+
 /* Device-side collate (replaces the index bookkeeping of PyG Batch.from_data_list + move_batch_to_device,
  * hydragnn/preprocess/load_data.py:157-164, train_validate_test.py:74-84): ptr [g+1] = exclusive scan of the per-graph
  * node counts.  batch[i] = graph of node i;  edge_index[:, k] = edge_index_local[:, k] + node_ptr[graph of edge k].      */

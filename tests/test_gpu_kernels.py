@@ -388,7 +388,7 @@ def test_painn_message_tiled_path_vs_oracle(f, n):
         torch.testing.assert_close(a.cpu(), b, rtol=5e-4, atol=5e-4)
 
 
-@pytest.mark.parametrize("f,last", [(1, False), (6, False), (64, False), (64, True), (7, True)])
+@pytest.mark.parametrize("f,last", [(1, False), (1, True), (6, False), (64, False), (64, True), (7, True)])
 def test_painn_update_vs_oracle(f, last):
     g = gen(200 + f)
     torch.manual_seed(f)
