@@ -14,6 +14,8 @@ Two layers:
 
 Nothing here falls back to ATen/PyG scatter kernels; a missing library raises in ``_lib.lib()``.
 """
+import os
+
 import torch
 from torch.autograd.function import once_differentiable
 
@@ -644,7 +646,7 @@ class PainnUpdateFn(torch.autograd.Function):
         return gs, gv.reshape(n, 3, f), gwuv[:f], gbuv[:f], gwuv[f:], gbuv[f:], gw1, gb1, gw2, gb2, None
 
 
-SCALAR_UPDATE = False   # PaiNN update block at node_size == 1 through the one-kernel path (enabled once verified on the GPU)
+SCALAR_UPDATE = os.environ.get("HGB_SCALAR", "1") == "1"   # PaiNN update block at node_size == 1 through the one-kernel path
 
 
 class PainnUpdateScalarFn(torch.autograd.Function):

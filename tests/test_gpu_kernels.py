@@ -417,7 +417,7 @@ def test_painn_update_vs_oracle(f, last):
 
 @pytest.mark.parametrize("last", [False, True])
 @pytest.mark.parametrize("n", [77, 100003])
-def pending_test_painn_scalar_update_kernel_vs_oracle(last, n, monkeypatch):
+def test_painn_scalar_update_kernel_vs_oracle(last, n, monkeypatch):
     """node_size == 1 (first layer, quirk Q4): the one-kernel update block against the oracle, including the 13 parameter
     gradients that are reduced across blocks."""
     monkeypatch.setattr(ops, "SCALAR_UPDATE", True)
@@ -504,7 +504,7 @@ def test_pna_aggregate_kernel_vs_torch(n, e, c):
     torch.testing.assert_close(ge.cpu().double(), gr, rtol=1e-3, atol=1e-4)
 
 
-def pending_test_collate_to_device_equals_from_data_list():
+def test_collate_to_device_equals_from_data_list():
     g = gen(77)
     samples = []
     for k in (5, 1, 9, 3):
