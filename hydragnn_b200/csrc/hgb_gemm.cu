@@ -88,13 +88,26 @@ __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ a, 
   }
 }
 
+// c[i] (+)= sum over split-K slices of part[s, i].  blockDim = (32, 8): x = output element, y = slice group (slices y, y+8, ...);
+// the 8 group sums are added in a fixed order, so the result does not depend on scheduling.
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t mn, int n, int64_t ldc,
                                      int beta_one, float* __restrict__ c) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < mn; i += (int64_t)gridDim.x * blockDim.x) {
+  __shared__ float red[8][33];
+  for (int64_t base = (int64_t)blockIdx.x * 32; base < mn; base += (int64_t)gridDim.x * 32) {
+    const int64_t i = base + threadIdx.x;
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += part[(int64_t)s * mn + i];
-    const int64_t o = (i / n) * ldc + (i % n);
-    c[o] = beta_one ? c[o] + acc : acc;
+    if (i < mn)
+      for (int s = threadIdx.y; s < splits; s += 8) acc += part[(int64_t)s * mn + i];
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && i < mn) {
+      float t = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+      const int64_t o = (i / n) * ldc + (i % n);
+      c[o] = beta_one ? c[o] + t : t;
+    }
+    __syncthreads();
   }
 }
 
@@ -127,7 +140,7 @@ static int launch_gemm(const float* a, const float* b, float* c, int m, int n, i
                                             bias, act, act_param, z);
   HGB_LAUNCH_CHECK("gemm");
   if (splits > 1) {
-    splitk_reduce_kernel<<<hgb_grid_for((int64_t)m * n, 256), 256, 0, st>>>((const float*)ws, splits, (int64_t)m * n, n, ldc,
+    splitk_reduce_kernel<<<hgb_grid_for((int64_t)m * n, 32), dim3(32, 8), 0, st>>>((const float*)ws, splits, (int64_t)m * n, n, ldc,
                                                                             beta_one, c);
     HGB_LAUNCH_CHECK("splitk_reduce");
   }
@@ -553,5 +566,94 @@ extern "C" int hgb_linear_smallk_bwd(const float* dy, const float* y, const floa
   HGB_LAUNCH_CHECK("linear_smallk_bwd");
   linear_smallk_reduce_kernel<<<(n * (k + 1) + 31) / 32, dim3(32, 8), 0, st>>>((const float*)workspace, nb_used, n, k, dw, lddw, db);
   HGB_LAUNCH_CHECK("linear_smallk_reduce");
+  return HGB_OK;
+}
+
+// ---- Linear(1,1) - act - Linear(1,out<=4) on one scalar per row (the scalar_message_mlp of a width-1 PaiNN layer, quirk Q4) ----
+// params8: 0 w1, 1 b1, 2 + j: w2[j], 6 + j... -> pack of 10 floats: [w1, b1, w2[0..3], b2[0..3]]; gradient pack has the same layout.
+__global__ void mlp2_scalar_fwd_kernel(const float* __restrict__ x, const float* __restrict__ pk, int n, int out, int act, float ap,
+                                       float* __restrict__ y) {
+  __shared__ float p[10];
+  if (threadIdx.x < 10) p[threadIdx.x] = pk[threadIdx.x];
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float h = hgb_act(fmaf(p[0], x[i], p[1]), act, ap);
+    for (int j = 0; j < out; ++j) y[(int64_t)i * out + j] = fmaf(p[2 + j], h, p[6 + j]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+mlp2_scalar_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ pk, int n, int out, int act,
+                       float ap, float* __restrict__ gx, float* __restrict__ part) {
+  __shared__ float p[10];
+  __shared__ float red[8][10];
+  if (threadIdx.x < 10) p[threadIdx.x] = pk[threadIdx.x];
+  __syncthreads();
+  float g[10];
+#pragma unroll
+  for (int q = 0; q < 10; ++q) g[q] = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float xi = x[i];
+    const float z = fmaf(p[0], xi, p[1]);
+    const float h = hgb_act(z, act, ap);
+    float gh = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < out) {
+        const float gj = gy[(int64_t)i * out + j];
+        gh = fmaf(gj, p[2 + j], gh);
+        g[2 + j] = fmaf(gj, h, g[2 + j]);
+        g[6 + j] += gj;
+      }
+    const float gz = gh * hgb_act_grad(h, z, act, ap);
+    g[0] = fmaf(gz, xi, g[0]);
+    g[1] += gz;
+    if (gx) gx[i] = gz * p[0];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 10; ++q) {
+    const float t = hgb_warp_sum(g[q]);
+    if (lane == 0) red[warp][q] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 10) {
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) t += red[w8][threadIdx.x];
+    part[blockIdx.x * 10 + threadIdx.x] = t;
+  }
+}
+
+__global__ void mlp2_scalar_reduce_kernel(const float* __restrict__ part, int nb, float* __restrict__ gp) {
+  if (threadIdx.x < 10) {
+    float t = 0.f;
+    for (int b = 0; b < nb; ++b) t += part[b * 10 + threadIdx.x];
+    gp[threadIdx.x] = t;
+  }
+}
+
+#define MLP2S_BLOCKS (HGB_NUM_SMS * 2)
+extern "C" int64_t hgb_mlp2_scalar_workspace_bytes(void) { return (int64_t)MLP2S_BLOCKS * 10 * 4; }
+
+extern "C" int hgb_mlp2_scalar_fwd(const float* x, const float* params10, int32_t n, int32_t out, int32_t act, float act_param, float* y,
+                                   hgb_stream_t stream) {
+  HGB_REQUIRE(n >= 0 && out >= 1 && out <= 4 && x && params10 && y, "mlp2_scalar_fwd: bad arguments (1 <= out <= 4)");
+  if (n == 0) return HGB_OK;
+  mlp2_scalar_fwd_kernel<<<hgb_grid_for(n, 256, HGB_NUM_SMS * 4), 256, 0, (cudaStream_t)stream>>>(x, params10, n, out, act, act_param, y);
+  HGB_LAUNCH_CHECK("mlp2_scalar_fwd");
+  return HGB_OK;
+}
+
+extern "C" int hgb_mlp2_scalar_bwd(const float* gy, const float* x, const float* params10, int32_t n, int32_t out, int32_t act,
+                                   float act_param, float* gx, float* gparams10, void* workspace, hgb_stream_t stream) {
+  HGB_REQUIRE(n >= 0 && out >= 1 && out <= 4 && gy && x && params10 && gparams10 && workspace, "mlp2_scalar_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) { cudaMemsetAsync(gparams10, 0, 40, st); return HGB_OK; }
+  const int nb = hgb_grid_for(n, 256, MLP2S_BLOCKS);
+  mlp2_scalar_bwd_kernel<<<nb, 256, 0, st>>>(gy, x, params10, n, out, act, act_param, gx, (float*)workspace);
+  HGB_LAUNCH_CHECK("mlp2_scalar_bwd");
+  mlp2_scalar_reduce_kernel<<<1, 32, 0, st>>>((const float*)workspace, nb, gparams10);
+  HGB_LAUNCH_CHECK("mlp2_scalar_reduce");
   return HGB_OK;
 }

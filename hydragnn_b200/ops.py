@@ -457,7 +457,38 @@ class Mlp2Fn(torch.autograd.Function):
         return (gx.reshape(shp) if gx is not None else None), gw1, gb1, None, None, gw2, gb2, None, None
 
 
+class Mlp2ScalarFn(torch.autograd.Function):
+    """Linear(1,1) - act - Linear(1,out<=4): one kernel forward, one kernel + a 10-value reduce backward."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, act1, p1, w2, b2):
+        n, out = x.shape[0], w2.shape[0]
+        pad = x.new_zeros(4 - out)
+        pk = torch.cat([w1.reshape(1), b1.reshape(1), w2.reshape(out), pad, b2.reshape(out), pad]).contiguous()
+        x1 = _chk(x.reshape(n).contiguous())
+        y = torch.empty(n, out, dtype=x.dtype, device=x.device)
+        _lib.call("hgb_mlp2_scalar_fwd", _p(x1), _p(pk), n, out, ACT_CODES[act1], float(p1), _p(y), _stream())
+        ctx.save_for_backward(x1, pk)
+        ctx.cfg = (ACT_CODES[act1], float(p1), out)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x1, pk = ctx.saved_tensors
+        code, p1, out = ctx.cfg
+        n = x1.shape[0]
+        gx = torch.empty_like(x1) if ctx.needs_input_grad[0] else None
+        gp = torch.empty(10, dtype=x1.dtype, device=x1.device)
+        ws = _ws(_lib.query("hgb_mlp2_scalar_workspace_bytes"), x1.device)
+        _lib.call("hgb_mlp2_scalar_bwd", _p(_chk(gy.contiguous())), _p(x1), _p(pk), n, out, code, p1, _p(gx), _p(gp), _p(ws), _stream())
+        return (gx.reshape(n, 1) if gx is not None else None), gp[0:1].reshape(1, 1), gp[1:2], None, None, gp[2:2 + out].reshape(out, 1), gp[6:6 + out]
+
+
 def mlp2(x, w1, b1, act1, p1, w2, b2, act2=None, p2=0.0):
+    if (SCALAR_UPDATE and act2 is None and b1 is not None and b2 is not None and x.dim() == 2 and x.shape[1] == 1
+            and w1.shape == (1, 1) and w2.shape[1] == 1 and w2.shape[0] <= 4):
+        return Mlp2ScalarFn.apply(x, w1, b1, act1, p1, w2, b2)          # width-1 layer (quirk Q4)
     return Mlp2Fn.apply(x, w1, b1, act1, p1, w2, b2, act2, p2)
 
 

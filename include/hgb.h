@@ -317,6 +317,14 @@ int hgb_painn_update_scalar_bwd(const float* gs_out, const float* gv_out, const 
                                 int32_t n, int32_t last, float* gs, float* gv, float* gparams16, void* workspace,
                                 hgb_stream_t stream);
 
+/* Linear(1,1) - act - Linear(1,out) with out <= 4 on one scalar per row (scalar_message_mlp of a width-1 PaiNN layer, quirk Q4):
+ * params10 / gparams10 (device) = [w1, b1, w2[0..3], b2[0..3]].  x [n], y [n,out]; gx may be NULL.                        */
+int64_t hgb_mlp2_scalar_workspace_bytes(void);
+int hgb_mlp2_scalar_fwd(const float* x, const float* params10, int32_t n, int32_t out, int32_t act, float act_param, float* y,
+                        hgb_stream_t stream);
+int hgb_mlp2_scalar_bwd(const float* gy, const float* x, const float* params10, int32_t n, int32_t out, int32_t act,
+                        float act_param, float* gx, float* gparams10, void* workspace, hgb_stream_t stream);
+
 /* Device-side collate (replaces the index bookkeeping of PyG Batch.from_data_list + move_batch_to_device,
  * hydragnn/preprocess/load_data.py:157-164, train_validate_test.py:74-84): ptr [g+1] = exclusive scan of the per-graph
  * node counts.  batch[i] = graph of node i;  edge_index[:, k] = edge_index_local[:, k] + node_ptr[graph of edge k].      */
