@@ -70,6 +70,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* holder, uint32_t cols) {
@@ -268,6 +269,7 @@ __global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant
     // quarter split the 32-column chunks between them (even / odd chunk index). =====
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
+    int stile = 0;
     int acc = 0;
     uint32_t aph = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -276,9 +278,10 @@ __global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant
       const int row = t * TILE_M + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * NO;
       uint8_t* stz = sOut + (size_t)(warp - 2) * 8192;          // this warp's staging tiles: [0] pre-activation, [1] output
-      uint8_t* sty = stz + 4096;
+      uint8_t* sty = stz + 4096;                                //   (no pre-activation wanted: both hold outputs, alternately)
       const int row0 = t * TILE_M + q * 32;
       for (int c0 = half * 32; c0 < NO; c0 += 64) {
+        if (!p.z) { sty = stz + (stile & 1) * 4096; ++stile; }
         float v[32];
         tmem_ld32(taddr + c0, v);
         {
@@ -289,7 +292,9 @@ __global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant
             v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
           }
         }
-        if (lane == 0) tma_store_wait_read();                 // the previous chunk's stores have finished reading the tiles
+        if (lane == 0) {                                      // the store that last read this tile has finished reading it
+          if (p.z) tma_store_wait_read(); else tma_store_wait_read_1();
+        }
         __syncwarp();
         if (p.z && !(p.z_deriv && p.act == HGB_ACT_SILU)) {
 #pragma unroll
