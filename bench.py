@@ -197,8 +197,9 @@ def run_engine(args):
 
     def step(d, known_e=None):
         """the full hot path on one resident batch"""
-        ei, _ = radius.radius_graph(d.pos, w["radius"], gptr, G, False, w["max_neighbours"], known_e=known_e)
+        ei, rowptr = radius.radius_graph(d.pos, w["radius"], gptr, G, False, w["max_neighbours"], known_e=known_e)
         d.edge_index = ei
+        d._hgb_col_sorted = (ei, rowptr)                      # what hb.get_radius_graph(...)(d) records: edges grouped by target
         d.__dict__.pop("_hgb_plan", None)                     # plans are rebuilt every step (new edges)
         opt.zero_grad()
         m = model.module

@@ -74,11 +74,17 @@ class EdgePlan:
     """Everything index-shaped a conv layer needs, built once per batch (SURVEY hard part H3: the
     stacks aggregate by ``edge_index[0]`` which is not the sorted row of a PyG radius graph)."""
 
-    def __init__(self, edge_index, num_nodes):
+    def __init__(self, edge_index, num_nodes, col_rowptr=None):
+        """``col_rowptr`` [N+1] int32 (optional): the edges are already grouped by ``edge_index[1]`` in ascending order with
+        these segment offsets (what the engine's own radius-graph kernels emit) -- that CSR view then needs no build."""
         ei = _chk(edge_index, torch.int64)
         self.num_nodes, self.num_edges = int(num_nodes), int(ei.shape[1])
         self.by_row = csr_build(ei[0], self.num_nodes)
-        self.by_col = csr_build(ei[1], self.num_nodes)
+        if col_rowptr is not None:
+            self.by_col = Csr(ei[1].to(torch.int32), col_rowptr, torch.arange(self.num_edges, dtype=torch.int32, device=ei.device),
+                              self.num_nodes)
+        else:
+            self.by_col = csr_build(ei[1], self.num_nodes)
         self.row, self.col = self.by_row.idx, self.by_col.idx
         self._nbr = {}
 
@@ -235,6 +241,7 @@ def raw_smallk_bwd(dy, y, z, x2, w, code=0, param=0.0, need_x=True, need_w=True,
     return dx, dw, db
 
 
+COL_HINT = os.environ.get("HGB_COL_HINT", "0") == "1"   # reuse the radius graph's by-target offsets as the by_col CSR
 ACT_DERIV = 100   # HGB_ACT_DERIV: "the tensor already holds act'(.)"
 
 

@@ -451,7 +451,9 @@ class Base(nn.Module):
         plan = data.__dict__.get("_hgb_plan") if hasattr(data, "__dict__") else None
         ei = data.edge_index
         if plan is None or plan.num_edges != ei.shape[1] or plan.row.device != ei.device or plan._src is not ei:
-            plan = ops.EdgePlan(ei, data.pos.shape[0] if data.pos is not None else data.x.shape[0])
+            hint = data.__dict__.get("_hgb_col_sorted") if hasattr(data, "__dict__") else None     # (edge_index, rowptr)
+            plan = ops.EdgePlan(ei, data.pos.shape[0] if data.pos is not None else data.x.shape[0],
+                                col_rowptr=hint[1] if (ops.COL_HINT and hint is not None and hint[0] is ei) else None)
             plan._src = ei
             try:
                 data._hgb_plan = plan
