@@ -241,7 +241,7 @@ def raw_smallk_bwd(dy, y, z, x2, w, code=0, param=0.0, need_x=True, need_w=True,
     return dx, dw, db
 
 
-COL_HINT = os.environ.get("HGB_COL_HINT", "0") == "1"   # reuse the radius graph's by-target offsets as the by_col CSR
+COL_HINT = os.environ.get("HGB_COL_HINT", "1") == "1"   # reuse the radius graph's by-target offsets as the by_col CSR
 ACT_DERIV = 100   # HGB_ACT_DERIV: "the tensor already holds act'(.)"
 
 
