@@ -372,12 +372,37 @@ class MatMul(torch.autograd.Function):
         return ga, gb, None, None
 
 
+class ColSum(torch.autograd.Function):
+    """``x.sum(0)`` of a 2-D tensor with the two-stage column-sum kernel; adjoint = row broadcast (closed with BiasAdd)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.rows = x.shape[0]
+        return raw_colsum(_chk(x if x.is_contiguous() else x.contiguous()))
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.unsqueeze(0).expand(ctx.rows, g.shape[0])
+
+
+class BiasAdd(torch.autograd.Function):
+    """``y + b`` (b broadcast over rows); the bias gradient is a ColSum, so any order of differentiation stays closed."""
+
+    @staticmethod
+    def forward(ctx, y, b):
+        return y + b
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, (ColSum.apply(g) if ctx.needs_input_grad[1] else None)
+
+
 def linear_any_order(x, weight, bias=None):
-    """``x @ W^T + b`` built from the closed primitives (+ an ATen broadcast add for the bias)."""
+    """``x @ W^T + b`` built from the closed primitives (MatMul, BiasAdd / ColSum)."""
     shp = x.shape
     y = MatMul.apply(x.reshape(-1, shp[-1]), weight, False, True)
     if bias is not None:
-        y = y + bias
+        y = BiasAdd.apply(y, bias)
     return y.reshape(shp[:-1] + (weight.shape[0],))
 
 
