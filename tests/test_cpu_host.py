@@ -253,3 +253,27 @@ def test_synthetic_workloads_shapes():
     assert torch.equal(make_samples("qm9_painn", 10).pos, b.pos)      # deterministic in the seed
     lj = make_samples("lj_egnn", 2)
     assert lj.cell.shape == (2, 3, 3) and bool(lj.pbc.all())
+
+
+def test_generated_mace_header_is_in_sync_with_the_tables(tmp_path):
+    """hgb_mace_gen.cuh is generated from hydragnn_b200/e3.py: regenerate it and compare with the committed file."""
+    sys.path.insert(0, os.path.join(ROOT, "hydragnn_b200", "csrc"))
+    try:
+        import gen_mace
+    finally:
+        sys.path.pop(0)
+    out = gen_mace.generate(str(tmp_path / "gen.cuh"))
+    assert open(out).read() == open(os.path.join(ROOT, "hydragnn_b200", "csrc", "hgb_mace_gen.cuh")).read()
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    import json
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--ref-graphs", "32"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
+              "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["metric"] == "atoms_per_sec_training_step" and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
