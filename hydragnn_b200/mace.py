@@ -6,8 +6,12 @@ the oracle.  What differs is the device layout: a feature with irreps ``F x 0e +
 ``[N, 2l+1, F]`` (channels contiguous), never e3nn's mul-major rows; an equivariant Linear is then one GEMM per degree
 on a ``[(N (2l+1)), F_in]`` view, and the tensor product / scatter work on whole channel rows.
 
-This file is the composed first version: gathers, the segmented scatter and every Linear run on libhgb kernels;
-the per-path coupling (``conv_tp``) and the symmetric contraction are expressed with ATen einsum glue on the device.
+First-order path (ordinary training, inference, first-order forces): ``conv_tp`` + the receiver scatter and the
+correlation-2 symmetric contraction are the fused kernels of hgb_mace.cu (``ops.MaceTpScatterFn``,
+``ops.MaceSymContractFn``), the radial MLP and every equivariant Linear run on the tcgen05 / SIMT Linear kernels, the
+spherical harmonics and the radial basis are ATen elementwise glue on [E, 9]-sized tensors.  Any-order path (MLIP double
+backward), correlation 3 and channel counts that are not a multiple of 32: the per-path coupling and the contraction are
+composed from gathers / segment sums / MatMuls plus ATen einsum glue.
 """
 import math
 
