@@ -277,3 +277,21 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert k in line, k
     assert line["impl"] == "reference" and line["metric"] == "atoms_per_sec_training_step" and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+def test_c4_and_c5_synthetic_workloads_and_multihead_indices():
+    b = make_samples("oc20_mace", 3)
+    assert b.pos.shape == (240, 3) and b.cell.shape == (3, 3, 3) and bool(b.pbc.all())
+    assert b.y.shape == (3 * 241, 1) and b.y_loc.tolist() == [[0, 1, 241]] * 3
+    assert float(b.x.min()) >= 1 and float(b.x.max()) <= 83
+    m = hb.create_model(use_gpu=False, **ARCH["oc20_mace"])
+    assert str(m) == "MACEStack" and m.head_type == ["graph", "node"] and m.head_dims == [1, 3]
+    hi = hb.get_head_indices(m, b)
+    assert hi[0].tolist() == [0, 241, 482] and hi[1].numel() == 3 * 240 and int(hi[1][0]) == 1 and int(hi[1][-1]) == 722
+    # energies and forces land where y_loc says
+    assert torch.equal(b.y[hi[1]].reshape(240, 3), b.forces)
+    p = make_samples("gfm_pnaeq", 2)
+    assert p.pe.shape == (80, 6) and p.pos.shape == (80, 3)
+    kw = dict(ARCH["gfm_pnaeq"], pna_deg=[0, 3, 5, 9])
+    g = hb.create_model(use_gpu=False, **kw)
+    assert str(g) == "PNAEqStack" and g.use_global_attn and len(g.graph_convs) == 3
