@@ -270,7 +270,7 @@ class MultiheadDecoder(nn.Module):
     """LinearMultiheadDecoderBlock (blocks.py:432-601) / NonLinearMultiheadDecoderBlock (:604-821): graph heads read
     the pooled scalar block, node heads start with an o3.Linear to scalars."""
 
-    def __init__(self, nonlinear, in_scalars, config_heads, head_dims, head_type, act, graph_pooling):
+    def __init__(self, nonlinear, in_scalars, config_heads, head_dims, head_type, act, graph_pooling, num_nodes=None):
         super().__init__()
         self.nonlinear, self.head_dims, self.head_type, self.graph_pooling = nonlinear, head_dims, head_type, graph_pooling
         self.graph_shared = nn.ModuleDict({})
@@ -304,6 +304,7 @@ class MultiheadDecoder(nn.Module):
                         raise ValueError("Node-level convolutional layers are not supported in MACE")
                     if a["type"] != "mlp":
                         raise ValueError("b200 engine: MACE node heads of type %r are not supported (use 'mlp')" % (a["type"],))
+                    assert num_nodes is not None, "num_nodes must be positive integer for MLP"          # blocks.py:499-502
                     head[br["type"]] = _NodeMLP(in_scalars, head_dims[ih], a["dim_headlayers"] if nonlinear else None, act)
             else:
                 raise ValueError("Unknown head type" + str(head_type[ih]) + "; currently only support 'graph' or 'node'")
@@ -421,7 +422,7 @@ class MACEStack(nn.Module):
 
     def _decoder(self, nonlinear, in_scalars):
         return MultiheadDecoder(nonlinear, in_scalars, self.config_heads, self.head_dims, self.head_type, self.activation_function,
-                                self.graph_pooling)
+                                self.graph_pooling, self.num_nodes)
 
     def _get_conv(self, lmax_in, last_layer):
         f = self.hidden_dim

@@ -43,7 +43,7 @@ ARCH = {
     # MACE knobs of tests/test_forces_equivariant.py:318-327, heads of multidataset/gfm_multitasking.json
     "oc20_mace": dict(mpnn_type="MACE", input_dim=1, hidden_dim=64, num_conv_layers=2, num_radial=8, radius=6.0,
                       max_neighbours=128, max_ell=2, node_max_ell=1, correlation=2, envelope_exponent=5, radial_type="bessel",
-                      avg_num_neighbors=45.0, output_dim=[1, 3], output_type=["graph", "node"], task_weights=[1.0, 1.0],
+                      avg_num_neighbors=45.0, num_nodes=80, output_dim=[1, 3], output_type=["graph", "node"], task_weights=[1.0, 1.0],
                       output_heads={"graph": {"num_sharedlayers": 2, "dim_sharedlayers": 50, "num_headlayers": 2,
                                               "dim_headlayers": [50, 25]},
                                     "node": {"num_headlayers": 2, "dim_headlayers": [200, 200], "type": "mlp"}},

@@ -12,7 +12,8 @@ reference's own call sites:
   o3.TensorProduct ("uvu")    mace_utils/modules/blocks.py:320-327
   nn.FullyConnectedNet        mace_utils/modules/blocks.py:344-349
 
-PARITY UNPINNED: the reference tests hold no value pins for MACE and e3nn cannot be run here, so the
+PARITY UNPINNED (this file only; the reference's in-repo MACE code on top of it IS pinned, see oracle/mace.py): the
+reference tests hold no value pins for MACE and e3nn cannot be run here, so the
 conventions below (real basis, signs, normalisations, parameter order) are from the published algorithm, checked only
 through properties: orthogonality of the Clebsch-Gordan tensors, their invariance under rotations, equivariance of the
 spherical harmonics (tests/test_oracle_mace.py).
@@ -61,6 +62,28 @@ class Irrep(tuple):
         return "%d%s" % (self.l, "e" if self.p == 1 else "o")
 
 
+class MulIr(tuple):
+    """One (mul, Irrep) entry; e3nn exposes ``.mul`` / ``.ir`` and prints as ``64x1o``."""
+
+    def __new__(cls, mul, ir):
+        return super().__new__(cls, (int(mul), Irrep(ir)))
+
+    @property
+    def mul(self):
+        return self[0]
+
+    @property
+    def ir(self):
+        return self[1]
+
+    @property
+    def dim(self):
+        return self[0] * self[1].dim
+
+    def __repr__(self):
+        return "%dx%r" % (self[0], self[1])
+
+
 class Irreps(tuple):
     """Tuple of (mul, Irrep).  Mirrors the subset of e3nn.o3.Irreps the reference uses."""
 
@@ -70,6 +93,8 @@ class Irreps(tuple):
         out = []
         if irreps is None:
             pass
+        elif isinstance(irreps, MulIr):
+            out.append(tuple(irreps))
         elif isinstance(irreps, Irrep):
             out.append((1, irreps))
         elif isinstance(irreps, str):
@@ -90,7 +115,7 @@ class Irreps(tuple):
                 else:
                     mul, ir = item
                     out.append((int(mul), Irrep(ir)))
-        return super().__new__(cls, out)
+        return super().__new__(cls, [MulIr(m, ir) for m, ir in out])
 
     @staticmethod
     def spherical_harmonics(lmax, p=-1):
@@ -266,6 +291,17 @@ def spherical_harmonics(lmax, vec, normalize=True, normalization="component"):
     return torch.cat(out, dim=-1).reshape(*shp, (lmax + 1) ** 2)
 
 
+class SphericalHarmonics(torch.nn.Module):
+    """o3.SphericalHarmonics(Irreps.spherical_harmonics(lmax), normalize, normalization) as a module."""
+
+    def __init__(self, irreps_out, normalize, normalization="integral"):
+        super().__init__()
+        self.lmax, self.normalize, self.normalization = Irreps(irreps_out).lmax, normalize, normalization
+
+    def forward(self, vec):
+        return spherical_harmonics(self.lmax, vec, self.normalize, self.normalization)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # o3.Linear
 # ---------------------------------------------------------------------------------------------------------------
@@ -274,7 +310,7 @@ class Linear(torch.nn.Module):
     ~ N(0, 1) in ONE flat `weight`; output block = sum_paths x W / sqrt(sum over the block's paths of mul_in)
     (path_normalization="element").  No biases (e3nn default)."""
 
-    def __init__(self, irreps_in, irreps_out):
+    def __init__(self, irreps_in, irreps_out, **_e3nn_defaults):      # internal_weights / shared_weights: e3nn defaults
         super().__init__()
         self.irreps_in, self.irreps_out = Irreps(irreps_in), Irreps(irreps_out)
         self.paths = [(i, o) for i, (_, ir_i) in enumerate(self.irreps_in) for o, (_, ir_o) in enumerate(self.irreps_out)
@@ -314,8 +350,9 @@ class TensorProductUVU(torch.nn.Module):
     c = sqrt((2 l_out + 1) / sum over instructions into io of mul_2)  (irrep_normalization="component",
     path_normalization="element", all variances 1)."""
 
-    def __init__(self, irreps1, irreps2, irreps_out, instructions):
+    def __init__(self, irreps1, irreps2, irreps_out, instructions, shared_weights=False, internal_weights=False):
         super().__init__()
+        assert not shared_weights and not internal_weights, "only the external-weight form the reference uses is restated"
         self.irreps1, self.irreps2, self.irreps_out = Irreps(irreps1), Irreps(irreps2), Irreps(irreps_out)
         self.instructions = [tuple(ins[:3]) for ins in instructions]
         fan = {}

@@ -10,8 +10,11 @@ Follows, line by line:
   tp_out_irreps_with_instructions, reshape_irreps        hydragnn/utils/model/irreps_tools.py:15-86
   Linear / NonLinear multihead decoders, LinearMLPNode, NonLinearMLPNode      blocks.py:432-960
 
-e3nn pieces come from oracle/e3.py (PARITY UNPINNED, see its header): results are checked through properties
-(rotation / translation / permutation invariance of the energy, equivariance of the forces).
+Pinning: tests/golden/models_mace.pt was produced by running the reference's OWN files listed above with only e3nn replaced
+(by oracle/e3.py), opt_einsum_fx by the identity and torch_scatter.scatter by index_add_ (tests/golden/make_golden.py);
+this restatement reproduces those outputs, forces, parameter gradients, state-dict keys and seeded initial values.  What
+stays unpinned is e3nn itself (oracle/e3.py, see its header), checked through properties (rotation / translation /
+permutation invariance of the energy, equivariance of the forces, identities of the coupling tensors).
 Distance transforms (Agnesi / Soft, radial.py:146-248) need ase.data.covalent_radii, which is not in this image:
 they raise NotImplementedError.
 """
@@ -182,7 +185,7 @@ class Contraction(nn.Module):
         self.correlation, self.lmax_out = correlation, irrep_out.l
         dtype = torch.get_default_dtype()
         for nu in range(1, correlation + 1):
-            self.register_buffer("U_matrix_%d" % nu, u_matrix_real(coupling, irrep_out, nu, dtype=torch.float64).to(dtype))
+            self.register_buffer("U_matrix_%d" % nu, u_matrix_real(coupling, irrep_out, nu, dtype=dtype))   # default dtype, as :107-116
         self.weights = nn.ParameterList([])
         num_equivariance = 2 * irrep_out.l + 1
         for i in range(correlation, 0, -1):
@@ -279,7 +282,7 @@ class _MLPNodeIrreps(nn.Module):
 class MultiheadDecoder(nn.Module):
     """LinearMultiheadDecoderBlock (blocks.py:432-601) / NonLinearMultiheadDecoderBlock (:604-821)."""
 
-    def __init__(self, nonlinear, input_irreps, config_heads, head_dims, head_type, act, graph_pooling):
+    def __init__(self, nonlinear, input_irreps, config_heads, head_dims, head_type, act, graph_pooling, num_nodes=None):
         super().__init__()
         self.nonlinear, self.head_dims, self.head_type, self.graph_pooling = nonlinear, head_dims, head_type, graph_pooling
         self.input_scalar_dim = input_irreps.count("0e")
@@ -314,6 +317,7 @@ class MultiheadDecoder(nn.Module):
                         raise ValueError("Node-level convolutional layers are not supported in MACE")
                     if arch["type"] != "mlp":
                         raise ValueError("oracle restates node heads of type 'mlp' only, got " + arch["type"])
+                    assert num_nodes is not None, "num_nodes must be positive integer for MLP"      # blocks.py:499-502
                     head[branch["type"]] = _MLPNodeIrreps(input_irreps, head_dims[ih], arch["dim_headlayers"] if nonlinear else None, act)
             else:
                 raise ValueError("Unknown head type" + head_type[ih])
@@ -369,7 +373,7 @@ class MACEOracle(nn.Module):
             raise ValueError("oracle MACE: GPS wrapping is not restated")
         if edge_dim:
             raise ValueError("oracle MACE: edge_attr is not restated")
-        self.mpnn_type, self.hidden_dim, self.input_dim = "MACE", hidden_dim, input_dim
+        self.mpnn_type, self.hidden_dim, self.input_dim, self.num_nodes = "MACE", hidden_dim, input_dim, num_nodes
         self.max_ell, self.node_max_ell, self.avg_num_neighbors = max_ell, node_max_ell, avg_num_neighbors
         self.head_dims, self.head_type = list(output_dim), list(output_type)
         self.num_heads, self.num_conv_layers = len(self.head_dims), num_conv_layers
@@ -423,7 +427,7 @@ class MACEOracle(nn.Module):
 
     def _decoder(self, nonlinear, irreps):
         return MultiheadDecoder(nonlinear, irreps, self.config_heads, self.head_dims, self.head_type, self.activation_function,
-                                self.graph_pooling)
+                                self.graph_pooling, self.num_nodes)
 
     def _get_conv(self, input_dim, output_dim, first_layer=False, last_layer=False):
         """MACEStack.py:277-377."""

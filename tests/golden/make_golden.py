@@ -190,6 +190,46 @@ def install_gps_stubs():
     return gps
 
 
+def install_mace_stubs():
+    """The reference's MACE path = its own files (MACEStack.py, mace_utils/modules/{blocks,radial,symmetric_contraction}.py,
+    mace_utils/tools/cg.py, irreps_tools.py) on top of e3nn 0.5.1, which is not installable here.  e3nn is replaced by the
+    oracle's restatement (oracle/e3.py: Irreps, wigner_3j, SphericalHarmonics, Linear, TensorProduct "uvu", FullyConnectedNet);
+    opt_einsum_fx (an einsum *optimiser*) by the identity; torch_scatter.scatter by index_add_; ase (only read by the distance
+    transforms, unused here) by an empty module.  Everything else that runs is the reference's code."""
+    from oracle import e3
+
+    def scatter(src, index, dim=0, dim_size=None, reduce="sum"):
+        n = int(index.max()) + 1 if dim_size is None else dim_size
+        out = src.new_zeros((n,) + tuple(src.shape[1:])).index_add_(0, index, src)
+        if reduce == "mean":
+            cnt = torch.bincount(index, minlength=n).clamp(min=1).to(src.dtype)
+            out = out / cnt.reshape((-1,) + (1,) * (src.dim() - 1))
+        return out
+
+    sys.modules["torch_scatter"].scatter = scatter
+    o3 = _mod("e3nn.o3", Irreps=e3.Irreps, Irrep=e3.Irrep, Linear=e3.Linear, TensorProduct=e3.TensorProductUVU,
+              SphericalHarmonics=e3.SphericalHarmonics, wigner_3j=e3.wigner_3j)
+    nn_ = _mod("e3nn.nn", FullyConnectedNet=e3.FullyConnectedNet, Activation=type("Activation", (torch.nn.Module,), {}))
+    _mod("e3nn", o3=o3, nn=nn_)
+    _mod("e3nn.util")
+    _mod("e3nn.util.jit", compile_mode=lambda mode: (lambda cls: cls))
+    _mod("e3nn.util.codegen", CodeGenMixin=type("CodeGenMixin", (), {}))
+    _mod("opt_einsum_fx", optimize_einsums_full=lambda model, example_inputs: model)
+    ase = _mod("ase")
+    ase.data = _mod("ase.data", covalent_radii=np.zeros(119))
+    _mod("hydragnn.utils.model.mace_utils")
+    _mod("hydragnn.utils.model.mace_utils.tools")
+    _mod("hydragnn.utils.model.mace_utils.modules")
+    _mod("hydragnn.utils.model.mace_utils.tools.compile", simplify_if_compile=lambda cls: cls)
+    base = REF + "/hydragnn/utils/model"
+    _load("hydragnn.utils.model.irreps_tools", base + "/irreps_tools.py")
+    _load("hydragnn.utils.model.mace_utils.tools.cg", base + "/mace_utils/tools/cg.py")
+    _load("hydragnn.utils.model.mace_utils.modules.radial", base + "/mace_utils/modules/radial.py")
+    _load("hydragnn.utils.model.mace_utils.modules.symmetric_contraction", base + "/mace_utils/modules/symmetric_contraction.py")
+    _load("hydragnn.utils.model.mace_utils.modules.blocks", base + "/mace_utils/modules/blocks.py")
+    return _load("hydragnn.models.MACEStack", REF + "/hydragnn/models/MACEStack.py")
+
+
 def toy_batch(gen, sizes, box, input_dim=1, dtype=torch.float32):
     """A few random molecules + an asymmetric hand-made edge list (every atom keeps its
     3 nearest in-graph neighbours as sources)."""
@@ -407,6 +447,37 @@ def main():
         hmodels[name] = {"state": state, "inputs": t2d(b), "pred": [p.detach() for p in pred], "loss": loss.detach(),
                          "grads": {n: (g.detach() if g is not None else None) for (n, _), g in zip(m.named_parameters(), grads)}}
     torch.save(hmodels, HERE + "/models_heads.pt")
+
+    # ---- MACE through the reference's own MACEStack / blocks / symmetric_contraction / cg / irreps_tools (e3nn restated) ----
+    mace = install_mace_stubs()
+    gen3 = torch.Generator().manual_seed(97531)
+    mmodels = {}
+    heads_mace = {"graph": [{"type": "branch-0", "architecture": {"num_sharedlayers": 2, "dim_sharedlayers": 5, "num_headlayers": 2,
+                                                                   "dim_headlayers": [10, 6]}}],
+                  "node": [{"type": "branch-0", "architecture": {"num_headlayers": 2, "dim_headlayers": [12, 12], "type": "mlp"}}]}
+    for name, (max_ell, node_max_ell, corr, layers, hidden) in {"mace_l2_nu2": (2, 1, 2, 2, 8), "mace_l2_nu3": (2, 2, 3, 3, 4),
+                                                                "mace_l3_nu2": (3, 2, 2, 2, 4), "mace_one_layer": (2, 1, 2, 1, 8)}.items():
+        b = toy_batch(gen3, [7, 9, 5], 3.5, input_dim=1)
+        b.y = torch.randn(b.x.shape[0], 1, generator=gen3)
+        torch.manual_seed(0)
+        m = mace.MACEStack("node_attributes, equiv_node_feat, inv_node_feat, edge_attributes, edge_features, edge_index",
+                           "node_attributes, edge_attributes, edge_features, edge_index", 6.0, "bessel", None, 8, None,
+                           max_ell, node_max_ell, 10.0, 5, corr, 1, hidden, [1, 3], 0, "", "", 0, ["graph", "node"], heads_mace,
+                           "relu", "mae", None, loss_weights=[1.0, 1.0], freeze_conv=False, initial_bias=None,
+                           num_conv_layers=layers, num_nodes=9, graph_pooling="mean")
+        m.eval()
+        state = {k: v.clone() for k, v in m.state_dict().items()}
+        inp = t2d(b)
+        pos0 = b.pos.clone().requires_grad_(True)
+        b.pos = pos0
+        pred = m(b)
+        obj = pred[0].sum() + pred[1].pow(2).sum()
+        forces = torch.autograd.grad(obj, pos0, retain_graph=True)[0]
+        grads = torch.autograd.grad(obj, list(m.parameters()), allow_unused=True)
+        mmodels[name] = {"state": state, "inputs": inp, "pred": [p.detach() for p in pred], "dobj_dpos": forces.detach(),
+                         "grads": {n: (g.detach() if g is not None else None) for (n, _), g in zip(m.named_parameters(), grads)},
+                         "cfg": dict(max_ell=max_ell, node_max_ell=node_max_ell, correlation=corr, num_conv_layers=layers, hidden_dim=hidden)}
+    torch.save(mmodels, HERE + "/models_mace.pt")
     print("golden vectors written to", HERE)
 
 

@@ -99,6 +99,12 @@ def test_mace_initialisation_matches_oracle_and_tables_agree():
         assert list(so.keys()) == list(se.keys())
         for k in so:
             assert so[k].shape == se[k].shape and torch.allclose(so[k].float(), se[k].float(), atol=1e-6), k
+    g = torch.load(os.path.join(ROOT, "tests/golden/models_mace.pt"))          # produced by the reference's own MACE files
+    for name, c in g.items():
+        se = hb.create_model(mpnn_type="MACE", use_gpu=False, **dict(MACE_KW, **c["cfg"])).state_dict()
+        assert list(se.keys()) == list(c["state"].keys()), name
+        for k, v in se.items():
+            assert v.shape == c["state"][k].shape and torch.allclose(v, c["state"][k], atol=1e-6), (name, k)
     for a in [(1, 1, 0), (1, 2, 3), (2, 2, 2), (3, 2, 1), (3, 3, 2)]:
         assert torch.allclose(pe3.w3j(*a), oe3.wigner_3j(*a), atol=1e-14)
     coupling = oe3.Irreps("1x0e+1x1o+1x2e")

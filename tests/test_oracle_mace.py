@@ -15,7 +15,7 @@ MACE_KW = dict(input_dim=1, hidden_dim=8, output_dim=[1, 3], output_type=["graph
                output_heads={"graph": {"num_sharedlayers": 2, "dim_sharedlayers": 5, "num_headlayers": 2, "dim_headlayers": [10, 6]},
                              "node": {"num_headlayers": 2, "dim_headlayers": [12, 12], "type": "mlp"}},
                activation_function="relu", loss_function_type="mae", task_weights=[1.0, 1.0], num_conv_layers=2, num_radial=8,
-               radius=6.0, max_ell=2, node_max_ell=1, avg_num_neighbors=10.0, envelope_exponent=5, correlation=2, graph_pooling="mean")
+               radius=6.0, max_ell=2, node_max_ell=1, avg_num_neighbors=10.0, envelope_exponent=5, correlation=2, graph_pooling="mean", num_nodes=9)
 
 
 def random_rotation(gen):
@@ -166,3 +166,35 @@ def test_mace_oracle_invariances_and_state_dict_layout():
     d3._num_graphs = 2
     o3 = m(d3)
     assert float((o3[0] - out[0]).abs().max()) < 1e-12 and float((o3[1] - out[1][perm]).abs().max()) < 1e-12
+
+
+def test_mace_oracle_matches_the_reference_own_code_golden(golden_dir):
+    """models_mace.pt: the reference's MACEStack / blocks / symmetric_contraction / cg / irreps_tools executed with e3nn
+    stubbed by oracle/e3.py (tests/golden/make_golden.py).  Same seed -> same keys and initial values; same inputs -> same
+    outputs, d(objective)/d(pos) and parameter gradients."""
+    g = torch.load(golden_dir + "/models_mace.pt")
+    for name, c in g.items():
+        torch.manual_seed(0)
+        m = mace.MACEOracle(**dict(MACE_KW, **c["cfg"]))
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(c["state"].keys()), name
+        for k, v in sd.items():
+            assert torch.equal(v, c["state"][k]), (name, k)
+        m.eval()
+        d = hb.Batch(**{k: v.clone() for k, v in c["inputs"].items()})
+        d._num_graphs = 3
+        d.pos.requires_grad_(True)
+        pred = m(d)
+        for p, q in zip(pred, c["pred"]):
+            torch.testing.assert_close(p, q, rtol=1e-5, atol=1e-6)
+        obj = pred[0].sum() + pred[1].pow(2).sum()
+        f, = torch.autograd.grad(obj, d.pos, retain_graph=True)
+        torch.testing.assert_close(f, c["dobj_dpos"], rtol=1e-4, atol=1e-7)
+        grads = torch.autograd.grad(obj, list(m.parameters()), allow_unused=True)
+        for (n, _), gr in zip(m.named_parameters(), grads):
+            ref = c["grads"][n]
+            assert (gr is None) == (ref is None), (name, n)
+            if gr is not None:
+                torch.testing.assert_close(gr, ref, rtol=1e-4, atol=1e-6 * max(1.0, float(ref.abs().max())))
+    with pytest.raises(AssertionError, match="num_nodes"):
+        mace.MACEOracle(**dict(MACE_KW, num_nodes=None))
