@@ -16,7 +16,8 @@ PARITY UNPINNED (this file only; the reference's in-repo MACE code on top of it 
 reference tests hold no value pins for MACE and e3nn cannot be run here, so the
 conventions below (real basis, signs, normalisations, parameter order) are from the published algorithm, checked only
 through properties: orthogonality of the Clebsch-Gordan tensors, their invariance under rotations, equivariance of the
-spherical harmonics (tests/test_oracle_mace.py).
+spherical harmonics, and against sympy (SU(2) Clebsch-Gordan coefficients; real spherical harmonics Z_lm with the polar
+axis on y, up to the Condon-Shortley sign pattern) -- tests/test_oracle_mace.py.
 """
 import math
 from fractions import Fraction

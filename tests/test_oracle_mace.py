@@ -198,3 +198,31 @@ def test_mace_oracle_matches_the_reference_own_code_golden(golden_dir):
                 torch.testing.assert_close(gr, ref, rtol=1e-4, atol=1e-6 * max(1.0, float(ref.abs().max())))
     with pytest.raises(AssertionError, match="num_nodes"):
         mace.MACEOracle(**dict(MACE_KW, num_nodes=None))
+
+
+def test_clebsch_gordan_and_harmonics_against_sympy():
+    """Independent of e3nn and of this repo: (i) the SU(2) Clebsch-Gordan coefficients behind the real Wigner 3j equal sympy's
+    for every j <= 3; (ii) the restated real harmonics ('integral' normalisation) equal the standard real spherical harmonics
+    Z_lm of sympy, evaluated with e3nn's axis convention (polar axis = y: (X, Y, Z)_std = (z, x, y)), up to the fixed sign
+    pattern sign(m) = -1 for m < 0, (-1)^m for m > 0 (sympy carries the Condon-Shortley phase, e3nn's basis does not)."""
+    sympy = pytest.importorskip("sympy")
+    from sympy.physics.quantum.cg import CG
+    for j1 in range(4):
+        for j2 in range(4):
+            for j3 in range(abs(j1 - j2), j1 + j2 + 1):
+                for m1 in range(-j1, j1 + 1):
+                    for m2 in range(-j2, j2 + 1):
+                        if abs(m1 + m2) <= j3:
+                            ref = float(CG(j1, m1, j2, m2, j3, m1 + m2).doit())
+                            assert abs(ref - e3._su2_cg_coeff(j1, m1, j2, m2, j3, m1 + m2)) < 1e-12, (j1, m1, j2, m2, j3)
+    th, ph = sympy.symbols("theta phi", real=True)
+    gen = torch.Generator().manual_seed(0)
+    v = torch.nn.functional.normalize(torch.randn(4, 3, generator=gen, dtype=torch.float64), dim=-1)
+    y = e3.spherical_harmonics(3, v, normalization="integral")
+    for l in range(4):
+        for m in range(-l, l + 1):
+            expr = sympy.Znm(l, m, th, ph).expand(func=True)
+            sign = 1.0 if m == 0 else (-1.0 if m < 0 else (-1.0) ** m)
+            for row, (x, yy, z) in enumerate(v.tolist()):
+                ref = float(sympy.re(expr.evalf(subs={th: math.acos(yy), ph: math.atan2(x, z)})))
+                assert abs(float(y[row, l * l + l + m]) - sign * ref) < 1e-12, (l, m)
