@@ -33,7 +33,19 @@ def _stamp():
     return h.hexdigest()
 
 
+def _ensure_generated():
+    """hgb_mace_gen.cuh is generated from hydragnn_b200/e3.py and committed; regenerate it only if it is missing."""
+    if not os.path.exists(os.path.join(CSRC, "hgb_mace_gen.cuh")):
+        sys.path.insert(0, CSRC)
+        try:
+            import gen_mace
+            gen_mace.generate()
+        finally:
+            sys.path.pop(0)
+
+
 def build(force=False, verbose=False):
+    _ensure_generated()
     stamp_file = os.path.join(CSRC, ".build_stamp")
     stamp = _stamp()
     if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
