@@ -141,8 +141,8 @@ int hgb_pool_bwd(const float* gout, const int32_t* graph_ptr, const int32_t* arg
                  int32_t g, int32_t c, int32_t mode, float* gx, hgb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * Dense layers: the cuBLAS call sites behind every nn.Linear of the path -- hydragnn/models/EGCLStack.py:196-229
- * (edge / node / coord MLPs), hydragnn/models/PAINNStack.py:96-104,206-214,281-296 (embeddings, message and update
+ * Dense layers: the cuBLAS call sites behind every nn.Linear of the path -- hydragnn/models/EGCLStack.py:207-240
+ * (edge / node / coord MLPs), hydragnn/models/PAINNStack.py:92-98,204-218,281-296 (embeddings, message and update
  * MLPs), hydragnn/models/Base.py:604-663,929-940 (shared layers, heads, MLPNode), mace_utils/modules/blocks.py:61-89,
  * 307-367 (o3.Linear, radial MLP)
  * ------------------------------------------------------------------------------------------ */
