@@ -27,7 +27,7 @@ def prototypes():
         src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
         src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
         _protos = {}
-        for m in re.finditer(r"(const char\*|int64_t|int)\s+(hgb_\w+)\s*\(([^)]*)\)\s*;", src):
+        for m in re.finditer(r"(const char\*|int64_t|int32_t|int)\s+(hgb_\w+)\s*\(([^)]*)\)\s*;", src):
             ret, name, args = m.group(1), m.group(2), m.group(3).strip()
             parsed = []
             if args and args != "void":
@@ -55,17 +55,39 @@ def lib():
         L = ctypes.CDLL(LIB_PATH)
         for name, (ret, args) in prototypes().items():
             fn = getattr(L, name)
-            fn.restype = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "const char*": ctypes.c_char_p}[ret]
+            fn.restype = {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "const char*": ctypes.c_char_p}[ret]
             fn.argtypes = [_ctype(t) for t, _ in args]
         _lib = L
     return _lib
 
 
+_trace = None
+
+
 def call(name, *args):
     """Invoke an int-returning entry point; raise on failure."""
-    rc = getattr(lib(), name)(*args)
+    L = lib()
+    if _trace is not None:
+        before = int(L.hgb_launch_count())
+    rc = getattr(L, name)(*args)
     if rc != 0:
-        raise RuntimeError("libhgb %s failed (%d): %s" % (name, rc, lib().hgb_last_error().decode()))
+        raise RuntimeError("libhgb %s failed (%d): %s" % (name, rc, L.hgb_last_error().decode()))
+    if _trace is not None:
+        names = [n for _, n in prototypes()[name][1]]
+        _trace.append((name, dict(zip(names, args)), int(L.hgb_launch_count()) - before))
+
+
+def trace_begin():
+    """Start recording (entry point, arguments by header name, kernels launched) of every call -- used by bench.py to attribute
+    profiled kernel durations to C-ABI calls and to evaluate their algorithmic-byte formulas."""
+    global _trace
+    _trace = []
+
+
+def trace_end():
+    global _trace
+    out, _trace = _trace, None
+    return out
 
 
 def query(name, *args):

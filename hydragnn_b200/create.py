@@ -172,8 +172,9 @@ class EnhancedModelWrapper(nn.Module):
         tasks_loss.append(peratom)
         if epw > 0:
             tot_loss = tot_loss + peratom * epw
-        forces_pred = -torch.autograd.grad(graph_energy_pred, data.pos, grad_outputs=torch.ones_like(graph_energy_pred),
-                                           retain_graph=graph_energy_pred.requires_grad, create_graph=create_graph)[0].float()
+        with ops.only_data_grads():      # the force pass needs d/dpos only: fused blocks skip their parameter gradients
+            forces_pred = -torch.autograd.grad(graph_energy_pred, data.pos, grad_outputs=torch.ones_like(graph_energy_pred),
+                                               retain_graph=graph_energy_pred.requires_grad, create_graph=create_graph)[0].float()
         force_loss = lf(forces_pred, data.forces.float(), True)
         tasks_loss.append(force_loss)
         if fw > 0:

@@ -6,6 +6,8 @@
 
 #include "hgb_common.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
 
@@ -118,7 +120,7 @@ __global__ void csr_hist_kernel(const int64_t* __restrict__ idx, int64_t e, int3
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t k = idx[i];
     if (k < 0 || k >= n) {
-      *bad = 1;
+      atomicOr(bad, 2);     // HGB guard bit "index outside [0, n)" (hydragnn_b200.ops.GUARD_BAD_INDEX)
       k = 0;
     }
     idx32[i] = (int32_t)k;
@@ -126,54 +128,61 @@ __global__ void csr_hist_kernel(const int64_t* __restrict__ idx, int64_t e, int3
   }
 }
 
-__global__ void csr_fill_kernel(const int32_t* __restrict__ idx32, int64_t e, const int32_t* __restrict__ rowptr,
-                                int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
-    int k = idx32[i];
-    int slot = atomicAdd(&cursor[k], 1);
-    perm[rowptr[k] + slot] = (int32_t)i;
-  }
+__global__ void iota_i32_kernel(int32_t* __restrict__ out, int64_t e) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) out[i] = (int32_t)i;
 }
 
-// restore ascending edge id inside every segment (segments are short: insertion sort per thread)
-__global__ void csr_sort_kernel(const int32_t* __restrict__ rowptr, int32_t n, int32_t* __restrict__ perm) {
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    int lo = rowptr[k], hi = rowptr[k + 1];
-    for (int a = lo + 1; a < hi; ++a) {
-      int v = perm[a];
-      int b = a - 1;
-      while (b >= lo && perm[b] > v) {
-        perm[b + 1] = perm[b];
-        --b;
-      }
-      perm[b + 1] = v;
-    }
-  }
+static inline int csr_key_bits(int32_t n) {
+  int bits = 1;
+  while (bits < 31 && (1ll << bits) < (int64_t)n) ++bits;
+  return bits;
+}
+
+static inline size_t csr_sort_temp_bytes(int64_t e, int32_t n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const int32_t*)nullptr, (int32_t*)nullptr, (const int32_t*)nullptr,
+                                  (int32_t*)nullptr, (int)(e > 0 ? e : 1), 0, csr_key_bits(n));
+  return (bytes + 255) & ~(size_t)255;
 }
 
 extern "C" int64_t hgb_csr_workspace_bytes(int64_t e, int32_t n) {
-  return 4 * ((int64_t)n + 8) * 2 + hgb_exclusive_scan_workspace_bytes(n) + 64;
+  // counts (n + 8) | iota [e] | sorted keys [e] | scan workspace | radix-sort temporaries
+  return 4 * ((int64_t)n + 8) + 8 * ((e + 63) & ~63ll) + hgb_exclusive_scan_workspace_bytes(n) + 256 +
+         (int64_t)csr_sort_temp_bytes(e, n) + 256;
 }
 
+// Stable by construction: a least-significant-digit radix sort of (key = idx, value = edge id) keeps equal keys in ascending edge
+// id, whatever the segment lengths (the round-1 per-segment insertion sort was quadratic in the longest segment).
 extern "C" int hgb_csr_build(const int64_t* idx, int64_t e, int32_t n, int32_t* idx32, int32_t* rowptr,
-                             int32_t* perm, void* workspace, hgb_stream_t stream) {
+                             int32_t* perm, int32_t* guard_flag, void* workspace, hgb_stream_t stream) {
   HGB_REQUIRE(e >= 0 && n >= 0 && rowptr && workspace, "csr_build: bad arguments");
+  HGB_REQUIRE(e < (1ll << 31), "csr_build: more than 2^31 - 1 entries");
   cudaStream_t st = (cudaStream_t)stream;
-  int32_t* count = (int32_t*)workspace;           // n + 8 (last slot: bad flag)
-  int32_t* cursor = count + n + 8;                // n + 8
-  void* scan_ws = (void*)(cursor + n + 8);
-  cudaMemsetAsync(count, 0, 4 * ((int64_t)n + 8) * 2, st);
+  const int64_t epad = (e + 63) & ~63ll;
+  int32_t* count = (int32_t*)workspace;           // n + 8 (slot n: bad-index flag of this call)
+  int32_t* iota = count + n + 8;
+  int32_t* keys_out = iota + epad;
+  char* scan_ws = (char*)(keys_out + epad);
+  scan_ws = (char*)(((uintptr_t)scan_ws + 255) & ~(uintptr_t)255);
+  char* sort_ws = scan_ws + ((hgb_exclusive_scan_workspace_bytes(n) + 255) & ~255ll);
+  cudaMemsetAsync(count, 0, 4 * ((int64_t)n + 8), st);
   if (e > 0) {
-    csr_hist_kernel<<<hgb_grid_for(e, 256), 256, 0, st>>>(idx, e, n, idx32, count, count + n);
+    csr_hist_kernel<<<hgb_grid_for(e, 256), 256, 0, st>>>(idx, e, n, idx32, count, guard_flag ? guard_flag : count + n);
     HGB_LAUNCH_CHECK("csr_hist");
   }
   int rc = hgb_exclusive_scan_i32(count, rowptr, n, scan_ws, stream);
   if (rc) return rc;
   if (e > 0) {
-    csr_fill_kernel<<<hgb_grid_for(e, 256), 256, 0, st>>>(idx32, e, rowptr, cursor, perm);
-    HGB_LAUNCH_CHECK("csr_fill");
-    csr_sort_kernel<<<hgb_grid_for(n, 128), 128, 0, st>>>(rowptr, n, perm);
-    HGB_LAUNCH_CHECK("csr_sort");
+    iota_i32_kernel<<<hgb_grid_for(e, 256), 256, 0, st>>>(iota, e);
+    HGB_LAUNCH_CHECK("csr_iota");
+    size_t temp = csr_sort_temp_bytes(e, n);
+    cudaError_t err = cub::DeviceRadixSort::SortPairs((void*)sort_ws, temp, (const int32_t*)idx32, keys_out, (const int32_t*)iota,
+                                                      perm, (int)e, 0, csr_key_bits(n), st);
+    if (err != cudaSuccess) {
+      hgb_set_error("csr_build: radix sort failed: %s", cudaGetErrorString(err));
+      return HGB_ECUDA;
+    }
+    // (the radix-sort kernels are library code and are not counted as libhgb launches)
   }
   return HGB_OK;
 }

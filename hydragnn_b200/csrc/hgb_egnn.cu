@@ -1,0 +1,639 @@
+// libhgb.so -- fused EGNN edge block (hydragnn/models/EGCLStack.py:245-258,278-291) with everything the MLIP double
+// backward needs, and the closed edge-length primitives (hydragnn/utils/model/operations.py:21-36).
+//
+// The edge MLP of E_GCL is  m_e = relu(W1 relu(W0 [x_row | x_col | d_e] + b0) + b1),  agg_i = sum_{row(e) = i} m_e.
+// Its first Linear is linear in the blocks of its input, so the host applies it per NODE (P = x W0a^T, Q = x W0b^T, N rows)
+// and the kernels see  z1_e = P[row] + Q[col] + d_e w_d + b0.  With ReLU the block is piecewise linear: every derivative
+// of any order is the same three tile GEMMs with 0/1 masks, which are stored as 2 x 64 bits per edge (CSR order):
+//
+//   egnn_edge_fwd     mode 0:  out_i = sum_e relu(W1 relu(z1_e) + b1)                  (writes the masks)
+//                     mode 1:  out_i = sum_e mask2 * (W1 (mask1 * u_e)),  u_e = P'[row] + Q'[col] + s'_e w_d
+//                              -- the tangent (JVP) of mode 0; it IS the backward of egnn_edge_bwd_data w.r.t. g_out
+//   egnn_edge_bwd_data         gz1_e = mask1 * (W1^T (mask2 * g_out[row]));  gP_i = sum_{row} gz1_e;  gs_e = w_d . gz1_e;
+//                              gz1 rows written once (edge order) for the by-col segment sum that yields gQ
+//   egnn_edge_wgrad            gW1 = sum_e (mask2 * g_out[row]) y_e^T,  y_e = relu(z1_e) (mode 0) or mask1 * u_e (mode 1)
+//
+// Layout of one CTA iteration: a tile of <= 32 consecutive nodes of the by-row CSR, its edges in chunks of 128; the per-edge
+// operand tile lives in shared memory K-MAJOR ([k][edge]), W1 (or W1^T) K-major next to it; 128 threads, each an 8 x (H/8)
+// register tile of the [128 x H] product (exact fp32 FMAs: the fp32 configs C1 / C3 must match the oracle to 1e-5); the
+// segment sums are ordered (CSR order = the reference's scatter_add_ order), atomics-free and deterministic.  Nothing per-edge
+// of width H crosses HBM in the forward; the backward writes gz1 [E, H] once because Q is gathered by the OTHER endpoint.
+#include "hgb_common.cuh"
+
+namespace {
+
+constexpr int TE = 128;        // edges per chunk
+constexpr int XS = TE + 4;     // row stride of the K-major operand tile (floats; keeps 16-byte alignment)
+constexpr int NBMAX = 32;      // nodes per tile (upper bound)
+constexpr int NT = 128;        // threads per CTA
+
+template <int H>
+struct Smem {
+  static constexpr int TN = H / 8;
+  static constexpr int MS = H + 4;                       // row stride of the row-major result tile
+  static constexpr int XT_FLOATS = (H * XS > TE * MS) ? H * XS : TE * MS;
+  float y[H * H];                                        // K-major weight operand
+  float xt[XT_FLOATS];                                   // K-major edge operand, later the row-major result tile
+  float nodev[NBMAX * (H + 1)];                          // P rows (fwd) / g_out rows (bwd) of the tile's nodes
+  float agg[NBMAX * H];                                  // ordered per-node accumulators
+  float vec[2 * H];                                      // w_d | b0  (or w_d | b1)
+  float b1[H];
+  float sval[TE];                                        // per-edge scalar (d_e or s'_e)
+  unsigned long long bits1[TE], bits2[TE];
+  int eid[TE], nloc[TE];
+  int rp[NBMAX + 1];
+  unsigned char maskb[TE * 8];
+};
+
+__device__ __forceinline__ int local_node(const int* rp, int nb, int p) {   // largest l with rp[l] <= p
+  int lo = 0, hi = nb;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (rp[mid] <= p) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// acc[8][TN] += XT[k][r0..r0+7] (x) Y[k][c0..c0+TN-1] over k
+template <int H>
+__device__ __forceinline__ void tile_gemm(const float* __restrict__ xt, const float* __restrict__ y, int r0, int c0,
+                                          float (&acc)[8][H / 8]) {
+  constexpr int TN = H / 8;
+#pragma unroll 4
+  for (int k = 0; k < H; ++k) {
+    const float4 a0 = *reinterpret_cast<const float4*>(xt + k * XS + r0);
+    const float4 a1 = *reinterpret_cast<const float4*>(xt + k * XS + r0 + 4);
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    float b[TN];
+#pragma unroll
+    for (int q = 0; q < TN / 4; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(y + k * H + c0 + 4 * q);
+      b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// forward / tangent
+// ------------------------------------------------------------------------------------------------------------------
+template <int H, bool TANGENT>
+__global__ void __launch_bounds__(NT) egnn_edge_fwd_kernel(
+    const float* __restrict__ pq, const float* __restrict__ s, const float* __restrict__ wd, const float* __restrict__ b0,
+    const float* __restrict__ w1, const float* __restrict__ b1, const int32_t* __restrict__ rowptr,
+    const int32_t* __restrict__ perm, const int32_t* __restrict__ nbr, int n, int nb, int ntiles,
+    unsigned long long* __restrict__ masks, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<H>& sm = *reinterpret_cast<Smem<H>*>(smem_raw);
+  constexpr int TN = H / 8, MS = Smem<H>::MS;
+  const int t = threadIdx.x;
+  const int r0 = (t >> 3) * 8, c0 = (t & 7) * TN;
+  // W1 [out][in] -> K-major for z2 = h W1^T: y[in][out]
+  for (int i = t; i < H * H; i += NT) sm.y[(i % H) * H + (i / H)] = w1[i];
+  for (int i = t; i < H; i += NT) {
+    sm.vec[i] = wd[i];
+    sm.vec[H + i] = (!TANGENT && b0) ? b0[i] : 0.f;
+    sm.b1[i] = (!TANGENT && b1) ? b1[i] : 0.f;
+  }
+  __syncthreads();
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n0 = tile * nb, n1 = min(n, n0 + nb), cntn = n1 - n0;
+    for (int i = t; i <= cntn; i += NT) sm.rp[i] = rowptr[n0 + i];
+    for (int i = t; i < cntn * H; i += NT) {
+      sm.nodev[(i / H) * (H + 1) + (i % H)] = pq[(int64_t)(n0 + i / H) * 2 * H + (i % H)];
+      sm.agg[i] = 0.f;
+    }
+    __syncthreads();
+    const int e_begin = sm.rp[0], e_end = sm.rp[cntn];
+    for (int e0 = e_begin; e0 < e_end; e0 += TE) {
+      const int cnt = min(TE, e_end - e0);
+      // ---- A: one thread per edge slot builds its column of the K-major operand ----
+      {
+        unsigned long long bits = 0ull;
+        if (t < cnt) {
+          const int p = e0 + t;
+          const int il = local_node(sm.rp, cntn, p);
+          const int eid = perm[p], j = nbr[p];
+          const float sv = s[eid];
+          sm.nloc[t] = il;
+          if (TANGENT) bits = masks[2 * (int64_t)p];
+          const float* qrow = pq + (int64_t)j * 2 * H + H;
+          const float* prow = sm.nodev + il * (H + 1);
+#pragma unroll 4
+          for (int q = 0; q < H / 4; ++q) {
+            const float4 qv = __ldg(reinterpret_cast<const float4*>(qrow) + q);
+            const float qq[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int k = 4 * q + c;
+              float z = prow[k] + qq[c];
+              z = fmaf(sv, sm.vec[k], z) + sm.vec[H + k];
+              float hval;
+              if (TANGENT) {
+                hval = ((bits >> k) & 1ull) ? z : 0.f;
+              } else {
+                const bool on = z > 0.f;
+                hval = on ? z : 0.f;
+                bits |= (unsigned long long)on << k;
+              }
+              sm.xt[k * XS + t] = hval;
+            }
+          }
+          if (!TANGENT) masks[2 * (int64_t)p] = bits;
+        } else {
+          for (int k = 0; k < H; ++k) sm.xt[k * XS + t] = 0.f;
+          sm.nloc[t] = 0;
+        }
+        if (TANGENT) sm.bits2[t] = t < cnt ? masks[2 * (int64_t)(e0 + t) + 1] : 0ull;
+      }
+      __syncthreads();
+      // ---- B: [128 x H] = operand^T x W1^T ----
+      float acc[8][TN];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = sm.b1[c0 + j];
+      tile_gemm<H>(sm.xt, sm.y, r0, c0, acc);
+      __syncthreads();                                   // every thread is done reading the operand tile
+      // ---- C: relu / mask, result tile row-major into the same buffer ----
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        unsigned int byte = 0;
+        if (TANGENT) {
+          const unsigned long long b2 = sm.bits2[r0 + i];
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = ((b2 >> (c0 + j)) & 1ull) ? acc[i][j] : 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < TN; ++j) {
+            const bool on = acc[i][j] > 0.f;
+            byte |= (unsigned int)on << j;
+            acc[i][j] = on ? acc[i][j] : 0.f;
+          }
+          sm.maskb[(r0 + i) * 8 + (t & 7)] = (unsigned char)byte;           // TN == 4: 4 valid bits per byte
+        }
+#pragma unroll
+        for (int q = 0; q < TN / 4; ++q)
+          *reinterpret_cast<float4*>(sm.xt + (r0 + i) * MS + c0 + 4 * q) =
+              make_float4(acc[i][4 * q], acc[i][4 * q + 1], acc[i][4 * q + 2], acc[i][4 * q + 3]);
+      }
+      __syncthreads();
+      // ---- D: ordered per-node sums; mask2 out ----
+      if (!TANGENT && t < cnt) {
+        unsigned long long b2 = 0ull;
+        if (TN == 8) {
+          b2 = *reinterpret_cast<const unsigned long long*>(sm.maskb + t * 8);
+        } else {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) b2 |= (unsigned long long)(sm.maskb[t * 8 + g] & 0xF) << (4 * g);
+        }
+        masks[2 * (int64_t)(e0 + t) + 1] = b2;
+      }
+      for (int i = t; i < cntn * H; i += NT) {
+        const int il = i / H, c = i % H;
+        const int lo = max(sm.rp[il], e0) - e0, hi = min(sm.rp[il + 1], e0 + cnt) - e0;
+        float a = sm.agg[i];
+        for (int p = lo; p < hi; ++p) a += sm.xt[p * MS + c];
+        sm.agg[i] = a;
+      }
+      __syncthreads();
+    }
+    for (int i = t; i < cntn * H; i += NT) out[(int64_t)n0 * H + i] = sm.agg[i];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward, data side
+// ------------------------------------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(NT) egnn_edge_bwd_data_kernel(
+    const float* __restrict__ g_out, const float* __restrict__ s, const float* __restrict__ wd, const float* __restrict__ w1,
+    const unsigned long long* __restrict__ masks, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm, int n,
+    int nb, int ntiles, float* __restrict__ g_p, int ldp, float* __restrict__ gz1, float* __restrict__ gs,
+    float* __restrict__ partial /* [grid][2H]: sum_e s_e gz1_e | sum_e gz1_e, or null */) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<H>& sm = *reinterpret_cast<Smem<H>*>(smem_raw);
+  constexpr int TN = H / 8, MS = Smem<H>::MS;
+  const int t = threadIdx.x;
+  const int r0 = (t >> 3) * 8, c0 = (t & 7) * TN;
+  // gh = gz2 W1: K = out, operand y[out][in] = W1 as stored
+  for (int i = t; i < H * H; i += NT) sm.y[i] = w1[i];
+  for (int i = t; i < H; i += NT) sm.vec[i] = wd[i];
+  float colsum_w = 0.f, colsum_1 = 0.f;                  // thread t < H (and t - H < H for H == 32: unused) owns column t % H
+  __syncthreads();
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n0 = tile * nb, n1 = min(n, n0 + nb), cntn = n1 - n0;
+    for (int i = t; i <= cntn; i += NT) sm.rp[i] = rowptr[n0 + i];
+    for (int i = t; i < cntn * H; i += NT) {
+      sm.nodev[(i / H) * (H + 1) + (i % H)] = g_out[(int64_t)n0 * H + i];
+      sm.agg[i] = 0.f;
+    }
+    __syncthreads();
+    const int e_begin = sm.rp[0], e_end = sm.rp[cntn];
+    for (int e0 = e_begin; e0 < e_end; e0 += TE) {
+      const int cnt = min(TE, e_end - e0);
+      if (t < cnt) {
+        const int p = e0 + t;
+        const int il = local_node(sm.rp, cntn, p);
+        const int eid = perm[p];
+        sm.eid[t] = eid;
+        sm.sval[t] = s[eid];
+        sm.bits1[t] = masks[2 * (int64_t)p];
+        const unsigned long long b2 = masks[2 * (int64_t)p + 1];
+        const float* grow = sm.nodev + il * (H + 1);
+#pragma unroll 8
+        for (int k = 0; k < H; ++k) sm.xt[k * XS + t] = ((b2 >> k) & 1ull) ? grow[k] : 0.f;
+      } else {
+        for (int k = 0; k < H; ++k) sm.xt[k * XS + t] = 0.f;
+        sm.bits1[t] = 0ull;
+        sm.sval[t] = 0.f;
+        sm.eid[t] = -1;
+      }
+      __syncthreads();
+      float acc[8][TN];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+      tile_gemm<H>(sm.xt, sm.y, r0, c0, acc);
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const unsigned long long b1 = sm.bits1[r0 + i];
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+          acc[i][j] = ((b1 >> (c0 + j)) & 1ull) ? acc[i][j] : 0.f;
+          dot = fmaf(acc[i][j], sm.vec[c0 + j], dot);
+        }
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+        const int eid = sm.eid[r0 + i];
+        if (eid >= 0) {
+          if ((t & 7) == 0) gs[eid] = dot;
+#pragma unroll
+          for (int q = 0; q < TN / 4; ++q)
+            *reinterpret_cast<float4*>(gz1 + (int64_t)eid * H + c0 + 4 * q) =
+                make_float4(acc[i][4 * q], acc[i][4 * q + 1], acc[i][4 * q + 2], acc[i][4 * q + 3]);
+        }
+#pragma unroll
+        for (int q = 0; q < TN / 4; ++q)
+          *reinterpret_cast<float4*>(sm.xt + (r0 + i) * MS + c0 + 4 * q) =
+              make_float4(acc[i][4 * q], acc[i][4 * q + 1], acc[i][4 * q + 2], acc[i][4 * q + 3]);
+      }
+      __syncthreads();
+      for (int i = t; i < cntn * H; i += NT) {
+        const int il = i / H, c = i % H;
+        const int lo = max(sm.rp[il], e0) - e0, hi = min(sm.rp[il + 1], e0 + cnt) - e0;
+        float a = sm.agg[i];
+        for (int p = lo; p < hi; ++p) a += sm.xt[p * MS + c];
+        sm.agg[i] = a;
+      }
+      if (partial && t < H) {
+        for (int p = 0; p < cnt; ++p) {
+          const float v = sm.xt[p * MS + t];
+          colsum_1 += v;
+          colsum_w = fmaf(sm.sval[p], v, colsum_w);
+        }
+      }
+      __syncthreads();
+    }
+    for (int i = t; i < cntn * H; i += NT) g_p[(int64_t)(n0 + i / H) * ldp + (i % H)] = sm.agg[i];
+    __syncthreads();
+  }
+  if (partial && t < H) {
+    partial[(int64_t)blockIdx.x * 2 * H + t] = colsum_w;
+    partial[(int64_t)blockIdx.x * 2 * H + H + t] = colsum_1;
+  }
+}
+
+// out[c] = sum_b partial[b][c]  (fixed order: deterministic)
+__global__ void egnn_reduce_partials_kernel(const float* __restrict__ partial, int nblocks, int width, float* __restrict__ out0,
+                                            int split, float* __restrict__ out1) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= width) return;
+  float a = 0.f;
+  for (int b = 0; b < nblocks; ++b) a += partial[(int64_t)b * width + c];
+  if (c < split) out0[c] = a; else if (out1) out1[c - split] = a;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// weight gradient:  gW1[out][in] = sum_e gz2[e][out] y[e][in],  gb1[out] = sum_e gz2[e][out]
+// ------------------------------------------------------------------------------------------------------------------
+template <int H>
+struct SmemW {
+  float x[TE * H];               // gz2, row-major [edge][out]
+  float y[TE * H];               // y,   row-major [edge][in]
+  float nodeg[NBMAX * H];        // g_out rows
+  float nodep[NBMAX * H];        // P rows
+  float vec[2 * H];
+  int rp[NBMAX + 1];
+};
+
+template <int H, bool TANGENT>
+__global__ void __launch_bounds__(NT) egnn_edge_wgrad_kernel(
+    const float* __restrict__ g_out, const float* __restrict__ pq, const float* __restrict__ s, const float* __restrict__ wd,
+    const float* __restrict__ b0, const unsigned long long* __restrict__ masks, const int32_t* __restrict__ rowptr,
+    const int32_t* __restrict__ perm, const int32_t* __restrict__ nbr, int n, int nb, int ntiles,
+    float* __restrict__ partial /* [grid][H*H + H] */) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemW<H>& sm = *reinterpret_cast<SmemW<H>*>(smem_raw);
+  constexpr int MO = 8, NI = (H * H) / (NT * MO);        // register tile: 8 outs x NI ins  (H = 64: 8 x 4, H = 32: 8 x 1)
+  constexpr int IG = H / NI;                             // threads along "in"
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int m0 = (t / IG) * MO, i0 = (t % IG) * NI;
+  for (int i = t; i < H; i += NT) {
+    sm.vec[i] = wd[i];
+    sm.vec[H + i] = (!TANGENT && b0) ? b0[i] : 0.f;
+  }
+  float acc[MO][NI];
+#pragma unroll
+  for (int i = 0; i < MO; ++i)
+#pragma unroll
+    for (int j = 0; j < NI; ++j) acc[i][j] = 0.f;
+  float bsum = 0.f;
+  __syncthreads();
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n0 = tile * nb, n1 = min(n, n0 + nb), cntn = n1 - n0;
+    for (int i = t; i <= cntn; i += NT) sm.rp[i] = rowptr[n0 + i];
+    for (int i = t; i < cntn * H; i += NT) {
+      sm.nodeg[i] = g_out[(int64_t)n0 * H + i];
+      sm.nodep[i] = pq[(int64_t)(n0 + i / H) * 2 * H + (i % H)];
+    }
+    __syncthreads();
+    const int e_begin = sm.rp[0], e_end = sm.rp[cntn];
+    for (int e0 = e_begin; e0 < e_end; e0 += TE) {
+      const int cnt = min(TE, e_end - e0);
+      // a warp per edge slot, lanes over channels
+      for (int r = warp; r < TE; r += NT / 32) {
+        if (r < cnt) {
+          const int p = e0 + r;
+          const int il = local_node(sm.rp, cntn, p);
+          const int eid = perm[p], j = nbr[p];
+          const float sv = s[eid];
+          const unsigned long long b1 = masks[2 * (int64_t)p], b2 = masks[2 * (int64_t)p + 1];
+          for (int c = lane; c < H; c += 32) {
+            sm.x[r * H + c] = ((b2 >> c) & 1ull) ? sm.nodeg[il * H + c] : 0.f;
+            float z = sm.nodep[il * H + c] + __ldg(pq + (int64_t)j * 2 * H + H + c);
+            z = fmaf(sv, sm.vec[c], z) + sm.vec[H + c];
+            sm.y[r * H + c] = TANGENT ? (((b1 >> c) & 1ull) ? z : 0.f) : (z > 0.f ? z : 0.f);
+          }
+        } else {
+          for (int c = lane; c < H; c += 32) { sm.x[r * H + c] = 0.f; sm.y[r * H + c] = 0.f; }
+        }
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int k = 0; k < TE; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(sm.x + k * H + m0);
+        const float4 a1 = *reinterpret_cast<const float4*>(sm.x + k * H + m0 + 4);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        float b[NI];
+        if constexpr (NI == 4) {
+          const float4 bv = *reinterpret_cast<const float4*>(sm.y + k * H + i0);
+          b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < NI; ++j) b[j] = sm.y[k * H + i0 + j];
+        }
+#pragma unroll
+        for (int i = 0; i < MO; ++i)
+#pragma unroll
+          for (int j = 0; j < NI; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      if (t < H)
+        for (int k = 0; k < cnt; ++k) bsum += sm.x[k * H + t];
+      __syncthreads();
+    }
+  }
+  float* out = partial + (int64_t)blockIdx.x * (H * H + H);
+#pragma unroll
+  for (int i = 0; i < MO; ++i)
+#pragma unroll
+    for (int j = 0; j < NI; ++j) out[(m0 + i) * H + i0 + j] = acc[i][j];
+  if (t < H) out[H * H + t] = bsum;
+}
+
+// out[c] = sum_e w[e] x[e][c]   (two-stage, deterministic)
+__global__ void weighted_colsum_stage1(const float* __restrict__ x, const float* __restrict__ w, int64_t e, int h,
+                                       float* __restrict__ partial) {
+  // blockDim.x = 256: 256 / h row-lanes x h columns
+  const int c = threadIdx.x % h, rl = threadIdx.x / h, nrl = blockDim.x / h;
+  float a = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * nrl + rl; r < e; r += (int64_t)gridDim.x * nrl) a = fmaf(w[r], x[r * h + c], a);
+  __shared__ float sm[256];
+  sm[threadIdx.x] = a;
+  __syncthreads();
+  if (rl == 0) {
+    for (int q = 1; q < nrl; ++q) a += sm[q * h + c];
+    partial[(int64_t)blockIdx.x * h + c] = a;
+  }
+}
+
+template <int H>
+int launch_fwd(bool tangent, const float* pq, const float* s, const float* wd, const float* b0, const float* w1, const float* b1,
+               const int32_t* rowptr, const int32_t* perm, const int32_t* nbr, int n, int nb, unsigned long long* masks, float* out,
+               cudaStream_t st) {
+  const int ntiles = (n + nb - 1) / nb;
+  const int grid = ntiles < HGB_NUM_SMS * 3 ? ntiles : HGB_NUM_SMS * 3;
+  const size_t bytes = sizeof(Smem<H>);
+  if (tangent) {
+    cudaFuncSetAttribute(egnn_edge_fwd_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    egnn_edge_fwd_kernel<H, true><<<grid, NT, bytes, st>>>(pq, s, wd, b0, w1, b1, rowptr, perm, nbr, n, nb, ntiles, masks, out);
+  } else {
+    cudaFuncSetAttribute(egnn_edge_fwd_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    egnn_edge_fwd_kernel<H, false><<<grid, NT, bytes, st>>>(pq, s, wd, b0, w1, b1, rowptr, perm, nbr, n, nb, ntiles, masks, out);
+  }
+  return grid;
+}
+
+}  // namespace
+
+extern "C" int32_t hgb_egnn_edge_supported(int32_t h) { return (h == 32 || h == 64) ? 1 : 0; }
+
+static inline int egnn_grid(int n, int nb) {
+  const int ntiles = (n + nb - 1) / nb;
+  return ntiles < HGB_NUM_SMS * 3 ? ntiles : HGB_NUM_SMS * 3;
+}
+
+extern "C" int64_t hgb_egnn_edge_workspace_bytes(int32_t n, int32_t h, int32_t nodes_per_tile) {
+  const int g = egnn_grid(n, nodes_per_tile > 0 ? nodes_per_tile : 1);
+  return (int64_t)g * ((int64_t)h * h + 2 * h) * 4 + 256;
+}
+
+extern "C" int hgb_egnn_edge_fwd(const float* pq, const float* s, const float* wd, const float* b0, const float* w1,
+                                 const float* b1, const int32_t* rowptr, const int32_t* perm, const int32_t* nbr, int32_t n,
+                                 int32_t h, int32_t nodes_per_tile, int32_t tangent, uint64_t* masks, float* out,
+                                 hgb_stream_t stream) {
+  if (n == 0) return HGB_OK;
+  HGB_REQUIRE(hgb_egnn_edge_supported(h), "egnn_edge_fwd: hidden width must be 32 or 64 (got %d)", h);
+  HGB_REQUIRE(pq && s && wd && w1 && rowptr && perm && nbr && masks && out && nodes_per_tile >= 1 && nodes_per_tile <= NBMAX,
+              "egnn_edge_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h == 64) launch_fwd<64>(tangent != 0, pq, s, wd, b0, w1, b1, rowptr, perm, nbr, n, nodes_per_tile, (unsigned long long*)masks, out, st);
+  else launch_fwd<32>(tangent != 0, pq, s, wd, b0, w1, b1, rowptr, perm, nbr, n, nodes_per_tile, (unsigned long long*)masks, out, st);
+  HGB_LAUNCH_CHECK("egnn_edge_fwd");
+  return HGB_OK;
+}
+
+extern "C" int hgb_egnn_edge_bwd_data(const float* g_out, const float* s, const float* wd, const float* w1, const uint64_t* masks,
+                                      const int32_t* rowptr, const int32_t* perm, int32_t n, int32_t h, int32_t nodes_per_tile,
+                                      float* g_p, int32_t ldp, float* gz1, float* gs, float* g_wd, float* g_b0, void* workspace,
+                                      hgb_stream_t stream) {
+  if (n == 0) return HGB_OK;
+  HGB_REQUIRE(hgb_egnn_edge_supported(h), "egnn_edge_bwd_data: hidden width must be 32 or 64 (got %d)", h);
+  HGB_REQUIRE(g_out && s && wd && w1 && masks && rowptr && perm && g_p && gz1 && gs && nodes_per_tile >= 1 && nodes_per_tile <= NBMAX,
+              "egnn_edge_bwd_data: bad arguments");
+  HGB_REQUIRE((!g_wd && !g_b0) || (g_wd && g_b0 && workspace), "egnn_edge_bwd_data: g_wd and g_b0 come together and need the workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = nodes_per_tile, ntiles = (n + nb - 1) / nb, grid = egnn_grid(n, nb);
+  float* partial = (g_wd || g_b0) ? (float*)workspace : nullptr;
+  if (h == 64) {
+    cudaFuncSetAttribute(egnn_edge_bwd_data_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<64>));
+    egnn_edge_bwd_data_kernel<64><<<grid, NT, sizeof(Smem<64>), st>>>(g_out, s, wd, w1, (const unsigned long long*)masks, rowptr, perm, n,
+                                                                     nb, ntiles, g_p, ldp, gz1, gs, partial);
+  } else {
+    cudaFuncSetAttribute(egnn_edge_bwd_data_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<32>));
+    egnn_edge_bwd_data_kernel<32><<<grid, NT, sizeof(Smem<32>), st>>>(g_out, s, wd, w1, (const unsigned long long*)masks, rowptr, perm, n,
+                                                                     nb, ntiles, g_p, ldp, gz1, gs, partial);
+  }
+  HGB_LAUNCH_CHECK("egnn_edge_bwd_data");
+  if (partial) {
+    egnn_reduce_partials_kernel<<<(2 * h + 127) / 128, 128, 0, st>>>(partial, grid, 2 * h, g_wd, h, g_b0);
+    HGB_LAUNCH_CHECK("egnn_reduce_partials");
+  }
+  return HGB_OK;
+}
+
+extern "C" int hgb_egnn_edge_wgrad(const float* g_out, const float* pq, const float* s, const float* wd, const float* b0,
+                                   const uint64_t* masks, const int32_t* rowptr, const int32_t* perm, const int32_t* nbr, int32_t n,
+                                   int32_t h, int32_t nodes_per_tile, int32_t tangent, float* g_w1, float* g_b1, void* workspace,
+                                   hgb_stream_t stream) {
+  HGB_REQUIRE(hgb_egnn_edge_supported(h), "egnn_edge_wgrad: hidden width must be 32 or 64 (got %d)", h);
+  HGB_REQUIRE(g_out && pq && s && wd && masks && rowptr && perm && nbr && g_w1 && workspace && nodes_per_tile >= 1 &&
+                  nodes_per_tile <= NBMAX, "egnn_edge_wgrad: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    cudaMemsetAsync(g_w1, 0, (size_t)h * h * 4, st);
+    if (g_b1) cudaMemsetAsync(g_b1, 0, (size_t)h * 4, st);
+    return HGB_OK;
+  }
+  const int nb = nodes_per_tile, ntiles = (n + nb - 1) / nb, grid = egnn_grid(n, nb);
+  float* partial = (float*)workspace;
+#define HGB_EGNN_WG(HH, TG)                                                                                                     \
+  do {                                                                                                                           \
+    cudaFuncSetAttribute(egnn_edge_wgrad_kernel<HH, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemW<HH>));   \
+    egnn_edge_wgrad_kernel<HH, TG><<<grid, NT, sizeof(SmemW<HH>), st>>>(g_out, pq, s, wd, b0, (const unsigned long long*)masks, \
+                                                                         rowptr, perm, nbr, n, nb, ntiles, partial);             \
+  } while (0)
+  if (h == 64) { if (tangent) HGB_EGNN_WG(64, true); else HGB_EGNN_WG(64, false); }
+  else { if (tangent) HGB_EGNN_WG(32, true); else HGB_EGNN_WG(32, false); }
+#undef HGB_EGNN_WG
+  HGB_LAUNCH_CHECK("egnn_edge_wgrad");
+  const int width = h * h + h;
+  egnn_reduce_partials_kernel<<<(width + 127) / 128, 128, 0, st>>>(partial, grid, width, g_w1, h * h, g_b1);
+  HGB_LAUNCH_CHECK("egnn_reduce_partials");
+  return HGB_OK;
+}
+
+extern "C" int64_t hgb_weighted_colsum_workspace_bytes(int32_t h) { return (int64_t)HGB_NUM_SMS * 4 * h * 4 + 256; }
+
+extern "C" int hgb_weighted_colsum(const float* x, const float* w, int64_t e, int32_t h, float* out, void* workspace,
+                                   hgb_stream_t stream) {
+  HGB_REQUIRE(x && w && out && workspace && h >= 1 && h <= 256 && 256 % h == 0, "weighted_colsum: bad arguments (h must divide 256)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = HGB_NUM_SMS * 4;
+  weighted_colsum_stage1<<<grid, 256, 0, st>>>(x, w, e, h, (float*)workspace);
+  HGB_LAUNCH_CHECK("weighted_colsum_stage1");
+  egnn_reduce_partials_kernel<<<(h + 127) / 128, 128, 0, st>>>((const float*)workspace, grid, h, out, h, nullptr);
+  HGB_LAUNCH_CHECK("weighted_colsum_stage2");
+  return HGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// closed edge-length primitives:  d_e = |pos[col] - pos[row] + shift_e|
+//   fwd:    d_e
+//   bwd:    gvec_e = gd_e * vhat_e                     (then edge_vec_scatter -> g_pos = sum_col gvec - sum_row gvec)
+//   bwd2:   given ggpos:  w_e = ggpos[col] - ggpos[row];  g_gd_e = <vhat_e, w_e>;  q_e = gd_e (w_e - vhat <vhat, w_e>) / d_e
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void edge_len_bwd_kernel(const float* __restrict__ pos, const int32_t* __restrict__ row, const int32_t* __restrict__ col,
+                                    const float* __restrict__ shifts, const float* __restrict__ gd, int64_t e,
+                                    float* __restrict__ gvec) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = row[i], c = col[i];
+    float vx = pos[3 * c] - pos[3 * r], vy = pos[3 * c + 1] - pos[3 * r + 1], vz = pos[3 * c + 2] - pos[3 * r + 2];
+    if (shifts) { vx += shifts[3 * i]; vy += shifts[3 * i + 1]; vz += shifts[3 * i + 2]; }
+    const float l = sqrtf(vx * vx + vy * vy + vz * vz);
+    const float k = l > 0.f ? gd[i] / l : 0.f;            // subgradient 0 at the origin, as torch.linalg.norm does
+    gvec[3 * i] = k * vx; gvec[3 * i + 1] = k * vy; gvec[3 * i + 2] = k * vz;
+  }
+}
+
+__global__ void edge_len_bwd2_kernel(const float* __restrict__ pos, const int32_t* __restrict__ row, const int32_t* __restrict__ col,
+                                     const float* __restrict__ shifts, const float* __restrict__ gd, const float* __restrict__ ggpos,
+                                     int64_t e, float* __restrict__ g_gd, float* __restrict__ q) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = row[i], c = col[i];
+    float vx = pos[3 * c] - pos[3 * r], vy = pos[3 * c + 1] - pos[3 * r + 1], vz = pos[3 * c + 2] - pos[3 * r + 2];
+    if (shifts) { vx += shifts[3 * i]; vy += shifts[3 * i + 1]; vz += shifts[3 * i + 2]; }
+    const float l = sqrtf(vx * vx + vy * vy + vz * vz);
+    const float il = l > 0.f ? 1.f / l : 0.f;
+    const float hx = vx * il, hy = vy * il, hz = vz * il;
+    const float wx = ggpos[3 * c] - ggpos[3 * r], wy = ggpos[3 * c + 1] - ggpos[3 * r + 1], wz = ggpos[3 * c + 2] - ggpos[3 * r + 2];
+    const float hw = hx * wx + hy * wy + hz * wz;
+    g_gd[i] = hw;
+    const float k = gd[i] * il;
+    q[3 * i] = k * (wx - hx * hw); q[3 * i + 1] = k * (wy - hy * hw); q[3 * i + 2] = k * (wz - hz * hw);
+  }
+}
+
+// g_pos[i] = sum_{col(e) = i} gvec_e - sum_{row(e) = i} gvec_e   (ordered: deterministic)
+__global__ void edge_vec_scatter_kernel(const float* __restrict__ gvec, const int32_t* __restrict__ col_rowptr,
+                                        const int32_t* __restrict__ col_perm, const int32_t* __restrict__ row_rowptr,
+                                        const int32_t* __restrict__ row_perm, int n, float* __restrict__ gpos) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float ax = 0.f, ay = 0.f, az = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+    for (int p = col_rowptr[i]; p < col_rowptr[i + 1]; ++p) {
+      const int64_t e = col_perm[p];
+      ax += gvec[3 * e]; ay += gvec[3 * e + 1]; az += gvec[3 * e + 2];
+    }
+    for (int p = row_rowptr[i]; p < row_rowptr[i + 1]; ++p) {
+      const int64_t e = row_perm[p];
+      bx += gvec[3 * e]; by += gvec[3 * e + 1]; bz += gvec[3 * e + 2];
+    }
+    gpos[3 * i] = ax - bx; gpos[3 * i + 1] = ay - by; gpos[3 * i + 2] = az - bz;
+  }
+}
+
+extern "C" int hgb_edge_len_bwd(const float* pos, const int32_t* row, const int32_t* col, const float* shifts, const float* gd,
+                                int64_t e, float* gvec, hgb_stream_t stream) {
+  HGB_REQUIRE(e >= 0 && pos && row && col && gd && gvec, "edge_len_bwd: bad arguments");
+  if (e == 0) return HGB_OK;
+  edge_len_bwd_kernel<<<hgb_grid_for(e, 256), 256, 0, (cudaStream_t)stream>>>(pos, row, col, shifts, gd, e, gvec);
+  HGB_LAUNCH_CHECK("edge_len_bwd");
+  return HGB_OK;
+}
+
+extern "C" int hgb_edge_len_bwd2(const float* pos, const int32_t* row, const int32_t* col, const float* shifts, const float* gd,
+                                 const float* ggpos, int64_t e, float* g_gd, float* q, hgb_stream_t stream) {
+  HGB_REQUIRE(e >= 0 && pos && row && col && gd && ggpos && g_gd && q, "edge_len_bwd2: bad arguments");
+  if (e == 0) return HGB_OK;
+  edge_len_bwd2_kernel<<<hgb_grid_for(e, 256), 256, 0, (cudaStream_t)stream>>>(pos, row, col, shifts, gd, ggpos, e, g_gd, q);
+  HGB_LAUNCH_CHECK("edge_len_bwd2");
+  return HGB_OK;
+}
+
+extern "C" int hgb_edge_vec_scatter(const float* gvec, const int32_t* col_rowptr, const int32_t* col_perm,
+                                    const int32_t* row_rowptr, const int32_t* row_perm, int32_t n, float* gpos,
+                                    hgb_stream_t stream) {
+  HGB_REQUIRE(n >= 0 && gvec && col_rowptr && col_perm && row_rowptr && row_perm && gpos, "edge_vec_scatter: bad arguments");
+  if (n == 0) return HGB_OK;
+  edge_vec_scatter_kernel<<<hgb_grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(gvec, col_rowptr, col_perm, row_rowptr, row_perm, n, gpos);
+  HGB_LAUNCH_CHECK("edge_vec_scatter");
+  return HGB_OK;
+}

@@ -39,7 +39,11 @@ extern "C" int hgb_loss_fwd_bwd(const float* pred, const float* target, int64_t 
 //   p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              int64_t count, float lr, float b1, float b2, float eps, float wd, float gscale,
-                             const float* __restrict__ step_dev) {
+                             const float* __restrict__ step_dev, const float* __restrict__ hyper_dev) {
+  if (hyper_dev) {           // learning rate / gradient scale live on the device: a captured step follows the scheduler
+    lr = hyper_dev[0];
+    gscale = hyper_dev[1];
+  }
   const float t = step_dev[0] + 1.f;
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
   const float step_size = lr / bc1;
@@ -58,11 +62,13 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
 __global__ void step_inc_kernel(float* step_dev) { step_dev[0] += 1.f; }
 
 extern "C" int hgb_adamw_step(float* p, const float* g, float* m, float* v, int64_t count, float lr, float beta1, float beta2,
-                              float eps, float weight_decay, float grad_scale, float* step_dev, hgb_stream_t stream) {
+                              float eps, float weight_decay, float grad_scale, float* step_dev, const float* hyper_dev,
+                              hgb_stream_t stream) {
   HGB_REQUIRE(count >= 0 && p && g && m && v && step_dev, "adamw_step: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   if (count > 0) {
-    adamw_kernel<<<hgb_grid_for(count, 256), 256, 0, st>>>(p, g, m, v, count, lr, beta1, beta2, eps, weight_decay, grad_scale, step_dev);
+    adamw_kernel<<<hgb_grid_for(count, 256), 256, 0, st>>>(p, g, m, v, count, lr, beta1, beta2, eps, weight_decay, grad_scale, step_dev,
+                                                           hyper_dev);
     HGB_LAUNCH_CHECK("adamw");
   }
   step_inc_kernel<<<1, 1, 0, st>>>(step_dev);

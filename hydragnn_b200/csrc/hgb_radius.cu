@@ -34,7 +34,7 @@ __global__ void radius_open_kernel(const float* __restrict__ pos, const int32_t*
       if (d2 < r2) {
         ++matches;
         if (loop || j != i) {
-          if (FILL) {
+          if (FILL && base + out < e) {   // e may be a caller-promised count (captured steps): never write past it
             ei[base + out] = j;
             ei[e + base + out] = i;
           }
@@ -135,7 +135,7 @@ template <bool FILL>
 __global__ void radius_pbc_kernel(const void* __restrict__ pos, int is64, const int32_t* __restrict__ gptr,
                                   const double* __restrict__ cell, const int32_t* __restrict__ nimg,
                                   const double* __restrict__ cutoff, int n, int g, int32_t* __restrict__ count,
-                                  const int32_t* __restrict__ candptr, int32_t* __restrict__ csrc,
+                                  const int32_t* __restrict__ candptr, int64_t cand_cap, int32_t* __restrict__ csrc,
                                   int32_t* __restrict__ cshift, double* __restrict__ clen) {
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const int k = find_graph(gptr, g, j);
@@ -161,7 +161,7 @@ __global__ void radius_pbc_kernel(const void* __restrict__ pos, int is64, const 
             double vx = __dadd_rn(bx, hx), vy = __dadd_rn(by, hy), vz = __dadd_rn(bz, hz);
             double d2 = __dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz));
             if (d2 < c2) {
-              if (FILL) {
+              if (FILL && base + cnt < cand_cap) {   // cand_cap may be a caller-promised count (captured steps)
                 csrc[base + cnt] = i;
                 cshift[3 * (int64_t)(base + cnt)] = sx;
                 cshift[3 * (int64_t)(base + cnt) + 1] = sy;
@@ -176,6 +176,7 @@ __global__ void radius_pbc_kernel(const void* __restrict__ pos, int is64, const 
       count[j] = cnt;
     } else {
       // sort this target's candidates by (len, src, S): insertion sort, segments are short
+      if (base + cnt > cand_cap) cnt = cand_cap > base ? (int)(cand_cap - base) : 0;
       for (int a = 1; a < cnt; ++a) {
         PbcCand v{clen[base + a], csrc[base + a], cshift[3 * (int64_t)(base + a)], cshift[3 * (int64_t)(base + a) + 1],
                   cshift[3 * (int64_t)(base + a) + 2]};
@@ -207,6 +208,7 @@ __global__ void radius_pbc_emit_kernel(const int32_t* __restrict__ gptr, const d
     const int ob = outptr[j], m = outptr[j + 1] - ob;
     for (int t = 0; t < m; ++t) {
       const int64_t o = ob + t;
+      if (o >= e) break;                       // e may be a caller-promised count (captured steps)
       ei[o] = csrc[cb + t];
       ei[e + o] = j;
       const int sx = cshift[3 * (int64_t)(cb + t)], sy = cshift[3 * (int64_t)(cb + t) + 1], sz = cshift[3 * (int64_t)(cb + t) + 2];
@@ -235,19 +237,19 @@ extern "C" int hgb_radius_pbc_count(const void* pos, int32_t pos_is_f64, const i
   HGB_REQUIRE(n >= 0 && cell && nimg && cutoff && cand_count, "radius_pbc_count: bad arguments");
   if (n == 0) return HGB_OK;
   radius_pbc_kernel<false><<<hgb_grid_for(n, 64), 64, 0, (cudaStream_t)stream>>>(
-      pos, pos_is_f64, graph_ptr, cell, nimg, cutoff, n, g, cand_count, nullptr, nullptr, nullptr, nullptr);
+      pos, pos_is_f64, graph_ptr, cell, nimg, cutoff, n, g, cand_count, nullptr, 0, nullptr, nullptr, nullptr);
   HGB_LAUNCH_CHECK("radius_pbc_count");
   return HGB_OK;
 }
 
 extern "C" int hgb_radius_pbc_fill(const void* pos, int32_t pos_is_f64, const int32_t* graph_ptr, const double* cell,
                                    const int32_t* nimg, const double* cutoff, int32_t n, int32_t g,
-                                   const int32_t* candptr, int32_t* cand_src, int32_t* cand_shift, double* cand_len,
-                                   hgb_stream_t stream) {
+                                   const int32_t* candptr, int64_t cand_capacity, int32_t* cand_src, int32_t* cand_shift,
+                                   double* cand_len, hgb_stream_t stream) {
   HGB_REQUIRE(n >= 0 && candptr && cand_src && cand_shift && cand_len, "radius_pbc_fill: bad arguments");
   if (n == 0) return HGB_OK;
   radius_pbc_kernel<true><<<hgb_grid_for(n, 64), 64, 0, (cudaStream_t)stream>>>(
-      pos, pos_is_f64, graph_ptr, cell, nimg, cutoff, n, g, nullptr, candptr, cand_src, cand_shift, cand_len);
+      pos, pos_is_f64, graph_ptr, cell, nimg, cutoff, n, g, nullptr, candptr, cand_capacity, cand_src, cand_shift, cand_len);
   HGB_LAUNCH_CHECK("radius_pbc_fill");
   return HGB_OK;
 }
@@ -274,5 +276,17 @@ extern "C" int hgb_clamp_i32(const int32_t* in, int32_t cap, int64_t n, int32_t*
   if (n == 0) return HGB_OK;
   clamp_i32_kernel<<<hgb_grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, cap, n, out);
   HGB_LAUNCH_CHECK("clamp_i32");
+  return HGB_OK;
+}
+
+// Device-side guard for captured steps that size their outputs from an earlier run of the same shape: *flag |= bit when
+// *value != expected (read back asynchronously by the host; see hydragnn_b200/ops.py::check_guard).
+__global__ void expect_i32_kernel(const int32_t* __restrict__ value, int32_t expected, int32_t bit, int32_t* __restrict__ flag) {
+  if (*value != expected) atomicOr(flag, bit);
+}
+extern "C" int hgb_expect_i32(const int32_t* value, int32_t expected, int32_t bit, int32_t* flag, hgb_stream_t stream) {
+  HGB_REQUIRE(value && flag, "expect_i32: bad arguments");
+  expect_i32_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(value, expected, bit, flag);
+  HGB_LAUNCH_CHECK("expect_i32");
   return HGB_OK;
 }

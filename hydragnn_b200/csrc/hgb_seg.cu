@@ -56,7 +56,8 @@ extern "C" int hgb_gather_rows(const float* x, const int32_t* idx, int64_t e, in
 // ---- segmented sum ------------------------------------------------------------------------------
 template <int VEC>
 __global__ void segment_sum_kernel(const float* __restrict__ m, const int32_t* __restrict__ rowptr,
-                                   const int32_t* __restrict__ perm, int n, int cv, int lanes, float* __restrict__ out) {
+                                   const int32_t* __restrict__ perm, int n, int cv, int lanes, float* __restrict__ out,
+                                   int ldo_v /* output row stride in V units */) {
   using V = typename VecT<VEC>::type;
   const int gpb = blockDim.x / lanes;
   const int sub = threadIdx.x % lanes;
@@ -78,24 +79,29 @@ __global__ void segment_sum_kernel(const float* __restrict__ m, const int32_t* _
         const int e0 = perm ? perm[p] : p;
         vadd(acc, __ldg(reinterpret_cast<const V*>(m) + (int64_t)e0 * cv + c));
       }
-      reinterpret_cast<V*>(out)[(int64_t)row * cv + c] = acc;
+      reinterpret_cast<V*>(out)[(int64_t)row * ldo_v + c] = acc;
     }
   }
 }
 
-extern "C" int hgb_segment_sum(const float* m, const int32_t* rowptr, const int32_t* perm, int32_t n, int32_t c,
-                               float* out, hgb_stream_t stream) {
-  HGB_REQUIRE(n >= 0 && c > 0 && rowptr && out, "segment_sum: bad arguments");
+extern "C" int hgb_segment_sum_strided(const float* m, const int32_t* rowptr, const int32_t* perm, int32_t n, int32_t c,
+                                       float* out, int32_t ldo, hgb_stream_t stream) {
+  HGB_REQUIRE(n >= 0 && c > 0 && rowptr && out && ldo >= c, "segment_sum: bad arguments");
   if (n == 0) return HGB_OK;
-  const bool v4 = (c % 4 == 0) && ((uintptr_t)m % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  const bool v4 = (c % 4 == 0) && (ldo % 4 == 0) && ((uintptr_t)m % 16 == 0) && ((uintptr_t)out % 16 == 0);
   const int cv = v4 ? c / 4 : c;
   const int lanes = group_lanes(cv);
   const int gpb = 256 / lanes;
   const int grid = hgb_grid_for(n, gpb);
-  if (v4) segment_sum_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(m, rowptr, perm, n, cv, lanes, out);
-  else segment_sum_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(m, rowptr, perm, n, cv, lanes, out);
+  if (v4) segment_sum_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(m, rowptr, perm, n, cv, lanes, out, ldo / 4);
+  else segment_sum_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(m, rowptr, perm, n, cv, lanes, out, ldo);
   HGB_LAUNCH_CHECK("segment_sum");
   return HGB_OK;
+}
+
+extern "C" int hgb_segment_sum(const float* m, const int32_t* rowptr, const int32_t* perm, int32_t n, int32_t c,
+                               float* out, hgb_stream_t stream) {
+  return hgb_segment_sum_strided(m, rowptr, perm, n, c, out, c, stream);
 }
 
 // ---- graph pooling (batch is sorted: a graph is a contiguous run of rows) -------------------------

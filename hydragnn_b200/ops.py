@@ -66,7 +66,7 @@ def csr_build(index64, n):
     rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
     perm = torch.empty(e, dtype=torch.int32, device=dev)
     ws = _ws(_lib.query("hgb_csr_workspace_bytes", e, n), dev)
-    _lib.call("hgb_csr_build", _p(index64), e, n, _p(idx32), _p(rowptr), _p(perm), _p(ws), _stream())
+    _lib.call("hgb_csr_build", _p(index64), e, n, _p(idx32), _p(rowptr), _p(perm), _p(guard_flag(dev)), _p(ws), _stream())
     return Csr(idx32, rowptr, perm, n)
 
 
@@ -110,6 +110,38 @@ def exclusive_scan(x):
     ws = _ws(_lib.query("hgb_exclusive_scan_workspace_bytes", x.numel()), x.device)
     _lib.call("hgb_exclusive_scan_i32", _p(x), _p(out), x.numel(), _p(ws), _stream())
     return out
+
+
+# ---- device-side guards of captured steps ---------------------------------------------------------------
+GUARD_EDGE_COUNT = 1        # a neighbour build produced a different number of edges / candidates than the captured size
+GUARD_BAD_INDEX = 2         # an index vector handed to csr_build had entries outside [0, n)
+_GUARD = {}
+
+
+def guard_flag(device):
+    """One int32 error word per device; kernels OR bits into it, ``check_guard`` reads it."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _GUARD:
+        _GUARD[key] = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", key))
+    return _GUARD[key]
+
+
+def expect_count(value_i32, expected, bit=GUARD_EDGE_COUNT):
+    _lib.call("hgb_expect_i32", _p(value_i32), int(expected), int(bit), _p(guard_flag(value_i32.device)), _stream())
+
+
+def check_guard(device=None):
+    """Host read (one sync) of the guard word; raises if a captured step saw a shape it was not captured for."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    word = int(guard_flag(dev).item())
+    if word:
+        guard_flag(dev).zero_()
+        what = []
+        if word & GUARD_EDGE_COUNT:
+            what.append("a neighbour build produced a different edge count than the one the step was captured with")
+        if word & GUARD_BAD_INDEX:
+            what.append("an index vector had entries outside [0, n)")
+        raise RuntimeError("hydragnn_b200 device guard tripped: " + "; ".join(what))
 
 
 # =====================================================================================================
@@ -819,6 +851,210 @@ class PnaAggregateFn(torch.autograd.Function):
 
 
 # =====================================================================================================
+# fused EGNN edge block + closed edge-length primitives (any order of differentiation the MLIP loss needs)
+# =====================================================================================================
+_DATA_ONLY = {"on": False}
+FUSED_EGNN = os.environ.get("HGB_FUSED_EGNN", "1") == "1"     # 0: the round-1 composed path (gather / Linear / segment-sum)
+
+
+class only_data_grads:
+    """Context manager for the FORCE pass of the MLIP loss (``torch.autograd.grad(E, pos, create_graph=True)``,
+    hydragnn/models/create.py:718-724): fused blocks skip their parameter gradients there -- autograd would compute and drop
+    them (custom Functions cannot see which of their outputs the engine needs)."""
+
+    def __enter__(self):
+        self.prev = _DATA_ONLY["on"]
+        _DATA_ONLY["on"] = True
+        return self
+
+    def __exit__(self, *exc):
+        _DATA_ONLY["on"] = self.prev
+        return False
+
+
+def egnn_nodes_per_tile(plan):
+    deg = max(1.0, plan.num_edges / max(plan.num_nodes, 1))
+    return int(max(1, min(32, 120 // deg)))
+
+
+def egnn_edge_supported(h):
+    return bool(_lib.query("hgb_egnn_edge_supported", int(h)))
+
+
+def _egnn_ws(n, h, npt, dev):
+    return _ws(_lib.query("hgb_egnn_edge_workspace_bytes", n, h, npt), dev)
+
+
+def _raw_egnn_fwd(pq, s, wd, b0, w1, b1, plan, npt, masks, tangent):
+    n, h = pq.shape[0], pq.shape[1] // 2
+    out = torch.empty(n, h, dtype=pq.dtype, device=pq.device)
+    csr = plan.by_row
+    _lib.call("hgb_egnn_edge_fwd", _p(pq), _p(s), _p(wd), _p(b0), _p(w1), _p(b1), _p(csr.rowptr), _p(csr.perm), _p(plan.nbr("row")), n, h,
+              npt, int(tangent), _p(masks), _p(out), _stream())
+    return out
+
+
+def _raw_egnn_bwd_data(g_out, s, wd, w1, masks, plan, npt, want_params):
+    """-> (g_pq [n, 2h], gz1 [e, h], gs [e], g_wd, g_b0)"""
+    n, h = g_out.shape
+    e = plan.num_edges
+    dev = g_out.device
+    g_pq = torch.empty(n, 2 * h, dtype=g_out.dtype, device=dev)
+    gz1 = torch.empty(e, h, dtype=g_out.dtype, device=dev)
+    gs = torch.empty(e, dtype=g_out.dtype, device=dev)
+    g_wd = torch.empty(h, dtype=g_out.dtype, device=dev) if want_params else None
+    g_b0 = torch.empty(h, dtype=g_out.dtype, device=dev) if want_params else None
+    ws = _egnn_ws(n, h, npt, dev) if want_params else None
+    csr = plan.by_row
+    _lib.call("hgb_egnn_edge_bwd_data", _p(g_out), _p(s), _p(wd), _p(w1), _p(masks), _p(csr.rowptr), _p(csr.perm), n, h, npt, _p(g_pq), 2 * h,
+              _p(gz1), _p(gs), _p(g_wd), _p(g_b0), _p(ws), _stream())
+    # g_q = by-col segment sum of gz1, written into the right half of g_pq
+    col = plan.by_col
+    gq = g_pq[:, h:]
+    _lib.call("hgb_segment_sum_strided", _p(gz1), _p(col.rowptr), _p(col.perm), n, h, _p(gq), 2 * h, _stream())
+    return g_pq, gz1, gs, g_wd, g_b0
+
+
+def _raw_egnn_wgrad(g_out, pq, s, wd, b0, masks, plan, npt, tangent, want_b1):
+    n, h = g_out.shape
+    dev = g_out.device
+    g_w1 = torch.empty(h, h, dtype=g_out.dtype, device=dev)
+    g_b1 = torch.empty(h, dtype=g_out.dtype, device=dev) if want_b1 else None
+    ws = _egnn_ws(n, h, npt, dev)
+    csr = plan.by_row
+    _lib.call("hgb_egnn_edge_wgrad", _p(g_out), _p(pq), _p(s), _p(wd), _p(b0), _p(masks), _p(csr.rowptr), _p(csr.perm), _p(plan.nbr("row")),
+              n, h, npt, int(tangent), _p(g_w1), _p(g_b1), _p(ws), _stream())
+    return g_w1, g_b1
+
+
+class EgnnEdgeFn(torch.autograd.Function):
+    """agg = sum_row relu(W1 relu(P[row] + Q[col] + s w_d + b0) + b1)  -- the edge model and the scatter of E_GCL
+    (hydragnn/models/EGCLStack.py:245-258) in one kernel.  Differentiable to the order the MLIP loss needs: its backward is
+    ``EgnnEdgeBwdFn`` (itself differentiable); parameter gradients come from the fused weight-gradient kernel."""
+
+    @staticmethod
+    def forward(ctx, pq, s, wd, b0, w1, b1, plan):
+        pq, s, wd, b0, w1, b1 = [_chk(t) for t in (pq, s, wd, b0, w1, b1)]
+        npt = egnn_nodes_per_tile(plan)
+        masks = torch.empty(plan.num_edges, 2, dtype=torch.int64, device=pq.device)
+        out = _raw_egnn_fwd(pq, s, wd, b0, w1, b1, plan, npt, masks, False)
+        ctx.save_for_backward(pq, s, wd, b0, w1, masks)
+        ctx.plan, ctx.npt = plan, npt
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        pq, s, wd, b0, w1, masks = ctx.saved_tensors
+        plan, npt = ctx.plan, ctx.npt
+        g_out = _chk(g_out.contiguous())
+        params = not _DATA_ONLY["on"]
+        if torch.is_grad_enabled():                       # create_graph=True: the force pass, differentiated again later
+            g_pq, gs, g_wd, g_b0 = EgnnEdgeBwdFn.apply(g_out, s, wd, w1, masks, plan, npt, params)
+        else:
+            g_pq, _, gs, g_wd, g_b0 = _raw_egnn_bwd_data(g_out, s, wd, w1, masks, plan, npt, params)
+        g_w1 = g_b1 = None
+        if params and (ctx.needs_input_grad[4] or ctx.needs_input_grad[5]):
+            with torch.no_grad():
+                g_w1, g_b1 = _raw_egnn_wgrad(g_out.detach(), pq, s, wd, b0, masks, plan, npt, False, True)
+        return g_pq, gs, g_wd, g_b0, g_w1, g_b1, None
+
+
+class EgnnEdgeBwdFn(torch.autograd.Function):
+    """(g_out, s, w_d, W1) -> (g_pq, gs[, g_wd, g_b0]): the data side of the block's backward as a differentiable op.  Its own
+    backward (the second backward pass of the force loss) is the block's TANGENT kernel plus two small parameter reductions:
+    with u_e = ggP[row] + ggQ[col] + ggs_e w_d,  d/d g_out = sum_row mask2 (W1 (mask1 u_e)),  d/d W1 = sum_e gz2_e (mask1 u_e)^T,
+    d/d w_d = sum_e ggs_e gz1_e.  (The masks make z1 / s enter only through constants: no gradient to s or P, Q here.)"""
+
+    @staticmethod
+    def forward(ctx, g_out, s, wd, w1, masks, plan, npt, params):
+        g_pq, gz1, gs, g_wd, g_b0 = _raw_egnn_bwd_data(g_out, s, wd, w1, masks, plan, npt, params)
+        ctx.save_for_backward(g_out, wd, w1, masks, gz1)
+        ctx.plan, ctx.npt, ctx.params = plan, npt, params
+        ctx.mark_non_differentiable(*[t for t in (g_wd, g_b0) if t is not None])
+        return g_pq, gs, g_wd, g_b0
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gg_pq, gg_s, _gwd, _gb0):
+        g_out, wd, w1, masks, gz1 = ctx.saved_tensors
+        plan, npt = ctx.plan, ctx.npt
+        n, h = g_out.shape
+        if gg_pq is None:
+            gg_pq = torch.zeros(n, 2 * h, dtype=g_out.dtype, device=g_out.device)
+        if gg_s is None:
+            gg_s = torch.zeros(plan.num_edges, dtype=g_out.dtype, device=g_out.device)
+        gg_pq, gg_s = _chk(gg_pq.contiguous()), _chk(gg_s.contiguous())
+        g_gout = _raw_egnn_fwd(gg_pq, gg_s, wd, None, w1, None, plan, npt, masks, True)
+        g_w1 = g_wd = None
+        if not _DATA_ONLY["on"]:
+            g_w1, _ = _raw_egnn_wgrad(g_out, gg_pq, gg_s, wd, None, masks, plan, npt, True, False)
+            g_wd = torch.empty(h, dtype=g_out.dtype, device=g_out.device)
+            ws = _ws(_lib.query("hgb_weighted_colsum_workspace_bytes", h), g_out.device)
+            _lib.call("hgb_weighted_colsum", _p(gz1), _p(gg_s), plan.num_edges, h, _p(g_wd), _p(ws), _stream())
+        return g_gout, None, g_wd, g_w1, None, None, None, None
+
+
+class EdgeLenFn(torch.autograd.Function):
+    """d_e = |pos[col] - pos[row] + shift_e| (hydragnn/utils/model/operations.py:21-36, the ``radial`` of E_GCL).  Backward =
+    ``EdgeLenBwdFn`` (differentiable once more: forces are differentiated by the MLIP loss)."""
+
+    @staticmethod
+    def forward(ctx, pos, shifts, plan):
+        pos = _chk(pos)
+        e = plan.num_edges
+        ln = torch.empty(e, dtype=pos.dtype, device=pos.device)
+        _lib.call("hgb_edge_geom_fwd", _p(pos), _p(plan.row), _p(plan.col), _p(_chk(shifts)), e, 0.0, None, _p(ln), None, _stream())
+        ctx.save_for_backward(pos, shifts)
+        ctx.plan = plan
+        return ln
+
+    @staticmethod
+    def backward(ctx, gd):
+        pos, shifts = ctx.saved_tensors
+        gd = _chk(gd.contiguous())
+        if torch.is_grad_enabled():
+            return EdgeLenBwdFn.apply(gd, pos, shifts, ctx.plan), None, None
+        return _raw_edge_len_bwd(gd, pos, shifts, ctx.plan), None, None
+
+
+def _edge_vec_scatter(gvec, plan):
+    gpos = torch.empty(plan.num_nodes, 3, dtype=gvec.dtype, device=gvec.device)
+    _lib.call("hgb_edge_vec_scatter", _p(gvec), _p(plan.by_col.rowptr), _p(plan.by_col.perm), _p(plan.by_row.rowptr), _p(plan.by_row.perm),
+              plan.num_nodes, _p(gpos), _stream())
+    return gpos
+
+
+def _raw_edge_len_bwd(gd, pos, shifts, plan):
+    gvec = torch.empty(plan.num_edges, 3, dtype=pos.dtype, device=pos.device)
+    _lib.call("hgb_edge_len_bwd", _p(pos), _p(plan.row), _p(plan.col), _p(shifts), _p(gd), plan.num_edges, _p(gvec), _stream())
+    return _edge_vec_scatter(gvec, plan)
+
+
+class EdgeLenBwdFn(torch.autograd.Function):
+    """(gd, pos) -> g_pos = scatter(gd_e * vhat_e); its backward yields d/d gd = <vhat_e, ggpos[col] - ggpos[row]> and the
+    curvature term d/d pos = scatter(gd_e (w_e - vhat <vhat, w_e>) / d_e)."""
+
+    @staticmethod
+    def forward(ctx, gd, pos, shifts, plan):
+        ctx.save_for_backward(gd, pos, shifts)
+        ctx.plan = plan
+        return _raw_edge_len_bwd(gd, pos, shifts, plan)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, ggpos):
+        gd, pos, shifts = ctx.saved_tensors
+        plan = ctx.plan
+        e = plan.num_edges
+        ggpos = _chk(ggpos.contiguous())
+        g_gd = torch.empty(e, dtype=pos.dtype, device=pos.device)
+        q = torch.empty(e, 3, dtype=pos.dtype, device=pos.device)
+        _lib.call("hgb_edge_len_bwd2", _p(pos), _p(plan.row), _p(plan.col), _p(shifts), _p(gd), _p(ggpos), e, _p(g_gd), _p(q), _stream())
+        g_pos = _edge_vec_scatter(q, plan) if ctx.needs_input_grad[1] else None
+        return g_gd, g_pos, None, None
+
+
+# =====================================================================================================
 # MACE: fused tensor-product + scatter, symmetric contraction (first-order blocks)
 # =====================================================================================================
 def mace_tp_supported(lin, lsh, f):
@@ -893,6 +1129,6 @@ class MaceSymContractFn(torch.autograd.Function):
         return gx, gwall, None, None, None
 
 
-def adamw_step(p, g, m, v, step_dev, lr, beta1, beta2, eps, weight_decay, grad_scale=1.0):
+def adamw_step(p, g, m, v, step_dev, lr, beta1, beta2, eps, weight_decay, grad_scale=1.0, hyper_dev=None):
     _lib.call("hgb_adamw_step", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
-              float(weight_decay), float(grad_scale), _p(step_dev), _stream())
+              float(weight_decay), float(grad_scale), _p(step_dev), _p(hyper_dev), _stream())

@@ -34,16 +34,24 @@ def radius_graph(pos, r, graph_ptr, num_graphs, loop=False, max_num_neighbors=32
     deg = torch.empty(n, dtype=torch.int32, device=pos.device)
     _lib.call("hgb_radius_graph_count", _p(pos), _p(graph_ptr), n, num_graphs, float(r), k, int(loop), _p(deg), _stream())
     rowptr = ops.exclusive_scan(deg)
-    e = int(rowptr[-1]) if known_e is None else int(known_e)   # the one host sync: the count sizes the output
+    if known_e is None:
+        e = int(rowptr[-1])                                    # the one host sync: the count sizes the output
+    else:
+        e = int(known_e)                                       # promised by the caller; verified on the device (ops.check_guard)
+        ops.expect_count(rowptr[-1:], e, ops.GUARD_EDGE_COUNT)
     ei = torch.empty(2, e, dtype=torch.int64, device=pos.device)
     _lib.call("hgb_radius_graph_fill", _p(pos), _p(graph_ptr), n, num_graphs, float(r), k, int(loop), _p(rowptr), e, _p(ei), _stream())
     return ei, rowptr
 
 
-def radius_graph_pbc(pos, cell, pbc, cutoff, graph_ptr, num_graphs, max_num_neighbors=32):
+def radius_graph_pbc(pos, cell, pbc, cutoff, graph_ptr, num_graphs, max_num_neighbors=32, known=None):
     """Batched periodic neighbour list with nearest-k truncation.  ``cutoff`` is a per-graph fp64 tensor.
-    Returns (edge_index [2,E], cell_shift [E,3] int32, edge_shifts [E,3] pos.dtype, in_degree [N] int32)."""
+    Returns (edge_index [2,E], cell_shift [E,3] int32, edge_shifts [E,3] pos.dtype, in_degree [N] int32).
+    ``known`` = (candidate count, edge count) from an earlier run on the same positions: no host read of either count, so the
+    build can be captured in a CUDA graph; both are verified on the device (``ops.check_guard``)."""
     assert pos.dtype in (torch.float32, torch.float64)
+    if not pos.is_cuda:
+        raise RuntimeError("hydragnn_b200 radius_graph_pbc needs CUDA tensors (move the sample to the device first)")
     pos = pos.contiguous()
     is64 = int(pos.dtype == torch.float64)
     dev = pos.device
@@ -57,23 +65,31 @@ def radius_graph_pbc(pos, cell, pbc, cutoff, graph_ptr, num_graphs, max_num_neig
     cnt = torch.empty(n, dtype=torch.int32, device=dev)
     _lib.call("hgb_radius_pbc_count", _p(pos), is64, _p(graph_ptr), _p(cell), _p(nimg), _p(cutoff), n, g, _p(cnt), st)
     candptr = ops.exclusive_scan(cnt)
-    c = int(candptr[-1])
+    if known is None:
+        c = int(candptr[-1])
+    else:
+        c = int(known[0])
+        ops.expect_count(candptr[-1:], c, ops.GUARD_EDGE_COUNT)
     csrc = torch.empty(max(c, 1), dtype=torch.int32, device=dev)
     cshift = torch.empty(max(c, 1), 3, dtype=torch.int32, device=dev)
     clen = torch.empty(max(c, 1), dtype=torch.float64, device=dev)
-    _lib.call("hgb_radius_pbc_fill", _p(pos), is64, _p(graph_ptr), _p(cell), _p(nimg), _p(cutoff), n, g, _p(candptr), _p(csrc),
-              _p(cshift), _p(clen), st)
+    _lib.call("hgb_radius_pbc_fill", _p(pos), is64, _p(graph_ptr), _p(cell), _p(nimg), _p(cutoff), n, g, _p(candptr), max(c, 1),
+              _p(csrc), _p(cshift), _p(clen), st)
     k = int(min(max_num_neighbors, _NO_CAP))
     deg = torch.empty(n, dtype=torch.int32, device=dev)
     _lib.call("hgb_clamp_i32", _p(cnt), k, n, _p(deg), st)
     outptr = ops.exclusive_scan(deg)
-    e = int(outptr[-1])
+    if known is None:
+        e = int(outptr[-1])
+    else:
+        e = int(known[1])
+        ops.expect_count(outptr[-1:], e, ops.GUARD_EDGE_COUNT)
     ei = torch.empty(2, e, dtype=torch.int64, device=dev)
     cell_shift = torch.empty(e, 3, dtype=torch.int32, device=dev)
     shifts = torch.empty(e, 3, dtype=pos.dtype, device=dev)
     _lib.call("hgb_radius_pbc_emit", _p(graph_ptr), _p(cell), n, g, _p(candptr), _p(csrc), _p(cshift), k, _p(outptr), e, _p(ei),
               _p(cell_shift), _p(shifts), is64, st)
-    return ei, cell_shift, shifts, deg
+    return ei, cell_shift, shifts, deg, outptr, c
 
 
 class RadiusGraph:
@@ -109,13 +125,16 @@ class RadiusGraphPBC(RadiusGraph):
             pos = pos.to(torch.get_default_dtype())
         dev = pos.device
         n = pos.shape[0]
+        if not pos.is_cuda:
+            raise RuntimeError("hydragnn_b200 RadiusGraphPBC runs on the device: move the sample / batch to CUDA first "
+                               "(the reference runs this transform on the CPU at preprocessing time)")
         gptr, g = _graph_ptr(data, n, dev)
         cell = torch.as_tensor(data.cell, dtype=torch.float64).reshape(g, 3, 3)
         pbc = torch.as_tensor(data.pbc).reshape(g, 3)
         cutoff = torch.full((g,), float(self.r), dtype=torch.float64, device=dev)
         node_graph = torch.repeat_interleave(torch.arange(g, device=dev), (gptr[1:] - gptr[:-1]).long())
         for attempt in range(3):                                    # radius growth x1.25 (:168-205)
-            ei, cs, sh, deg = radius_graph_pbc(pos, cell, pbc, cutoff, gptr, g, self.max_num_neighbors)
+            ei, cs, sh, deg, outptr, _ = radius_graph_pbc(pos, cell, pbc, cutoff, gptr, g, self.max_num_neighbors)
             lonely = deg == 0
             if not bool(lonely.any()):
                 break

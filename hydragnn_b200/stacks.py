@@ -129,8 +129,33 @@ class E_GCL(nn.Module):
             nn.init.xavier_uniform_(last.weight, gain=0.001)
             self.coord_mlp = nn.Sequential(nn.Linear(hidden_channels, hidden_channels), nn.ReLU(), last, nn.Tanh())
 
-    def forward(self, x, coord, plan, edge_attr=None, edge_shifts=None, higher_order=False):
+    def _fused_ok(self, x, edge_attr):
+        hid = self.edge_mlp[2].weight.shape[0]
+        return (ops.FUSED_EGNN and not self.equivariant and edge_attr is None and x.is_cuda and ops.egnn_edge_supported(hid)
+                and self.edge_mlp[2].weight.shape[1] == hid)
+
+    def _forward_fused(self, x, coord, plan, edge_shifts, higher_order, cache):
+        """edge model + scatter in ONE kernel (csrc/hgb_egnn.cu), any order of differentiation the MLIP loss needs; the node
+        model stays a Linear-ReLU-Linear chain (fused first-order block, or closed primitives in any-order mode)."""
+        lin0, fin = self.edge_mlp[0], x.shape[1]
+        w0 = lin0.weight
+        key = (coord.data_ptr(), coord._version, id(plan))
+        if cache is not None and cache.get("key") == key:
+            radial = cache["radial"]                         # the geometry of a non-equivariant stack is the same in every layer
+        else:
+            radial = ops.EdgeLenFn.apply(coord, edge_shifts, plan)
+            if cache is not None:
+                cache["key"], cache["radial"] = key, radial
+        lin = ops.linear_any_order if higher_order else ops.linear_act
+        pq = lin(x, torch.cat([w0[:, :fin], w0[:, fin:2 * fin]], dim=0), None)          # [N, 2H] = [x W0a^T | x W0b^T]
+        agg = ops.EgnnEdgeFn.apply(pq, radial, w0[:, 2 * fin], lin0.bias, self.edge_mlp[2].weight, self.edge_mlp[2].bias, plan)
+        out = run_mlp(self.node_mlp, torch.cat([x, agg], dim=1), higher_order)       # :262-263
+        return out, coord
+
+    def forward(self, x, coord, plan, edge_attr=None, edge_shifts=None, higher_order=False, cache=None):
         n = x.shape[0]
+        if self._fused_ok(x, edge_attr):
+            return self._forward_fused(x, coord, plan, edge_shifts, higher_order, cache)
         # geometry with eps = 1.0 (quirk Q3, EGCLStack.py:280-282); "radial" is the length
         if higher_order:
             vec = GatherRows.apply(coord, plan.by_col) - GatherRows.apply(coord, plan.by_row)
@@ -234,7 +259,7 @@ class EGNNConv(nn.Module):
         self.module_0 = egcl
 
     def forward(self, inv_node_feat, equiv_node_feat, plan, edge_attr=None, edge_shifts=None, geom=None, higher_order=False):
-        x, pos = self.module_0(inv_node_feat, equiv_node_feat, plan, edge_attr, edge_shifts, higher_order)
+        x, pos = self.module_0(inv_node_feat, equiv_node_feat, plan, edge_attr, edge_shifts, higher_order, cache=geom)
         return x, pos
 
 
@@ -578,8 +603,8 @@ class EGCLStack(Base):
         shifts = data.edge_shifts                                            # zeros if absent (EGCLStack.py:114-118)
         if self.use_global_attn:
             x, e = self._gps_embed(data, higher)
-            return x, data.pos, {"edge_attr": e, "edge_shifts": shifts}
-        return data.x, data.pos, {"edge_attr": data.edge_attr if self.use_edge_attr else None, "edge_shifts": shifts}
+            return x, data.pos, {"edge_attr": e, "edge_shifts": shifts, "geom": {}}
+        return data.x, data.pos, {"edge_attr": data.edge_attr if self.use_edge_attr else None, "edge_shifts": shifts, "geom": {}}
 
     def __str__(self):
         return "EGCLStack"

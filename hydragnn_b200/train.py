@@ -61,13 +61,21 @@ def get_head_indices(model, data):
     return out
 
 
-class FlatAdamW:
-    """torch.optim.AdamW semantics over one flat buffer.  After construction every parameter of ``model`` is
-    a view into ``self.flat_p`` (so checkpoints / ``state_dict`` are unchanged)."""
+class FlatAdamW(torch.optim.Optimizer):
+    """torch.optim.AdamW semantics over one flat buffer (``hydragnn/utils/optimizer/optimizer.py:12-40`` default).  After
+    construction every parameter of ``model`` is a view into ``self.flat_p`` (so checkpoints / ``state_dict`` are unchanged).
+
+    It IS a ``torch.optim.Optimizer`` (one param group), so ``ReduceLROnPlateau`` and the reference's checkpoint helpers accept
+    it; ``state_dict()`` / ``load_state_dict()`` speak torch.optim.AdamW's format (per-parameter ``step`` / ``exp_avg`` /
+    ``exp_avg_sq``), so optimizer checkpoints move between the reference and the engine in both directions.  The learning rate
+    and the 1/world gradient scale are read by the kernel from a DEVICE vector that ``step()`` refreshes whenever
+    ``param_groups[0]["lr"]`` changed -- a CUDA-graph-captured step therefore follows a scheduler."""
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
-        self.params = [p for p in model.parameters() if p.requires_grad]
-        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        params = [p for p in (model.parameters() if isinstance(model, torch.nn.Module) else model) if p.requires_grad]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.params = params
+        self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
         dev = self.params[0].device
         n = sum(p.numel() for p in self.params)
         self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
@@ -83,7 +91,12 @@ class FlatAdamW:
         self.m = torch.zeros_like(self.flat_p)
         self.v = torch.zeros_like(self.flat_p)
         self.step_dev = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.param_groups = [{"lr": lr, "params": self.params}]     # ReduceLROnPlateau-compatible surface
+        self.hyper_dev = torch.tensor([lr, 1.0], dtype=torch.float32, device=dev)      # {lr, grad_scale} read by the kernel
+        self._hyper_host = (float(lr), 1.0)
+
+    @property
+    def lr(self):
+        return self.param_groups[0]["lr"]
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
@@ -95,19 +108,60 @@ class FlatAdamW:
         torch.cat(gs, out=self.flat_g)
         return self.flat_g
 
-    def step(self, grad_scale=1.0):
-        lr = self.param_groups[0]["lr"]
-        ops.adamw_step(self.flat_p, self.flat_g, self.m, self.v, self.step_dev, lr, self.betas[0], self.betas[1], self.eps,
-                       self.weight_decay, grad_scale)
+    def sync_hyper(self, grad_scale=None):
+        """Push lr / grad_scale to the device if they changed (a tiny async H2D copy, outside any captured graph)."""
+        want = (float(self.param_groups[0]["lr"]), self._hyper_host[1] if grad_scale is None else float(grad_scale))
+        if want != self._hyper_host:
+            self.hyper_dev.copy_(torch.tensor(want, dtype=torch.float32), non_blocking=False)
+            self._hyper_host = want
 
+    def step(self, grad_scale=1.0, closure=None):
+        capturing = self.flat_p.is_cuda and torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            self.sync_hyper(grad_scale)
+        elif float(grad_scale) != self._hyper_host[1]:
+            raise RuntimeError("FlatAdamW: call sync_hyper(grad_scale) before capturing a step with a new gradient scale")
+        ops.adamw_step(self.flat_p, self.flat_g, self.m, self.v, self.step_dev, self.param_groups[0]["lr"], self.betas[0],
+                       self.betas[1], self.eps, self.weight_decay, grad_scale, hyper_dev=self.hyper_dev)
+
+    # ---- torch.optim.AdamW checkpoint format ---------------------------------------------------------------
     def state_dict(self):
-        return {"m": self.m, "v": self.v, "step": self.step_dev, "lr": self.param_groups[0]["lr"]}
+        state = {}
+        for i, (off, k) in enumerate(self.slices):
+            shp = self.params[i].shape
+            state[i] = {"step": self.step_dev.detach().clone().reshape(()).cpu(), "exp_avg": self.m[off:off + k].view(shp).clone(),
+                        "exp_avg_sq": self.v[off:off + k].view(shp).clone()}
+        g = self.param_groups[0]
+        group = {k: v for k, v in g.items() if k != "params"}
+        group.update(betas=self.betas, eps=self.eps, weight_decay=self.weight_decay, amsgrad=False, maximize=False,
+                     params=list(range(len(self.params))))
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
-        self.m.copy_(sd["m"])
-        self.v.copy_(sd["v"])
-        self.step_dev.copy_(sd["step"])
-        self.param_groups[0]["lr"] = sd["lr"]
+        if "state" not in sd:                                       # round-1 flat format {m, v, step, lr}
+            self.m.copy_(sd["m"])
+            self.v.copy_(sd["v"])
+            self.step_dev.copy_(sd["step"])
+            self.param_groups[0]["lr"] = sd["lr"]
+            return
+        groups = sd["param_groups"]
+        order = [i for g in groups for i in g["params"]]
+        if len(order) != len(self.params):
+            raise ValueError("FlatAdamW.load_state_dict: %d parameters in the checkpoint, %d in the model" % (len(order), len(self.params)))
+        step = None
+        for j, (off, k) in zip(order, self.slices):
+            st = sd["state"].get(j, sd["state"].get(str(j)))
+            if st is None:
+                self.m[off:off + k].zero_()
+                self.v[off:off + k].zero_()
+                continue
+            self.m[off:off + k].copy_(st["exp_avg"].reshape(-1))
+            self.v[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+            step = float(st["step"]) if step is None else max(step, float(st["step"]))
+        self.step_dev.fill_(0.0 if step is None else step)
+        g0 = groups[0]
+        self.param_groups[0]["lr"] = g0["lr"]
+        self.betas, self.eps, self.weight_decay = tuple(g0.get("betas", self.betas)), g0.get("eps", self.eps), g0.get("weight_decay", self.weight_decay)
 
 
 class DistributedModel(torch.nn.Module):
@@ -157,15 +211,26 @@ def train_step(model, opt, data, compute_grad_energy=False, head_index=None):
     return loss.detach(), [t.detach() for t in tasks]
 
 
-class GraphedTrainStep:
-    """CUDA-graph capture of ``train_step`` for a fixed-shape batch living in static device buffers.
-    ``refill(data)`` copies a new batch of the same shape into the static buffers; ``run()`` replays.
-    (The all-reduce stays outside the graph when world_size > 1: backward is one graph, optimizer another.)"""
+def _capturable_allreduce(flat):
+    """The step's only collective, on the CURRENT stream (NCCL collectives are CUDA-graph capturable)."""
+    dist.all_reduce(flat)
 
-    def __init__(self, model, opt, static_data, compute_grad_energy=False, warmup=3):
+
+class GraphedTrainStep:
+    """CUDA-graph capture of ``train_step`` for a fixed-shape batch living in static device buffers: forward + loss + backward
+    + flatten + the flat NCCL all-reduce + fused AdamW are ONE graph (`hydragnn/utils/distributed/distributed.py:479` and
+    `train_validate_test.py:737-769` in one replay).  ``refill(data)`` copies a new batch of the same shape -- positions,
+    features, targets AND topology (``edge_index`` / ``batch``) -- into the static buffers; the index plans (CSR views of
+    ``edge_index``, graph offsets) are rebuilt INSIDE the captured region, so a refilled topology is honoured.  With
+    ``neighbour_build=(radius, max_neighbours)`` the radius graph itself is part of the captured step (edge count promised by the
+    warm-up run and verified on the device -- ``ops.check_guard``)."""
+
+    def __init__(self, model, opt, static_data, compute_grad_energy=False, warmup=3, capture_allreduce=True):
         self.model, self.opt, self.data, self.mlip = model, opt, static_data, compute_grad_energy
         self.head_index = None if compute_grad_energy else get_head_indices(model, static_data)
         self.ws, _ = world()
+        self.capture_allreduce = bool(capture_allreduce)
+        self.opt.sync_hyper(1.0 / self.ws)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -176,26 +241,33 @@ class GraphedTrainStep:
                 self.opt.step(1.0 / self.ws)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        self.g_opt = None
         self.g_fb = torch.cuda.CUDAGraph()
+        one_graph = self.ws == 1 or self.capture_allreduce
         with torch.cuda.graph(self.g_fb):
             self._fwd_bwd()
-            if self.ws == 1:
-                self.opt.step(1.0)
-        if self.ws > 1:
+            if one_graph:
+                if self.ws > 1:
+                    _capturable_allreduce(self.opt.flat_g)
+                self.opt.step(1.0 / self.ws)
+        if not one_graph:
             self.g_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g_opt):
                 self.opt.step(1.0 / self.ws)
 
     def _fwd_bwd(self):
         m = self.model.module
+        d = self.data
+        for k in ("_hgb_plan", "_hgb_gcsr"):          # index plans are part of the step (stale CSR after refill)
+            d.__dict__.pop(k, None)
         self.opt.zero_grad()
         if self.mlip:
-            self.data.pos.requires_grad_(True)
-            pred = self.model(self.data)
-            loss, _ = m.energy_force_loss(pred, self.data)
+            d.pos.requires_grad_(True)
+            pred = self.model(d)
+            loss, _ = m.energy_force_loss(pred, d)
         else:
-            pred = self.model(self.data)
-            loss, _ = m.loss(pred, self.data.y, self.head_index)
+            pred = self.model(d)
+            loss, _ = m.loss(pred, d.y, self.head_index)
         loss.backward()
         self.opt.gather_grads()
         self.loss = loss.detach()
@@ -204,11 +276,14 @@ class GraphedTrainStep:
         for k, v in data.items():
             if torch.is_tensor(v):
                 dst = self.data[k]
+                if dst.shape != v.shape:
+                    raise ValueError("GraphedTrainStep.refill: %s has shape %s, the captured step has %s" % (k, tuple(v.shape), tuple(dst.shape)))
                 dst.detach().copy_(v, non_blocking=True)
 
     def run(self):
+        self.opt.sync_hyper()                       # a scheduler may have changed the learning rate
         self.g_fb.replay()
-        if self.ws > 1:
+        if self.g_opt is not None:
             dist.all_reduce(self.opt.flat_g)
             self.g_opt.replay()
         return self.loss

@@ -83,11 +83,12 @@ int hgb_radius_pbc_count(const void* pos, int32_t pos_is_f64, const int32_t* gra
                          const double* cell, const int32_t* nimg, const double* cutoff, int32_t n,
                          int32_t g, int32_t* cand_count, hgb_stream_t stream);
 /* Pass 2: candptr [n+1] = exclusive scan of cand_count; fills cand_src [c] int32, cand_shift [c,3]
- * int32, cand_len [c] fp64 and sorts every target's segment by (len, src, Sx, Sy, Sz).           */
+ * int32, cand_len [c] fp64 and sorts every target's segment by (len, src, Sx, Sy, Sz).
+ * cand_capacity = c, the number of entries the three buffers hold (nothing is written past it).   */
 int hgb_radius_pbc_fill(const void* pos, int32_t pos_is_f64, const int32_t* graph_ptr,
                         const double* cell, const int32_t* nimg, const double* cutoff, int32_t n,
-                        int32_t g, const int32_t* candptr, int32_t* cand_src, int32_t* cand_shift,
-                        double* cand_len, hgb_stream_t stream);
+                        int32_t g, const int32_t* candptr, int64_t cand_capacity, int32_t* cand_src,
+                        int32_t* cand_shift, double* cand_len, hgb_stream_t stream);
 /* Pass 3: keeps the first min(count, max_neighbors) candidates of every target.  outptr [n+1] =
  * exclusive scan of min(cand_count, max_neighbors) (hgb_clamp_i32 + scan).  Writes edge_index
  * [2,e] int64 (src; dst), cell_shift [e,3] int32 and edge_shifts [e,3] fp32/fp64 = S @ cell
@@ -99,6 +100,12 @@ int hgb_radius_pbc_emit(const int32_t* graph_ptr, const double* cell, int32_t n,
                         hgb_stream_t stream);
 /* out[i] = min(in[i], cap) */
 int hgb_clamp_i32(const int32_t* in, int32_t cap, int64_t n, int32_t* out, hgb_stream_t stream);
+/* Device-side guard for CUDA-graph-captured steps whose output sizes were promised by the caller
+ * (edge counts measured on an earlier run): *flag |= bit when *value != expected.  The host reads
+ * the flag asynchronously (hydragnn_b200.ops.check_guard); replaces the host read of the count at
+ * graph_samples_checks_and_updates.py:128-133 that a captured step cannot do.                      */
+int hgb_expect_i32(const int32_t* value, int32_t expected, int32_t bit, int32_t* flag,
+                   hgb_stream_t stream);
 
 /* exclusive prefix sum of int32 (out has n+1 entries, out[n] = total).  workspace: >= 4*(n/1024+2) bytes */
 int hgb_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* workspace,
@@ -109,9 +116,11 @@ int64_t hgb_exclusive_scan_workspace_bytes(int64_t n);
  * idx == k are perm[rowptr[k] .. rowptr[k+1]) in ascending edge id (stable).  Also writes idx32 [e].
  * This is what lets every scatter of the reference (ATen scatter_add_/index_add_,
  * hydragnn/models/EGCLStack.py:294-300, hydragnn/models/PAINNStack.py:263-266) run as an
- * atomics-free segmented reduction.  workspace: hgb_csr_workspace_bytes(e, n).                  */
+ * atomics-free segmented reduction.  workspace: hgb_csr_workspace_bytes(e, n).
+ * guard_flag (optional, device int32): bit 2 is OR-ed in when an entry lies outside [0, n) (such
+ * entries are counted under node 0 so that nothing is written out of bounds).                      */
 int hgb_csr_build(const int64_t* idx, int64_t e, int32_t n, int32_t* idx32, int32_t* rowptr,
-                  int32_t* perm, void* workspace, hgb_stream_t stream);
+                  int32_t* perm, int32_t* guard_flag, void* workspace, hgb_stream_t stream);
 int64_t hgb_csr_workspace_bytes(int64_t e, int32_t n);
 /* out[p] = idx[perm[p]]: the neighbour node of every CSR slot */
 int hgb_gather_i32(const int32_t* idx, const int32_t* perm, int64_t e, int32_t* out, hgb_stream_t stream);
@@ -128,6 +137,9 @@ int hgb_gather_rows(const float* x, const int32_t* idx, int64_t e, int32_t c, fl
  * E*C*4 + E*4 + N*C*4 (SURVEY 8d "scatter primitive").                                          */
 int hgb_segment_sum(const float* m, const int32_t* rowptr, const int32_t* perm, int32_t n, int32_t c,
                     float* out, hgb_stream_t stream);
+/* the same with an output row stride ldo >= c (writes a column block of a wider matrix) */
+int hgb_segment_sum_strided(const float* m, const int32_t* rowptr, const int32_t* perm, int32_t n,
+                            int32_t c, float* out, int32_t ldo, hgb_stream_t stream);
 /* PNA min / max aggregators (PyG DegreeScalerAggregation, hydragnn/models/PNAEqStack.py:396-400): for every
  * (segment, channel) the EDGE id of the minimum / maximum (first wins on ties, -1 for an empty segment); the
  * values and their gradients are gathers at those ids.  argmin / argmax are [n,c] int64.                    */
@@ -295,6 +307,57 @@ int hgb_mha_bwd(const float* qkv, const float* out, const float* lse, const floa
                 int32_t heads, float* gqkv, hgb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused EGNN edge block (hydragnn/models/EGCLStack.py:245-258 edge_model, :256-263 the scatter of
+ * node_model, :278-291 forward; unsorted_segment_sum :294-300).  The first Linear of edge_mlp is
+ * applied per node by the caller: pq [n, 2h] = [x W0[:, :fin]^T | x W0[:, fin:2fin]^T]; the kernels
+ * see z1_e = P[row] + Q[col] + s_e w_d + b0 with s_e = |pos[col] - pos[row] + shift| (quirk Q3).
+ * CSR = by edge_index[0] (the aggregation index): rowptr [n+1], perm [e] (edge ids), nbr [e] =
+ * edge_index[1][perm].  masks [e, 2] uint64 (CSR order): ReLU patterns of z1 and z2, written by the
+ * forward and read by every derivative kernel (the block is piecewise linear).  h in {32, 64}.
+ * nodes_per_tile in [1, 32]: consecutive nodes per CTA tile (pick ~ 128 / mean degree).
+ * ------------------------------------------------------------------------------------------ */
+int32_t hgb_egnn_edge_supported(int32_t h);
+int64_t hgb_egnn_edge_workspace_bytes(int32_t n, int32_t h, int32_t nodes_per_tile);
+/* tangent == 0:  out[i] = sum_{row(e)=i} relu(W1 relu(z1_e) + b1)          (writes masks)
+ * tangent != 0:  out[i] = sum_{row(e)=i} mask2 * (W1 (mask1 * (P[row] + Q[col] + s_e w_d)))   (reads masks;
+ *                b0 / b1 ignored) -- the JVP of the block, which is the adjoint of hgb_egnn_edge_bwd_data
+ *                with respect to its g_out (needed by the force loss, create.py:718-724).                    */
+int hgb_egnn_edge_fwd(const float* pq, const float* s, const float* wd, const float* b0, const float* w1,
+                      const float* b1, const int32_t* rowptr, const int32_t* perm, const int32_t* nbr,
+                      int32_t n, int32_t h, int32_t nodes_per_tile, int32_t tangent, uint64_t* masks,
+                      float* out, hgb_stream_t stream);
+/* gz1_e = mask1 * (W1^T (mask2 * g_out[row(e)])).  Writes g_p [n, h] (row stride ldp) = sum_{row} gz1,
+ * gz1 [e, h] in EDGE order (the caller's by-col segment sum gives g_q), gs [e] = w_d . gz1_e and, when
+ * g_wd / g_b0 are given (both or neither), g_wd = sum_e s_e gz1_e and g_b0 = sum_e gz1_e.
+ * workspace: hgb_egnn_edge_workspace_bytes.                                                            */
+int hgb_egnn_edge_bwd_data(const float* g_out, const float* s, const float* wd, const float* w1,
+                           const uint64_t* masks, const int32_t* rowptr, const int32_t* perm, int32_t n,
+                           int32_t h, int32_t nodes_per_tile, float* g_p, int32_t ldp, float* gz1, float* gs,
+                           float* g_wd, float* g_b0, void* workspace, hgb_stream_t stream);
+/* g_w1 [h, h] = sum_e (mask2 * g_out[row]) y_e^T with y_e = relu(z1_e) (tangent == 0) or
+ * mask1 * (P[row] + Q[col] + s_e w_d) (tangent != 0); g_b1 [h] (optional) = sum_e mask2 * g_out[row].   */
+int hgb_egnn_edge_wgrad(const float* g_out, const float* pq, const float* s, const float* wd, const float* b0,
+                        const uint64_t* masks, const int32_t* rowptr, const int32_t* perm, const int32_t* nbr,
+                        int32_t n, int32_t h, int32_t nodes_per_tile, int32_t tangent, float* g_w1, float* g_b1,
+                        void* workspace, hgb_stream_t stream);
+/* out [h] = sum_e w[e] x[e, :]  (h divides 256) */
+int hgb_weighted_colsum(const float* x, const float* w, int64_t e, int32_t h, float* out, void* workspace,
+                        hgb_stream_t stream);
+int64_t hgb_weighted_colsum_workspace_bytes(int32_t h);
+/* Closed edge-length primitives for d_e = |pos[col] - pos[row] + shift_e| (operations.py:21-36; the length
+ * itself is hgb_edge_geom_fwd).  bwd: gvec_e = gd_e vhat_e.  bwd2 (adjoint of bwd + scatter with respect to
+ * gd and pos): w_e = ggpos[col] - ggpos[row]; g_gd_e = <vhat_e, w_e>; q_e = gd_e (w_e - vhat <vhat, w_e>) / d_e.
+ * scatter: g_pos[i] = sum_{col(e)=i} gvec_e - sum_{row(e)=i} gvec_e (ordered).                           */
+int hgb_edge_len_bwd(const float* pos, const int32_t* row, const int32_t* col, const float* shifts,
+                     const float* gd, int64_t e, float* gvec, hgb_stream_t stream);
+int hgb_edge_len_bwd2(const float* pos, const int32_t* row, const int32_t* col, const float* shifts,
+                      const float* gd, const float* ggpos, int64_t e, float* g_gd, float* q,
+                      hgb_stream_t stream);
+int hgb_edge_vec_scatter(const float* gvec, const int32_t* col_rowptr, const int32_t* col_perm,
+                         const int32_t* row_rowptr, const int32_t* row_perm, int32_t n, float* gpos,
+                         hgb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Loss / optimizer (hydragnn/train/train_validate_test.py:736-769, torch.optim.AdamW)
  * ------------------------------------------------------------------------------------------ */
 
@@ -304,10 +367,12 @@ int hgb_loss_fwd_bwd(const float* pred, const float* target, int64_t count, int3
                      float* loss, float* gpred, hgb_stream_t stream);
 /* Fused AdamW over one flat parameter buffer: p, g, m, v [count]; `grad_scale` multiplies g first
  * (1/world_size after the flat all-reduce); step is 1-based and read from device (`step_dev`, fp32,
- * incremented by the kernel) so the launch is CUDA-graph capturable.                               */
+ * incremented by the kernel) so the launch is CUDA-graph capturable.  hyper_dev (optional, device,
+ * 2 floats {lr, grad_scale}): when given it overrides the by-value lr / grad_scale, so a captured
+ * step follows a learning-rate scheduler (train_validate_test.py:452-476 steps ReduceLROnPlateau). */
 int hgb_adamw_step(float* p, const float* g, float* m, float* v, int64_t count, float lr, float beta1,
                    float beta2, float eps, float weight_decay, float grad_scale, float* step_dev,
-                   hgb_stream_t stream);
+                   const float* hyper_dev, hgb_stream_t stream);
 
 /* PaiNN update block at node_size == 1 (the reference's first layer runs at width input_dim, quirk Q4): the whole block
  * (PAINNStack.py:298-328) per node in one kernel.  params16 / gparams16 (device, 16 floats): 0 uw, 1 ub, 2 vw, 3 vb,

@@ -351,7 +351,11 @@ def create_model(**kw):
     (:164) and wraps the stack for MLIP training when asked (:586-756)."""
     from .mlip import MLIPWrapper
     torch.manual_seed(0)
-    model = OracleModel(**kw)
+    if kw.get("mpnn_type") == "MACE":                      # create.py:542-582 -> MACEStack
+        from .mace import MACEOracle
+        model = MACEOracle(**{k: v for k, v in kw.items() if k != "mpnn_type"})
+    else:
+        model = OracleModel(**kw)
     if kw.get("enable_interatomic_potential", False):
         model = MLIPWrapper(model, kw.get("energy_weight", 0.0), kw.get("energy_peratom_weight", 0.0),
                             kw.get("force_weight", 0.0))

@@ -35,7 +35,7 @@ def test_cabi_library_loads_and_exports_every_declared_symbol():
     # every signature in the header is plain C: no torch / C++ types
     for name, (ret, args) in protos.items():
         for t, _ in args:
-            assert re.fullmatch(r"(const )?(void|float|double|int32_t|int64_t|int|hgb_stream_t)\*?", t), (name, t)
+            assert re.fullmatch(r"(const )?(void|float|double|int32_t|int64_t|uint64_t|int|hgb_stream_t)\*?", t), (name, t)
 
 
 def test_ops_refuse_cpu_tensors_no_fallback():
@@ -197,6 +197,56 @@ def test_flat_adamw_views_share_storage():
     assert float(flat.sum()) == 2.0 * (n - k3)
 
 
+def test_flat_adamw_is_a_torch_optimizer_and_speaks_adamw_checkpoints(monkeypatch):
+    """ReduceLROnPlateau must accept it (train_validate_test.py:452-476 steps the scheduler), and optimizer
+    checkpoints must move between torch.optim.AdamW (the reference, optimizer.py:12-40) and the engine in both directions."""
+    from hydragnn_b200 import ops
+
+    def cpu_adamw(p, g, m, v, step_dev, lr, b1, b2, eps, wd, gscale=1.0, hyper_dev=None):    # CPU stand-in for the CUDA kernel
+        if hyper_dev is not None:
+            lr, gscale = float(hyper_dev[0]), float(hyper_dev[1])
+        step_dev += 1
+        t = float(step_dev)
+        g = g * gscale
+        p.mul_(1 - lr * wd); m.mul_(b1).add_(g, alpha=1 - b1); v.mul_(b2).addcmul_(g, g, value=1 - b2)
+        p.addcdiv_(m / (1 - b1 ** t), (v / (1 - b2 ** t)).sqrt() + eps, value=-lr)
+
+    monkeypatch.setattr(ops, "adamw_step", cpu_adamw)
+    kw = dict(MODEL_KW["painn_graph_mean"], use_gpu=False)
+    a, b = hb.create_model(**kw), hb.create_model(**kw)
+    oa, ob = hb.FlatAdamW(a, lr=1e-2), torch.optim.AdamW(b.parameters(), lr=1e-2, weight_decay=1e-2)
+    assert isinstance(oa, torch.optim.Optimizer)
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(oa, mode="min", factor=0.5, patience=0)
+    gen = torch.Generator().manual_seed(0)
+    for it in range(3):
+        for p, q in zip(a.parameters(), b.parameters()):
+            p.grad = torch.randn(p.shape, generator=gen)
+            q.grad = p.grad.clone()
+        oa.gather_grads()
+        oa.step()
+        ob.step()
+    for p, q in zip(a.parameters(), b.parameters()):
+        torch.testing.assert_close(p, q, rtol=1e-5, atol=1e-7)
+    # torch -> engine -> torch round trip of the optimizer state
+    c = hb.create_model(**kw)
+    oc = hb.FlatAdamW(c, lr=1.0)
+    oc.load_state_dict(ob.state_dict())
+    assert oc.lr == 1e-2 and float(oc.step_dev) == 3.0
+    torch.testing.assert_close(oc.m, oa.m, rtol=1e-5, atol=1e-7)
+    d = hb.create_model(**kw)
+    od = torch.optim.AdamW(d.parameters(), lr=5.0)
+    od.load_state_dict(oa.state_dict())
+    assert od.param_groups[0]["lr"] == 1e-2
+    s0 = od.state[next(iter(d.parameters()))]
+    torch.testing.assert_close(s0["exp_avg"], ob.state[next(iter(b.parameters()))]["exp_avg"], rtol=1e-5, atol=1e-7)
+    # the scheduler drives the lr the kernel reads (device vector)
+    sched.step(1.0)
+    sched.step(2.0)
+    assert oa.lr == 5e-3
+    oa.sync_hyper()
+    assert abs(float(oa.hyper_dev[0]) - 5e-3) < 1e-9
+
+
 WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
@@ -204,7 +254,9 @@ import hydragnn_b200 as hb
 from hydragnn_b200 import ops, train
 from hydragnn_b200.synthetic import ARCH
 
-def torch_adamw(p, g, m, v, step_dev, lr, b1, b2, eps, wd, gscale=1.0):   # CPU stand-in for the CUDA kernel (test only)
+def torch_adamw(p, g, m, v, step_dev, lr, b1, b2, eps, wd, gscale=1.0, hyper_dev=None):   # CPU stand-in for the CUDA kernel (test only)
+    if hyper_dev is not None:
+        lr, gscale = float(hyper_dev[0]), float(hyper_dev[1])
     step_dev += 1
     t = float(step_dev)
     g = g * gscale
@@ -286,7 +338,7 @@ def test_bench_reference_arm_prints_the_contract_line():
 
 
 def test_c4_and_c5_synthetic_workloads_and_multihead_indices():
-    b = make_samples("oc20_mace", 3)
+    b = make_samples("oc20_mace_80", 3)
     assert b.pos.shape == (240, 3) and b.cell.shape == (3, 3, 3) and bool(b.pbc.all())
     assert b.y.shape == (3 * 241, 1) and b.y_loc.tolist() == [[0, 1, 241]] * 3
     assert float(b.x.min()) >= 1 and float(b.x.max()) <= 83
@@ -296,8 +348,20 @@ def test_c4_and_c5_synthetic_workloads_and_multihead_indices():
     assert hi[0].tolist() == [0, 241, 482] and hi[1].numel() == 3 * 240 and int(hi[1][0]) == 1 and int(hi[1][-1]) == 722
     # energies and forces land where y_loc says
     assert torch.equal(b.y[hi[1]].reshape(240, 3), b.forces)
-    p = make_samples("gfm_pnaeq", 2)
+    p = make_samples("gfm_pnaeq_mini", 2)
     assert p.pe.shape == (80, 6) and p.pos.shape == (80, 3)
-    kw = dict(ARCH["gfm_pnaeq"], pna_deg=[0, 3, 5, 9])
+    # the full C4 / C5 workloads draw their graph sizes: U{60..100} periodic cells, {9, 21, 80, 200} clusters
+    c4 = make_samples("oc20_mace", 16)
+    ns = (c4.ptr[1:] - c4.ptr[:-1])
+    assert int(ns.min()) >= 60 and int(ns.max()) <= 100 and c4.cell.shape == (16, 3, 3) and c4.pos.shape[0] == int(ns.sum())
+    assert torch.allclose(c4.cell[:, 0, 0].double() ** 3 * 0.05, ns.double(), rtol=1e-5)
+    assert c4.y.shape[0] == 16 + 3 * int(ns.sum()) and c4.y_loc[:, 2].tolist() == (1 + 3 * ns).tolist()
+    hi4 = hb.get_head_indices(m, c4)
+    assert torch.equal(c4.y[hi4[1]].reshape(-1, 3), c4.forces)
+    c5 = make_samples("gfm_pnaeq", 64)
+    n5 = (c5.ptr[1:] - c5.ptr[:-1])
+    assert set(n5.tolist()) <= {9, 21, 80, 200} and len(set(n5.tolist())) == 4 and c5.pe.shape == (int(n5.sum()), 6)
+    assert torch.equal(c5.batch, torch.repeat_interleave(torch.arange(64), n5))
+    kw = dict(ARCH["gfm_pnaeq_mini"], pna_deg=[0, 3, 5, 9])
     g = hb.create_model(use_gpu=False, **kw)
     assert str(g) == "PNAEqStack" and g.use_global_attn and len(g.graph_convs) == 3

@@ -1,0 +1,338 @@
+"""GPU tests added in round 2: engine vs ORACLE at the C4 (periodic MACE) and C5 (PNAEq + GPS, mixed
+graph sizes) shapes, the tensor-core (TF32) bench precision against the oracle directly, the CUDA-graph step after a refill
+with a different topology, the device-side guards of captured neighbour builds, and the radix-sort CSR build on long segments.
+
+Tolerances: integer outputs bit-exact; fp32 engine vs fp32 oracle rel-L2 <= 1e-5 on outputs (2e-5 for the deepest models),
+parameter gradients rel-L2 <= 1e-3; TF32 mode <= 2e-2."""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import hydragnn_b200 as hb  # noqa: E402
+from hydragnn_b200 import ops, radius  # noqa: E402
+from hydragnn_b200.synthetic import ARCH, WORKLOADS, make_samples  # noqa: E402
+import oracle  # noqa: E402
+from oracle.workloads import add_edges_cpu, arch_for  # noqa: E402
+
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    return float((a.double().cpu() - b.double().cpu()).norm() / b.double().cpu().norm().clamp(min=1e-30))
+
+
+def _gpu_batch(cpu, name, g):
+    """device twin of a CPU batch with its edges built by the ENGINE's neighbour kernels"""
+    w = WORKLOADS[name]
+    d = make_samples(name, g).to(DEV)
+    d._num_graphs = g
+    if w.get("pbc") or w.get("pbc_box"):
+        d = hb.get_radius_graph_pbc(w["radius"], w["max_neighbours"])(d)
+    else:
+        d = hb.get_radius_graph(w["radius"], w["max_neighbours"])(d)
+    if w.get("pe_dim"):
+        d.rel_pe = (d.pe[d.edge_index[0]] - d.pe[d.edge_index[1]]).abs()
+    return d
+
+
+def _canon(ei, sh=None):
+    """canonical edge order (dst asc, then src asc, then shift) for set comparison"""
+    key = ei[1].double() * 1e7 + ei[0].double()
+    if sh is not None:
+        key = key * 1e3 + (sh * torch.tensor([1.0, 3.0, 9.0], dtype=sh.dtype, device=sh.device)).sum(1).double() * 1e-2
+    o = torch.argsort(key, stable=True)
+    return o
+
+
+def _grad_rel(em_params, om_params):
+    """rel-L2 over all parameter gradients; accepts parameter lists (same order) or modules (matched by name)."""
+    if isinstance(em_params, torch.nn.Module):
+        en, on = dict(em_params.named_parameters()), dict(om_params.named_parameters())
+        assert set(en) == set(on)
+        em_params, om_params = [en[k] for k in on], [on[k] for k in on]
+    num = den = 0.0
+    for p, q in zip(em_params, om_params):
+        if q.grad is None:
+            continue
+        assert p.grad is not None
+        num += float((p.grad.double().cpu() - q.grad.double()).pow(2).sum())
+        den += float(q.grad.double().pow(2).sum())
+    return (num / max(den, 1e-300)) ** 0.5
+
+
+# ---- C4: periodic MACE at the oc20 shape -------------------------------------------------------------------------------
+def test_oc20_mace_shape_engine_matches_oracle_forward_loss_and_gradients():
+    name, g = "oc20_mace", 3
+    cpu = add_edges_cpu(make_samples(name, g), name)
+    gpu = _gpu_batch(cpu, name, g)
+    # a2: the batched periodic neighbour list equals the oracle's per-sample lists, bit for bit (edges AND shifts)
+    assert gpu.edge_index.shape == cpu.edge_index.shape
+    assert torch.equal(gpu.edge_index.cpu(), cpu.edge_index)
+    assert torch.equal(gpu.edge_shifts.cpu(), cpu.edge_shifts.to(gpu.edge_shifts.dtype))
+    kw = arch_for(name, cpu)
+    om = oracle.base.create_model(**kw)
+    em = hb.create_model(**kw)
+    em.load_state_dict(om.state_dict())
+    hi_c = hb.get_head_indices(om, cpu)
+    hi_g = [h.to(DEV) for h in hi_c]
+    po, pe = om(cpu), em(gpu)
+    for a, b in zip(pe, po):
+        assert rel_l2(a.detach(), b.detach()) < 2e-5
+    lo, to = om.loss(po, cpu.y, hi_c)
+    le, te = em.loss(pe, gpu.y, hi_g)
+    torch.testing.assert_close(le.detach().cpu(), lo.detach(), rtol=2e-5, atol=1e-6)
+    lo.backward()
+    le.backward()
+    assert _grad_rel(em, om) < 1e-3
+
+
+def test_oc20_mace_shape_mlip_forces_and_double_backward_match_oracle():
+    """C4 shape with the MLIP wrapper: energy from a node head, forces = -dE/dpos through the periodic shifts, and the
+    gradient of the force loss (double backward through the MACE interaction / product blocks)."""
+    name, g = "oc20_mace", 2
+    cpu = add_edges_cpu(make_samples(name, g), name)
+    gpu = _gpu_batch(cpu, name, g)
+    kw = dict(arch_for(name, cpu), hidden_dim=32, output_dim=[1], output_type=["node"], task_weights=[1.0], loss_function_type="mse",
+              output_heads={"node": {"num_headlayers": 2, "dim_headlayers": [32, 16], "type": "mlp"}},
+              enable_interatomic_potential=True, energy_weight=1.0, energy_peratom_weight=1.0, force_weight=1.0)
+    om = oracle.base.create_model(**kw)
+    em = hb.create_model(**kw)
+    em.model.load_state_dict(om.model.state_dict())
+    om.train()
+    em.train()
+    cpu.pos.requires_grad_(True)
+    gpu.pos.requires_grad_(True)
+    lo, to = om.energy_force_loss(om(cpu), cpu)
+    le, te = em.energy_force_loss(em(gpu), gpu)
+    for a, b in zip(te, to):
+        torch.testing.assert_close(a.detach().cpu().double(), b.detach().double(), rtol=1e-4, atol=1e-6)
+    lo.backward()
+    le.backward()
+    assert _grad_rel(em.model, om.model) < 2e-3
+
+
+# ---- C5: PNAEq + GPS on mixed graph sizes -----------------------------------------------------------------------------------
+def test_gfm_pnaeq_gps_mixed_sizes_engine_matches_oracle():
+    name, g = "gfm_pnaeq", 12
+    cpu = add_edges_cpu(make_samples(name, g), name)
+    sizes = set((cpu.ptr[1:] - cpu.ptr[:-1]).tolist())
+    assert len(sizes) >= 3                                           # the batch really mixes {9, 21, 80, 200}
+    gpu = _gpu_batch(cpu, name, g)
+    assert torch.equal(gpu.edge_index.cpu(), cpu.edge_index)            # a1 at k = 20 on mixed sizes: bit-exact
+    kw = arch_for(name, cpu)
+    om = oracle.base.create_model(**kw).eval()                          # eval: dropout off, BatchNorm running stats
+    em = hb.create_model(**kw).eval()
+    em.load_state_dict(om.state_dict())
+    hi_c = hb.get_head_indices(om, cpu)
+    hi_g = [h.to(DEV) for h in hi_c]
+    po, pe = om(cpu), em(gpu)
+    for a, b in zip(pe, po):
+        assert rel_l2(a.detach(), b.detach()) < 2e-5
+    lo, _ = om.loss(po, cpu.y, hi_c)
+    le, _ = em.loss(pe, gpu.y, hi_g)
+    torch.testing.assert_close(le.detach().cpu(), lo.detach(), rtol=2e-5, atol=1e-6)
+    lo.backward()
+    le.backward()
+    assert _grad_rel(em, om) < 1e-3
+
+
+# ---- bench precision (TF32 tensor cores) against the ORACLE, first hand ---------------------------------------------------------
+@pytest.mark.parametrize("name,g", [("qm9_painn", 512), ("oc20_mace", 2)])
+def test_tensor_core_mode_against_oracle(name, g):
+    cpu = add_edges_cpu(make_samples(name, g), name)
+    gpu = _gpu_batch(cpu, name, g)
+    kw = arch_for(name, cpu)
+    om = oracle.base.create_model(**kw)
+    em = hb.set_precision(hb.create_model(**kw), "bf16")
+    em.load_state_dict(om.state_dict())
+    hi_c = hb.get_head_indices(om, cpu)
+    hi_g = [h.to(DEV) for h in hi_c]
+    po, pe = om(cpu), em(gpu)
+    for a, b in zip(pe, po):
+        assert rel_l2(a.detach(), b.detach()) < 2e-2
+    lo, _ = om.loss(po, cpu.y, hi_c)
+    le, _ = em.loss(pe, gpu.y, hi_g)
+    assert abs(float(le) - float(lo)) <= 2e-2 * abs(float(lo))
+    lo.backward()
+    le.backward()
+    assert _grad_rel(em, om) < 2e-2
+
+
+# ---- CUDA-graph step: refill with a different topology (train.py:203) ----------------------------------------------
+def test_graphed_step_refill_with_new_topology_equals_eager():
+    name, g = "qm9_painn", 128
+    base = make_samples(name, g, seed=1).to(DEV)
+    base._num_graphs = g
+    base = hb.get_radius_graph(7.0, 5)(base)
+    e = base.edge_index.shape[1]
+    # a second batch with the SAME shapes but different positions / edges: permute whole graphs (edge count is preserved)
+    perm = torch.randperm(g, generator=torch.Generator().manual_seed(3))
+    other = make_samples(name, g, seed=1)
+    n = 9
+    rows = (perm[:, None] * n + torch.arange(n)[None, :]).reshape(-1)
+    other.pos, other.x, other.y = other.pos[rows].contiguous(), other.x[rows].contiguous(), other.y[perm].contiguous()
+    other = other.to(DEV)
+    other._num_graphs = g
+    other = hb.get_radius_graph(7.0, 5)(other)
+    assert other.edge_index.shape[1] == e and not torch.equal(other.edge_index, base.edge_index)
+    m1 = hb.get_distributed_model(hb.create_model(**ARCH[name]))
+    m2 = copy.deepcopy(m1)
+    o1, o2 = hb.FlatAdamW(m1, lr=1e-3), hb.FlatAdamW(m2, lr=1e-3)
+    static = base.clone()
+    static._num_graphs = g
+    gs = hb.GraphedTrainStep(m1, o1, static, warmup=2)              # 2 warm-up steps on `base`
+    for _ in range(2):
+        hb.train_step(m2, o2, base)
+    l_graph = [float(gs.run())]                                     # step 3 on `base`
+    l_eager = [float(hb.train_step(m2, o2, base)[0])]
+    refill = hb.Batch(x=other.x, pos=other.pos, y=other.y, edge_index=other.edge_index, batch=other.batch)
+    gs.refill(refill)
+    l_graph.append(float(gs.run()))                                 # step 4 on `other`: new edges, same shapes
+    l_eager.append(float(hb.train_step(m2, o2, other)[0]))
+    for a, b in zip(l_graph, l_eager):
+        assert abs(a - b) <= 1e-5 * abs(b) + 1e-7, (l_graph, l_eager)
+    for p, q in zip(m1.parameters(), m2.parameters()):
+        torch.testing.assert_close(p, q, rtol=1e-4, atol=1e-6)
+    # the captured step follows the scheduler: lr lives on the device
+    o1.param_groups[0]["lr"] = 0.0
+    before = [p.detach().clone() for p in m1.parameters()]
+    gs.run()
+    torch.cuda.synchronize()
+    for p, q in zip(m1.parameters(), before):
+        torch.testing.assert_close(p, q * (1 - 0.0), rtol=0, atol=0)
+
+
+# ---- device-side guards ------------------------------------------------------------------------------------------------------
+def test_known_edge_count_guard_trips_on_mismatch_and_never_writes_out_of_bounds():
+    name, g = "qm9_painn", 64
+    b = make_samples(name, g).to(DEV)
+    gptr = b.ptr.int()
+    ei, rowptr = radius.radius_graph(b.pos, 7.0, gptr, g, False, 5)
+    e = ei.shape[1]
+    ops.check_guard(DEV)
+    ei2, _ = radius.radius_graph(b.pos, 7.0, gptr, g, False, 5, known_e=e)       # the promised count is right: no trip
+    torch.cuda.synchronize()
+    ops.check_guard(DEV)
+    assert torch.equal(ei2, ei)
+    ei3, _ = radius.radius_graph(b.pos, 7.0, gptr, g, False, 5, known_e=e - 7)   # too small: guarded writes + flag
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="edge count"):
+        ops.check_guard(DEV)
+    ops.check_guard(DEV)                                                         # the flag was cleared by the raise
+    # an out-of-range index handed to the CSR build is flagged too (hgb_core.cu:121)
+    bad = torch.tensor([0, 1, 5, 2], dtype=torch.int64, device=DEV)
+    ops.csr_build(bad, 4)
+    with pytest.raises(RuntimeError, match="outside"):
+        ops.check_guard(DEV)
+
+
+def test_pbc_transform_refuses_cpu_samples():
+    b = make_samples("lj_egnn", 2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        hb.get_radius_graph_pbc(5.0, 5)(b)
+
+
+def test_csr_build_is_stable_on_long_segments():
+    gen = torch.Generator().manual_seed(0)
+    for n, e in [(1, 100000), (7, 300001), (5000, 20000), (3, 0)]:
+        idx = torch.randint(0, n, (e,), generator=gen)
+        c = ops.csr_build(idx.to(DEV), n)
+        cnt = torch.bincount(idx, minlength=n)
+        assert torch.equal(c.rowptr.cpu().long(), torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(cnt, 0)]))
+        if e:
+            assert torch.equal(c.perm.cpu().long(), torch.argsort(idx, stable=True))
+    ops.check_guard(DEV)
+
+
+# ---- fused EGNN edge block (row a4) ---------------------------------------------------------------------------------------
+def _egnn_losses(em, gpu, mlip):
+    for p in em.parameters():
+        p.grad = None
+    d = gpu.clone()
+    d._num_graphs = gpu._num_graphs
+    if mlip:
+        d.pos.requires_grad_(True)
+        loss, tasks = em.energy_force_loss(em(d), d)
+    else:
+        inner = em.model if hasattr(em, "model") else em
+        pred = inner(d)
+        loss = sum((p_ ** 2).mean() for p_ in pred)
+        tasks = []
+    loss.backward()
+    return loss.detach(), [t.detach() for t in tasks], [None if p.grad is None else p.grad.clone() for p in em.parameters()]
+
+
+@pytest.mark.parametrize("name,g,k", [("md17_egnn", 24, 5), ("lj_egnn", 6, 5), ("md17_egnn", 5, 20), ("lj_egnn", 3, 64)])
+@pytest.mark.parametrize("mlip", [True, False])
+def test_fused_egnn_block_equals_composed_path_and_oracle(name, g, k, mlip):
+    """hgb_egnn_edge_{fwd,bwd_data,wgrad} (+ tangent mode in the double backward) against the round-1 composed path
+    (gather / Linear / segment-sum closed primitives) and against the oracle: loss terms, and every parameter gradient of the
+    MLIP loss (second derivatives through the fused block).  k = 20 / 64 exercises multi-chunk node tiles."""
+    w = dict(WORKLOADS[name], max_neighbours=k)
+    cpu = make_samples(name, g)
+    gpu = make_samples(name, g).to(DEV)
+    gpu._num_graphs = g
+    tr = hb.get_radius_graph_pbc if w.get("pbc") else hb.get_radius_graph
+    gpu = tr(w["radius"], k)(gpu)
+    cpu.edge_index = gpu.edge_index.cpu()
+    cpu.edge_shifts = gpu.edge_shifts.cpu() if gpu.edge_shifts is not None else torch.zeros(cpu.edge_index.shape[1], 3)
+    kw = dict(ARCH[name])
+    om = oracle.base.create_model(**kw).train()
+    em = hb.create_model(**kw).train()
+    em.model.load_state_dict(om.model.state_dict())
+    assert ops.egnn_edge_supported(kw["hidden_dim"])
+    launches = hb._lib.launch_count()
+    l1, t1, g1 = _egnn_losses(em, gpu, mlip)
+    ops.FUSED_EGNN = False
+    try:
+        l0, t0, g0 = _egnn_losses(em, gpu, mlip)
+    finally:
+        ops.FUSED_EGNN = True
+    torch.testing.assert_close(l1, l0, rtol=2e-5, atol=1e-7)
+    for a, b in zip(t1, t0):
+        torch.testing.assert_close(a, b, rtol=2e-5, atol=1e-7)
+    num = sum(float((a - b).double().pow(2).sum()) for a, b in zip(g1, g0) if b is not None)
+    den = sum(float(b.double().pow(2).sum()) for b in g0 if b is not None)
+    assert (num / den) ** 0.5 < 1e-4, (num / den) ** 0.5
+    if mlip:                                                     # and first hand against the oracle
+        cpu.pos.requires_grad_(True)
+        lo, to = om.energy_force_loss(om(cpu), cpu)
+        lo.backward()
+        torch.testing.assert_close(l1.cpu(), lo.detach(), rtol=1e-4, atol=1e-6)
+        for a, b in zip(t1, to):
+            torch.testing.assert_close(a.cpu().double(), b.detach().double(), rtol=1e-4, atol=1e-6)
+        num = sum(float((a.cpu().double() - q.grad.double()).pow(2).sum()) for a, q in zip(g1, om.parameters()) if q.grad is not None)
+        den = sum(float(q.grad.double().pow(2).sum()) for q in om.parameters() if q.grad is not None)
+        assert (num / den) ** 0.5 < 1e-3, (num / den) ** 0.5
+
+
+def test_edge_len_primitives_double_backward_matches_autograd():
+    g = torch.Generator().manual_seed(0)
+    n, e = 50, 400
+    pos = torch.randn(n, 3, generator=g)
+    ei = torch.randint(0, n, (2, e), generator=g)
+    ei[1] = torch.where(ei[1] == ei[0], (ei[1] + 1) % n, ei[1])
+    sh = torch.randn(e, 3, generator=g) * 0.1
+    coef, tgt = torch.randn(e, generator=g), torch.randn(n, 3, generator=g)
+
+    def run(pos_, dev):
+        p = pos_.clone().to(dev).requires_grad_(True)
+        if dev == "cpu":
+            d = (p.double()[ei[1]] - p.double()[ei[0]] + sh.double()).norm(dim=1)
+            c, t = coef.double(), tgt.double()
+        else:
+            plan = ops.EdgePlan(ei.to(dev), n)
+            d = ops.EdgeLenFn.apply(p, sh.to(dev), plan)
+            c, t = coef.to(dev), tgt.to(dev)
+        en = (c * d * d).sum()
+        f, = torch.autograd.grad(en, p, create_graph=True)
+        loss = ((f - t) ** 2).sum() + en
+        loss.backward()
+        return d.detach(), f.detach(), p.grad.detach()
+
+    d0, f0, g0 = run(pos, "cpu")
+    d1, f1, g1 = run(pos, DEV)
+    assert rel_l2(d1, d0) < 1e-6 and rel_l2(f1, f0) < 1e-5 and rel_l2(g1, g0) < 1e-5
