@@ -16,4 +16,6 @@ from .radius import (get_radius_graph, get_radius_graph_config, get_radius_graph
 from .train import (FlatAdamW, GraphedTrainStep, get_distributed_model, get_head_indices, train,  # noqa: F401
                     train_step, validate)
 
-__version__ = "0.1.0"
+from .padded import PaddedGraphStep  # noqa: F401
+
+__version__ = "0.2.0"

@@ -158,7 +158,20 @@ class EnhancedModelWrapper(nn.Module):
         else:
             raise ValueError("Force predictions are only supported for node or graph energy heads.")
         graph_energy_true = data.energy.squeeze().float()
-        tasks_loss = [lf(graph_energy_pred, graph_energy_true, True)]
+        valid = data.__dict__.get("_hgb_valid") if hasattr(data, "__dict__") else None
+        if valid is not None:
+            # capacity-padded batch (hydragnn_b200/padded.py): means run over the real graphs / atoms only; the counts live
+            # on the device, nothing is read back
+            gcsr = data._hgb_gcsr
+            gmask = (torch.arange(gcsr.n, device=valid.device) < valid[0]).to(graph_energy_pred.dtype)
+            nmask = (torch.arange(data.pos.shape[0], device=valid.device) < valid[1]).to(graph_energy_pred.dtype)
+            gcount = valid[0].to(graph_energy_pred.dtype).clamp(min=1)
+            ncount = (valid[1].to(graph_energy_pred.dtype) * 3).clamp(min=1)
+            energy_loss = lambda a, b: lf.masked_any_order(a, b, gmask, gcount)                      # noqa: E731
+            force_loss_fn = lambda a, b: lf.masked_any_order(a, b, nmask[:, None], ncount)           # noqa: E731
+        else:
+            energy_loss = force_loss_fn = lambda a, b: lf(a, b, True)                                # noqa: E731
+        tasks_loss = [energy_loss(graph_energy_pred, graph_energy_true)]
         ew, epw, fw = self.energy_weight, self.energy_peratom_weight, self.force_weight
         if ew <= 0 and epw <= 0 and fw <= 0:
             raise ValueError("All interatomic potential loss weights are zero; set at least one of energy_weight, "
@@ -168,14 +181,14 @@ class EnhancedModelWrapper(nn.Module):
             tot_loss = tot_loss + tasks_loss[0] * ew
         gcsr = data._hgb_gcsr
         natoms = (gcsr.rowptr[1:] - gcsr.rowptr[:-1]).to(graph_energy_pred.dtype)
-        peratom = lf(graph_energy_pred / natoms, graph_energy_true / natoms, True)
+        peratom = energy_loss(graph_energy_pred / natoms, graph_energy_true / natoms)
         tasks_loss.append(peratom)
         if epw > 0:
             tot_loss = tot_loss + peratom * epw
         with ops.only_data_grads():      # the force pass needs d/dpos only: fused blocks skip their parameter gradients
             forces_pred = -torch.autograd.grad(graph_energy_pred, data.pos, grad_outputs=torch.ones_like(graph_energy_pred),
                                                retain_graph=graph_energy_pred.requires_grad, create_graph=create_graph)[0].float()
-        force_loss = lf(forces_pred, data.forces.float(), True)
+        force_loss = force_loss_fn(forces_pred, data.forces.float())
         tasks_loss.append(force_loss)
         if fw > 0:
             tot_loss = tot_loss + force_loss * fw

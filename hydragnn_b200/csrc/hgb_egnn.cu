@@ -42,7 +42,7 @@ struct Smem {
   unsigned long long bits1[TE], bits2[TE];
   int eid[TE], nloc[TE];
   int rp[NBMAX + 1];
-  unsigned char maskb[TE * 8];
+  alignas(8) unsigned char maskb[TE * 8];
 };
 
 __device__ __forceinline__ int local_node(const int* rp, int nb, int p) {   // largest l with rp[l] <= p
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(NT) egnn_edge_bwd_data_kernel(
   // gh = gz2 W1: K = out, operand y[out][in] = W1 as stored
   for (int i = t; i < H * H; i += NT) sm.y[i] = w1[i];
   for (int i = t; i < H; i += NT) sm.vec[i] = wd[i];
-  float colsum_w = 0.f, colsum_1 = 0.f;                  // thread t < H (and t - H < H for H == 32: unused) owns column t % H
+  double colsum_w = 0.0, colsum_1 = 0.0;                 // thread t < H owns column t; fp64: these sums cancel heavily (terms O(1), result O(1e-2))
   __syncthreads();
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int n0 = tile * nb, n1 = min(n, n0 + nb), cntn = n1 - n0;
@@ -297,8 +297,8 @@ __global__ void __launch_bounds__(NT) egnn_edge_bwd_data_kernel(
       if (partial && t < H) {
         for (int p = 0; p < cnt; ++p) {
           const float v = sm.xt[p * MS + t];
-          colsum_1 += v;
-          colsum_w = fmaf(sm.sval[p], v, colsum_w);
+          colsum_1 += (double)v;
+          colsum_w += (double)sm.sval[p] * (double)v;
         }
       }
       __syncthreads();
@@ -307,8 +307,8 @@ __global__ void __launch_bounds__(NT) egnn_edge_bwd_data_kernel(
     __syncthreads();
   }
   if (partial && t < H) {
-    partial[(int64_t)blockIdx.x * 2 * H + t] = colsum_w;
-    partial[(int64_t)blockIdx.x * 2 * H + H + t] = colsum_1;
+    partial[(int64_t)blockIdx.x * 2 * H + t] = (float)colsum_w;
+    partial[(int64_t)blockIdx.x * 2 * H + H + t] = (float)colsum_1;
   }
 }
 
@@ -317,9 +317,9 @@ __global__ void egnn_reduce_partials_kernel(const float* __restrict__ partial, i
                                             int split, float* __restrict__ out1) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= width) return;
-  float a = 0.f;
-  for (int b = 0; b < nblocks; ++b) a += partial[(int64_t)b * width + c];
-  if (c < split) out0[c] = a; else if (out1) out1[c - split] = a;
+  double a = 0.0;
+  for (int b = 0; b < nblocks; ++b) a += (double)partial[(int64_t)b * width + c];
+  if (c < split) out0[c] = (float)a; else if (out1) out1[c - split] = (float)a;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(NT) egnn_edge_wgrad_kernel(
     float* __restrict__ partial /* [grid][H*H + H] */) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemW<H>& sm = *reinterpret_cast<SmemW<H>*>(smem_raw);
-  constexpr int MO = 8, NI = (H * H) / (NT * MO);        // register tile: 8 outs x NI ins  (H = 64: 8 x 4, H = 32: 8 x 1)
+  constexpr int MO = H == 64 ? 8 : 4, NI = (H * H) / (NT * MO);   // register tile: MO outs x NI ins  (H = 64: 8 x 4, H = 32: 4 x 2)
   constexpr int IG = H / NI;                             // threads along "in"
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int m0 = (t / IG) * MO, i0 = (t % IG) * NI;
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(NT) egnn_edge_wgrad_kernel(
   for (int i = 0; i < MO; ++i)
 #pragma unroll
     for (int j = 0; j < NI; ++j) acc[i][j] = 0.f;
-  float bsum = 0.f;
+  double bsum = 0.0;
   __syncthreads();
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int n0 = tile * nb, n1 = min(n, n0 + nb), cntn = n1 - n0;
@@ -369,37 +369,70 @@ __global__ void __launch_bounds__(NT) egnn_edge_wgrad_kernel(
     const int e_begin = sm.rp[0], e_end = sm.rp[cntn];
     for (int e0 = e_begin; e0 < e_end; e0 += TE) {
       const int cnt = min(TE, e_end - e0);
-      // a warp per edge slot, lanes over channels
-      for (int r = warp; r < TE; r += NT / 32) {
-        if (r < cnt) {
-          const int p = e0 + r;
-          const int il = local_node(sm.rp, cntn, p);
-          const int eid = perm[p], j = nbr[p];
-          const float sv = s[eid];
-          const unsigned long long b1 = masks[2 * (int64_t)p], b2 = masks[2 * (int64_t)p + 1];
-          for (int c = lane; c < H; c += 32) {
-            sm.x[r * H + c] = ((b2 >> c) & 1ull) ? sm.nodeg[il * H + c] : 0.f;
-            float z = sm.nodep[il * H + c] + __ldg(pq + (int64_t)j * 2 * H + H + c);
-            z = fmaf(sv, sm.vec[c], z) + sm.vec[H + c];
-            sm.y[r * H + c] = TANGENT ? (((b1 >> c) & 1ull) ? z : 0.f) : (z > 0.f ? z : 0.f);
+      // producer: every lane first fetches the metadata of ONE edge slot of its warp's 32 (one parallel round of dependent
+      // loads), then the warp walks its slots with lanes over channels (float4): the row loads of successive slots are
+      // independent and pipeline.
+      {
+        constexpr int LPE = H / 4;                       // lanes per edge row
+        constexpr int EPI = 32 / LPE;                    // edge slots per warp iteration (H = 64: 2, H = 32: 4)
+        const int slot = warp * 32 + lane;
+        int m_il = 0, m_j = 0;
+        float m_s = 0.f;
+        unsigned long long m_b1 = 0ull, m_b2 = 0ull;
+        if (slot < cnt) {
+          const int p = e0 + slot;
+          m_il = local_node(sm.rp, cntn, p);
+          m_j = nbr[p];
+          m_s = s[perm[p]];
+          m_b1 = masks[2 * (int64_t)p];
+          m_b2 = masks[2 * (int64_t)p + 1];
+        }
+        const int sub = lane / LPE, c4 = (lane % LPE) * 4;
+#pragma unroll 4
+        for (int it = 0; it < 32 / EPI; ++it) {
+          const int src = it * EPI + sub;                // lane (within the warp) that holds this slot's metadata
+          const int r = warp * 32 + src;
+          const int il = __shfl_sync(0xffffffffu, m_il, src), j = __shfl_sync(0xffffffffu, m_j, src);
+          const float sv = __shfl_sync(0xffffffffu, m_s, src);
+          const unsigned long long b1 = __shfl_sync(0xffffffffu, m_b1, src), b2 = __shfl_sync(0xffffffffu, m_b2, src);
+          float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), yv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < cnt) {
+            const float4 gv = *reinterpret_cast<const float4*>(sm.nodeg + il * H + c4);
+            const float4 pv = *reinterpret_cast<const float4*>(sm.nodep + il * H + c4);
+            const float4 qv = __ldg(reinterpret_cast<const float4*>(pq + (int64_t)j * 2 * H + H + c4));
+            const float4 wv = *reinterpret_cast<const float4*>(sm.vec + c4);
+            const float4 bv = *reinterpret_cast<const float4*>(sm.vec + H + c4);
+            const float g4[4] = {gv.x, gv.y, gv.z, gv.w};
+            const float z4[4] = {fmaf(sv, wv.x, pv.x + qv.x) + bv.x, fmaf(sv, wv.y, pv.y + qv.y) + bv.y,
+                                 fmaf(sv, wv.z, pv.z + qv.z) + bv.z, fmaf(sv, wv.w, pv.w + qv.w) + bv.w};
+            float xo[4], yo[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              xo[c] = ((b2 >> (c4 + c)) & 1ull) ? g4[c] : 0.f;
+              yo[c] = TANGENT ? (((b1 >> (c4 + c)) & 1ull) ? z4[c] : 0.f) : (z4[c] > 0.f ? z4[c] : 0.f);
+            }
+            xv = make_float4(xo[0], xo[1], xo[2], xo[3]);
+            yv = make_float4(yo[0], yo[1], yo[2], yo[3]);
           }
-        } else {
-          for (int c = lane; c < H; c += 32) { sm.x[r * H + c] = 0.f; sm.y[r * H + c] = 0.f; }
+          *reinterpret_cast<float4*>(sm.x + r * H + c4) = xv;
+          *reinterpret_cast<float4*>(sm.y + r * H + c4) = yv;
         }
       }
       __syncthreads();
 #pragma unroll 4
       for (int k = 0; k < TE; ++k) {
-        const float4 a0 = *reinterpret_cast<const float4*>(sm.x + k * H + m0);
-        const float4 a1 = *reinterpret_cast<const float4*>(sm.x + k * H + m0 + 4);
-        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        float b[NI];
+        float a[MO], b[NI];
+#pragma unroll
+        for (int q = 0; q < MO / 4; ++q) {
+          const float4 av = *reinterpret_cast<const float4*>(sm.x + k * H + m0 + 4 * q);
+          a[4 * q] = av.x; a[4 * q + 1] = av.y; a[4 * q + 2] = av.z; a[4 * q + 3] = av.w;
+        }
         if constexpr (NI == 4) {
           const float4 bv = *reinterpret_cast<const float4*>(sm.y + k * H + i0);
           b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
         } else {
-#pragma unroll
-          for (int j = 0; j < NI; ++j) b[j] = sm.y[k * H + i0 + j];
+          const float2 bv = *reinterpret_cast<const float2*>(sm.y + k * H + i0);
+          b[0] = bv.x; b[1] = bv.y;
         }
 #pragma unroll
         for (int i = 0; i < MO; ++i)
@@ -407,7 +440,7 @@ __global__ void __launch_bounds__(NT) egnn_edge_wgrad_kernel(
           for (int j = 0; j < NI; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
       }
       if (t < H)
-        for (int k = 0; k < cnt; ++k) bsum += sm.x[k * H + t];
+        for (int k = 0; k < cnt; ++k) bsum += (double)sm.x[k * H + t];
       __syncthreads();
     }
   }
@@ -416,7 +449,7 @@ __global__ void __launch_bounds__(NT) egnn_edge_wgrad_kernel(
   for (int i = 0; i < MO; ++i)
 #pragma unroll
     for (int j = 0; j < NI; ++j) out[(m0 + i) * H + i0 + j] = acc[i][j];
-  if (t < H) out[H * H + t] = bsum;
+  if (t < H) out[H * H + t] = (float)bsum;
 }
 
 // out[c] = sum_e w[e] x[e][c]   (two-stage, deterministic)
@@ -424,14 +457,14 @@ __global__ void weighted_colsum_stage1(const float* __restrict__ x, const float*
                                        float* __restrict__ partial) {
   // blockDim.x = 256: 256 / h row-lanes x h columns
   const int c = threadIdx.x % h, rl = threadIdx.x / h, nrl = blockDim.x / h;
-  float a = 0.f;
-  for (int64_t r = (int64_t)blockIdx.x * nrl + rl; r < e; r += (int64_t)gridDim.x * nrl) a = fmaf(w[r], x[r * h + c], a);
-  __shared__ float sm[256];
+  double a = 0.0;
+  for (int64_t r = (int64_t)blockIdx.x * nrl + rl; r < e; r += (int64_t)gridDim.x * nrl) a += (double)w[r] * (double)x[r * h + c];
+  __shared__ double sm[256];
   sm[threadIdx.x] = a;
   __syncthreads();
   if (rl == 0) {
     for (int q = 1; q < nrl; ++q) a += sm[q * h + c];
-    partial[(int64_t)blockIdx.x * h + c] = a;
+    partial[(int64_t)blockIdx.x * h + c] = (float)a;
   }
 }
 

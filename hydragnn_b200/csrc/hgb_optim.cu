@@ -3,9 +3,16 @@
 
 // single block: deterministic tree reduction; count is small (number of targets in the batch)
 __global__ void loss_fwd_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t count, int mode,
-                                    float gscale, float* __restrict__ loss, float* __restrict__ gpred) {
+                                    float gscale, float* __restrict__ loss, float* __restrict__ gpred,
+                                    const int32_t* __restrict__ valid_rows, int row_width) {
   __shared__ float sm[1024];
   float acc = 0.f;
+  const int64_t total = count;
+  if (valid_rows) {          // capacity-padded batch: only the first *valid_rows rows are real (hydragnn_b200/padded.py)
+    const int64_t v = (int64_t)valid_rows[0] * row_width;
+    count = v < count ? (v > 0 ? v : 1) : count;
+    for (int64_t i = count + threadIdx.x; gpred && i < total; i += blockDim.x) gpred[i] = 0.f;
+  }
   const float inv = 1.f / (float)count;
   for (int64_t i = threadIdx.x; i < count; i += blockDim.x) {
     const float d = pred[i] - target[i];
@@ -27,9 +34,10 @@ __global__ void loss_fwd_bwd_kernel(const float* __restrict__ pred, const float*
 }
 
 extern "C" int hgb_loss_fwd_bwd(const float* pred, const float* target, int64_t count, int32_t mode, float gscale, float* loss,
-                                float* gpred, hgb_stream_t stream) {
+                                float* gpred, const int32_t* valid_rows, int32_t row_width, hgb_stream_t stream) {
   HGB_REQUIRE(count > 0 && pred && target && loss && (mode == 0 || mode == 1), "loss_fwd_bwd: bad arguments");
-  loss_fwd_bwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pred, target, count, mode, gscale, loss, gpred);
+  HGB_REQUIRE(!valid_rows || row_width > 0, "loss_fwd_bwd: row_width must be positive with valid_rows");
+  loss_fwd_bwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pred, target, count, mode, gscale, loss, gpred, valid_rows, row_width);
   HGB_LAUNCH_CHECK("loss_fwd_bwd");
   return HGB_OK;
 }

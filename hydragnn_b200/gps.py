@@ -7,6 +7,7 @@ in/out projections and the MLP are the engine's Linear kernels; BatchNorm stays 
 the north star); dropout is ATen RNG.
 """
 import math
+import os
 
 import torch
 from torch import nn
@@ -29,6 +30,9 @@ class PyGBatchNorm(nn.Module):
         return self.module(x)
 
 
+TC_ATTENTION = os.environ.get("HGB_TC_ATTENTION", "1") == "1"    # 0: the SIMT kernels of csrc/hgb_attn.cu for every head_dim
+
+
 class MhaFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, heads):
@@ -37,7 +41,13 @@ class MhaFn(torch.autograd.Function):
         f = f3 // 3
         out = torch.empty(n, f, dtype=qkv.dtype, device=qkv.device)
         lse = torch.empty(n, heads, dtype=qkv.dtype, device=qkv.device)
-        _lib.call("hgb_mha_fwd", _p(qkv), n, f, heads, _p(out), _p(lse), _stream())
+        # head_dim 8: tensor-core kernels (3xTF32 = fp32-level accuracy in fp32 mode, plain TF32 under precision="bf16")
+        ctx.tc = bool(TC_ATTENTION and _lib.query("hgb_mha_tc_supported", f, heads))
+        ctx.exact = 0 if ops._TC["enabled"] else 1
+        if ctx.tc:
+            _lib.call("hgb_mha_tc_fwd", _p(qkv), n, f, heads, ctx.exact, _p(out), _p(lse), _stream())
+        else:
+            _lib.call("hgb_mha_fwd", _p(qkv), n, f, heads, _p(out), _p(lse), _stream())
         ctx.save_for_backward(qkv, out, lse)
         ctx.heads = heads
         return out
@@ -48,7 +58,12 @@ class MhaFn(torch.autograd.Function):
         qkv, out, lse = ctx.saved_tensors
         n, f = out.shape
         gqkv = torch.empty_like(qkv)
-        _lib.call("hgb_mha_bwd", _p(qkv), _p(out), _p(lse), _p(_chk(gout)), n, f, ctx.heads, _p(gqkv), _stream())
+        if ctx.tc:
+            ws = torch.empty(n * ctx.heads, dtype=qkv.dtype, device=qkv.device)
+            _lib.call("hgb_mha_tc_bwd", _p(qkv), _p(out), _p(lse), _p(_chk(gout.contiguous())), n, f, ctx.heads, ctx.exact, _p(ws), _p(gqkv),
+                      _stream())
+        else:
+            _lib.call("hgb_mha_bwd", _p(qkv), _p(out), _p(lse), _p(_chk(gout)), n, f, ctx.heads, _p(gqkv), _stream())
         return gqkv, None
 
 

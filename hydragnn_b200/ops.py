@@ -175,11 +175,30 @@ def raw_gemm(a, b, ta, tb, out=None, beta_one=False):
     assert k == k2, "gemm inner dimensions differ"
     if out is None:
         out = torch.empty(m, n, dtype=a.dtype, device=a.device)
+    if gemm3_ok(a, b, out, m, n, k, ta, tb):
+        # fp32-accurate tensor-core path (4xTF32 split products, fp32 register accumulation): csrc/hgb_gemm3.cu
+        nbytes = _lib.query("hgb_gemm3_workspace_bytes", m, n, k, int(ta))
+        ws = _ws(nbytes, a.device) if nbytes else None
+        _lib.call("hgb_gemm3", _p(a), _p(b), _p(out), m, n, k, int(ta), int(tb), a.stride(0), b.stride(0), out.stride(0), int(beta_one),
+                  None, 0, 0.0, None, _p(ws), _stream())
+        return out
     nbytes = _lib.query("hgb_gemm_workspace_bytes", m, n, k, int(ta))
     ws = _ws(nbytes, a.device) if nbytes else None
     _lib.call("hgb_gemm", _p(a), _p(b), _p(out), m, n, k, int(ta), int(tb), a.stride(0), b.stride(0), out.stride(0),
               int(beta_one), _p(ws), nbytes, _stream())
     return out
+
+
+GEMM3 = os.environ.get("HGB_GEMM3", "0") == "1"      # 1: exact-fp32 GEMMs on the 4xTF32 mma.sync kernels (csrc/hgb_gemm3.cu); measured
+                                                     # slower than the SIMT tiles on B200 (legacy mma.sync issues 1 per ~10 clk per SMSP): off
+
+
+def gemm3_ok(a, b, out, m, n, k, ta, tb):
+    if not GEMM3 or a.dtype != torch.float32:
+        return False
+    if a.data_ptr() % 16 or out.data_ptr() % 16 or (ta and b.data_ptr() % 16):
+        return False
+    return bool(_lib.query("hgb_gemm3_supported", m, n, k, int(ta), int(tb), a.stride(0), b.stride(0), out.stride(0)))
 
 
 def raw_colsum(x2d):
@@ -676,6 +695,10 @@ def raw_linear(x2, w, b, code=0, param=0.0, want_z=False):
     n = w.shape[0]
     y = torch.empty(m, n, dtype=x2.dtype, device=x2.device)
     z = torch.empty_like(y) if want_z else None
+    if gemm3_ok(x2, w, y, m, n, k, False, True):
+        _lib.call("hgb_gemm3", _p(x2), _p(w), _p(y), m, n, k, 0, 1, x2.stride(0), w.stride(0), n, 0, _p(b), code, float(param), _p(z), None,
+                  _stream())
+        return y, z
     _lib.call("hgb_linear_fwd", _p(x2), _p(w), _p(b), m, n, k, x2.stride(0), w.stride(0), code, float(param), _p(y), _p(z), _stream())
     return y, z
 
@@ -809,11 +832,12 @@ class LossFn(torch.autograd.Function):
     """mean squared / absolute error with its gradient produced in the same pass."""
 
     @staticmethod
-    def forward(ctx, pred, target, mode):
+    def forward(ctx, pred, target, mode, valid_rows=None, row_width=1):
         pred, target = _chk(pred), _chk(target)
         loss = torch.empty(1, dtype=pred.dtype, device=pred.device)
         gpred = torch.empty_like(pred)
-        _lib.call("hgb_loss_fwd_bwd", _p(pred), _p(target), pred.numel(), mode, 1.0, _p(loss), _p(gpred), _stream())
+        _lib.call("hgb_loss_fwd_bwd", _p(pred), _p(target), pred.numel(), mode, 1.0, _p(loss), _p(gpred), _p(valid_rows), int(row_width),
+                  _stream())
         ctx.save_for_backward(gpred)
         return loss.reshape(())
 
@@ -821,7 +845,7 @@ class LossFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, g):
         (gpred,) = ctx.saved_tensors
-        return gpred * g, None, None
+        return gpred * g, None, None, None, None
 
 
 class PnaAggregateFn(torch.autograd.Function):

@@ -24,17 +24,21 @@ def _graph_ptr(data, n, device):
     return ops.graph_ptr_from_batch(batch.to(device), g).rowptr, g
 
 
-def radius_graph(pos, r, graph_ptr, num_graphs, loop=False, max_num_neighbors=32, known_e=None):
+def radius_graph(pos, r, graph_ptr, num_graphs, loop=False, max_num_neighbors=32, known_e=None, capacity=None):
     """edge_index [2,E] int64 (row 0 = source/neighbour, row 1 = target/query), targets ascending.
     ``known_e``: edge count from an earlier run on the same positions -- skips the host read of the count so
-    the whole build can be captured in a CUDA graph."""
+    the whole build can be captured in a CUDA graph (the count is verified on the device).
+    ``capacity``: allocate ``edge_index [2, capacity]`` and fill its head; the true count stays on the device as
+    ``rowptr[-1]`` (``hydragnn_b200.padded`` fills the tail with dummy edges) -- no host read either."""
     pos = ops._chk(pos)
     n = pos.shape[0]
     k = int(min(max_num_neighbors, _NO_CAP - 1))
     deg = torch.empty(n, dtype=torch.int32, device=pos.device)
     _lib.call("hgb_radius_graph_count", _p(pos), _p(graph_ptr), n, num_graphs, float(r), k, int(loop), _p(deg), _stream())
     rowptr = ops.exclusive_scan(deg)
-    if known_e is None:
+    if capacity is not None:
+        e = int(capacity)
+    elif known_e is None:
         e = int(rowptr[-1])                                    # the one host sync: the count sizes the output
     else:
         e = int(known_e)                                       # promised by the caller; verified on the device (ops.check_guard)

@@ -80,6 +80,17 @@ class _Loss:
             val = ops.LossFn.apply(pred.reshape(-1), target.reshape(-1), self.mode)
         return torch.sqrt(val) if self.sqrt else val
 
+    def masked(self, pred, target, valid_rows, row_width):
+        """Mean over the first ``valid_rows[0]`` rows only (capacity-padded batches, hydragnn_b200/padded.py)."""
+        val = ops.LossFn.apply(pred.reshape(-1), target.to(pred.dtype).reshape(-1), self.mode, valid_rows, row_width)
+        return torch.sqrt(val) if self.sqrt else val
+
+    def masked_any_order(self, pred, target, mask, count):
+        """Any-order differentiable masked mean: ``mask`` is 0/1 per element, ``count`` the (device) number of real elements."""
+        d = (pred - target.to(pred.dtype)) * mask
+        val = ((d * d).sum() if self.mode == 0 else d.abs().sum()) / count
+        return torch.sqrt(val) if self.sqrt else val
+
 
 def run_mlp(seq, x, higher_order=False):
     """Execute an ``nn.Sequential`` of Linear / activation modules on the engine: every Linear (with the

@@ -12,6 +12,8 @@ hydragnn/utils/distributed/distributed.py:396-481, redesigned for one NVSwitch b
 * ``GraphedTrainStep`` captures forward + loss + backward + flatten + optimizer of a fixed-shape batch in a CUDA
   graph (all kernels are launched through ctypes on the capturing stream; nothing synchronises).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -289,10 +291,57 @@ class GraphedTrainStep:
         return self.loss
 
 
-def train(loader, model, opt, verbosity=0, profiler=None, use_deepspeed=False, compute_grad_energy=False, precision="fp32"):
-    """Epoch loop with the reference's signature and return values (train_error, tasks_error)."""
+FAST_TRAIN = os.environ.get("HGB_FAST_TRAIN", "1") == "1"
+
+
+def _train_fast(loader, model, opt, compute_grad_energy, neighbour_build):
+    """The epoch through ONE capacity-padded captured step (hydragnn_b200/padded.py): no per-step host synchronisation; the
+    epoch sums stay on the device until the end."""
+    from .padded import PaddedGraphStep
+    dev = next(model.parameters()).device
+    nbatch = len(loader)
+    if dist.is_initialized():
+        t = torch.tensor([nbatch], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        nbatch = int(t)
+    fast = getattr(opt, "_hgb_fast", None)
+    total = tasks_tot = None
+    nsamp = 0
+    for ibatch, data in enumerate(loader):
+        if ibatch >= nbatch:
+            break
+        if fast is None or fast.model is not model or fast.mlip != bool(compute_grad_energy) or fast.nb != neighbour_build:
+            fast = opt._hgb_fast = PaddedGraphStep(model, opt, data, compute_grad_energy, neighbour_build)
+        g = fast.load(data)
+        loss, tasks = fast.run()
+        total = loss * g if total is None else total + loss * g
+        tasks_tot = tasks * g if tasks_tot is None else tasks_tot + tasks * g
+        nsamp += g
+    fast.check()                                              # one host read per epoch: device guards of the captured steps
+    return total / nsamp, tasks_tot / nsamp
+
+
+def train(loader, model, opt, verbosity=0, profiler=None, use_deepspeed=False, compute_grad_energy=False, precision="fp32",
+          fast=None, neighbour_build=None):
+    """Epoch loop with the reference's signature and return values (train_error, tasks_error).
+
+    ``fast`` (default: on for models ``padded.supported`` accepts): run every batch through one capacity-padded CUDA-graph step
+    instead of eager launches -- same arithmetic, no per-step host sync.  ``neighbour_build`` = (radius, max_neighbours) builds
+    the radius graph on the device inside that step; by default the batches carry ``edge_index`` as the reference's do."""
     resolve_precision(precision)
     dev = next(model.parameters()).device
+    from . import padded
+    if fast is None:
+        fast = FAST_TRAIN and dev.type == "cuda" and padded.supported(model) and isinstance(opt, FlatAdamW)
+    if fast:
+        model.train()
+        train_error, tasks_error = _train_fast(loader, model, opt, compute_grad_energy, neighbour_build)
+        ws, _ = world()
+        if ws > 1:
+            dist.all_reduce(train_error)
+            dist.all_reduce(tasks_error)
+            train_error, tasks_error = train_error / ws, tasks_error / ws
+        return train_error, tasks_error
     total, tasks_tot, nsamp = None, None, 0
     model.train()
     nbatch = len(loader)

@@ -100,6 +100,12 @@ int hgb_radius_pbc_emit(const int32_t* graph_ptr, const double* cell, int32_t n,
                         hgb_stream_t stream);
 /* out[i] = min(in[i], cap) */
 int hgb_clamp_i32(const int32_t* in, int32_t cap, int64_t n, int32_t* out, hgb_stream_t stream);
+/* Capacity padding of a captured neighbour build (hydragnn_b200/padded.py): edge_index [2, e_cap] holds *e_real real
+ * edges (written by hgb_radius_graph_fill with e = e_cap); slots [*e_real, e_cap) are filled with dummy edges between
+ * consecutive FILLER nodes n_real .. n_cap-1 (atoms of the masked filler graphs), so every kernel of the step runs on
+ * static shapes.  Sets guard bit 1 in *flag when *e_real > e_cap.                                                       */
+int hgb_pad_edges(const int32_t* e_real, const int32_t* n_real, int32_t n_cap, int64_t e_cap, int64_t* edge_index,
+                  int32_t* flag, hgb_stream_t stream);
 /* Device-side guard for CUDA-graph-captured steps whose output sizes were promised by the caller
  * (edge counts measured on an earlier run): *flag |= bit when *value != expected.  The host reads
  * the flag asynchronously (hydragnn_b200.ops.check_guard); replaces the host read of the count at
@@ -306,6 +312,29 @@ int hgb_mha_fwd(const float* qkv, int32_t n, int32_t f, int32_t heads, float* ou
 int hgb_mha_bwd(const float* qkv, const float* out, const float* lse, const float* gout, int32_t n, int32_t f,
                 int32_t heads, float* gqkv, hgb_stream_t stream);
 
+/* The same attention on the tensor cores for head_dim == 8 (the GPS configuration of qm9.json / C5: 64 channels, 8 heads):
+ * mma.sync m16n8k8 TF32 with fp32 accumulation; one score block of 16 queries x 8 keys per instruction, the accumulator
+ * layout of S re-used as the A operand of P V through a key permutation (no shuffles).  exact != 0: every product as three
+ * TF32 products of a hi/lo split (fp32-level accuracy, the fp32 configs); exact == 0: plain TF32 (precision="bf16").
+ * delta_ws: n * heads floats of scratch.  Same lse / layout contract as hgb_mha_fwd / hgb_mha_bwd.                       */
+int32_t hgb_mha_tc_supported(int32_t f, int32_t heads);
+int hgb_mha_tc_fwd(const float* qkv, int32_t n, int32_t f, int32_t heads, int32_t exact, float* out, float* lse,
+                   hgb_stream_t stream);
+int hgb_mha_tc_bwd(const float* qkv, const float* out, const float* lse, const float* gout, int32_t n, int32_t f,
+                   int32_t heads, int32_t exact, float* delta_ws, float* gqkv, hgb_stream_t stream);
+
+/* fp32-ACCURATE tensor-core GEMMs for the exact-fp32 mode (nn.Linear forward / dgrad / wgrad of every stack under
+ * precision "fp32", e.g. EGCLStack.py:245-263, PNAEqStack.py:326-476, Base.py heads): mma.sync m16n8k8 TF32 with every
+ * product expanded into the four products of a hi/lo split and the long sums kept in fp32 registers (csrc/hgb_gemm3.cu).
+ * Same operand convention as hgb_gemm; bias / act / z (pre-activation) only for trans_a == 0.
+ * hgb_gemm3_supported tells which shapes take this path (large m or a long reduction; everything else stays on hgb_gemm). */
+int32_t hgb_gemm3_supported(int32_t m, int32_t n, int32_t k, int32_t trans_a, int32_t trans_b, int64_t lda,
+                            int64_t ldb, int64_t ldc);
+int64_t hgb_gemm3_workspace_bytes(int32_t m, int32_t n, int32_t k, int32_t trans_a);
+int hgb_gemm3(const float* a, const float* b, float* c, int32_t m, int32_t n, int32_t k, int32_t trans_a,
+              int32_t trans_b, int64_t lda, int64_t ldb, int64_t ldc, int32_t beta_one, const float* bias,
+              int32_t act, float act_param, float* z, void* workspace, hgb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fused EGNN edge block (hydragnn/models/EGCLStack.py:245-258 edge_model, :256-263 the scatter of
  * node_model, :278-291 forward; unsorted_segment_sum :294-300).  The first Linear of edge_mlp is
@@ -362,9 +391,12 @@ int hgb_edge_vec_scatter(const float* gvec, const int32_t* col_rowptr, const int
  * ------------------------------------------------------------------------------------------ */
 
 /* loss[0] = mean((pred - target)^2) (mode 0) or mean(|pred - target|) (mode 1);
- * gpred = d loss / d pred * gscale.  Single-block deterministic reduction.                         */
+ * gpred = d loss / d pred * gscale.  Single-block deterministic reduction.
+ * valid_rows (optional, device int32): capacity-padded batches -- only the first *valid_rows rows of
+ * row_width entries are real: the mean runs over them and gpred is zero beyond.                      */
 int hgb_loss_fwd_bwd(const float* pred, const float* target, int64_t count, int32_t mode, float gscale,
-                     float* loss, float* gpred, hgb_stream_t stream);
+                     float* loss, float* gpred, const int32_t* valid_rows, int32_t row_width,
+                     hgb_stream_t stream);
 /* Fused AdamW over one flat parameter buffer: p, g, m, v [count]; `grad_scale` multiplies g first
  * (1/world_size after the flat all-reduce); step is 1-based and read from device (`step_dev`, fp32,
  * incremented by the kernel) so the launch is CUDA-graph capturable.  hyper_dev (optional, device,

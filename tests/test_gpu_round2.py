@@ -166,7 +166,7 @@ def test_graphed_step_refill_with_new_topology_equals_eager():
     name, g = "qm9_painn", 128
     base = make_samples(name, g, seed=1).to(DEV)
     base._num_graphs = g
-    base = hb.get_radius_graph(7.0, 5)(base)
+    base = hb.get_radius_graph(3.0, 5)(base)                        # r = 3: the edge pattern depends on the geometry
     e = base.edge_index.shape[1]
     # a second batch with the SAME shapes but different positions / edges: permute whole graphs (edge count is preserved)
     perm = torch.randperm(g, generator=torch.Generator().manual_seed(3))
@@ -176,7 +176,7 @@ def test_graphed_step_refill_with_new_topology_equals_eager():
     other.pos, other.x, other.y = other.pos[rows].contiguous(), other.x[rows].contiguous(), other.y[perm].contiguous()
     other = other.to(DEV)
     other._num_graphs = g
-    other = hb.get_radius_graph(7.0, 5)(other)
+    other = hb.get_radius_graph(3.0, 5)(other)
     assert other.edge_index.shape[1] == e and not torch.equal(other.edge_index, base.edge_index)
     m1 = hb.get_distributed_model(hb.create_model(**ARCH[name]))
     m2 = copy.deepcopy(m1)
@@ -336,3 +336,135 @@ def test_edge_len_primitives_double_backward_matches_autograd():
     d0, f0, g0 = run(pos, "cpu")
     d1, f1, g1 = run(pos, DEV)
     assert rel_l2(d1, d0) < 1e-6 and rel_l2(f1, f0) < 1e-5 and rel_l2(g1, g0) < 1e-5
+
+
+# ---- tensor-core attention, head_dim 8 (row a9) ---------------------------------------------------------------------------
+@pytest.mark.parametrize("n,f,heads", [(1, 8, 1), (65, 16, 2), (300, 64, 8), (1000, 64, 8), (4099, 64, 8)])
+@pytest.mark.parametrize("mode", ["exact", "tf32"])
+def test_tensor_core_attention_matches_fp64_reference(n, f, heads, mode):
+    """hgb_mha_tc_{fwd,bwd}: 3xTF32 ("exact") within the fp32 parity tolerance, plain TF32 within the bf16-config tolerance;
+    the SIMT kernels are the second witness."""
+    from hydragnn_b200 import gps
+    g = torch.Generator().manual_seed(n + f)
+    qkv = torch.randn(n, 3 * f, generator=g)
+    go = torch.randn(n, f, generator=g)
+    qr = qkv.double().requires_grad_(True)
+    q, k, v = [t.reshape(n, heads, f // heads).transpose(0, 1) for t in qr.split(f, dim=1)]
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(0, 1).reshape(n, f)
+    gr, = torch.autograd.grad(ref, qr, go.double())
+    assert hb._lib.query("hgb_mha_tc_supported", f, heads)
+    qe = qkv.to(DEV).requires_grad_(True)
+    with ops.tensor_cores(mode == "tf32"):
+        out = gps.MhaFn.apply(qe, heads)
+    ge, = torch.autograd.grad(out, qe, go.to(DEV))
+    tol_o, tol_g = (2e-6, 1e-5) if mode == "exact" else (2e-3, 5e-3)
+    assert rel_l2(out.detach(), ref.detach()) < tol_o
+    assert rel_l2(ge, gr) < tol_g
+    gps.TC_ATTENTION = False
+    try:
+        qs = qkv.to(DEV).requires_grad_(True)
+        outs = gps.MhaFn.apply(qs, heads)
+        gs, = torch.autograd.grad(outs, qs, go.to(DEV))
+    finally:
+        gps.TC_ATTENTION = True
+    assert rel_l2(out.detach(), outs.detach()) < 10 * tol_o and rel_l2(ge, gs) < 10 * tol_g
+
+
+# ---- the API path IS the fast path: capacity-padded captured step behind hb.train (rows a11 / f3) -------------------------------
+def _loader(name, sizes, with_edges, seed0=10):
+    w = WORKLOADS[name]
+    out = []
+    for i, g in enumerate(sizes):
+        b = make_samples(name, g, seed=seed0 + i)
+        if with_edges:
+            d = b.clone().to(DEV)
+            d._num_graphs = g
+            d = (hb.get_radius_graph_pbc if w.get("pbc") else hb.get_radius_graph)(w["radius"], w["max_neighbours"])(d)
+            b.edge_index = d.edge_index.cpu()
+            if d.edge_shifts is not None:
+                b.edge_shifts = d.edge_shifts.cpu()
+        for k in ("cell", "pbc", "ptr"):
+            b.__dict__.pop(k, None)
+        out.append(b)
+    return out
+
+
+@pytest.mark.parametrize("name,mlip,build", [("qm9_painn", False, False), ("qm9_painn", False, True), ("md17_egnn", True, False),
+                                             ("md17_egnn", True, True), ("lj_egnn", True, False)])
+def test_train_fast_path_equals_eager_on_variable_batches(name, mlip, build):
+    """hb.train(loader, ...) through ONE capacity-padded CUDA-graph step (filler graphs + dummy edges, masked losses) gives the
+    losses and the parameters of the eager per-batch path, for batches whose graph / node / edge counts all differ."""
+    w = WORKLOADS[name]
+    sizes = [24, 17, 31, 24, 9]
+    loader = _loader(name, sizes, with_edges=True)
+    nb = (w["radius"], w["max_neighbours"]) if build else None
+    m1 = hb.get_distributed_model(hb.create_model(**ARCH[name]))
+    m2 = copy.deepcopy(m1)
+    o1, o2 = hb.FlatAdamW(m1, lr=1e-3), hb.FlatAdamW(m2, lr=1e-3)
+    launches = []
+    for epoch in range(2):
+        e_fast, t_fast = hb.train([b.clone() for b in loader], m1, o1, compute_grad_energy=mlip, fast=True, neighbour_build=nb)
+        e_eager, t_eager = hb.train([b.clone() for b in loader], m2, o2, compute_grad_energy=mlip, fast=False)
+        torch.testing.assert_close(e_fast, e_eager, rtol=2e-4, atol=1e-6)
+        torch.testing.assert_close(t_fast.reshape(-1), t_eager.reshape(-1), rtol=2e-4, atol=1e-6)
+    for p, q in zip(m1.parameters(), m2.parameters()):
+        torch.testing.assert_close(p, q, rtol=2e-3, atol=2e-6)
+    fast = o1._hgb_fast
+    assert fast.recaptures <= 1                                      # one capture (plus at most one growth) served 10 steps
+    # a batch that does not fit re-captures with grown capacities instead of failing
+    big = _loader(name, [80], with_edges=True, seed0=77)
+    hb.train(big, m1, o1, compute_grad_energy=mlip, fast=True, neighbour_build=nb)
+    assert o1._hgb_fast.recaptures >= 1
+
+
+# ---- fp32-accurate tensor-core GEMMs (4xTF32) used by the exact-fp32 mode ---------------------------------------------------
+@pytest.mark.parametrize("m,n,k", [(5000, 64, 64), (4097, 200, 128), (20000, 24, 8), (513, 64, 16), (3000, 192, 64)])
+def test_gemm3_rows_forms_match_fp64(m, n, k, monkeypatch):
+    g = torch.Generator().manual_seed(m + n + k)
+    x, w, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) * 0.3, torch.randn(n, generator=g)
+    xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
+    monkeypatch.setattr(ops, "GEMM3", True)
+    assert ops.gemm3_ok(xd, wd, torch.empty(m, n, device=DEV), m, n, k, False, True)
+    before = hb._lib.launch_count()
+    y, z = ops.raw_linear(xd, wd, bd, ops.ACT_CODES["silu"], 0.0, want_z=True)          # x W^T + b, SiLU, pre-activation kept
+    zr = x.double() @ w.double().t() + b.double()
+    assert rel_l2(z, zr) < 5e-7 and rel_l2(y, torch.nn.functional.silu(zr)) < 5e-7
+    gy = torch.randn(m, n, generator=g)
+    dx = ops.raw_gemm(gy.to(DEV), wd, False, False)                                        # dgrad: g W
+    assert rel_l2(dx, gy.double() @ w.double()) < 5e-7
+    # strided operand (a column block of a wider matrix), accumulate into the output
+    wide = torch.randn(m, k + 8, generator=g).to(DEV)
+    out = torch.ones(m, n, device=DEV)
+    ops.raw_gemm(wide[:, 4:4 + k], wd, False, True, out=out, beta_one=True)
+    assert rel_l2(out, 1.0 + wide[:, 4:4 + k].double().cpu() @ w.double().t()) < 5e-7
+
+
+@pytest.mark.parametrize("r,mo,no", [(50000, 64, 64), (4099, 192, 64), (100000, 64, 128), (9000, 16, 8)])
+def test_gemm3_weight_gradient_form_matches_fp64(r, mo, no):
+    g = torch.Generator().manual_seed(r + mo)
+    dz, x = torch.randn(r, mo, generator=g), torch.randn(r, no, generator=g)
+    ops.GEMM3 = True
+    assert ops.gemm3_ok(dz.to(DEV), x.to(DEV), torch.empty(mo, no, device=DEV), mo, no, r, True, False)
+    dw = ops.raw_gemm(dz.to(DEV), x.to(DEV), True, False)
+    ref = dz.double().t() @ x.double()
+    assert rel_l2(dw, ref) < 5e-7
+    # the SIMT kernel is the second witness
+    ops.GEMM3 = False
+    try:
+        dw2 = ops.raw_gemm(dz.to(DEV), x.to(DEV), True, False)
+    finally:
+        ops.GEMM3 = False
+    assert rel_l2(dw2, ref) < 5e-6
+
+
+def test_pna_aggregate_kernel_hand_computed_cases():
+    """hgb_pna_aggregate_fwd on the hand-worked segments of tests/test_oracle_golden.py (two values, single edge, EMPTY segment,
+    equal values): [mean | min | max | std] with PyG's std convention (sqrt(relu(var) + 1e-5), forced to 0 at the floor)."""
+    x = torch.tensor([[1.0], [3.0], [2.0], [5.0], [5.0], [5.0]], device=DEV)
+    index = torch.tensor([0, 0, 1, 3, 3, 3], device=DEV)
+    csr = ops.csr_build(index, 4)
+    out = ops.PnaAggregateFn.apply(x.requires_grad_(True), csr)
+    want = torch.tensor([[2.0, 1.0, 3.0, 1.0], [2.0, 2.0, 2.0, 0.0], [0.0, 0.0, 0.0, 0.0], [5.0, 5.0, 5.0, 0.0]])
+    torch.testing.assert_close(out.detach().cpu(), want, rtol=1e-6, atol=1e-6)
+    out.sum().backward()                                           # subgradients exist everywhere (no NaN from the std floor)
+    assert bool(torch.isfinite(x.grad).all())

@@ -243,3 +243,37 @@ def test_node_heads_mlp_per_node_and_conv_match_reference_golden(golden_dir):
             assert (gr is None) == (ref is None), (name, n)
             if gr is not None:
                 torch.testing.assert_close(gr, ref, rtol=1e-4, atol=1e-5)      # biases in front of a BatchNorm: exact gradient 0, fp noise
+
+
+# ---- PNA DegreeScalerAggregation: hand-computed known answers (the golden for PNAEq stubs PyG's aggregator with the
+# oracle's own restatement, so the 20-way aggregation is pinned HERE against numbers worked out by hand from the published
+# definitions [PNA, Corso et al. 2020, eqs. 5-7; torch_geometric 2.6.1 DegreeScalerAggregation / aggr.StdAggregation]) ----------
+def test_degree_scaler_aggregation_hand_computed_cases():
+    import math
+    from oracle.pnaeq import DegreeScalerAggregation, X_AGGREGATORS, X_SCALERS, sanitize_degree
+    # in-degree histogram of the "training set": 2 nodes of degree 1, 1 node of degree 2, 1 node of degree 3 (bin 0 empty)
+    deg = torch.tensor([0.0, 2.0, 1.0, 1.0])
+    avg_lin = (1 * 2 + 2 * 1 + 3 * 1) / 4                              # 1.75
+    avg_log = (2 * math.log(2) + math.log(3) + math.log(4)) / 4
+    dsa = DegreeScalerAggregation(X_AGGREGATORS, X_SCALERS, deg)
+    assert abs(float(dsa.avg_deg_lin) - avg_lin) < 1e-6 and abs(float(dsa.avg_deg_log) - avg_log) < 1e-6
+    # 4 target nodes, one feature: node 0 <- {1, 3} ; node 1 <- {2} (single edge) ; node 2 <- {} (empty) ; node 3 <- {5, 5, 5}
+    x = torch.tensor([[1.0], [3.0], [2.0], [5.0], [5.0], [5.0]], dtype=torch.float64)
+    index = torch.tensor([0, 0, 1, 3, 3, 3])
+    out = dsa.double()(x, index, 4)                                   # [4, 4 aggr x 5 scalers]
+    eps_std = math.sqrt(1e-5)
+    # aggregators, by hand: [mean, min, max, std];  std = sqrt(relu(E[x^2] - E[x]^2) + 1e-5), forced to 0 when <= sqrt(1e-5)
+    aggr = {0: [2.0, 1.0, 3.0, math.sqrt((1 + 9) / 2 - 4 + 0.0)],      # var = 1 -> clamp(min = 1e-5) keeps 1 -> std 1
+            1: [2.0, 2.0, 2.0, 0.0],                                   # single edge: variance 0 -> clamped to 1e-5 -> masked to 0
+            2: [0.0, 0.0, 0.0, 0.0],                                   # empty segment: every aggregator yields 0
+            3: [5.0, 5.0, 5.0, 0.0]}                                   # equal values: variance 0 -> 0
+    cnt = {0: 2, 1: 1, 2: 0, 3: 3}
+    for node in range(4):
+        d = max(cnt[node], 1)                                          # deg clamped to >= 1 (an isolated node scales like degree 1)
+        scal = [1.0, math.log(d + 1) / avg_log, avg_log / math.log(d + 1), d / avg_lin, avg_lin / d]
+        want = [a * s for s in scal for a in aggr[node]]              # scaler-major: [identity x 4 aggr | amplification x 4 | ...]
+        torch.testing.assert_close(out[node], torch.tensor(want, dtype=torch.float64), rtol=1e-6, atol=1e-7)   # avg_deg buffers are fp32
+    assert eps_std > 0
+    # degree histogram hygiene (PNAEqStack.py:75-90): empty -> [1], nan / -inf -> 1, +inf -> largest finite, everything >= 1
+    assert sanitize_degree([]).tolist() == [1.0]
+    assert sanitize_degree([0.0, float("nan"), 3.0, float("inf"), float("-inf")]).tolist() == [1.0, 1.0, 3.0, 3.0, 1.0]
