@@ -113,7 +113,7 @@ class ClockSampler:
             except Exception as ex:  # pragma: no cover
                 self.err = repr(ex)
                 return
-            time.sleep(0.02)
+            time.sleep(0.004)
 
     def mark_begin(self):
         self._t0 = time.perf_counter()
@@ -139,7 +139,7 @@ class ClockSampler:
                  "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
         reasons = sorted(k for k, v in names.items() if bits & v)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(inside),
-                "power_w_max": max((r[2] for r in inside), default=None), "source": "in-process NVML, 20 ms period, timed windows only"}
+                "power_w_max": max((r[2] for r in inside), default=None), "source": "in-process NVML, 4 ms period, timed windows only"}
 
 
 # -----------------------------------------------------------------------------------------------------------
@@ -310,13 +310,13 @@ def run_engine(args):
             ei, _, sh, deg, outptr, c = radius.radius_graph_pbc(d.pos.detach(), d.cell, d.pbc, d._cutoff, d.ptr, G, w["max_neighbours"],
                                                                 known=known)
             d.edge_index, d.edge_shifts = ei, sh
-            d._hgb_col_sorted = (ei, outptr)
+            d._hgb_col_sorted = (ei, outptr, d.ptr)
             sizes = (c, int(ei.shape[1]))
         else:
             ei, rowptr = radius.radius_graph(d.pos.detach(), w["radius"], d.ptr, G, False, w["max_neighbours"],
                                              known_e=None if known is None else known[1])
             d.edge_index = ei
-            d._hgb_col_sorted = (ei, rowptr)                  # what hb.get_radius_graph(...)(d) records: edges grouped by target
+            d._hgb_col_sorted = (ei, rowptr, d.ptr)           # what hb.get_radius_graph(...)(d) records: edges grouped by target / graph
             sizes = (0, int(ei.shape[1]))
         if gps:                                               # serialized_dataset_loader.py:186-189
             d.rel_pe = (d.pe[d.edge_index[0]] - d.pe[d.edge_index[1]]).abs()
@@ -549,9 +549,21 @@ def run_engine(args):
                 "e2e": {"value": e2e, "unit": "atoms/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                         "timing": stats_e2e},
                 "roofline": roof, "step_roofline": step_roof, "kernel_shares": shares, "cpu_baseline": cpu_base}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    _shutdown(ws, dev, [graphs, g_opt])
+
+
+def _shutdown(ws, dev, keep_alive):
+    """Leave without tearing NCCL down: destroying a process group whose collectives live inside captured CUDA graphs can block
+    forever at interpreter exit (observed: the 2-GPU run printed its line and then hung in teardown).  Every rank drains its GPU,
+    meets the others once, flushes and exits the process directly."""
+    torch.cuda.synchronize()
     if ws > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+        torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def kernel_shares_and_roofline(step_fn, _lib, args, N, E, G):

@@ -3,8 +3,9 @@
 //
 // head_dim 8 is exactly one k-step of mma.sync.m16n8k8 (TF32 in, fp32 accumulate): a score block S[16 queries x 8 keys] is
 // ONE instruction, P V another.  The softmax exponentials then bound the kernel (SFU), not the FMAs as in the SIMT kernels of
-// hgb_attn.cu.  SPLIT = 4 runs every product as hi*hi + hi*lo + lo*hi + lo*lo of a TF32 split (fp32-level accuracy: C5 is an
-// fp32 config, parity tolerance 1e-5); SPLIT = 1 is plain TF32 for precision="bf16".  Scores are kept in base 2 (log2 e folded
+// hgb_attn.cu.  SPLIT = 3 runs every product as hi*hi + hi*lo + lo*hi of a TF32 split ("3xTF32": the dropped lo*lo term is
+// 2^-22 |a||b|, below the fp32 rounding of the sums -- measured 1e-6 against fp64; C5 is an fp32 config, parity tolerance 1e-5;
+// SPLIT = 4 adds lo*lo); SPLIT = 1 is plain TF32 for precision="bf16".  Scores are kept in base 2 (log2 e folded
 // into the query scale) so that the exponentials are bare ex2.approx with no argument-scaling error.
 //
 // Fragment trick: the accumulator layout of S (thread holds keys 2t, 2t+1 of rows g, g+8) is fed back as the A operand of
@@ -280,7 +281,7 @@ extern "C" int hgb_mha_tc_fwd(const float* qkv, int32_t n, int32_t f, int32_t he
   const float scale = 1.f / sqrtf((float)D);
   dim3 grid((n + ROWS - 1) / ROWS, heads);
   cudaStream_t st = (cudaStream_t)stream;
-  if (exact) mha_tc_fwd_kernel<4><<<grid, WARPS * 32, 0, st>>>(qkv, n, f, scale, out, lse);
+  if (exact) mha_tc_fwd_kernel<3><<<grid, WARPS * 32, 0, st>>>(qkv, n, f, scale, out, lse);
   else mha_tc_fwd_kernel<1><<<grid, WARPS * 32, 0, st>>>(qkv, n, f, scale, out, lse);
   HGB_LAUNCH_CHECK("mha_tc_fwd");
   return HGB_OK;
@@ -298,9 +299,9 @@ extern "C" int hgb_mha_tc_bwd(const float* qkv, const float* out, const float* l
   mha_tc_delta_kernel<<<(int)((cnt + 255) / 256), 256, 0, st>>>(out, gout, n, f, heads, delta_ws);
   HGB_LAUNCH_CHECK("mha_tc_delta");
   if (exact) {
-    mha_tc_bwd_q_kernel<4><<<grid, WARPS * 32, 0, st>>>(qkv, lse, delta_ws, gout, n, f, scale, gqkv);
+    mha_tc_bwd_q_kernel<3><<<grid, WARPS * 32, 0, st>>>(qkv, lse, delta_ws, gout, n, f, scale, gqkv);
     HGB_LAUNCH_CHECK("mha_tc_bwd_q");
-    mha_tc_bwd_kv_kernel<4><<<grid, WARPS * 32, 0, st>>>(qkv, lse, delta_ws, gout, n, f, scale, gqkv);
+    mha_tc_bwd_kv_kernel<3><<<grid, WARPS * 32, 0, st>>>(qkv, lse, delta_ws, gout, n, f, scale, gqkv);
   } else {
     mha_tc_bwd_q_kernel<1><<<grid, WARPS * 32, 0, st>>>(qkv, lse, delta_ws, gout, n, f, scale, gqkv);
     HGB_LAUNCH_CHECK("mha_tc_bwd_q");

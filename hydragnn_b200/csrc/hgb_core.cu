@@ -187,6 +187,61 @@ extern "C" int hgb_csr_build(const int64_t* idx, int64_t e, int32_t n, int32_t* 
   return HGB_OK;
 }
 
+// Stable CSR fill for index vectors whose entries are GROUPED: the edges of graph g are the contiguous range
+// [edge_ptr[node_ptr[g]], edge_ptr[node_ptr[g + 1]]) and only reference nodes of graph g (what the engine's radius-graph kernels
+// emit: edges sorted by target, graphs never interact).  One warp per graph walks its edges 32 at a time; equal keys inside a
+// warp-step are ranked with match_any (lower lanes first), so every segment comes out in ascending edge id -- no sort at all.
+__global__ void csr_fill_grouped_kernel(const int32_t* __restrict__ idx32, const int32_t* __restrict__ node_ptr,
+                                        const int32_t* __restrict__ edge_ptr, int g, const int32_t* __restrict__ rowptr,
+                                        int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int k = blockIdx.x * wpb + (threadIdx.x >> 5); k < g; k += gridDim.x * wpb) {
+    const int e0 = edge_ptr[node_ptr[k]], e1 = edge_ptr[node_ptr[k + 1]];
+    for (int base = e0; base < e1; base += 32) {
+      const int e = base + lane;
+      const bool on = e < e1;
+      const int key = on ? idx32[e] : -1 - lane;                 // distinct dummies: never match a real key
+      const unsigned peers = __match_any_sync(0xffffffffu, key);
+      const int rank = __popc(peers & ((1u << lane) - 1u));
+      int cur = 0;
+      if (on) cur = cursor[key];
+      __syncwarp();
+      if (on) {
+        perm[rowptr[key] + cur + rank] = e;
+        if (rank == 0) cursor[key] = cur + __popc(peers);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+extern "C" int64_t hgb_csr_grouped_workspace_bytes(int64_t e, int32_t n) {
+  return 4 * ((int64_t)n + 8) * 2 + hgb_exclusive_scan_workspace_bytes(n) + 512;
+}
+
+extern "C" int hgb_csr_build_grouped(const int64_t* idx, int64_t e, int32_t n, const int32_t* node_ptr, const int32_t* edge_ptr,
+                                     int32_t g, int32_t* idx32, int32_t* rowptr, int32_t* perm, int32_t* guard_flag,
+                                     void* workspace, hgb_stream_t stream) {
+  HGB_REQUIRE(e >= 0 && n >= 0 && g >= 0 && node_ptr && edge_ptr && rowptr && workspace, "csr_build_grouped: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t* count = (int32_t*)workspace;           // n + 8
+  int32_t* cursor = count + n + 8;                // n + 8
+  char* scan_ws = (char*)(cursor + n + 8);
+  scan_ws = (char*)(((uintptr_t)scan_ws + 255) & ~(uintptr_t)255);
+  cudaMemsetAsync(count, 0, 4 * ((int64_t)n + 8) * 2, st);
+  if (e > 0) {
+    csr_hist_kernel<<<hgb_grid_for(e, 256), 256, 0, st>>>(idx, e, n, idx32, count, guard_flag ? guard_flag : count + n);
+    HGB_LAUNCH_CHECK("csr_hist");
+  }
+  int rc = hgb_exclusive_scan_i32(count, rowptr, n, scan_ws, stream);
+  if (rc) return rc;
+  if (e > 0 && g > 0) {
+    csr_fill_grouped_kernel<<<hgb_grid_for(g, 8), 256, 0, st>>>(idx32, node_ptr, edge_ptr, g, rowptr, cursor, perm);
+    HGB_LAUNCH_CHECK("csr_fill_grouped");
+  }
+  return HGB_OK;
+}
+
 // out[p] = idx[perm[p]]  (the neighbour of every CSR slot, so the fused kernels do one dependent index load less)
 __global__ void gather_i32_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ perm, int64_t e, int32_t* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) out[i] = idx[perm[i]];

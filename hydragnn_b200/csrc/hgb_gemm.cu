@@ -20,8 +20,8 @@ __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ a, 
                                                    int64_t ldc, int beta_one, int k_per_split, float* __restrict__ part,
                                                    const float* __restrict__ bias, int act, float act_param,
                                                    float* __restrict__ zout) {
-  __shared__ float As[BK][BM + 4];
-  __shared__ float Bs[BK][BN + 4];
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int kbeg = blockIdx.z * k_per_split;
@@ -54,11 +54,10 @@ __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ a, 
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < BK; ++q) {
-      float ra[TM], rb[TN];
-#pragma unroll
-      for (int i = 0; i < TM; ++i) ra[i] = As[q][ty * TM + i];
-#pragma unroll
-      for (int j = 0; j < TN; ++j) rb[j] = Bs[q][tx * TN + j];
+      // one 16-byte shared-memory load per operand (TM = TN = 4; rows of As / Bs are 272 B apart: 16-byte aligned)
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[q][ty * TM]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[q][tx * TN]);
+      const float ra[TM] = {a4.x, a4.y, a4.z, a4.w}, rb[TN] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll

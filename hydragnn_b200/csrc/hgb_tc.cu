@@ -151,11 +151,19 @@ struct LinParams {
   int z_deriv;          // forward with a SiLU and z != NULL: z receives silu'(pre-activation) instead of the pre-activation
   int stages;
   int tmem_cols;
+  int split;            // 1: fp32-accurate mode -- every operand is split into a TF32 hi / lo pair and each k-step runs the three
+                        //    products hi*hi + lo*hi + hi*lo (3xTF32); four extra warps (10..13) split the A stages in shared memory
 };
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 
 constexpr int TILE_M = 128;
 
-__global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_y,
+__global__ void __launch_bounds__(448, 1) tc_linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_y,
                                                            const __grid_constant__ CUtensorMap tmap_z, const LinParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -163,13 +171,17 @@ __global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant
   const int NO = p.no;
   const uint32_t b_bytes = (uint32_t)KB * NO * 128;
   constexpr uint32_t a_stage = TILE_M * 128;   // one pipeline stage = one [128 x 32 fp32] k-block (16 KB)
+  const uint32_t b_pad = (b_bytes + 1023) & ~1023u;
   uint8_t* sB = smem;
-  uint8_t* sA = smem + ((b_bytes + 1023) & ~1023u);
+  uint8_t* sBlo = sB + b_pad;                                 // split mode only
+  uint8_t* sA = sB + (p.split ? 2 : 1) * (size_t)b_pad;
   const int S = p.stages;
-  uint8_t* sOut = sA + (size_t)S * a_stage;                   // 8 epilogue warps x 2 staging tiles x 4 KB (1024-aligned)
+  uint8_t* sAlo = sA + (size_t)S * a_stage;                   // split mode only
+  uint8_t* sOut = sA + (size_t)(p.split ? 2 : 1) * S * a_stage;   // 8 epilogue warps x 2 staging tiles x 4 KB (1024-aligned)
   uint64_t* full = reinterpret_cast<uint64_t*>(sOut + 8 * 2 * 4096);
   uint64_t* empty = full + S;
-  uint64_t* tfull = empty + S;
+  uint64_t* full2 = empty + S;                                // split mode: "stage s is split" (4 splitter warps arrive)
+  uint64_t* tfull = full2 + S;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
   float* sbias = reinterpret_cast<float*>(tmem_holder + 4);   // [NO], 16-byte aligned
@@ -180,7 +192,7 @@ __global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant
 
   // ---- one-time setup -------------------------------------------------------------------------------
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(full2 + s, 4); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 8); }
     fence_barrier_init();
   }
@@ -191,6 +203,34 @@ __global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant
   const uint32_t tmem_base = *tmem_holder;
   const uint32_t idesc = make_idesc(TILE_M, NO, 0, 0);
 
+  if (warp >= 10) {
+    // ===== splitter warps (split mode only; the launch has 320 threads otherwise): as soon as the TMA has landed stage s, rewrite it
+    // in place as the TF32 "hi" part and put the "lo" remainder at the same (swizzled) offsets of the twin buffer, then release the
+    // stage to the MMA warp.  Elementwise on 16 KB: 8 float4 per thread. =====
+    int s = 0;
+    uint32_t ph = 0;
+    const int tl = threadIdx.x - 320;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(full + s, ph);
+        float4* pa = reinterpret_cast<float4*>(sA + (size_t)s * a_stage);
+        float4* pl = reinterpret_cast<float4*>(sAlo + (size_t)s * a_stage);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int idx = i * 128 + tl;
+          const float4 v = pa[idx];
+          float4 h, l;
+          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+          l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+          pa[idx] = h;
+          pl[idx] = l;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full2 + s);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+  } else
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
@@ -217,13 +257,21 @@ __global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant
         tc_fence_after();
         const uint32_t d_addr = tmem_base + (uint32_t)acc * NO;
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(full + s, ph);
+          mbar_wait(p.split ? full2 + s : full + s, ph);
           tc_fence_after();
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
             const uint64_t ad = make_desc(sA_addr + s * a_stage + k4 * 32, 16, 1024);
             const uint64_t bd = make_desc(sB_addr + kb * NO * 128 + k4 * 32, 16, 1024);
-            umma_tf32(d_addr, ad, bd, idesc, (kb | k4) != 0);
+            if (p.split) {      // small terms first: lo*hi + hi*lo + hi*hi
+              const uint64_t adl = make_desc(smem_u32(sAlo) + s * a_stage + k4 * 32, 16, 1024);
+              const uint64_t bdl = make_desc(smem_u32(sBlo) + kb * NO * 128 + k4 * 32, 16, 1024);
+              umma_tf32(d_addr, adl, bd, idesc, (kb | k4) != 0);
+              umma_tf32(d_addr, ad, bdl, idesc, 1);
+              umma_tf32(d_addr, ad, bd, idesc, 1);
+            } else {
+              umma_tf32(d_addr, ad, bd, idesc, (kb | k4) != 0);
+            }
           }
           umma_commit(empty + s);    // smem stage free once these MMAs have read it
           if (++s == S) { s = 0; ph ^= 1; }
@@ -260,7 +308,15 @@ __global__ void __launch_bounds__(320, 1) tc_linear_kernel(const __grid_constant
         }
 #pragma unroll
         for (int u = 0; u < SU; ++u)
-          if (off[u] != 0xffffffffu) *reinterpret_cast<float*>(sB + off[u]) = val[u];
+          if (off[u] != 0xffffffffu) {
+            if (p.split) {
+              const float hi = tf32_rna(val[u]);
+              *reinterpret_cast<float*>(sB + off[u]) = hi;
+              *reinterpret_cast<float*>(sBlo + off[u]) = tf32_rna(val[u] - hi);
+            } else {
+              *reinterpret_cast<float*>(sB + off[u]) = val[u];
+            }
+          }
       }
       fence_proxy_async();
     }
@@ -586,7 +642,7 @@ extern "C" int hgb_tc_linear_supported(int32_t m, int32_t n_out, int32_t k_red) 
 // one (<= 256) x (<= 256) piece: y[m, no] = act(a[m, kr] . B^T + bias) + addend, y / z / addend with row stride ldy
 static int tc_linear_piece(const float* a, int64_t lda, const float* w, int64_t ldw, int32_t trans_b, const float* bias, int32_t m,
                            int32_t n_out, int32_t k_red, int32_t act, float act_param, float* y, float* z, const float* addend,
-                           const float* gsrc, int32_t gact, int64_t ldy, hgb_stream_t stream) {
+                           const float* gsrc, int32_t gact, int64_t ldy, int32_t exact, hgb_stream_t stream) {
   HGB_REQUIRE(a && w && y && m >= 128 && shape_ok(k_red, n_out), "tc_linear: unsupported shape m=%d n=%d k=%d", m, n_out, k_red);
   HGB_REQUIRE(lda % 4 == 0 && ldy % 4 == 0 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!z || (uintptr_t)z % 16 == 0),
               "tc_linear: operands must be 16-byte aligned with a row stride that is a multiple of 4");
@@ -601,14 +657,16 @@ static int tc_linear_piece(const float* a, int64_t lda, const float* w, int64_t 
   p.m = m; p.kr = k_red; p.no = n_out; p.w = w; p.ldw = ldw; p.trans_b = trans_b; p.bias = bias; p.act = act; p.act_param = act_param;
   p.y = y; p.z = z; p.addend = addend; p.ldy = ldy; p.gsrc = gsrc; p.gact = gact; p.z_deriv = (!gsrc && gact == HGB_ACT_DERIV) ? 1 : 0;
   const int KB = k_red / 32;
+  const int dup = exact ? 2 : 1;                   // split mode keeps a hi and a lo copy of the weights and of every A stage
   const size_t b_bytes = ((size_t)KB * n_out * 128 + 1023) & ~(size_t)1023;
   const size_t a_stage = (size_t)TILE_M * 128;
-  int stages = (int)((224 * 1024 - 2048 - 65536 - b_bytes - (size_t)n_out * 4) / a_stage);
+  int stages = (int)((224 * 1024 - 2048 - 65536 - dup * b_bytes - (size_t)n_out * 4) / (dup * a_stage));
   if (stages > 6) stages = 6;
   HGB_REQUIRE(stages >= 2, "tc_linear: weight operand does not fit shared memory (n=%d k=%d)", n_out, k_red);
   p.stages = stages;
+  p.split = exact ? 1 : 0;
   p.tmem_cols = pow2_cols(2 * n_out);
-  const size_t smem = 1024 + b_bytes + stages * a_stage + 65536 + (2 * stages + 4) * 8 + 16 + (size_t)n_out * 4 + 16;
+  const size_t smem = 1024 + dup * b_bytes + dup * stages * a_stage + 65536 + (3 * stages + 4) * 8 + 16 + (size_t)n_out * 4 + 16;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -616,7 +674,7 @@ static int tc_linear_piece(const float* a, int64_t lda, const float* w, int64_t 
   }
   const int ntiles = (m + TILE_M - 1) / TILE_M;
   const int grid = ntiles < HGB_NUM_SMS ? ntiles : HGB_NUM_SMS;
-  tc_linear_kernel<<<grid, 320, smem, (cudaStream_t)stream>>>(tm, tmy, tmz, p);
+  tc_linear_kernel<<<grid, exact ? 448 : 320, smem, (cudaStream_t)stream>>>(tm, tmy, tmz, p);
   HGB_LAUNCH_CHECK("tc_linear");
   return HGB_OK;
 }
@@ -626,12 +684,12 @@ static int tc_linear_piece(const float* a, int64_t lda, const float* w, int64_t 
 // only: an activation or a saved pre-activation needs the whole sum first).
 extern "C" int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_t ldw, int32_t trans_b, const float* bias, int32_t m,
                              int32_t n_out, int32_t k_red, int32_t act, float act_param, float* y, float* z, const float* addend,
-                             const float* gsrc, int32_t gact, hgb_stream_t stream) {
+                             const float* gsrc, int32_t gact, int32_t exact, hgb_stream_t stream) {
   HGB_REQUIRE(a && w && y && hgb_tc_linear_supported(m, n_out, k_red), "tc_linear: unsupported shape m=%d n=%d k=%d", m, n_out, k_red);
   HGB_REQUIRE(k_red <= 256 || (act == HGB_ACT_NONE && !z && !gsrc), "tc_linear: reduction length %d > 256 needs a plain linear layer", k_red);
   // piece sizes: the B piece (kc x nc fp32) stays resident in shared memory next to >= 2 A stages and the epilogue tiles
   const int kc_max = k_red < 256 ? k_red : 256;
-  int nc_max = (int)((122 * 1024) / (4 * (size_t)kc_max) / 32) * 32;
+  int nc_max = (int)(((exact ? 48 : 122) * 1024) / (4 * (size_t)kc_max) / 32) * 32;     // split mode: two weight copies + two copies per A stage
   if (nc_max > 256) nc_max = 256;
   for (int c0 = 0; c0 < n_out; c0 += nc_max) {
     const int nc = n_out - c0 < nc_max ? n_out - c0 : nc_max;
@@ -641,7 +699,7 @@ extern "C" int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_
       const float* wp = trans_b ? w + (int64_t)k0 * ldw + c0 : w + (int64_t)c0 * ldw + k0;
       const float* add = k0 == 0 ? (addend ? addend + c0 : nullptr) : y + c0;
       int rc = tc_linear_piece(a + k0, lda, wp, ldw, trans_b, (bias && k0 == 0) ? bias + c0 : nullptr, m, nc, kc, act, act_param, y + c0,
-                               z ? z + c0 : nullptr, add, gsrc ? gsrc + c0 : nullptr, gact, n_out, stream);
+                               z ? z + c0 : nullptr, add, gsrc ? gsrc + c0 : nullptr, gact, n_out, exact, stream);
       if (rc) return rc;
     }
   }

@@ -134,13 +134,13 @@ class Interaction(nn.Module):
                     off += size
             out = self.linear(msgs, higher)
             return [o / self.avg for o in out], sc
+        # any-order / general-shape path: per-edge sender rows (GatherRows) and one closed TpOut primitive per path
+        # (csrc/hgb_mace_any.cu) -- no einsum; every derivative of any order is again a libhgb kernel
         up_s = [gather(u.reshape(u.shape[0], -1), plan.by_row).reshape(e, u.shape[1], f) for u in up]
         per_l = [[] for _ in range(self.lmax_sh + 1)]
         for k, (l1, l2, l3) in enumerate(self.paths):
             y = sh[:, l2 * l2:(l2 + 1) ** 2]
-            t = torch.einsum("ijk,ej->eik", getattr(self, "_cg%d" % k), y)            # [E, 2l1+1, 2l3+1]
-            m = torch.einsum("eik,eif->ekf", t, up_s[l1]) * tpw[:, None, k * f:(k + 1) * f]
-            per_l[l3].append(m)
+            per_l[l3].append(ops.TpOut.apply(up_s[l1], y, tpw[:, k * f:(k + 1) * f], getattr(self, "_cg%d" % k)))   # [E, 2l3+1, F]
         msgs = []
         for l3, parts in enumerate(per_l):
             if parts:
@@ -185,15 +185,19 @@ class Contraction(nn.Module):
     def forward(self, x, zcsr):
         c, e = self.correlation, min(self.l_out, 1)
         n, f = x.shape[0], self.f
-        pick = lambda w: ops.GatherRows.apply(w.reshape(NUM_ELEMENTS, -1), zcsr).reshape(n, w.shape[1], f)
-        lead = "".join(ALPHABET[:c + e - 1])
-        out = torch.einsum(lead + "ik,bkc,bic->bc" + lead, getattr(self, "U_matrix_%d" % c), pick(self.weights_max), x)
+        # weights picked by element, rows = (node, channel), columns = k:  [N F, K]  (closed GatherRows + a layout copy)
+        pick = lambda w: ops.GatherRows.apply(w.reshape(NUM_ELEMENTS, -1), zcsr).reshape(n, w.shape[1], f).transpose(1, 2).reshape(n * f, -1)
+        # symmetric_contraction.py:217-239 without einsum: every "U x weights" product is a closed MatMul, every contraction with
+        # x a closed ChanCL step (csrc/hgb_mace_any.cu)
+        u = getattr(self, "U_matrix_%d" % c)                                          # [lead..., i, k]
+        ni, nk = u.shape[-2], u.shape[-1]
+        t = ops.MatMul.apply(pick(self.weights_max), u.reshape(-1, nk), False, True)  # [N F, P i]
+        out = ops.ChanCL.apply(t.reshape(n, f, -1, ni), x)                            # [N, F, P]
         for k, weight in enumerate(self.weights):
             i = c - k - 1
-            lead_w = "".join(ALPHABET[:i + e])
-            ct = torch.einsum(lead_w + "k,bkc->bc" + lead_w, getattr(self, "U_matrix_%d" % i), pick(weight)) + out
-            lead_f = "".join(ALPHABET[:i - 1 + e])
-            out = torch.einsum("bc" + lead_f + "i,bic->bc" + lead_f, ct, x)
+            u = getattr(self, "U_matrix_%d" % i)
+            ct = ops.MatMul.apply(pick(weight), u.reshape(-1, u.shape[-1]), False, True).reshape(n, f, -1) + out
+            out = ops.ChanCL.apply(ct.reshape(n, f, -1, ni), x)
         return out.reshape(n, f, -1).transpose(1, 2)                                  # [N, 2 l_out + 1, F]
 
 

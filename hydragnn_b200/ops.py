@@ -70,16 +70,34 @@ def csr_build(index64, n):
     return Csr(idx32, rowptr, perm, n)
 
 
+def csr_build_grouped(index64, n, node_ptr, edge_ptr, g):
+    """``csr_build`` for edges grouped by graph (radius-graph output): sort-free, see hgb_csr_build_grouped."""
+    index64 = _chk(index64, torch.int64)
+    e = index64.numel()
+    dev = index64.device
+    idx32 = torch.empty(e, dtype=torch.int32, device=dev)
+    rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    perm = torch.empty(e, dtype=torch.int32, device=dev)
+    ws = _ws(_lib.query("hgb_csr_grouped_workspace_bytes", e, n), dev)
+    _lib.call("hgb_csr_build_grouped", _p(index64), e, n, _p(node_ptr), _p(edge_ptr), int(g), _p(idx32), _p(rowptr), _p(perm),
+              _p(guard_flag(dev)), _p(ws), _stream())
+    return Csr(idx32, rowptr, perm, n)
+
+
 class EdgePlan:
     """Everything index-shaped a conv layer needs, built once per batch (SURVEY hard part H3: the
     stacks aggregate by ``edge_index[0]`` which is not the sorted row of a PyG radius graph)."""
 
-    def __init__(self, edge_index, num_nodes, col_rowptr=None):
+    def __init__(self, edge_index, num_nodes, col_rowptr=None, graph_ptr=None):
         """``col_rowptr`` [N+1] int32 (optional): the edges are already grouped by ``edge_index[1]`` in ascending order with
-        these segment offsets (what the engine's own radius-graph kernels emit) -- that CSR view then needs no build."""
+        these segment offsets (what the engine's own radius-graph kernels emit) -- that CSR view then needs no build.  With
+        ``graph_ptr`` [G+1] int32 as well, the by-source view is filled graph by graph without a sort."""
         ei = _chk(edge_index, torch.int64)
         self.num_nodes, self.num_edges = int(num_nodes), int(ei.shape[1])
-        self.by_row = csr_build(ei[0], self.num_nodes)
+        if col_rowptr is not None and graph_ptr is not None and GROUPED_CSR:
+            self.by_row = csr_build_grouped(ei[0], self.num_nodes, graph_ptr, col_rowptr, graph_ptr.numel() - 1)
+        else:
+            self.by_row = csr_build(ei[0], self.num_nodes)
         if col_rowptr is not None:
             self.by_col = Csr(ei[1].to(torch.int32), col_rowptr, torch.arange(self.num_edges, dtype=torch.int32, device=ei.device),
                               self.num_nodes)
@@ -169,7 +187,8 @@ def raw_segment_sum(m, rowptr, perm, n):
 
 def raw_gemm(a, b, ta, tb, out=None, beta_one=False):
     """op(a) @ op(b) for 2-D row-major (possibly row-strided) operands."""
-    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    # unit inner stride (a one-column matrix may carry any inner stride: it is never used)
+    assert a.dim() == 2 and b.dim() == 2 and (a.stride(1) == 1 or a.shape[1] == 1) and (b.stride(1) == 1 or b.shape[1] == 1)
     m, k = (a.shape[1], a.shape[0]) if ta else (a.shape[0], a.shape[1])
     k2, n = (b.shape[1], b.shape[0]) if tb else (b.shape[0], b.shape[1])
     assert k == k2, "gemm inner dimensions differ"
@@ -211,6 +230,7 @@ def raw_colsum(x2d):
 
 # ---- tensor-core (tcgen05 / TF32) dense layers: enabled per model by precision="bf16" -----------------
 _TC = {"enabled": False}
+_DATA_ONLY = {"on": False}     # inside ``only_data_grads()``: the force pass of the MLIP loss
 
 
 class tensor_cores:
@@ -229,8 +249,11 @@ class tensor_cores:
         return False
 
 
+EXACT_TC = os.environ.get("HGB_EXACT_TC", "1") == "1"     # fp32 mode: large-M Linears on tcgen05 with the 3xTF32 split (fp32-accurate)
+
+
 def tc_ok(m, n_out, k_red, *tensors):
-    if not _TC["enabled"]:
+    if not (_TC["enabled"] or EXACT_TC):
         return False
     if not _lib.query("hgb_tc_linear_supported", m, n_out, k_red):
         return False
@@ -245,7 +268,7 @@ def raw_tc_linear(a2, w, trans_b, bias, n_out, k_red, code=0, param=0.0, want_z=
     y = torch.empty(m, n_out, dtype=a2.dtype, device=a2.device)
     z = torch.empty_like(y) if want_z else None
     _lib.call("hgb_tc_linear", _p(a2), a2.stride(0), _p(w), w.stride(0), int(trans_b), _p(bias), m, n_out, k_red, code, float(param),
-              _p(y), _p(z), _p(addend), _p(gsrc), int(gact), _stream())
+              _p(y), _p(z), _p(addend), _p(gsrc), int(gact), 0 if _TC["enabled"] else 1, _stream())
     return y, z
 
 
@@ -292,6 +315,7 @@ def raw_smallk_bwd(dy, y, z, x2, w, code=0, param=0.0, need_x=True, need_w=True,
     return dx, dw, db
 
 
+GROUPED_CSR = os.environ.get("HGB_GROUPED_CSR", "1") == "1"   # sort-free by-source CSR for radius-graph edges
 COL_HINT = os.environ.get("HGB_COL_HINT", "1") == "1"   # reuse the radius graph's by-target offsets as the by_col CSR
 ACT_DERIV = 100   # HGB_ACT_DERIV: "the tensor already holds act'(.)"
 
@@ -339,7 +363,7 @@ def linear_bwd_dispatch(dz, x2, w, need_x=True, need_w=True, need_b=True, dx_add
         else:
             dx = through_act(raw_gemm(dz, w, False, False))
     if need_w or need_b:
-        if tc_ok(m, n, k, dz, x2) and k + 16 <= 256:
+        if _TC["enabled"] and tc_ok(m, n, k, dz, x2) and k + 16 <= 256:      # tc_wgrad has no fp32-accurate mode
             dw, db = raw_tc_wgrad(dz, x2, want_bias=need_b)
         else:
             if need_w:
@@ -393,16 +417,17 @@ class MatMul(torch.autograd.Function):
     tcgen05 TF32 kernels; the flag travels with the node so that (double) backward passes outside the context keep it."""
 
     @staticmethod
-    def forward(ctx, a, b, ta, tb):
+    def forward(ctx, a, b, ta, tb, b_is_weight=False):
         ctx.save_for_backward(a, b)
         ctx.ta, ctx.tb, ctx.tc = ta, tb, _TC["enabled"]
+        ctx.b_is_weight = bool(b_is_weight)
         a2, b2 = _row_major_2d(a), _row_major_2d(b)
-        if ctx.tc:
+        if ctx.tc or EXACT_TC:      # precision "bf16": plain TF32; "fp32": the 3xTF32 split inside the same kernel (exact flag)
             if not ta and tb and tc_ok(a2.shape[0], b2.shape[0], a2.shape[1], a2, b2):         # [m,k] x [n,k]^T
                 return raw_tc_linear(a2, b2, False, None, b2.shape[0], a2.shape[1])[0]
             if not ta and not tb and tc_ok(a2.shape[0], b2.shape[1], a2.shape[1], a2, b2):     # [m,n] x [n,k]
                 return raw_tc_linear(a2, b2, True, None, b2.shape[1], a2.shape[1])[0]
-            if ta and not tb and tc_ok(a2.shape[0], a2.shape[1], b2.shape[1], a2, b2) and b2.shape[1] + 16 <= 256:
+            if ctx.tc and ta and not tb and tc_ok(a2.shape[0], a2.shape[1], b2.shape[1], a2, b2) and b2.shape[1] + 16 <= 256:
                 return raw_tc_wgrad(a2, b2, want_bias=False)[0]                                    # [m,n]^T x [m,k]
         return raw_gemm(a2, b2, ta, tb)
 
@@ -416,11 +441,13 @@ class MatMul(torch.autograd.Function):
                 #  C = A B     : gA = G B^T      C = A^T B   : gA = B G^T
                 #  C = A B^T   : gA = G B        C = A^T B^T : gA = B^T G^T
                 ga = MatMul.apply(b, g, tb, True) if ta else MatMul.apply(g, b, False, not tb)
-            if ctx.needs_input_grad[1]:
+            # the force pass of the MLIP loss (only_data_grads) differentiates w.r.t. positions only: weight gradients computed
+            # there would be thrown away by autograd (a custom Function cannot see which outputs the engine needs)
+            if ctx.needs_input_grad[1] and not (ctx.b_is_weight and _DATA_ONLY["on"]):
                 #  C = A B     : gB = A^T G      C = A B^T   : gB = G^T A
                 #  C = A^T B   : gB = A G        C = A^T B^T : gB = G^T A^T
                 gb = MatMul.apply(g, a, True, ta) if tb else MatMul.apply(a, g, not ta, False)
-        return ga, gb, None, None
+        return ga, gb, None, None, None
 
 
 class ColSum(torch.autograd.Function):
@@ -445,13 +472,13 @@ class BiasAdd(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return g, (ColSum.apply(g) if ctx.needs_input_grad[1] else None)
+        return g, (ColSum.apply(g) if (ctx.needs_input_grad[1] and not _DATA_ONLY["on"]) else None)
 
 
 def linear_any_order(x, weight, bias=None):
     """``x @ W^T + b`` built from the closed primitives (MatMul, BiasAdd / ColSum)."""
     shp = x.shape
-    y = MatMul.apply(x.reshape(-1, shp[-1]), weight, False, True)
+    y = MatMul.apply(x.reshape(-1, shp[-1]), weight, False, True, True)
     if bias is not None:
         y = BiasAdd.apply(y, bias)
     return y.reshape(shp[:-1] + (weight.shape[0],))
@@ -875,9 +902,72 @@ class PnaAggregateFn(torch.autograd.Function):
 
 
 # =====================================================================================================
+# grouped dense layers (multi-branch decoding)
+# =====================================================================================================
+class GroupedLinearFn(torch.autograd.Function):
+    """``y[r] = act(x[r] W_g^T + b_g)`` for rows sorted by group (``rowptr`` [groups + 1] on the device): the per-dataset branch
+    heads of hydragnn/models/Base.py:770-780,816-840 as ONE launch per layer, no host read of the group sizes."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, rowptr, act, act_param):
+        x, w = _chk(x.contiguous()), _chk(w.contiguous())
+        b = _chk(b.contiguous()) if b is not None else None
+        groups, n, k = w.shape
+        m = x.shape[0]
+        code = ACT_CODES[act]
+        y = torch.empty(m, n, dtype=x.dtype, device=x.device)
+        z = torch.empty_like(y) if code == ACT_CODES["silu"] else None
+        _lib.call("hgb_grouped_linear", _p(x), k, _p(w), _p(b), _p(rowptr), groups, m, n, k, 0, code, float(act_param), _p(y), _p(z), _stream())
+        ctx.save_for_backward(x, w, y if code not in (0, ACT_CODES["silu"]) else None, z, rowptr)
+        ctx.cfg = (code, float(act_param), b is not None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, w, y, z, rowptr = ctx.saved_tensors
+        code, param, has_b = ctx.cfg
+        groups, n, k = w.shape
+        m = x.shape[0]
+        gy = _chk(gy.contiguous())
+        dz = raw_act_bwd(gy, y, z, code, param) if code != 0 else gy
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty(m, k, dtype=x.dtype, device=x.device)
+            _lib.call("hgb_grouped_linear", _p(dz), n, _p(w), None, _p(rowptr), groups, m, k, n, 1, 0, 0.0, _p(gx), None, _stream())
+        if ctx.needs_input_grad[1] or (has_b and ctx.needs_input_grad[2]):
+            gw = torch.empty_like(w)
+            gb = torch.empty(groups, n, dtype=x.dtype, device=x.device) if has_b else None
+            _lib.call("hgb_grouped_wgrad", _p(dz), _p(x), k, _p(rowptr), groups, m, n, k, _p(gw), _p(gb), _stream())
+        return gx, gw, gb, None, None, None
+
+
+def grouped_mlp(seq_by_group, x, rowptr):
+    """Run structurally identical ``nn.Sequential`` MLPs (one per group) on rows sorted by group.  Returns None when the
+    branches do not share one architecture (the caller then falls back to per-branch launches)."""
+    from torch import nn
+    from .stacks import _act_code
+    mods = [list(s) for s in seq_by_group]
+    if any(len(m) != len(mods[0]) for m in mods):
+        return None
+    i = 0
+    while i < len(mods[0]):
+        layer = [m[i] for m in mods]
+        if not all(isinstance(l, nn.Linear) for l in layer) or len({tuple(l.weight.shape) for l in layer}) != 1:
+            return None
+        code = _act_code(mods[0][i + 1]) if i + 1 < len(mods[0]) else None
+        if i + 1 < len(mods[0]) and code is None:
+            return None
+        w = torch.stack([l.weight for l in layer])
+        b = torch.stack([l.bias for l in layer]) if layer[0].bias is not None else None
+        x = GroupedLinearFn.apply(x, w, b, rowptr, code[0] if code else None, code[1] if code else 0.0)
+        i += 2 if code else 1
+    return x
+
+
+# =====================================================================================================
 # fused EGNN edge block + closed edge-length primitives (any order of differentiation the MLIP loss needs)
 # =====================================================================================================
-_DATA_ONLY = {"on": False}
 FUSED_EGNN = os.environ.get("HGB_FUSED_EGNN", "1") == "1"     # 0: the round-1 composed path (gather / Linear / segment-sum)
 
 
@@ -958,10 +1048,11 @@ class EgnnEdgeFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pq, s, wd, b0, w1, b1, plan):
-        pq, s, wd, b0, w1, b1 = [_chk(t) for t in (pq, s, wd, b0, w1, b1)]
         npt = egnn_nodes_per_tile(plan)
         masks = torch.empty(plan.num_edges, 2, dtype=torch.int64, device=pq.device)
-        out = _raw_egnn_fwd(pq, s, wd, b0, w1, b1, plan, npt, masks, False)
+        out = _raw_egnn_fwd(_chk(pq), _chk(s), _chk(wd), _chk(b0), _chk(w1), _chk(b1), plan, npt, masks, False)
+        # save the INPUTS themselves (w_d is a column view of edge_mlp[0].weight): the differentiable backward below must see
+        # tensors that are connected to the graph, not contiguous copies made for the kernel
         ctx.save_for_backward(pq, s, wd, b0, w1, masks)
         ctx.plan, ctx.npt = plan, npt
         return out
@@ -975,11 +1066,11 @@ class EgnnEdgeFn(torch.autograd.Function):
         if torch.is_grad_enabled():                       # create_graph=True: the force pass, differentiated again later
             g_pq, gs, g_wd, g_b0 = EgnnEdgeBwdFn.apply(g_out, s, wd, w1, masks, plan, npt, params)
         else:
-            g_pq, _, gs, g_wd, g_b0 = _raw_egnn_bwd_data(g_out, s, wd, w1, masks, plan, npt, params)
+            g_pq, _, gs, g_wd, g_b0 = _raw_egnn_bwd_data(g_out, _chk(s), _chk(wd), _chk(w1), masks, plan, npt, params)
         g_w1 = g_b1 = None
         if params and (ctx.needs_input_grad[4] or ctx.needs_input_grad[5]):
             with torch.no_grad():
-                g_w1, g_b1 = _raw_egnn_wgrad(g_out.detach(), pq, s, wd, b0, masks, plan, npt, False, True)
+                g_w1, g_b1 = _raw_egnn_wgrad(g_out.detach(), _chk(pq), _chk(s), _chk(wd), _chk(b0), masks, plan, npt, False, True)
         return g_pq, gs, g_wd, g_b0, g_w1, g_b1, None
 
 
@@ -991,7 +1082,8 @@ class EgnnEdgeBwdFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, g_out, s, wd, w1, masks, plan, npt, params):
-        g_pq, gz1, gs, g_wd, g_b0 = _raw_egnn_bwd_data(g_out, s, wd, w1, masks, plan, npt, params)
+        wd, w1 = _chk(wd), _chk(w1)
+        g_pq, gz1, gs, g_wd, g_b0 = _raw_egnn_bwd_data(_chk(g_out), _chk(s), wd, w1, masks, plan, npt, params)
         ctx.save_for_backward(g_out, wd, w1, masks, gz1)
         ctx.plan, ctx.npt, ctx.params = plan, npt, params
         ctx.mark_non_differentiable(*[t for t in (g_wd, g_b0) if t is not None])
@@ -1024,11 +1116,11 @@ class EdgeLenFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pos, shifts, plan):
-        pos = _chk(pos)
+        posc = _chk(pos)
         e = plan.num_edges
         ln = torch.empty(e, dtype=pos.dtype, device=pos.device)
-        _lib.call("hgb_edge_geom_fwd", _p(pos), _p(plan.row), _p(plan.col), _p(_chk(shifts)), e, 0.0, None, _p(ln), None, _stream())
-        ctx.save_for_backward(pos, shifts)
+        _lib.call("hgb_edge_geom_fwd", _p(posc), _p(plan.row), _p(plan.col), _p(_chk(shifts)), e, 0.0, None, _p(ln), None, _stream())
+        ctx.save_for_backward(pos, shifts)              # the input itself: the differentiable backward must stay connected to it
         ctx.plan = plan
         return ln
 
@@ -1038,7 +1130,7 @@ class EdgeLenFn(torch.autograd.Function):
         gd = _chk(gd.contiguous())
         if torch.is_grad_enabled():
             return EdgeLenBwdFn.apply(gd, pos, shifts, ctx.plan), None, None
-        return _raw_edge_len_bwd(gd, pos, shifts, ctx.plan), None, None
+        return _raw_edge_len_bwd(gd, _chk(pos), _chk(shifts), ctx.plan), None, None
 
 
 def _edge_vec_scatter(gvec, plan):
@@ -1060,6 +1152,7 @@ class EdgeLenBwdFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, gd, pos, shifts, plan):
+        gd, pos, shifts = _chk(gd), _chk(pos), _chk(shifts)
         ctx.save_for_backward(gd, pos, shifts)
         ctx.plan = plan
         return _raw_edge_len_bwd(gd, pos, shifts, plan)
@@ -1151,6 +1244,121 @@ class MaceSymContractFn(torch.autograd.Function):
                   _stream())
         gwall = raw_segment_sum(gw_node, zcsr.rowptr, zcsr.perm, zcsr.n).reshape(wall.shape)
         return gx, gwall, None, None, None
+
+
+# ---- closed MACE primitives (any order of differentiation): csrc/hgb_mace_any.cu -----------------------------------------
+def _tp_call(mode, p0, p1, p2, cg, out_shape):
+    p0, p1, p2, cg = _chk(p0.contiguous()), _chk(p1.contiguous()), _chk(p2.contiguous()), _chk(cg.contiguous())
+    ni, nj, nk = cg.shape
+    e, f = p0.shape[0], p0.shape[2]
+    out = torch.empty(out_shape, dtype=p0.dtype, device=p0.device)
+    _lib.call("hgb_mace_tp_path", mode, _p(p0), _p(p1), _p(p2), _p(cg), e, f, ni, nj, nk, _p(out), _stream())
+    return out
+
+
+class TpOut(torch.autograd.Function):
+    """o[e, k, f] = w[e, f] sum_ij C[i, j, k] a[e, i, f] y[e, j]: one tensor-product path on per-edge operands (blocks.py:386-392).
+    Derivatives are TpOut (C permuted), TpY and TpW again: closed under autograd."""
+
+    @staticmethod
+    def forward(ctx, a, y, w, cg):
+        ctx.save_for_backward(a, y, w, cg)
+        return _tp_call(0, a, y, w, cg, (a.shape[0], cg.shape[2], a.shape[2]))
+
+    @staticmethod
+    def backward(ctx, g):
+        a, y, w, cg = ctx.saved_tensors
+        ga = TpOut.apply(g, y, w, cg.permute(2, 1, 0)) if ctx.needs_input_grad[0] else None
+        gy = TpY.apply(a, g, w, cg) if ctx.needs_input_grad[1] else None
+        gw = TpW.apply(a, y, g, cg) if ctx.needs_input_grad[2] else None
+        return ga, gy, gw, None
+
+
+class TpY(torch.autograd.Function):
+    """o[e, j] = sum_f w[e, f] sum_ik C[i, j, k] a[e, i, f] g[e, k, f]"""
+
+    @staticmethod
+    def forward(ctx, a, g, w, cg):
+        ctx.save_for_backward(a, g, w, cg)
+        return _tp_call(1, a, g, w, cg, (a.shape[0], cg.shape[1]))
+
+    @staticmethod
+    def backward(ctx, gy):
+        a, g, w, cg = ctx.saved_tensors
+        ga = TpOut.apply(g, gy, w, cg.permute(2, 1, 0)) if ctx.needs_input_grad[0] else None
+        gg = TpOut.apply(a, gy, w, cg) if ctx.needs_input_grad[1] else None
+        gw = TpW.apply(a, gy, g, cg) if ctx.needs_input_grad[2] else None
+        return ga, gg, gw, None
+
+
+class TpW(torch.autograd.Function):
+    """o[e, f] = sum_ijk C[i, j, k] a[e, i, f] y[e, j] g[e, k, f]"""
+
+    @staticmethod
+    def forward(ctx, a, y, g, cg):
+        ctx.save_for_backward(a, y, g, cg)
+        return _tp_call(2, a, y, g, cg, (a.shape[0], a.shape[2]))
+
+    @staticmethod
+    def backward(ctx, gw):
+        a, y, g, cg = ctx.saved_tensors
+        ga = TpOut.apply(g, y, gw, cg.permute(2, 1, 0)) if ctx.needs_input_grad[0] else None
+        gy = TpY.apply(a, g, gw, cg) if ctx.needs_input_grad[1] else None
+        gg = TpOut.apply(a, y, gw, cg) if ctx.needs_input_grad[2] else None
+        return ga, gy, gg, None
+
+
+def _chan_call(mode, p0, p1, n, f, p, ni, out_shape):
+    p0, p1 = _chk(p0.contiguous()), _chk(p1.contiguous())
+    out = torch.empty(out_shape, dtype=p0.dtype, device=p0.device)
+    _lib.call("hgb_mace_chan_contract", mode, _p(p0), _p(p1), n, f, p, ni, _p(out), _stream())
+    return out
+
+
+class ChanCL(torch.autograd.Function):
+    """o[b, c, p] = sum_i t[b, c, p, i] x[b, i, c] (one contraction step of symmetric_contraction.py:228-239)"""
+
+    @staticmethod
+    def forward(ctx, t, x):
+        ctx.save_for_backward(t, x)
+        n, f, p, ni = t.shape
+        return _chan_call(0, t, x, n, f, p, ni, (n, f, p))
+
+    @staticmethod
+    def backward(ctx, g):
+        t, x = ctx.saved_tensors
+        return (ChanOU.apply(g, x) if ctx.needs_input_grad[0] else None), (ChanRP.apply(g, t) if ctx.needs_input_grad[1] else None)
+
+
+class ChanOU(torch.autograd.Function):
+    """o[b, c, p, i] = g[b, c, p] x[b, i, c]"""
+
+    @staticmethod
+    def forward(ctx, g, x):
+        ctx.save_for_backward(g, x)
+        n, f, p = g.shape
+        ni = x.shape[1]
+        return _chan_call(1, g, x, n, f, p, ni, (n, f, p, ni))
+
+    @staticmethod
+    def backward(ctx, go):
+        g, x = ctx.saved_tensors
+        return (ChanCL.apply(go, x) if ctx.needs_input_grad[0] else None), (ChanRP.apply(g, go) if ctx.needs_input_grad[1] else None)
+
+
+class ChanRP(torch.autograd.Function):
+    """o[b, i, c] = sum_p g[b, c, p] t[b, c, p, i]"""
+
+    @staticmethod
+    def forward(ctx, g, t):
+        ctx.save_for_backward(g, t)
+        n, f, p, ni = t.shape
+        return _chan_call(2, g, t, n, f, p, ni, (n, ni, f))
+
+    @staticmethod
+    def backward(ctx, gx):
+        g, t = ctx.saved_tensors
+        return (ChanCL.apply(t, gx) if ctx.needs_input_grad[0] else None), (ChanOU.apply(g, gx) if ctx.needs_input_grad[1] else None)
 
 
 def adamw_step(p, g, m, v, step_dev, lr, beta1, beta2, eps, weight_decay, grad_scale=1.0, hyper_dev=None):

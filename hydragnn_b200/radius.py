@@ -108,7 +108,7 @@ class RadiusGraph:
             raise RuntimeError("b200 radius graph: open-boundary search runs in fp32 (got %s)" % pos.dtype)
         gptr, g = _graph_ptr(data, pos.shape[0], pos.device)
         data.edge_index, rowptr = radius_graph(pos, self.r, gptr, g, self.loop, self.max_num_neighbors)
-        data._hgb_col_sorted = (data.edge_index, rowptr)      # edges are grouped by target: the by-target CSR is free
+        data._hgb_col_sorted = (data.edge_index, rowptr, gptr)   # edges grouped by target and by graph: both CSR views are cheap
         data.edge_attr = None                     # PyG RadiusGraph.forward resets edge_attr [3P-memory B.6]
         return data
 

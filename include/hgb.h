@@ -128,6 +128,13 @@ int64_t hgb_exclusive_scan_workspace_bytes(int64_t n);
 int hgb_csr_build(const int64_t* idx, int64_t e, int32_t n, int32_t* idx32, int32_t* rowptr,
                   int32_t* perm, int32_t* guard_flag, void* workspace, hgb_stream_t stream);
 int64_t hgb_csr_workspace_bytes(int64_t e, int32_t n);
+/* The same CSR view for index vectors that are GROUPED by graph (what the radius-graph kernels of this library emit: edges
+ * sorted by target, graph k's edges = [edge_ptr[node_ptr[k]], edge_ptr[node_ptr[k+1]]) and referencing only its own nodes):
+ * one warp per graph fills the segments in ascending edge id with warp-level ranking -- no sort.  node_ptr [g+1], edge_ptr [n+1]. */
+int hgb_csr_build_grouped(const int64_t* idx, int64_t e, int32_t n, const int32_t* node_ptr, const int32_t* edge_ptr,
+                          int32_t g, int32_t* idx32, int32_t* rowptr, int32_t* perm, int32_t* guard_flag,
+                          void* workspace, hgb_stream_t stream);
+int64_t hgb_csr_grouped_workspace_bytes(int64_t e, int32_t n);
 /* out[p] = idx[perm[p]]: the neighbour node of every CSR slot */
 int hgb_gather_i32(const int32_t* idx, const int32_t* perm, int64_t e, int32_t* out, hgb_stream_t stream);
 
@@ -201,11 +208,14 @@ int64_t hgb_linear_smallk_bwd_workspace_bytes(int32_t m, int32_t n, int32_t k);
  * gradient THROUGH the activation that produced this layer's input (gsrc = its saved pre-activation for SiLU,
  * its output for the others; gact = HGB_ACT_DERIV: gsrc already holds act'), which removes the separate
  * activation-backward pass.  Forward calls with gsrc = NULL, gact = HGB_ACT_DERIV, act = SiLU and z != NULL store
- * silu'(pre-activation) in z instead of the pre-activation.  n_out, k_red up to 1024 are cut into <= 256 pieces.                                                                     */
+ * silu'(pre-activation) in z instead of the pre-activation.  n_out, k_red up to 1024 are cut into <= 256 pieces.
+ * exact != 0: fp32-accurate mode for the fp32 configs -- every operand is split in shared memory into a TF32 hi / lo
+ * pair (four extra warps split each A stage as the TMA lands it) and each k-step issues hi*hi + lo*hi + hi*lo
+ * ("3xTF32", error ~1e-6 relative against fp64, tests/test_gpu_round2.py).                                             */
 int hgb_tc_linear_supported(int32_t m, int32_t n_out, int32_t k_red);
 int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_t ldw, int32_t trans_b, const float* bias,
                   int32_t m, int32_t n_out, int32_t k_red, int32_t act, float act_param, float* y, float* z,
-                  const float* addend, const float* gsrc, int32_t gact, hgb_stream_t stream);
+                  const float* addend, const float* gsrc, int32_t gact, int32_t exact, hgb_stream_t stream);
 /* dw[n_out,k_out] (row stride lddw) (+)= dz[m,n_out]^T . x[m,k_out] and db[n_out] (+)= column sums of dz
  * (db may be NULL) in one pass: both operands are consumed MN-major straight from the row-major tensors, the
  * bias gradient rides along as extra all-ones columns of the B operand.  Deterministic two-stage reduce.      */
@@ -322,6 +332,33 @@ int hgb_mha_tc_fwd(const float* qkv, int32_t n, int32_t f, int32_t heads, int32_
                    hgb_stream_t stream);
 int hgb_mha_tc_bwd(const float* qkv, const float* out, const float* lse, const float* gout, int32_t n, int32_t f,
                    int32_t heads, int32_t exact, float* delta_ws, float* gqkv, hgb_stream_t stream);
+
+/* Closed (any-order differentiable) MACE primitives for the force-training path and for shapes outside the fused first-order
+ * kernels (replace the torch.einsum compositions of round 1; hydragnn/utils/model/mace_utils/modules/blocks.py:386-397,
+ * symmetric_contraction.py:217-239).  cg [ni, nj, nk]: real coupling tensor of ONE tensor-product path (each <= 7).
+ *   tp_path mode 0:  out [e, nk, f] = p2[e, f] * sum_ij cg[i, j, k] p0[e, i, f] p1[e, j]            (a, y, w)
+ *           mode 1:  out [e, nj]    = sum_f p2[e, f] sum_ik cg[i, j, k] p0[e, i, f] p1[e, k, f]      (a, g, w)
+ *           mode 2:  out [e, f]     = sum_ijk cg[i, j, k] p0[e, i, f] p1[e, j] p2[e, k, f]            (a, y, g)
+ *   chan_contract mode 0: out [n, f, p]     = sum_i p0[n, f, p, i] p1[n, i, f]
+ *                 mode 1: out [n, f, p, ni] = p0[n, f, p] p1[n, i, f]
+ *                 mode 2: out [n, ni, f]    = sum_p p0[n, f, p] p1[n, f, p, i]
+ * Each family is closed under differentiation (the derivative of every mode is another mode, possibly with cg permuted).  */
+int hgb_mace_tp_path(int32_t mode, const float* p0, const float* p1, const float* p2, const float* cg, int64_t e, int32_t f,
+                     int32_t ni, int32_t nj, int32_t nk, float* out, hgb_stream_t stream);
+int hgb_mace_chan_contract(int32_t mode, const float* p0, const float* p1, int64_t n, int32_t f, int32_t p, int32_t ni,
+                           float* out, hgb_stream_t stream);
+
+/* Grouped dense layers for multi-branch decoding (hydragnn/models/Base.py:770-780 graph heads, :816-840 node heads,
+ * hydragnn/models/MultiTaskModelMP.py): rows sorted by dataset branch, rowptr [groups + 1] on the device, every 64-row tile
+ * picks the weight matrix of its group -- one launch per layer instead of a boolean-mask loop over `dataset_name.unique()`.
+ * trans_w == 0: y [m, n] = act(x [m, k] W_g^T + b_g), w [groups, n, k], bias [groups, n] (optional), z = pre-activation (optional).
+ * trans_w != 0: y [m, n] = x [m, k] W_g with w [groups, k, n] (the data gradient; no bias / act).                          */
+int hgb_grouped_linear(const float* x, int64_t ldx, const float* w, const float* bias, const int32_t* rowptr, int32_t groups,
+                       int32_t m, int32_t n, int32_t k, int32_t trans_w, int32_t act, float act_param, float* y, float* z,
+                       hgb_stream_t stream);
+/* dw [groups, n, k] = per-group dy [m, n]^T x [m, k]; db [groups, n] (optional) = per-group column sums of dy */
+int hgb_grouped_wgrad(const float* dy, const float* x, int64_t ldx, const int32_t* rowptr, int32_t groups, int32_t m, int32_t n,
+                      int32_t k, float* dw, float* db, hgb_stream_t stream);
 
 /* fp32-ACCURATE tensor-core GEMMs for the exact-fp32 mode (nn.Linear forward / dgrad / wgrad of every stack under
  * precision "fp32", e.g. EGCLStack.py:245-263, PNAEqStack.py:326-476, Base.py heads): mma.sync m16n8k8 TF32 with every

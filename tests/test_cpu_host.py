@@ -145,7 +145,7 @@ def test_create_model_config_surface():
                                 equivariance=None, pe_dim=0, global_attn_engine=None),
            "Training": {"loss_function_type": "mse", "precision": "bf16"}}
     m = hb.create_model_config(cfg)
-    assert m.precision == "bf16" and str(m) == "PAINNStack"
+    assert m.precision == "bf16" and str(m) == "Base" and type(m).__name__ == "PAINNStack"
     cfg["Training"]["precision"] = "fp64"
     with pytest.raises(ValueError):
         hb.create_model_config(cfg)
@@ -364,4 +364,4 @@ def test_c4_and_c5_synthetic_workloads_and_multihead_indices():
     assert torch.equal(c5.batch, torch.repeat_interleave(torch.arange(64), n5))
     kw = dict(ARCH["gfm_pnaeq_mini"], pna_deg=[0, 3, 5, 9])
     g = hb.create_model(use_gpu=False, **kw)
-    assert str(g) == "PNAEqStack" and g.use_global_attn and len(g.graph_convs) == 3
+    assert str(g) == "Base" and type(g).__name__ == "PNAEqStack" and g.use_global_attn and len(g.graph_convs) == 3

@@ -468,3 +468,99 @@ def test_pna_aggregate_kernel_hand_computed_cases():
     torch.testing.assert_close(out.detach().cpu(), want, rtol=1e-6, atol=1e-6)
     out.sum().backward()                                           # subgradients exist everywhere (no NaN from the std floor)
     assert bool(torch.isfinite(x.grad).all())
+
+
+# ---- multi-branch decoding as grouped GEMMs (row f4) ---------------------------------------------------------------------------
+def test_multibranch_grouped_decoding_matches_oracle():
+    """Three dataset branches, a graph head and a node head: the engine sorts rows by branch on the device and runs every head layer
+    as one grouped GEMM (hgb_grouped_linear / hgb_grouped_wgrad); outputs, loss and every parameter gradient equal the oracle's
+    boolean-mask loop (Base.py:770-780, 816-840).  A branch that receives no graph in this batch gets zero gradients."""
+    name, g = "qm9_painn", 40
+    cpu = add_edges_cpu(make_samples(name, g), name)
+    gen = torch.Generator().manual_seed(5)
+    ids = torch.randint(0, 3, (g, 1), generator=gen)
+    ids[ids == 2] = 0                                                # branch 2 stays empty in this batch
+    cpu.dataset_name = ids
+    n = cpu.pos.shape[0]
+    cpu.y = torch.cat([torch.randn(g, 1, generator=gen), torch.randn(g, 9 * 3, generator=gen)], dim=1).reshape(-1, 1)
+    cpu.y_loc = torch.tensor([[0, 1, 28]]).expand(g, 3).contiguous()
+    arch_g = {"num_sharedlayers": 2, "dim_sharedlayers": 10, "num_headlayers": 2, "dim_headlayers": [20, 10]}
+    arch_n = {"num_headlayers": 2, "dim_headlayers": [24, 12], "type": "mlp"}
+    kw = dict(ARCH[name], output_dim=[1, 3], output_type=["graph", "node"], task_weights=[1.0, 1.0],
+              output_heads={"graph": [{"type": "branch-%d" % b, "architecture": dict(arch_g)} for b in range(3)],
+                            "node": [{"type": "branch-%d" % b, "architecture": dict(arch_n)} for b in range(3)]})
+    om = oracle.base.create_model(**kw)
+    em = hb.create_model(**kw)
+    em.load_state_dict(om.state_dict())
+    gpu = cpu.clone().to(DEV)
+    gpu._num_graphs = g
+    hi_c = hb.get_head_indices(om, cpu)
+    hi_g = [h.to(DEV) for h in hi_c]
+    before = hb._lib.launch_count()
+    hb._lib.trace_begin()
+    po, pe = om(cpu), em(gpu)
+    calls = [c[0] for c in hb._lib.trace_end()]
+    assert "hgb_grouped_linear" in calls                             # the grouped path ran (not the per-branch fallback)
+    for a, b in zip(pe, po):
+        assert rel_l2(a.detach(), b.detach()) < 1e-5
+    lo, _ = om.loss(po, cpu.y, hi_c)
+    le, _ = em.loss(pe, gpu.y, hi_g)
+    torch.testing.assert_close(le.detach().cpu(), lo.detach(), rtol=1e-5, atol=1e-6)
+    lo.backward()
+    le.backward()
+    assert _grad_rel(em, om) < 1e-4
+    en = dict(em.named_parameters())
+    for k, q in om.named_parameters():
+        if "branch-2" in k:
+            assert q.grad is None or float(q.grad.abs().max()) == 0.0
+            assert en[k].grad is None or float(en[k].grad.abs().max()) == 0.0
+
+
+def test_grouped_csr_build_equals_radix_sort_build():
+    """hgb_csr_build_grouped (one warp per graph, match_any ranking, no sort) gives the SAME rowptr / perm as the radix-sort build
+    for the radius-graph output of mixed-size batches, open and periodic."""
+    for name, g in (("gfm_pnaeq", 24), ("qm9_painn", 300), ("oc20_mace", 3)):
+        w = WORKLOADS[name]
+        d = make_samples(name, g).to(DEV)
+        d._num_graphs = g
+        d.ptr = d.ptr.int()
+        if w.get("pbc_box"):
+            cut = torch.full((g,), float(w["radius"]), dtype=torch.float64, device=DEV)
+            ei, _, _, _, outptr, _ = radius.radius_graph_pbc(d.pos, d.cell, d.pbc, cut, d.ptr, g, w["max_neighbours"])
+            rowptr = outptr
+        else:
+            ei, rowptr = radius.radius_graph(d.pos, w["radius"], d.ptr, g, False, w["max_neighbours"])
+        n = d.pos.shape[0]
+        a = ops.EdgePlan(ei, n, col_rowptr=rowptr, graph_ptr=d.ptr)
+        b = ops.EdgePlan(ei, n)
+        assert torch.equal(a.by_row.rowptr, b.by_row.rowptr) and torch.equal(a.by_row.perm, b.by_row.perm)
+        assert torch.equal(a.by_row.idx, b.by_row.idx)
+        assert torch.equal(a.by_col.rowptr, b.by_col.rowptr) and torch.equal(a.by_col.perm, b.by_col.perm)
+    ops.check_guard(DEV)
+
+
+# ---- tcgen05 Linears in fp32 mode: the 3xTF32 split inside tc_linear (exact flag) -------------------------------------------
+@pytest.mark.parametrize("m,n,k", [(5000, 64, 64), (4097, 192, 128), (128, 32, 32), (30000, 64, 128), (2000, 448, 64)])
+def test_tc_linear_exact_mode_matches_fp64(m, n, k):
+    """fp32 mode routes the large-M Linears through the SAME tcgen05 kernel with every operand split into TF32 hi / lo pairs in
+    shared memory (hi*hi + lo*hi + hi*lo per k-step): results within ~1e-6 of fp64, i.e. fp32-level -- the plain TF32 mode of the
+    bf16 configs is ~1e-3."""
+    g = torch.Generator().manual_seed(m + n)
+    x, w, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) * 0.3, torch.randn(n, generator=g)
+    xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
+    assert ops.EXACT_TC and not ops._TC["enabled"] and ops.tc_ok(m, n, k, xd)
+    hb._lib.trace_begin()
+    y, z, _ = ops.linear_fwd_dispatch_ex(xd, wd, bd, ops.ACT_CODES["silu"], 0.0, want_z=True)
+    calls = [c for c in hb._lib.trace_end() if c[0] == "hgb_tc_linear"]
+    assert calls and all(c[1]["exact"] == 1 for c in calls)
+    zr = x.double() @ w.double().t() + b.double()
+    assert rel_l2(z, zr) < 2e-6, rel_l2(z, zr)
+    assert rel_l2(y, torch.nn.functional.silu(zr)) < 2e-6
+    gy = torch.randn(m, n, generator=g)
+    add = torch.randn(m, k, generator=g)
+    dx, _, _ = ops.linear_bwd_dispatch(gy.to(DEV), xd, wd, True, False, False, dx_addend=add.to(DEV))    # dgrad (+ addend epilogue)
+    assert rel_l2(dx, gy.double() @ w.double() + add.double()) < 2e-6
+    with ops.tensor_cores(True):                                                                       # plain TF32 for comparison
+        y32, _ = ops.linear_fwd_dispatch(xd, wd, bd)
+    e_tf32 = rel_l2(y32, zr)
+    assert 1e-5 < e_tf32 < 5e-3                                                                        # the split is what buys the accuracy
