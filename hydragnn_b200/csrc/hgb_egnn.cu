@@ -343,10 +343,12 @@ __global__ void __launch_bounds__(NT) egnn_edge_wgrad_kernel(
     float* __restrict__ partial /* [grid][H*H + H] */) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemW<H>& sm = *reinterpret_cast<SmemW<H>*>(smem_raw);
-  constexpr int MO = H == 64 ? 8 : 4, NI = (H * H) / (NT * MO);   // register tile: MO outs x NI ins  (H = 64: 8 x 4, H = 32: 4 x 2)
-  constexpr int IG = H / NI;                             // threads along "in"
+  // register tile 8 outs x 8 ins; the (H/8)^2 tiles need (H/8)^2 threads, so the 128 threads form NSL slices of the edge (k)
+  // dimension (H = 64: 2 slices of 64 edges, H = 32: 8 slices of 16) whose partial sums are reduced with the per-CTA partials
+  constexpr int MO = 8, NI = 8, TPS = (H / 8) * (H / 8), NSL = NT / TPS, KSL = TE / NSL;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int m0 = (t / IG) * MO, i0 = (t % IG) * NI;
+  const int slice = t / TPS, tt = t % TPS;
+  const int m0 = (tt / (H / 8)) * MO, i0 = (tt % (H / 8)) * NI;
   for (int i = t; i < H; i += NT) {
     sm.vec[i] = wd[i];
     sm.vec[H + i] = (!TANGENT && b0) ? b0[i] : 0.f;
@@ -420,20 +422,14 @@ __global__ void __launch_bounds__(NT) egnn_edge_wgrad_kernel(
       }
       __syncthreads();
 #pragma unroll 4
-      for (int k = 0; k < TE; ++k) {
-        float a[MO], b[NI];
-#pragma unroll
-        for (int q = 0; q < MO / 4; ++q) {
-          const float4 av = *reinterpret_cast<const float4*>(sm.x + k * H + m0 + 4 * q);
-          a[4 * q] = av.x; a[4 * q + 1] = av.y; a[4 * q + 2] = av.z; a[4 * q + 3] = av.w;
-        }
-        if constexpr (NI == 4) {
-          const float4 bv = *reinterpret_cast<const float4*>(sm.y + k * H + i0);
-          b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
-        } else {
-          const float2 bv = *reinterpret_cast<const float2*>(sm.y + k * H + i0);
-          b[0] = bv.x; b[1] = bv.y;
-        }
+      for (int kk = 0; kk < KSL; ++kk) {
+        const int k = slice * KSL + kk;
+        const float4 a0 = *reinterpret_cast<const float4*>(sm.x + k * H + m0);
+        const float4 a1 = *reinterpret_cast<const float4*>(sm.x + k * H + m0 + 4);
+        const float4 b0v = *reinterpret_cast<const float4*>(sm.y + k * H + i0);
+        const float4 b1v = *reinterpret_cast<const float4*>(sm.y + k * H + i0 + 4);
+        const float a[MO] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float b[NI] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
 #pragma unroll
         for (int i = 0; i < MO; ++i)
 #pragma unroll
@@ -444,12 +440,15 @@ __global__ void __launch_bounds__(NT) egnn_edge_wgrad_kernel(
       __syncthreads();
     }
   }
-  float* out = partial + (int64_t)blockIdx.x * (H * H + H);
+  float* out = partial + ((int64_t)blockIdx.x * NSL + slice) * (H * H + H);
 #pragma unroll
   for (int i = 0; i < MO; ++i)
 #pragma unroll
     for (int j = 0; j < NI; ++j) out[(m0 + i) * H + i0 + j] = acc[i][j];
-  if (t < H) out[H * H + t] = (float)bsum;
+  // bias column sums: thread t < H owns column t (summed over every edge of this CTA); they go into slice 0's partial
+  if (t < H)
+    for (int sl = 0; sl < NSL; ++sl)
+      partial[((int64_t)blockIdx.x * NSL + sl) * (H * H + H) + H * H + t] = sl == 0 ? (float)bsum : 0.f;
 }
 
 // out[c] = sum_e w[e] x[e][c]   (two-stage, deterministic)
@@ -494,9 +493,11 @@ static inline int egnn_grid(int n, int nb) {
   return ntiles < HGB_NUM_SMS * 3 ? ntiles : HGB_NUM_SMS * 3;
 }
 
+static inline int egnn_wgrad_slices(int h) { return NT / ((h / 8) * (h / 8)); }
+
 extern "C" int64_t hgb_egnn_edge_workspace_bytes(int32_t n, int32_t h, int32_t nodes_per_tile) {
   const int g = egnn_grid(n, nodes_per_tile > 0 ? nodes_per_tile : 1);
-  return (int64_t)g * ((int64_t)h * h + 2 * h) * 4 + 256;
+  return (int64_t)g * egnn_wgrad_slices(h) * ((int64_t)h * h + 2 * h) * 4 + 256;
 }
 
 extern "C" int hgb_egnn_edge_fwd(const float* pq, const float* s, const float* wd, const float* b0, const float* w1,
@@ -569,7 +570,7 @@ extern "C" int hgb_egnn_edge_wgrad(const float* g_out, const float* pq, const fl
 #undef HGB_EGNN_WG
   HGB_LAUNCH_CHECK("egnn_edge_wgrad");
   const int width = h * h + h;
-  egnn_reduce_partials_kernel<<<(width + 127) / 128, 128, 0, st>>>(partial, grid, width, g_w1, h * h, g_b1);
+  egnn_reduce_partials_kernel<<<(width + 127) / 128, 128, 0, st>>>(partial, grid * egnn_wgrad_slices(h), width, g_w1, h * h, g_b1);
   HGB_LAUNCH_CHECK("egnn_reduce_partials");
   return HGB_OK;
 }

@@ -110,6 +110,87 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
   }
 }
 
+// ---- weight-gradient form with a long reduction:  C[mo, no] = sum_r A[r, mo]^T B[r, no],  r up to 10^6 rows ----------------------
+// The generic kernel above splits K over hundreds of tiny CTAs (64 x 64 x 16 tiles, 4 x 4 register tiles: 2 FMA per shared-memory
+// word).  Here every CTA streams 128-row chunks of both operands through shared memory with cp.async, keeps the WHOLE [mo, no]
+// result in registers as 8 x 8 tiles (the (mo/8)(no/8) tiles take that many threads; the 128 threads form NSL slices of the chunk's
+// rows), and writes one partial per (CTA, slice); a fixed-order reduce finishes.  Exact fp32 FMAs.
+constexpr int TNF_ROWS = 128, TNF_THREADS = 128;
+
+__device__ __forceinline__ void tnf_cp16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+
+__global__ void __launch_bounds__(TNF_THREADS) gemm_tn_fast_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                   int64_t lda, int64_t ldb, int r_total, int mo, int no,
+                                                                   int chunks_per_cta, float* __restrict__ part) {
+  extern __shared__ __align__(16) float tnf_smem[];
+  float* sa = tnf_smem;                         // [TNF_ROWS][mo]
+  float* sb = sa + TNF_ROWS * mo;               // [TNF_ROWS][no]
+  const int t = threadIdx.x;
+  const int tps = (mo / 8) * (no / 8), nsl = TNF_THREADS / tps, ksl = TNF_ROWS / nsl;
+  const int slice = t / tps, tt = t % tps;
+  const int m0 = (tt / (no / 8)) * 8, n0 = (tt % (no / 8)) * 8;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const int nchunks = (r_total + TNF_ROWS - 1) / TNF_ROWS;
+  const int c_beg = blockIdx.x * chunks_per_cta, c_end = min(nchunks, c_beg + chunks_per_cta);
+  const int ca = mo / 4, cb = no / 4;
+  for (int ch = c_beg; ch < c_end; ++ch) {
+    const int row0 = ch * TNF_ROWS;
+    __syncthreads();
+    for (int i = t; i < TNF_ROWS * ca; i += TNF_THREADS) {
+      const int r = i / ca, c4 = i - r * ca;
+      float* dst = sa + r * mo + 4 * c4;
+      if (row0 + r < r_total) tnf_cp16(dst, a + (int64_t)(row0 + r) * lda + 4 * c4);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int i = t; i < TNF_ROWS * cb; i += TNF_THREADS) {
+      const int r = i / cb, c4 = i - r * cb;
+      float* dst = sb + r * no + 4 * c4;
+      if (row0 + r < r_total) tnf_cp16(dst, b + (int64_t)(row0 + r) * ldb + 4 * c4);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+#pragma unroll 4
+    for (int kk = 0; kk < ksl; ++kk) {
+      const int k = slice * ksl + kk;
+      const float4 a0 = *reinterpret_cast<const float4*>(sa + k * mo + m0);
+      const float4 a1 = *reinterpret_cast<const float4*>(sa + k * mo + m0 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(sb + k * no + n0);
+      const float4 b1 = *reinterpret_cast<const float4*>(sb + k * no + n0 + 4);
+      const float ra[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float rb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ra[i], rb[j], acc[i][j]);
+    }
+  }
+  float* out = part + ((int64_t)blockIdx.x * nsl + slice) * mo * no;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    *reinterpret_cast<float4*>(out + (m0 + i) * no + n0) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    *reinterpret_cast<float4*>(out + (m0 + i) * no + n0 + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+  }
+}
+
+static bool tn_fast_ok(int m, int n, int k, int64_t lda, int64_t ldb, const void* a, const void* b) {
+  if (k < 8192 || m % 8 || n % 8 || lda % 4 || ldb % 4) return false;
+  if (((uintptr_t)a % 16) || ((uintptr_t)b % 16)) return false;
+  const int tps = (m / 8) * (n / 8);
+  if (tps < 1 || tps > TNF_THREADS || (TNF_THREADS % tps) != 0) return false;
+  return (size_t)TNF_ROWS * (m + n) * 4 <= 160 * 1024;
+}
+static int tn_fast_grid(int k) {
+  const int nchunks = (k + TNF_ROWS - 1) / TNF_ROWS;
+  return nchunks < HGB_NUM_SMS * 2 ? nchunks : HGB_NUM_SMS * 2;
+}
+
 static int pick_splits(int m, int n, int k) {
   const int tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
   if (tiles >= HGB_NUM_SMS || k < 4096) return 1;
@@ -121,7 +202,15 @@ static int pick_splits(int m, int n, int k) {
 
 extern "C" int64_t hgb_gemm_workspace_bytes(int32_t m, int32_t n, int32_t k, int32_t trans_a) {
   const int s = pick_splits(m, n, k);
-  return s > 1 ? (int64_t)s * m * n * 4 : 0;
+  int64_t bytes = s > 1 ? (int64_t)s * m * n * 4 : 0;
+  if (trans_a && m % 8 == 0 && n % 8 == 0 && m > 0 && n > 0) {
+    const int tps = (m / 8) * (n / 8);
+    if (tps >= 1 && tps <= TNF_THREADS && TNF_THREADS % tps == 0) {
+      const int64_t fast = (int64_t)tn_fast_grid(k) * (TNF_THREADS / tps) * m * n * 4;
+      if (fast > bytes) bytes = fast;
+    }
+  }
+  return bytes;
 }
 
 template <bool TA, bool TB>
@@ -157,6 +246,23 @@ extern "C" int hgb_gemm(const float* a, const float* b, float* c, int32_t m, int
     return HGB_OK;
   }
   if (trans_a && trans_b) return launch_gemm<true, true>(a, b, c, m, n, k, lda, ldb, ldc, beta_one, workspace, workspace_bytes, nullptr, 0, 0.f, nullptr, st);
+  if (trans_a && tn_fast_ok(m, n, k, lda, ldb, a, b)) {
+    const int tps = (m / 8) * (n / 8), nsl = TNF_THREADS / tps;
+    const int grid0 = tn_fast_grid(k);
+    if (workspace && workspace_bytes >= (int64_t)grid0 * nsl * m * n * 4) {
+      const int nchunks = (k + TNF_ROWS - 1) / TNF_ROWS;
+      const int cpc = (nchunks + grid0 - 1) / grid0;
+      const int grid = (nchunks + cpc - 1) / cpc;
+      const size_t smem = (size_t)TNF_ROWS * (m + n) * 4;
+      cudaFuncSetAttribute(gemm_tn_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      gemm_tn_fast_kernel<<<grid, TNF_THREADS, smem, st>>>(a, b, lda, ldb, k, m, n, cpc, (float*)workspace);
+      HGB_LAUNCH_CHECK("gemm_tn_fast");
+      splitk_reduce_kernel<<<hgb_grid_for((int64_t)m * n, 32), dim3(32, 8), 0, st>>>((const float*)workspace, grid * nsl, (int64_t)m * n, n,
+                                                                              ldc, beta_one, c);
+      HGB_LAUNCH_CHECK("splitk_reduce");
+      return HGB_OK;
+    }
+  }
   if (trans_a) return launch_gemm<true, false>(a, b, c, m, n, k, lda, ldb, ldc, beta_one, workspace, workspace_bytes, nullptr, 0, 0.f, nullptr, st);
   if (trans_b) return launch_gemm<false, true>(a, b, c, m, n, k, lda, ldb, ldc, beta_one, workspace, workspace_bytes, nullptr, 0, 0.f, nullptr, st);
   return launch_gemm<false, false>(a, b, c, m, n, k, lda, ldb, ldc, beta_one, workspace, workspace_bytes, nullptr, 0, 0.f, nullptr, st);

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(448, 1) tc_linear_kernel(const __grid_constant
   uint64_t* tfull = full2 + S;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* sbias = reinterpret_cast<float*>(tmem_holder + 4);   // [NO], 16-byte aligned
+  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_holder + 4) + 15) & ~(uintptr_t)15);   // [NO], 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = (p.m + TILE_M - 1) / TILE_M;
@@ -660,13 +660,13 @@ static int tc_linear_piece(const float* a, int64_t lda, const float* w, int64_t 
   const int dup = exact ? 2 : 1;                   // split mode keeps a hi and a lo copy of the weights and of every A stage
   const size_t b_bytes = ((size_t)KB * n_out * 128 + 1023) & ~(size_t)1023;
   const size_t a_stage = (size_t)TILE_M * 128;
-  int stages = (int)((224 * 1024 - 2048 - 65536 - dup * b_bytes - (size_t)n_out * 4) / (dup * a_stage));
+  int stages = (int)((224 * 1024 - 2048 - 256 - 65536 - dup * b_bytes - (size_t)n_out * 4) / (dup * a_stage));
   if (stages > 6) stages = 6;
   HGB_REQUIRE(stages >= 2, "tc_linear: weight operand does not fit shared memory (n=%d k=%d)", n_out, k_red);
   p.stages = stages;
   p.split = exact ? 1 : 0;
   p.tmem_cols = pow2_cols(2 * n_out);
-  const size_t smem = 1024 + dup * b_bytes + dup * stages * a_stage + 65536 + (3 * stages + 4) * 8 + 16 + (size_t)n_out * 4 + 16;
+  const size_t smem = 1024 + dup * b_bytes + dup * stages * a_stage + 65536 + (3 * stages + 4) * 8 + 16 + (size_t)n_out * 4 + 48;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -689,7 +689,7 @@ extern "C" int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_
   HGB_REQUIRE(k_red <= 256 || (act == HGB_ACT_NONE && !z && !gsrc), "tc_linear: reduction length %d > 256 needs a plain linear layer", k_red);
   // piece sizes: the B piece (kc x nc fp32) stays resident in shared memory next to >= 2 A stages and the epilogue tiles
   const int kc_max = k_red < 256 ? k_red : 256;
-  int nc_max = (int)(((exact ? 48 : 122) * 1024) / (4 * (size_t)kc_max) / 32) * 32;     // split mode: two weight copies + two copies per A stage
+  int nc_max = (int)(((exact ? 40 : 122) * 1024) / (4 * (size_t)kc_max) / 32) * 32;     // split mode: two weight copies + two copies per A stage
   if (nc_max > 256) nc_max = 256;
   for (int c0 = 0; c0 < n_out; c0 += nc_max) {
     const int nc = n_out - c0 < nc_max ? n_out - c0 : nc_max;

@@ -332,7 +332,7 @@ def linear_fwd_dispatch_ex(x2, w, b, code=0, param=0.0, want_z=False, z_deriv=Fa
     n = w.shape[0]
     if smallk_ok(n, k):
         return raw_smallk_fwd(x2, w, b, code, param, want_z) + (False,)
-    if tc_ok(m, n, k, x2):
+    if tc_ok(m, n, k, x2) and (k <= 256 or (code == 0 and not want_z)):     # a reduction cut into pieces needs a plain linear layer
         deriv = bool(z_deriv and want_z and code == ACT_CODES["silu"])
         return raw_tc_linear(x2, w, False, b, n, k, code, param, want_z, gact=ACT_DERIV if deriv else 0) + (deriv,)
     return raw_linear(x2, w, b, code, param, want_z) + (False,)
@@ -356,7 +356,7 @@ def linear_bwd_dispatch(dz, x2, w, need_x=True, need_w=True, need_b=True, dx_add
         return through_act(dx + dx_addend if (dx is not None and dx_addend is not None) else dx), dw, db
     dx = dw = db = None
     if need_x:
-        if tc_ok(m, k, n, dz, dx_addend, dx_gsrc):
+        if tc_ok(m, k, n, dz, dx_addend, dx_gsrc) and (n <= 256 or dx_gsrc is None):
             dx = raw_tc_linear(dz, w, True, None, k, n, param=dx_gparam, addend=dx_addend, gsrc=dx_gsrc, gact=dx_gact)[0]
         elif dx_addend is not None:
             dx = through_act(raw_gemm(dz, w, False, False, out=dx_addend.clone(), beta_one=True))

@@ -1,2 +1,2 @@
-timeout 600 python -m pytest tests -m gpu -q --tb=short -x 2>&1 | tail -25
-bash profiles/run_benches.sh r02g md17_egnn gfm_pnaeq lj_egnn 2>&1 | grep -v "^  k " | tail -50
+timeout 700 python -m pytest tests -m gpu -q --tb=short 2>&1 | tail -25
+bash profiles/run_benches.sh r02g md17_egnn gfm_pnaeq 2>&1 | grep -v "^  k " | tail -40

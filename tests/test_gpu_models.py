@@ -210,7 +210,10 @@ def test_force_equivariance_and_translation_invariance():
         f0, e0 = forces(b.pos)
         f1, e1 = forces(b.pos @ q.t() + torch.tensor([1.0, -2.0, 0.5], device=DEV))
         scale = float(f0.abs().max().clamp(min=1e-6))
-        assert float((f1 - f0 @ q.t()).abs().max()) / scale < 1e-4, name
+        err = float((f1 - f0 @ q.t()).abs().max())
+        # the reference's criterion is the ABSOLUTE max force error < 1e-4 (tests/test_forces_equivariant.py:476, "max_error < 1e-4");
+        # the relative figure is kept as a second, looser bound (random-init forces are ~5e-3, fp32 rounding of O(1) activations ~1e-6)
+        assert err < 1e-4 and err / scale < 5e-3, (name, err, err / scale)
         assert float((e1 - e0).abs().max()) / float(e0.abs().max().clamp(min=1e-6)) < 1e-4, name
 
 

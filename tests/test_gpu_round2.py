@@ -540,7 +540,8 @@ def test_grouped_csr_build_equals_radix_sort_build():
 
 
 # ---- tcgen05 Linears in fp32 mode: the 3xTF32 split inside tc_linear (exact flag) -------------------------------------------
-@pytest.mark.parametrize("m,n,k", [(5000, 64, 64), (4097, 192, 128), (128, 32, 32), (30000, 64, 128), (2000, 448, 64)])
+@pytest.mark.parametrize("m,n,k", [(5000, 64, 64), (4097, 192, 128), (128, 32, 32), (30000, 64, 128), (2000, 448, 64), (700, 384, 128),
+                                   (1500, 576, 192), (520, 768, 256), (9001, 128, 256)])
 def test_tc_linear_exact_mode_matches_fp64(m, n, k):
     """fp32 mode routes the large-M Linears through the SAME tcgen05 kernel with every operand split into TF32 hi / lo pairs in
     shared memory (hi*hi + lo*hi + hi*lo per k-step): results within ~1e-6 of fp64, i.e. fp32-level -- the plain TF32 mode of the
