@@ -327,10 +327,12 @@ __global__ void egnn_reduce_partials_kernel(const float* __restrict__ partial, i
 // ------------------------------------------------------------------------------------------------------------------
 template <int H>
 struct SmemW {
-  float x[TE * H];               // gz2, row-major [edge][out]
-  float y[TE * H];               // y,   row-major [edge][in]
-  float nodeg[NBMAX * H];        // g_out rows
-  float nodep[NBMAX * H];        // P rows
+  static constexpr int RS = H + 4;   // row stride of the operand tiles: 16-byte aligned rows, 4-way (not 32-way) conflicts for the
+                                     // one-thread-per-edge producer that writes whole rows
+  float x[TE * RS];              // gz2, row-major [edge][out]
+  float y[TE * RS];              // y,   row-major [edge][in]
+  float nodeg[NBMAX * (H + 1)];  // g_out rows
+  float nodep[NBMAX * (H + 1)];  // P rows
   float vec[2 * H];
   int rp[NBMAX + 1];
 };
@@ -343,12 +345,12 @@ __global__ void __launch_bounds__(NT) egnn_edge_wgrad_kernel(
     float* __restrict__ partial /* [grid][H*H + H] */) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemW<H>& sm = *reinterpret_cast<SmemW<H>*>(smem_raw);
-  // register tile 8 outs x 8 ins; the (H/8)^2 tiles need (H/8)^2 threads, so the 128 threads form NSL slices of the edge (k)
-  // dimension (H = 64: 2 slices of 64 edges, H = 32: 8 slices of 16) whose partial sums are reduced with the per-CTA partials
-  constexpr int MO = 8, NI = 8, TPS = (H / 8) * (H / 8), NSL = NT / TPS, KSL = TE / NSL;
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  // register tile MO outs x NI ins (8 x 8 at H = 64, 4 x 4 at H = 32): 64 threads cover the [H, H] result, so the 128 threads form
+  // two slices of the chunk's 128 edges (k dimension) whose partial sums are reduced together with the per-CTA partials
+  constexpr int MO = H == 64 ? 8 : 4, NI = MO, TPS = (H / MO) * (H / NI), NSL = NT / TPS, KSL = TE / NSL, RS = SmemW<H>::RS;
+  const int t = threadIdx.x;
   const int slice = t / TPS, tt = t % TPS;
-  const int m0 = (tt / (H / 8)) * MO, i0 = (tt % (H / 8)) * NI;
+  const int m0 = (tt / (H / NI)) * MO, i0 = (tt % (H / NI)) * NI;
   for (int i = t; i < H; i += NT) {
     sm.vec[i] = wd[i];
     sm.vec[H + i] = (!TANGENT && b0) ? b0[i] : 0.f;
@@ -364,79 +366,68 @@ __global__ void __launch_bounds__(NT) egnn_edge_wgrad_kernel(
     const int n0 = tile * nb, n1 = min(n, n0 + nb), cntn = n1 - n0;
     for (int i = t; i <= cntn; i += NT) sm.rp[i] = rowptr[n0 + i];
     for (int i = t; i < cntn * H; i += NT) {
-      sm.nodeg[i] = g_out[(int64_t)n0 * H + i];
-      sm.nodep[i] = pq[(int64_t)(n0 + i / H) * 2 * H + (i % H)];
+      sm.nodeg[(i / H) * (H + 1) + (i % H)] = g_out[(int64_t)n0 * H + i];
+      sm.nodep[(i / H) * (H + 1) + (i % H)] = pq[(int64_t)(n0 + i / H) * 2 * H + (i % H)];
     }
     __syncthreads();
     const int e_begin = sm.rp[0], e_end = sm.rp[cntn];
     for (int e0 = e_begin; e0 < e_end; e0 += TE) {
       const int cnt = min(TE, e_end - e0);
-      // producer: every lane first fetches the metadata of ONE edge slot of its warp's 32 (one parallel round of dependent
-      // loads), then the warp walks its slots with lanes over channels (float4): the row loads of successive slots are
-      // independent and pipeline.
+      // producer: one thread per edge slot writes its two operand rows (as the forward kernel does for its operand column)
       {
-        constexpr int LPE = H / 4;                       // lanes per edge row
-        constexpr int EPI = 32 / LPE;                    // edge slots per warp iteration (H = 64: 2, H = 32: 4)
-        const int slot = warp * 32 + lane;
-        int m_il = 0, m_j = 0;
-        float m_s = 0.f;
-        unsigned long long m_b1 = 0ull, m_b2 = 0ull;
-        if (slot < cnt) {
-          const int p = e0 + slot;
-          m_il = local_node(sm.rp, cntn, p);
-          m_j = nbr[p];
-          m_s = s[perm[p]];
-          m_b1 = masks[2 * (int64_t)p];
-          m_b2 = masks[2 * (int64_t)p + 1];
-        }
-        const int sub = lane / LPE, c4 = (lane % LPE) * 4;
+        float* xr = sm.x + t * RS;
+        float* yr = sm.y + t * RS;
+        if (t < cnt) {
+          const int p = e0 + t;
+          const int il = local_node(sm.rp, cntn, p);
+          const int j = nbr[p];
+          const float sv = s[perm[p]];
+          const unsigned long long b1 = masks[2 * (int64_t)p], b2 = masks[2 * (int64_t)p + 1];
+          const float* qrow = pq + (int64_t)j * 2 * H + H;
+          const float* grow = sm.nodeg + il * (H + 1);
+          const float* prow = sm.nodep + il * (H + 1);
 #pragma unroll 4
-        for (int it = 0; it < 32 / EPI; ++it) {
-          const int src = it * EPI + sub;                // lane (within the warp) that holds this slot's metadata
-          const int r = warp * 32 + src;
-          const int il = __shfl_sync(0xffffffffu, m_il, src), j = __shfl_sync(0xffffffffu, m_j, src);
-          const float sv = __shfl_sync(0xffffffffu, m_s, src);
-          const unsigned long long b1 = __shfl_sync(0xffffffffu, m_b1, src), b2 = __shfl_sync(0xffffffffu, m_b2, src);
-          float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), yv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (r < cnt) {
-            const float4 gv = *reinterpret_cast<const float4*>(sm.nodeg + il * H + c4);
-            const float4 pv = *reinterpret_cast<const float4*>(sm.nodep + il * H + c4);
-            const float4 qv = __ldg(reinterpret_cast<const float4*>(pq + (int64_t)j * 2 * H + H + c4));
-            const float4 wv = *reinterpret_cast<const float4*>(sm.vec + c4);
-            const float4 bv = *reinterpret_cast<const float4*>(sm.vec + H + c4);
-            const float g4[4] = {gv.x, gv.y, gv.z, gv.w};
-            const float z4[4] = {fmaf(sv, wv.x, pv.x + qv.x) + bv.x, fmaf(sv, wv.y, pv.y + qv.y) + bv.y,
-                                 fmaf(sv, wv.z, pv.z + qv.z) + bv.z, fmaf(sv, wv.w, pv.w + qv.w) + bv.w};
+          for (int q = 0; q < H / 4; ++q) {
+            const float4 qv = __ldg(reinterpret_cast<const float4*>(qrow) + q);
+            const float qq[4] = {qv.x, qv.y, qv.z, qv.w};
             float xo[4], yo[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              xo[c] = ((b2 >> (c4 + c)) & 1ull) ? g4[c] : 0.f;
-              yo[c] = TANGENT ? (((b1 >> (c4 + c)) & 1ull) ? z4[c] : 0.f) : (z4[c] > 0.f ? z4[c] : 0.f);
+              const int k = 4 * q + c;
+              const float z = fmaf(sv, sm.vec[k], prow[k] + qq[c]) + sm.vec[H + k];
+              xo[c] = ((b2 >> k) & 1ull) ? grow[k] : 0.f;
+              yo[c] = TANGENT ? (((b1 >> k) & 1ull) ? z : 0.f) : (z > 0.f ? z : 0.f);
             }
-            xv = make_float4(xo[0], xo[1], xo[2], xo[3]);
-            yv = make_float4(yo[0], yo[1], yo[2], yo[3]);
+            *reinterpret_cast<float4*>(xr + 4 * q) = make_float4(xo[0], xo[1], xo[2], xo[3]);
+            *reinterpret_cast<float4*>(yr + 4 * q) = make_float4(yo[0], yo[1], yo[2], yo[3]);
           }
-          *reinterpret_cast<float4*>(sm.x + r * H + c4) = xv;
-          *reinterpret_cast<float4*>(sm.y + r * H + c4) = yv;
+        } else {
+#pragma unroll 4
+          for (int q = 0; q < H / 4; ++q) {
+            *reinterpret_cast<float4*>(xr + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(yr + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
       }
       __syncthreads();
 #pragma unroll 4
       for (int kk = 0; kk < KSL; ++kk) {
         const int k = slice * KSL + kk;
-        const float4 a0 = *reinterpret_cast<const float4*>(sm.x + k * H + m0);
-        const float4 a1 = *reinterpret_cast<const float4*>(sm.x + k * H + m0 + 4);
-        const float4 b0v = *reinterpret_cast<const float4*>(sm.y + k * H + i0);
-        const float4 b1v = *reinterpret_cast<const float4*>(sm.y + k * H + i0 + 4);
-        const float a[MO] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float b[NI] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
+        float a[MO], b[NI];
+#pragma unroll
+        for (int q = 0; q < MO / 4; ++q) {
+          const float4 av = *reinterpret_cast<const float4*>(sm.x + k * RS + m0 + 4 * q);
+          a[4 * q] = av.x; a[4 * q + 1] = av.y; a[4 * q + 2] = av.z; a[4 * q + 3] = av.w;
+          const float4 bv = *reinterpret_cast<const float4*>(sm.y + k * RS + i0 + 4 * q);
+          b[4 * q] = bv.x; b[4 * q + 1] = bv.y; b[4 * q + 2] = bv.z; b[4 * q + 3] = bv.w;
+        }
 #pragma unroll
         for (int i = 0; i < MO; ++i)
 #pragma unroll
           for (int j = 0; j < NI; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
       }
       if (t < H)
-        for (int k = 0; k < cnt; ++k) bsum += (double)sm.x[k * H + t];
+        for (int k = 0; k < cnt; ++k) bsum += (double)sm.x[k * RS + t];
       __syncthreads();
     }
   }
@@ -493,7 +484,7 @@ static inline int egnn_grid(int n, int nb) {
   return ntiles < HGB_NUM_SMS * 3 ? ntiles : HGB_NUM_SMS * 3;
 }
 
-static inline int egnn_wgrad_slices(int h) { return NT / ((h / 8) * (h / 8)); }
+static inline int egnn_wgrad_slices(int h) { return 2; }     // see egnn_edge_wgrad_kernel: 64 tile threads, two k-slices
 
 extern "C" int64_t hgb_egnn_edge_workspace_bytes(int32_t n, int32_t h, int32_t nodes_per_tile) {
   const int g = egnn_grid(n, nodes_per_tile > 0 ? nodes_per_tile : 1);

@@ -285,8 +285,8 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __rest
 extern "C" int hgb_act_bwd(const float* dy, const float* y, const float* z, int64_t count, int32_t act, float act_param,
                            float* dz, hgb_stream_t stream) {
   HGB_REQUIRE(count >= 0 && dy && dz, "act_bwd: bad arguments");
-  HGB_REQUIRE(act != HGB_ACT_SILU || z, "act_bwd: SiLU needs the pre-activation z");
-  HGB_REQUIRE(act == HGB_ACT_SILU || act == HGB_ACT_NONE || y, "act_bwd: needs the activation output y");
+  HGB_REQUIRE((act != HGB_ACT_SILU && act != HGB_ACT_DERIV) || z, "act_bwd: SiLU needs the pre-activation z (HGB_ACT_DERIV: the stored derivative)");
+  HGB_REQUIRE(act == HGB_ACT_SILU || act == HGB_ACT_DERIV || act == HGB_ACT_NONE || y, "act_bwd: needs the activation output y");
   if (count == 0) return HGB_OK;
   act_bwd_kernel<<<hgb_grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, z, count, act, act_param, dz);
   HGB_LAUNCH_CHECK("act_bwd");

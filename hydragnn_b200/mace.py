@@ -14,6 +14,7 @@ backward), correlation 3 and channel counts that are not a multiple of 32: the p
 composed from gathers / segment sums / MatMuls plus ATen einsum glue.
 """
 import math
+import os
 
 import torch
 from torch import nn
@@ -22,6 +23,7 @@ from . import e3, ops
 from .stacks import (_act_code, activation_function_selection, loss_function_selection, run_mlp)
 
 NUM_ELEMENTS = 118
+EDGE_EMBED_KERNEL = os.environ.get("HGB_MACE_EDGE_EMBED", "1") == "1"   # 0: spherical harmonics / radial basis as ATen glue
 
 
 def _lin(x, w_t, higher, act=None):
@@ -484,13 +486,17 @@ class MACEStack(nn.Module):
         cnt = (gcsr.rowptr[1:] - gcsr.rowptr[:-1]).clamp(min=1).to(pos.dtype)
         gsum = ops.SegmentSum.apply(pos, ops.Csr(gcsr.idx, gcsr.rowptr, None, gcsr.n))
         pos = pos - ops.GatherRows.apply(gsum / cnt[:, None], gcsr)
-        vec = ops.GatherRows.apply(pos, plan.by_col) - ops.GatherRows.apply(pos, plan.by_row)
         shifts = getattr(data, "edge_shifts", None)
-        if shifts is not None:
-            vec = vec + shifts
-        dist = vec.pow(2).sum(-1, keepdim=True).sqrt()
-        sh = e3.spherical_harmonics_cl(self.max_ell, vec / dist.clamp(min=1e-12))
-        radial = self._radial(dist)
+        if not higher and self.radial_type == "bessel" and EDGE_EMBED_KERNEL:
+            # first-order path: geometry, spherical harmonics and Bessel x cutoff of every edge in ONE kernel
+            sh, radial = ops.MaceEdgeEmbedFn.apply(pos, shifts, plan, self.max_ell, self.num_bessel, self.radius, self.p_cut)
+        else:
+            vec = ops.GatherRows.apply(pos, plan.by_col) - ops.GatherRows.apply(pos, plan.by_row)
+            if shifts is not None:
+                vec = vec + shifts
+            dist = vec.pow(2).sum(-1, keepdim=True).sqrt()
+            sh = e3.spherical_harmonics_cl(self.max_ell, vec / dist.clamp(min=1e-12))
+            radial = self._radial(dist)
         # node attributes (process_node_attributes, MACEStack.py:501-535): element index instead of a one-hot matrix
         z = data.x.squeeze()
         assert z.dim() == 1, "MACE only supports raw atomic numbers as node_attributes."

@@ -1361,6 +1361,35 @@ class ChanRP(torch.autograd.Function):
         return (ChanCL.apply(t, gx) if ctx.needs_input_grad[0] else None), (ChanOU.apply(g, gx) if ctx.needs_input_grad[1] else None)
 
 
+class MaceEdgeEmbedFn(torch.autograd.Function):
+    """(pos, shifts) -> (sh [E, (L+1)^2], radial [E, R]): spherical harmonics and Bessel x polynomial-cutoff basis of every edge in
+    one kernel (first-order path; MACEStack.py:455-466, blocks.py:164-177), analytic d/dpos in the backward."""
+
+    @staticmethod
+    def forward(ctx, pos, shifts, plan, lmax, num_bessel, r_max, p):
+        pos, shifts = _chk(pos), _chk(shifts)
+        e = plan.num_edges
+        ns = (lmax + 1) ** 2
+        sh = torch.empty(e, ns, dtype=pos.dtype, device=pos.device)
+        radial = torch.empty(e, num_bessel, dtype=pos.dtype, device=pos.device)
+        _lib.call("hgb_mace_edge_embed_fwd", _p(pos), _p(plan.row), _p(plan.col), _p(shifts), e, int(lmax), int(num_bessel), float(r_max),
+                  float(p), _p(sh), _p(radial), _stream())
+        ctx.save_for_backward(pos, shifts)
+        ctx.plan, ctx.cfg = plan, (int(lmax), int(num_bessel), float(r_max), float(p))
+        return sh, radial
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_sh, g_radial):
+        pos, shifts = ctx.saved_tensors
+        plan, (lmax, nb, rc, p) = ctx.plan, ctx.cfg
+        e = plan.num_edges
+        gvec = torch.empty(e, 3, dtype=pos.dtype, device=pos.device)
+        _lib.call("hgb_mace_edge_embed_bwd", _p(pos), _p(plan.row), _p(plan.col), _p(shifts), _p(_chk(g_sh.contiguous())),
+                  _p(_chk(g_radial.contiguous())), e, lmax, nb, rc, p, _p(gvec), _stream())
+        return _edge_vec_scatter(gvec, plan), None, None, None, None, None, None
+
+
 def adamw_step(p, g, m, v, step_dev, lr, beta1, beta2, eps, weight_decay, grad_scale=1.0, hyper_dev=None):
     _lib.call("hgb_adamw_step", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
               float(weight_decay), float(grad_scale), _p(step_dev), _p(hyper_dev), _stream())

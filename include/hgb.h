@@ -348,6 +348,16 @@ int hgb_mace_tp_path(int32_t mode, const float* p0, const float* p1, const float
 int hgb_mace_chan_contract(int32_t mode, const float* p0, const float* p1, int64_t n, int32_t f, int32_t p, int32_t ni,
                            float* out, hgb_stream_t stream);
 
+/* MACE edge embedding in one pass per edge: vec = pos[col] - pos[row] + shift -> real spherical harmonics
+ * sh [e, (lmax+1)^2] (component normalisation, e3nn axis convention; MACEStack.py:455-466) and the Bessel basis times the
+ * polynomial cutoff radial [e, num_bessel] (mace_utils/modules/radial.py:18-60,110-148; blocks.py:164-177).  lmax <= 3.
+ * bwd: g_vec [e, 3] = d L / d vec from g_sh / g_radial (either may be NULL); hgb_edge_vec_scatter turns it into d L / d pos.  */
+int hgb_mace_edge_embed_fwd(const float* pos, const int32_t* row, const int32_t* col, const float* shifts, int64_t e, int32_t lmax,
+                            int32_t num_bessel, float r_max, float p, float* sh, float* radial, hgb_stream_t stream);
+int hgb_mace_edge_embed_bwd(const float* pos, const int32_t* row, const int32_t* col, const float* shifts, const float* g_sh,
+                            const float* g_radial, int64_t e, int32_t lmax, int32_t num_bessel, float r_max, float p, float* g_vec,
+                            hgb_stream_t stream);
+
 /* Grouped dense layers for multi-branch decoding (hydragnn/models/Base.py:770-780 graph heads, :816-840 node heads,
  * hydragnn/models/MultiTaskModelMP.py): rows sorted by dataset branch, rowptr [groups + 1] on the device, every 64-row tile
  * picks the weight matrix of its group -- one launch per layer instead of a boolean-mask loop over `dataset_name.unique()`.
