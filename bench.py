@@ -348,7 +348,7 @@ def run_engine(args):
     hidx = [None if mlip else hb.get_head_indices(model, d) for d in devb]
     capture_ar = ws > 1 and not args.no_capture_allreduce
 
-    def step(d, hi, known=None, with_opt=True):
+    def step(d, hi, known=None, with_opt=True, collective=True):
         """the full hot path on one resident batch"""
         build_edges(d, known)
         opt.zero_grad()
@@ -358,10 +358,9 @@ def run_engine(args):
             loss, _ = m.energy_force_loss(model(d), d)
         else:
             loss, _ = m.loss(model(d), d.y, hi)
-        loss.backward()
-        flat = opt.gather_grads()
+        flat = opt.backward(loss)
         if with_opt:
-            if ws > 1:
+            if ws > 1 and collective:
                 dist.all_reduce(flat)
             opt.step(1.0 / ws)
         return loss.detach()
@@ -511,7 +510,9 @@ def run_engine(args):
     roof, shares = None, None
     if rank == 0 and not args.skip_kernel_shares:
         try:
-            roof, shares = kernel_shares_and_roofline(lambda: step(devb[0], hidx[0], known=sizes[0]), _lib, args, n_atoms[0], n_edges[0], G)
+            # rank 0 profiles one eager step on its own: no collective in it (the other ranks are not taking part)
+            roof, shares = kernel_shares_and_roofline(lambda: step(devb[0], hidx[0], known=sizes[0], collective=False), _lib, args,
+                                                      n_atoms[0], n_edges[0], G)
         except Exception as ex:  # pragma: no cover
             roof, shares = {"error": repr(ex)}, None
     hbm, _, src = peaks()
@@ -521,7 +522,7 @@ def run_engine(args):
                  "roofline_atoms_per_s_per_gpu": hbm * 1e9 / (wl["mult"] * wl["fwd_bytes"])}
 
     cpu_base = None
-    if rank == 0 and not args.skip_cpu_baseline:
+    if rank == 0 and ws == 1 and not args.skip_cpu_baseline:          # the CPU baseline is reported at N = 1 only
         rate, dt, atoms, threads, per_threads = cpu_step_rate(args.workload, args.ref_graphs, 3, 1)
         cpu_base = {"value": rate, "unit": "atoms/s", "cores": threads, "kind": "port",
                     "sample": "%d graphs (%d atoms) per step, 3 timed steps after 1 warm-up; edges prebuilt" % (args.ref_graphs, atoms),

@@ -68,15 +68,41 @@ __device__ __forceinline__ void split4(const float (&x)[4], float (&hi)[4], floa
   }
 }
 
-// stage rows [r0, r0 + CH) of one 8-wide column block of a row-major matrix into shared memory (zero beyond n)
+// stage rows [r0, r0 + CH) of one 8-wide column block of a row-major matrix into shared memory (zero beyond n), already split into
+// the TF32 hi part (dst) and the lo remainder (dst + TILE): the split is done once per element here instead of once per warp and use
+constexpr int TILE = CH * RS;
+template <int SPLIT>
 __device__ __forceinline__ void stage(float* dst, const float* __restrict__ src, int ld, int col, int r0, int n, float mul) {
   for (int i = threadIdx.x; i < CH * 2; i += WARPS * 32) {
     const int r = i >> 1, half = i & 1;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r0 + r < n) v = __ldg(reinterpret_cast<const float4*>(src + (int64_t)(r0 + r) * ld + col) + half);
     v.x *= mul; v.y *= mul; v.z *= mul; v.w *= mul;
-    *reinterpret_cast<float4*>(dst + r * RS + 4 * half) = v;
+    float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    *reinterpret_cast<float4*>(dst + r * RS + 4 * half) = h;
+    if (SPLIT >= 3)
+      *reinterpret_cast<float4*>(dst + TILE + r * RS + 4 * half) =
+          make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
   }
+}
+
+// c (+)= A B with the B fragment read from a pre-split shared-memory tile: element offsets o0 / o1 into the hi tile, lo tile at + TILE
+template <int SPLIT>
+__device__ __forceinline__ void mma_sm(float (&c)[4], const float (&ahi)[4], const float (&alo)[4], const float* tile, int o0, int o1) {
+  const float b0h = tile[o0], b1h = tile[o1];
+  if (SPLIT >= 3) {
+    const float b0l = tile[TILE + o0], b1l = tile[TILE + o1];
+    if (SPLIT == 4) mma8(c, alo, b0l, b1l);
+    mma8(c, alo, b0h, b1h);
+    mma8(c, ahi, b0l, b1l);
+  }
+  mma8(c, ahi, b0h, b1h);
+}
+template <int SPLIT>
+__device__ __forceinline__ void mma_sm_add(float (&c)[4], const float (&ahi)[4], const float (&alo)[4], const float* tile, int o0, int o1) {
+  float d[4] = {0.f, 0.f, 0.f, 0.f};
+  mma_sm<SPLIT>(d, ahi, alo, tile, o0, o1);
+  c[0] += d[0]; c[1] += d[1]; c[2] += d[2]; c[3] += d[3];
 }
 
 // A-operand fragment of rows [r0 + g, r0 + g + 8] of an 8-wide block, straight from global memory (zero beyond n)
@@ -93,7 +119,7 @@ __device__ __forceinline__ void load_a(float (&a)[4], const float* __restrict__ 
 template <int SPLIT>
 __global__ void __launch_bounds__(WARPS * 32) mha_tc_fwd_kernel(const float* __restrict__ qkv, int n, int f, float scale,
                                                                 float* __restrict__ out, float* __restrict__ lse) {
-  __shared__ __align__(16) float sk[CH * RS], sv[CH * RS];
+  __shared__ __align__(16) float sk[2 * TILE], sv[2 * TILE];      // hi | lo
   const int h = blockIdx.y, nh = gridDim.y, f3 = 3 * f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int r0 = blockIdx.x * ROWS + warp * 16;
@@ -104,14 +130,14 @@ __global__ void __launch_bounds__(WARPS * 32) mha_tc_fwd_kernel(const float* __r
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   for (int j0 = 0; j0 < n; j0 += CH) {
     __syncthreads();
-    stage(sk, qkv, f3, f + h * D, j0, n, 1.f);
-    stage(sv, qkv, f3, 2 * f + h * D, j0, n, 1.f);
+    stage<SPLIT>(sk, qkv, f3, f + h * D, j0, n, 1.f);
+    stage<SPLIT>(sv, qkv, f3, 2 * f + h * D, j0, n, 1.f);
     __syncthreads();
     float s[CH / 8][4];
 #pragma unroll
     for (int kb = 0; kb < CH / 8; ++kb) {
       s[kb][0] = s[kb][1] = s[kb][2] = s[kb][3] = 0.f;
-      mma_acc<SPLIT>(s[kb], qh, ql, sk[(kb * 8 + g) * RS + t], sk[(kb * 8 + g) * RS + t + 4]);
+      mma_sm<SPLIT>(s[kb], qh, ql, sk, (kb * 8 + g) * RS + t, (kb * 8 + g) * RS + t + 4);
       const int key = j0 + kb * 8 + 2 * t;
       if (key >= n) s[kb][0] = s[kb][2] = -INFINITY;
       if (key + 1 >= n) s[kb][1] = s[kb][3] = -INFINITY;
@@ -137,7 +163,7 @@ __global__ void __launch_bounds__(WARPS * 32) mha_tc_fwd_kernel(const float* __r
       l0 += p[0] + p[2];
       l1 += p[1] + p[3];
       split4<SPLIT>(p, ph, pl);
-      mma_add<SPLIT>(o, ph, pl, sv[(kb * 8 + 2 * t) * RS + g], sv[(kb * 8 + 2 * t + 1) * RS + g]);
+      mma_sm_add<SPLIT>(o, ph, pl, sv, (kb * 8 + 2 * t) * RS + g, (kb * 8 + 2 * t + 1) * RS + g);
     }
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -173,7 +199,7 @@ template <int SPLIT>
 __global__ void __launch_bounds__(WARPS * 32) mha_tc_bwd_q_kernel(const float* __restrict__ qkv, const float* __restrict__ lse,
                                                                   const float* __restrict__ delta, const float* __restrict__ gout,
                                                                   int n, int f, float scale, float* __restrict__ gqkv) {
-  __shared__ __align__(16) float sk[CH * RS], sv[CH * RS];
+  __shared__ __align__(16) float sk[2 * TILE], sv[2 * TILE];
   const int h = blockIdx.y, nh = gridDim.y, f3 = 3 * f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int r0 = blockIdx.x * ROWS + warp * 16;
@@ -188,14 +214,14 @@ __global__ void __launch_bounds__(WARPS * 32) mha_tc_bwd_q_kernel(const float* _
   float dq[4] = {0.f, 0.f, 0.f, 0.f};
   for (int j0 = 0; j0 < n; j0 += CH) {
     __syncthreads();
-    stage(sk, qkv, f3, f + h * D, j0, n, 1.f);
-    stage(sv, qkv, f3, 2 * f + h * D, j0, n, 1.f);
+    stage<SPLIT>(sk, qkv, f3, f + h * D, j0, n, 1.f);
+    stage<SPLIT>(sv, qkv, f3, 2 * f + h * D, j0, n, 1.f);
     __syncthreads();
 #pragma unroll
     for (int kb = 0; kb < CH / 8; ++kb) {
       float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
-      mma_acc<SPLIT>(s, qh, ql, sk[(kb * 8 + g) * RS + t], sk[(kb * 8 + g) * RS + t + 4]);
-      mma_acc<SPLIT>(dp, goh, gol, sv[(kb * 8 + g) * RS + t], sv[(kb * 8 + g) * RS + t + 4]);
+      mma_sm<SPLIT>(s, qh, ql, sk, (kb * 8 + g) * RS + t, (kb * 8 + g) * RS + t + 4);
+      mma_sm<SPLIT>(dp, goh, gol, sv, (kb * 8 + g) * RS + t, (kb * 8 + g) * RS + t + 4);
       const int key = j0 + kb * 8 + 2 * t;
       const bool v0 = key < n, v1 = key + 1 < n;
       float ds[4], dsh[4], dsl[4];
@@ -205,7 +231,7 @@ __global__ void __launch_bounds__(WARPS * 32) mha_tc_bwd_q_kernel(const float* _
       ds[2] = v1 ? exp2f(s[1] - ls0) * (dp[1] - dl0) : 0.f;
       ds[3] = v1 ? exp2f(s[3] - ls1) * (dp[3] - dl1) : 0.f;
       split4<SPLIT>(ds, dsh, dsl);
-      mma_add<SPLIT>(dq, dsh, dsl, sk[(kb * 8 + 2 * t) * RS + g], sk[(kb * 8 + 2 * t + 1) * RS + g]);
+      mma_sm_add<SPLIT>(dq, dsh, dsl, sk, (kb * 8 + 2 * t) * RS + g, (kb * 8 + 2 * t + 1) * RS + g);
     }
   }
   if (ra < n) *reinterpret_cast<float2*>(gqkv + (int64_t)ra * f3 + h * D + 2 * t) = make_float2(dq[0] * scale, dq[1] * scale);
@@ -217,7 +243,7 @@ template <int SPLIT>
 __global__ void __launch_bounds__(WARPS * 32) mha_tc_bwd_kv_kernel(const float* __restrict__ qkv, const float* __restrict__ lse,
                                                                    const float* __restrict__ delta, const float* __restrict__ gout,
                                                                    int n, int f, float scale, float* __restrict__ gqkv) {
-  __shared__ __align__(16) float sq[CH * RS], sg[CH * RS];
+  __shared__ __align__(16) float sq[2 * TILE], sg[2 * TILE];
   __shared__ float sl[CH], sd[CH];
   const int h = blockIdx.y, nh = gridDim.y, f3 = 3 * f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -231,8 +257,8 @@ __global__ void __launch_bounds__(WARPS * 32) mha_tc_bwd_kv_kernel(const float* 
   float dk[4] = {0.f, 0.f, 0.f, 0.f}, dv[4] = {0.f, 0.f, 0.f, 0.f};
   for (int i0 = 0; i0 < n; i0 += CH) {
     __syncthreads();
-    stage(sq, qkv, f3, h * D, i0, n, scale);
-    stage(sg, gout, f, h * D, i0, n, 1.f);
+    stage<SPLIT>(sq, qkv, f3, h * D, i0, n, scale);
+    stage<SPLIT>(sg, gout, f, h * D, i0, n, 1.f);
     for (int i = threadIdx.x; i < CH; i += WARPS * 32) {
       sl[i] = i0 + i < n ? lse[(int64_t)(i0 + i) * nh + h] * LOG2E : 0.f;
       sd[i] = i0 + i < n ? delta[(int64_t)(i0 + i) * nh + h] : 0.f;
@@ -241,8 +267,8 @@ __global__ void __launch_bounds__(WARPS * 32) mha_tc_bwd_kv_kernel(const float* 
 #pragma unroll
     for (int qb = 0; qb < CH / 8; ++qb) {
       float st[4] = {0.f, 0.f, 0.f, 0.f}, dpt[4] = {0.f, 0.f, 0.f, 0.f};      // S^T, dP^T: rows = keys, cols = queries
-      mma_acc<SPLIT>(st, kh, kl, sq[(qb * 8 + g) * RS + t], sq[(qb * 8 + g) * RS + t + 4]);
-      mma_acc<SPLIT>(dpt, vh, vl, sg[(qb * 8 + g) * RS + t], sg[(qb * 8 + g) * RS + t + 4]);
+      mma_sm<SPLIT>(st, kh, kl, sq, (qb * 8 + g) * RS + t, (qb * 8 + g) * RS + t + 4);
+      mma_sm<SPLIT>(dpt, vh, vl, sg, (qb * 8 + g) * RS + t, (qb * 8 + g) * RS + t + 4);
       const int qi = qb * 8 + 2 * t;
       const bool v0 = i0 + qi < n, v1 = i0 + qi + 1 < n;
       const float lq0 = sl[qi], lq1 = sl[qi + 1], dq0 = sd[qi], dq1 = sd[qi + 1];
@@ -254,8 +280,8 @@ __global__ void __launch_bounds__(WARPS * 32) mha_tc_bwd_kv_kernel(const float* 
       ds[2] = p[2] * (dpt[1] - dq1); ds[3] = p[3] * (dpt[3] - dq1);
       split4<SPLIT>(p, ph, pl);
       split4<SPLIT>(ds, dsh, dsl);
-      mma_add<SPLIT>(dv, ph, pl, sg[(qb * 8 + 2 * t) * RS + g], sg[(qb * 8 + 2 * t + 1) * RS + g]);
-      mma_add<SPLIT>(dk, dsh, dsl, sq[(qb * 8 + 2 * t) * RS + g], sq[(qb * 8 + 2 * t + 1) * RS + g]);
+      mma_sm_add<SPLIT>(dv, ph, pl, sg, (qb * 8 + 2 * t) * RS + g, (qb * 8 + 2 * t + 1) * RS + g);
+      mma_sm_add<SPLIT>(dk, dsh, dsl, sq, (qb * 8 + 2 * t) * RS + g, (qb * 8 + 2 * t + 1) * RS + g);
     }
   }
   if (ra < n) {

@@ -115,7 +115,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
 // word).  Here every CTA streams 128-row chunks of both operands through shared memory with cp.async, keeps the WHOLE [mo, no]
 // result in registers as 8 x 8 tiles (the (mo/8)(no/8) tiles take that many threads; the 128 threads form NSL slices of the chunk's
 // rows), and writes one partial per (CTA, slice); a fixed-order reduce finishes.  Exact fp32 FMAs.
-constexpr int TNF_ROWS = 128, TNF_THREADS = 128;
+constexpr int TNF_ROWS = 64, TNF_THREADS = 128;      // rows per pipeline stage; two stages are in flight (cp.async double buffer)
 
 __device__ __forceinline__ void tnf_cp16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -125,8 +125,7 @@ __global__ void __launch_bounds__(TNF_THREADS) gemm_tn_fast_kernel(const float* 
                                                                    int64_t lda, int64_t ldb, int r_total, int mo, int no,
                                                                    int chunks_per_cta, float* __restrict__ part) {
   extern __shared__ __align__(16) float tnf_smem[];
-  float* sa = tnf_smem;                         // [TNF_ROWS][mo]
-  float* sb = sa + TNF_ROWS * mo;               // [TNF_ROWS][no]
+  const int stage_floats = TNF_ROWS * (mo + no);
   const int t = threadIdx.x;
   const int tps = (mo / 8) * (no / 8), nsl = TNF_THREADS / tps, ksl = TNF_ROWS / nsl;
   const int slice = t / tps, tt = t % tps;
@@ -139,9 +138,10 @@ __global__ void __launch_bounds__(TNF_THREADS) gemm_tn_fast_kernel(const float* 
   const int nchunks = (r_total + TNF_ROWS - 1) / TNF_ROWS;
   const int c_beg = blockIdx.x * chunks_per_cta, c_end = min(nchunks, c_beg + chunks_per_cta);
   const int ca = mo / 4, cb = no / 4;
-  for (int ch = c_beg; ch < c_end; ++ch) {
+  auto issue = [&](int ch, int buf) {
+    float* sa = tnf_smem + buf * stage_floats;
+    float* sb = sa + TNF_ROWS * mo;
     const int row0 = ch * TNF_ROWS;
-    __syncthreads();
     for (int i = t; i < TNF_ROWS * ca; i += TNF_THREADS) {
       const int r = i / ca, c4 = i - r * ca;
       float* dst = sa + r * mo + 4 * c4;
@@ -154,8 +154,20 @@ __global__ void __launch_bounds__(TNF_THREADS) gemm_tn_fast_kernel(const float* 
       if (row0 + r < r_total) tnf_cp16(dst, b + (int64_t)(row0 + r) * ldb + 4 * c4);
       else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (c_beg < c_end) issue(c_beg, 0);
+  for (int ch = c_beg; ch < c_end; ++ch) {
+    const int buf = (ch - c_beg) & 1;
+    if (ch + 1 < c_end) {
+      issue(ch + 1, buf ^ 1);                       // the other buffer was released by the barrier at the end of the last iteration
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     __syncthreads();
+    const float* sa = tnf_smem + buf * stage_floats;
+    const float* sb = sa + TNF_ROWS * mo;
 #pragma unroll 4
     for (int kk = 0; kk < ksl; ++kk) {
       const int k = slice * ksl + kk;
@@ -170,6 +182,7 @@ __global__ void __launch_bounds__(TNF_THREADS) gemm_tn_fast_kernel(const float* 
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ra[i], rb[j], acc[i][j]);
     }
+    __syncthreads();                                // everyone is done with `buf` before the next iteration refills it
   }
   float* out = part + ((int64_t)blockIdx.x * nsl + slice) * mo * no;
 #pragma unroll
@@ -184,11 +197,11 @@ static bool tn_fast_ok(int m, int n, int k, int64_t lda, int64_t ldb, const void
   if (((uintptr_t)a % 16) || ((uintptr_t)b % 16)) return false;
   const int tps = (m / 8) * (n / 8);
   if (tps < 1 || tps > TNF_THREADS || (TNF_THREADS % tps) != 0) return false;
-  return (size_t)TNF_ROWS * (m + n) * 4 <= 160 * 1024;
+  return (size_t)2 * TNF_ROWS * (m + n) * 4 <= 160 * 1024 && (TNF_ROWS % (TNF_THREADS / tps)) == 0;
 }
 static int tn_fast_grid(int k) {
   const int nchunks = (k + TNF_ROWS - 1) / TNF_ROWS;
-  return nchunks < HGB_NUM_SMS * 2 ? nchunks : HGB_NUM_SMS * 2;
+  return nchunks < HGB_NUM_SMS * 3 ? nchunks : HGB_NUM_SMS * 3;
 }
 
 static int pick_splits(int m, int n, int k) {
@@ -253,7 +266,7 @@ extern "C" int hgb_gemm(const float* a, const float* b, float* c, int32_t m, int
       const int nchunks = (k + TNF_ROWS - 1) / TNF_ROWS;
       const int cpc = (nchunks + grid0 - 1) / grid0;
       const int grid = (nchunks + cpc - 1) / cpc;
-      const size_t smem = (size_t)TNF_ROWS * (m + n) * 4;
+      const size_t smem = (size_t)2 * TNF_ROWS * (m + n) * 4;
       cudaFuncSetAttribute(gemm_tn_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       gemm_tn_fast_kernel<<<grid, TNF_THREADS, smem, st>>>(a, b, lda, ldb, k, m, n, cpc, (float*)workspace);
       HGB_LAUNCH_CHECK("gemm_tn_fast");

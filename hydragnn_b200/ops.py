@@ -338,7 +338,116 @@ def linear_fwd_dispatch_ex(x2, w, b, code=0, param=0.0, want_z=False, z_deriv=Fa
     return raw_linear(x2, w, b, code, param, want_z) + (False,)
 
 
-def linear_bwd_dispatch(dz, x2, w, need_x=True, need_w=True, need_b=True, dx_addend=None, dx_gsrc=None, dx_gact=0, dx_gparam=0.0):
+# ---- weight gradient next to the data gradient ---------------------------------------------------------------------------------
+# The weight gradient and the data gradient of a layer read the same dZ and are independent of each other.  ``fork_join`` launches
+# the weight-gradient kernels on a SIDE stream forked from the current one, lets the caller launch the data gradient on the main
+# stream, and joins before either result is handed to autograd -- in a captured step the two become parallel branches of the CUDA
+# graph.  Inside ``deferred_weight_gradients()`` (the engine's own step: FlatAdamW.backward) the join of a LEAF parameter that has
+# not received a gradient in this backward pass moves to the end of the pass (an autograd-engine callback): nothing reads such a
+# gradient on the main stream before the optimizer (AccumulateGrad takes the tensor over without a kernel), so the weight-gradient
+# kernels overlap everything that follows.  The inputs of the deferred kernels are kept referenced until the join, which stops
+# autograd from accumulating into them in place (it only does that to tensors nobody else holds).  Derived weights (scaled, sliced,
+# concatenated: MACE, PNAEq) are read by their own backward nodes right away -- those join immediately; so does everything outside
+# the context, where gradient hooks (torch DDP's reducer, user hooks) may read a gradient the moment it is accumulated.
+WGRAD_OVERLAP = os.environ.get("HGB_WGRAD_OVERLAP", "1") == "1"
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=key)
+    return _SIDE[key]
+
+
+_PENDING = {"keys": set(), "leaves": set(), "hold": [], "bytes": 0}
+_DEFER = {"on": False}
+HOLD_LIMIT = 8 << 30          # bytes of deferred-kernel inputs kept alive before a join is forced
+
+
+class deferred_weight_gradients:
+    """Context manager around ``loss.backward()`` of a step whose gradients are first read by ``FlatAdamW.gather_grads``."""
+
+    def __enter__(self):
+        self.prev = _DEFER["on"]
+        _DEFER["on"] = True
+        return self
+
+    def __exit__(self, *exc):
+        _DEFER["on"] = self.prev
+        join_side_streams()
+
+
+def join_side_streams():
+    """Join every side stream with deferred weight-gradient work (end of a backward pass; also called by FlatAdamW.gather_grads)."""
+    for key in list(_PENDING["keys"]):
+        torch.cuda.current_stream(key).wait_stream(_SIDE[key])
+    _PENDING["keys"].clear()
+    _PENDING["leaves"].clear()
+    _PENDING["hold"].clear()
+    _PENDING["bytes"] = 0
+
+
+class fork_join:
+    """``with fork_join(dz, x2) as fj: w = fj.side(lambda: wgrad(...)); dx = dgrad(...)`` -- ``w`` and ``dx`` are both ready (in stream
+    order) when the block exits."""
+
+    def __init__(self, *inputs, defer_for=None):
+        """``defer_for``: the leaf parameters whose gradients the side work produces (or None): if every one is a leaf that has no
+        gradient yet and was not served earlier in this backward pass, the join is deferred to the end of the pass."""
+        self.inputs = [t for t in inputs if t is not None]
+        self.on = bool(WGRAD_OVERLAP and self.inputs and self.inputs[0].is_cuda)
+        self.defer = False
+        if self.on and defer_for and _DEFER["on"]:
+            ok = all(p is not None and p.is_leaf and p.requires_grad and p.grad is None and id(p) not in _PENDING["leaves"] for p in defer_for)
+            if ok:
+                try:
+                    torch.autograd.Variable._execution_engine.queue_callback(join_side_streams)
+                    self.defer = True
+                    self.leaf_ids = [id(p) for p in defer_for]
+                except RuntimeError:             # not inside a backward pass
+                    self.defer = False
+
+    def __enter__(self):
+        if self.on:
+            dev = self.inputs[0].device
+            self.main = torch.cuda.current_stream(dev)
+            self.sidestream = _side_stream(dev)
+            self.sidestream.wait_stream(self.main)
+            self.outs = []
+        return self
+
+    def side(self, fn):
+        if not self.on:
+            return fn()
+        with torch.cuda.stream(self.sidestream):
+            out = fn()
+        self.outs.append(out)
+        return out
+
+    def __exit__(self, *exc):
+        if self.on:
+            if self.defer:
+                key = self.inputs[0].device.index if self.inputs[0].device.index is not None else torch.cuda.current_device()
+                _PENDING["keys"].add(key)
+                _PENDING["leaves"].update(self.leaf_ids)
+                _PENDING["hold"].append(self.inputs)           # referenced -> autograd will not accumulate into them in place
+                _PENDING["bytes"] += sum(t.numel() * t.element_size() for t in self.inputs)
+                if _PENDING["bytes"] > HOLD_LIMIT:
+                    join_side_streams()
+            else:
+                self.main.wait_stream(self.sidestream)
+            for t in self.inputs:
+                t.record_stream(self.sidestream)
+            for out in self.outs:
+                for t in (out if isinstance(out, (tuple, list)) else (out,)):
+                    if torch.is_tensor(t):
+                        t.record_stream(self.main)
+        return False
+
+
+def linear_bwd_dispatch(dz, x2, w, need_x=True, need_w=True, need_b=True, dx_addend=None, dx_gsrc=None, dx_gact=0, dx_gparam=0.0,
+                        leaves=None):
     """(dx, dw, db) of y = x2 W^T + b given dz.  ``dx_addend`` (same shape as dx) is accumulated into dx.  With ``dx_gsrc``
     the layer's input was act(.) and dx is returned already multiplied by act'(dx_gsrc) (SiLU: pre-activation, else output):
     on the tensor-core path that happens in the dgrad epilogue."""
@@ -355,21 +464,19 @@ def linear_bwd_dispatch(dz, x2, w, need_x=True, need_w=True, need_b=True, dx_add
         dx, dw, db = raw_smallk_bwd(dz, None, None, x2, w, 0, 0.0, need_x, need_w, need_b)
         return through_act(dx + dx_addend if (dx is not None and dx_addend is not None) else dx), dw, db
     dx = dw = db = None
-    if need_x:
-        if tc_ok(m, k, n, dz, dx_addend, dx_gsrc) and (n <= 256 or dx_gsrc is None):
-            dx = raw_tc_linear(dz, w, True, None, k, n, param=dx_gparam, addend=dx_addend, gsrc=dx_gsrc, gact=dx_gact)[0]
-        elif dx_addend is not None:
-            dx = through_act(raw_gemm(dz, w, False, False, out=dx_addend.clone(), beta_one=True))
-        else:
-            dx = through_act(raw_gemm(dz, w, False, False))
-    if need_w or need_b:
-        if _TC["enabled"] and tc_ok(m, n, k, dz, x2) and k + 16 <= 256:      # tc_wgrad has no fp32-accurate mode
-            dw, db = raw_tc_wgrad(dz, x2, want_bias=need_b)
-        else:
-            if need_w:
-                dw = raw_gemm(dz, x2, True, False)
-            if need_b:
-                db = raw_colsum(dz)
+    with fork_join(dz, x2, defer_for=leaves) as fj:
+        if need_w or need_b:                                                     # side stream: the weight gradient
+            if _TC["enabled"] and tc_ok(m, n, k, dz, x2) and k + 16 <= 256:      # tc_wgrad has no fp32-accurate mode
+                dw, db = fj.side(lambda: raw_tc_wgrad(dz, x2, want_bias=need_b))
+            else:
+                dw, db = fj.side(lambda: ((raw_gemm(dz, x2, True, False) if need_w else None), (raw_colsum(dz) if need_b else None)))
+        if need_x:                                                               # main stream: the data gradient
+            if tc_ok(m, k, n, dz, dx_addend, dx_gsrc) and (n <= 256 or dx_gsrc is None):
+                dx = raw_tc_linear(dz, w, True, None, k, n, param=dx_gparam, addend=dx_addend, gsrc=dx_gsrc, gact=dx_gact)[0]
+            elif dx_addend is not None:
+                dx = through_act(raw_gemm(dz, w, False, False, out=dx_addend.clone(), beta_one=True))
+            else:
+                dx = through_act(raw_gemm(dz, w, False, False))
     return dx, dw, db
 
 
@@ -502,6 +609,7 @@ class LinearAct(torch.autograd.Function):
         ctx.save_for_backward(x2, w, y if code not in (0, ACT_CODES["silu"]) else None, z)
         ctx.code, ctx.param, ctx.shp, ctx.has_bias = code, float(act_param), shp, bias is not None
         ctx.tc = _TC["enabled"]                      # the backward runs outside the forward's precision context
+        ctx.leaves = [weight] + ([bias] if bias is not None else [])     # who receives the weight gradient (leaf parameters?)
         return y.reshape(shp[:-1] + (n,))
 
     @staticmethod
@@ -522,7 +630,7 @@ class LinearAct(torch.autograd.Function):
             dz = gy2
         with tensor_cores(ctx.tc):
             gx, gw, gb = linear_bwd_dispatch(dz, x2, w, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
-                                             ctx.has_bias and ctx.needs_input_grad[2])
+                                             ctx.has_bias and ctx.needs_input_grad[2], leaves=ctx.leaves)
         if gx is not None:
             gx = gx.reshape(ctx.shp)
         return gx, gw, gb, None, None
@@ -540,6 +648,7 @@ class Mlp2Fn(torch.autograd.Function):
     def forward(ctx, x, w1, b1, act1, p1, w2, b2, act2, p2):
         shp = x.shape
         x2 = _row_major_2d(x)
+        w1_in, w2_in = w1, w2
         w1 = w1 if w1.stride(1) == 1 else w1.contiguous()
         w2 = w2 if w2.stride(1) == 1 else w2.contiguous()
         c1, c2 = ACT_CODES[act1], ACT_CODES[act2]
@@ -549,6 +658,8 @@ class Mlp2Fn(torch.autograd.Function):
         ctx.save_for_backward(x2, w1, w2, h, z1, y if c2 not in (0, silu) else None, z2)
         ctx.cfg = (ACT_DERIV if deriv else c1, float(p1), c2, float(p2), shp, b1 is not None, b2 is not None)
         ctx.tc = _TC["enabled"]
+        ctx.leaves1 = [w1_in] + ([b1] if b1 is not None else [])
+        ctx.leaves2 = [w2_in] + ([b2] if b2 is not None else [])
         return y.reshape(shp[:-1] + (w2.shape[0],))
 
     @staticmethod
@@ -561,9 +672,10 @@ class Mlp2Fn(torch.autograd.Function):
         dz2 = raw_act_bwd(gy2, y, z2, c2, p2) if c2 != 0 else gy2
         with tensor_cores(ctx.tc):
             dz1, gw2, gb2 = linear_bwd_dispatch(dz2, h, w2, True, ctx.needs_input_grad[5], has_b2 and ctx.needs_input_grad[6],
-                                                dx_gsrc=(z1 if c1 in (ACT_CODES["silu"], ACT_DERIV) else h), dx_gact=c1, dx_gparam=p1)
+                                                dx_gsrc=(z1 if c1 in (ACT_CODES["silu"], ACT_DERIV) else h), dx_gact=c1, dx_gparam=p1,
+                                                leaves=ctx.leaves2)
             gx, gw1, gb1 = linear_bwd_dispatch(dz1, x2, w1, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
-                                               has_b1 and ctx.needs_input_grad[2])
+                                               has_b1 and ctx.needs_input_grad[2], leaves=ctx.leaves1)
         return (gx.reshape(shp) if gx is not None else None), gw1, gb1, None, None, gw2, gb2, None, None
 
 
@@ -762,6 +874,7 @@ class PainnUpdateFn(torch.autograd.Function):
         ctx.save_for_backward(v2, y_uv, mlp_in, z1, h, a, wuv, w1, w2)
         ctx.last = bool(last)
         ctx.tc = _TC["enabled"]
+        ctx.leaves = ([uw, ub, vw, vb], [w1, b1], [w2, b2])
         if last:
             return s_out, s_out.new_zeros(0)
         return s_out, v_out
@@ -779,15 +892,15 @@ class PainnUpdateFn(torch.autograd.Function):
         ga = torch.empty_like(a)
         _lib.call("hgb_painn_update_post_bwd_a", _p(gs_out), _p(gv_out), _p(uv), _p(vv), ld, n, f, int(last), _p(ga), _stream())
         with tensor_cores(ctx.tc):
-            gz1, gw2, gb2 = linear_bwd_dispatch(ga, h, w2, dx_gsrc=z1, dx_gact=ctx.z1_code)     # dgrad through the SiLU
-            g_mlp_in, gw1, gb1 = linear_bwd_dispatch(gz1, mlp_in, w1)
+            gz1, gw2, gb2 = linear_bwd_dispatch(ga, h, w2, dx_gsrc=z1, dx_gact=ctx.z1_code, leaves=ctx.leaves[2])     # dgrad through the SiLU
+            g_mlp_in, gw1, gb1 = linear_bwd_dispatch(gz1, mlp_in, w1, leaves=ctx.leaves[1])
         g_uv = torch.empty_like(y_uv)                                                # [3n, 2f] = [guv | gvv]
         gs = torch.empty_like(gs_out)
         _lib.call("hgb_painn_update_bwd", _p(gs_out), _p(gv_out), _p(g_mlp_in), _p(a), _p(uv), _p(vv), ld, _p(mlp_in), n, f,
                   int(last), _p(g_uv), _p(g_uv[:, f:]), _p(gs), None, _stream())
         with tensor_cores(ctx.tc):
             # gv = gv_out (direct path, added in the dgrad epilogue) + [guv | gvv] [U; V]
-            gv, gwuv, gbuv = linear_bwd_dispatch(g_uv, v2, wuv, dx_addend=None if last else gv_out.reshape(3 * n, f))
+            gv, gwuv, gbuv = linear_bwd_dispatch(g_uv, v2, wuv, dx_addend=None if last else gv_out.reshape(3 * n, f), leaves=ctx.leaves[0])
         return gs, gv.reshape(n, 3, f), gwuv[:f], gbuv[:f], gwuv[f:], gbuv[f:], gw1, gb1, gw2, gb2, None
 
 

@@ -30,6 +30,22 @@ def _round_up(x, m):
     return ((int(x) + m - 1) // m) * m
 
 
+def filler_layout(batch_vec, g, n_cap, g_cap):
+    """Host-side layout of a padded batch: (ptr [g_cap + 1] int32, batch [n_cap] int64, fill = number of filler atoms).
+    Unused graph slots g .. g_cap - 1 each receive two filler atoms, the last one all that remain."""
+    n = int(batch_vec.numel())
+    unused, fill = g_cap - g, n_cap - n
+    if unused < 1 or fill < 2 * unused:
+        raise ValueError("padded batch does not fit: %d graphs / %d atoms into capacities %d / %d" % (g, n, g_cap, n_cap))
+    counts = torch.full((unused,), 2, dtype=torch.int64)
+    counts[-1] = fill - 2 * (unused - 1)
+    allc = torch.cat([torch.bincount(batch_vec, minlength=g), counts])
+    ptr = torch.zeros(g_cap + 1, dtype=torch.int32)
+    ptr[1:] = torch.cumsum(allc, 0).to(torch.int32)
+    bfull = torch.cat([batch_vec, torch.repeat_interleave(torch.arange(g, g_cap), counts)])
+    return ptr, bfull, fill
+
+
 def supported(model):
     m = getattr(model, "module", model)
     inner = getattr(m, "model", m)
@@ -131,8 +147,7 @@ class PaddedGraphStep:
             loss, tasks = m.energy_force_loss(self.model(d), d)
         else:
             loss, tasks = self._masked_loss(self.model(d))
-        loss.backward()
-        self.opt.gather_grads()
+        self.opt.backward(loss)
         if with_opt:
             if self.ws > 1:
                 dist.all_reduce(self.opt.flat_g)
@@ -178,17 +193,10 @@ class PaddedGraphStep:
         h, d = self.hosts[self._turn], self.data
         if self._copied[self._turn] is not None:
             self._copied[self._turn].synchronize()          # the copy that last read this staging set has finished (two steps ago)
-        fill = self.n_cap - n
         # filler atoms: two per unused slot, the rest in the last slot; on a line 1.5 A apart
-        counts = torch.full((unused,), 2, dtype=torch.int64)
-        counts[-1] = fill - 2 * (unused - 1)
-        bvec = batch.batch.to("cpu", torch.int64)
-        real_counts = torch.bincount(bvec, minlength=g)
-        allc = torch.cat([real_counts, counts])
-        h["ptr"][0] = 0
-        h["ptr"][1:] = torch.cumsum(allc, 0).to(torch.int32)
-        h["batch"][:n] = bvec
-        h["batch"][n:] = torch.repeat_interleave(torch.arange(g, self.g_cap), counts)
+        ptr, bfull, fill = filler_layout(batch.batch.to("cpu", torch.int64), g, self.n_cap, self.g_cap)
+        h["ptr"].copy_(ptr)
+        h["batch"].copy_(bfull)
         h["valid"][0], h["valid"][1], h["valid"][2] = g, n, e
         for key in self._widths:
             if key not in h:

@@ -104,8 +104,16 @@ class FlatAdamW(torch.optim.Optimizer):
         for p in self.params:
             p.grad = None
 
+    def backward(self, loss):
+        """``loss.backward()`` with the weight-gradient kernels of leaf parameters left running on the side stream until the flat
+        gradient is gathered (ops.deferred_weight_gradients), then ``gather_grads()``."""
+        with ops.deferred_weight_gradients():
+            loss.backward()
+        return self.gather_grads()
+
     def gather_grads(self):
         """autograd's per-parameter gradients -> the flat buffer (parameters nobody used contribute zeros)."""
+        ops.join_side_streams()                     # weight-gradient kernels run on a side stream (ops.fork_join)
         gs = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params]
         torch.cat(gs, out=self.flat_g)
         return self.flat_g
@@ -204,8 +212,7 @@ def train_step(model, opt, data, compute_grad_energy=False, head_index=None):
             head_index = get_head_indices(model, data)
         pred = model(data)
         loss, tasks = m.loss(pred, data.y, head_index)
-    loss.backward()
-    flat = opt.gather_grads()
+    flat = opt.backward(loss)
     ws, _ = world()
     if ws > 1:
         dist.all_reduce(flat)                                       # the only collective of the step
@@ -270,8 +277,7 @@ class GraphedTrainStep:
         else:
             pred = self.model(d)
             loss, _ = m.loss(pred, d.y, self.head_index)
-        loss.backward()
-        self.opt.gather_grads()
+        self.opt.backward(loss)
         self.loss = loss.detach()
 
     def refill(self, data):

@@ -365,3 +365,21 @@ def test_c4_and_c5_synthetic_workloads_and_multihead_indices():
     kw = dict(ARCH["gfm_pnaeq_mini"], pna_deg=[0, 3, 5, 9])
     g = hb.create_model(use_gpu=False, **kw)
     assert str(g) == "Base" and type(g).__name__ == "PNAEqStack" and g.use_global_attn and len(g.graph_convs) == 3
+
+
+def test_padded_batch_filler_layout():
+    """host side of the capacity-padded step (hydragnn_b200/padded.py): unused graph slots get two filler atoms each, the last
+    one the remainder; ptr / batch stay sorted and consistent; a batch that does not fit raises."""
+    from hydragnn_b200.padded import filler_layout, supported
+    bvec = torch.tensor([0, 0, 0, 1, 1, 2, 2, 2, 2])
+    ptr, bfull, fill = filler_layout(bvec, 3, n_cap=20, g_cap=6)
+    assert ptr.tolist() == [0, 3, 5, 9, 11, 13, 20] and fill == 11
+    assert bfull.tolist() == bvec.tolist() + [3, 3, 4, 4] + [5] * 7 and bool((bfull[1:] >= bfull[:-1]).all())
+    with pytest.raises(ValueError):
+        filler_layout(bvec, 3, n_cap=12, g_cap=6)          # 3 unused slots need 6 filler atoms
+    with pytest.raises(ValueError):
+        filler_layout(bvec, 3, n_cap=20, g_cap=3)          # no filler graph
+    m = hb.create_model(use_gpu=False, **ARCH["qm9_painn"])
+    assert supported(m)
+    kw = dict(ARCH["gfm_pnaeq_mini"], pna_deg=[0, 3, 5, 9])
+    assert not supported(hb.create_model(use_gpu=False, **kw))                        # global attention: filler atoms would leak

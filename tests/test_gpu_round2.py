@@ -602,3 +602,42 @@ def test_mace_edge_embed_kernel_matches_aten_glue_and_oracle(lmax):
     v32 = (pos[ei[1]] - pos[ei[0]] + shifts).to(DEV)
     sh_a = ee3.spherical_harmonics_cl(lmax, v32 / v32.norm(dim=1, keepdim=True))
     assert rel_l2(sh_e.detach(), sh_a) < 2e-6
+
+
+# ---- weight gradients on a side stream (ops.fork_join): same bits as the single-stream order -------------------------------------
+@pytest.mark.parametrize("name,g,prec", [("qm9_painn", 512, "bf16"), ("qm9_painn", 512, "fp32"), ("md17_egnn", 64, "fp32"),
+                                         ("oc20_mace", 2, "fp32"), ("gfm_pnaeq", 4, "fp32")])
+@pytest.mark.parametrize("deferred", [False, True])
+def test_side_stream_weight_gradients_equal_single_stream(name, g, prec, deferred, monkeypatch):
+    """Deferred joins (leaf parameters, inside ops.deferred_weight_gradients = FlatAdamW.backward) and immediate joins (derived
+    weights, or outside that context) must both hand over finished gradients: every kernel is deterministic, so the gradients with
+    and without the side stream agree bit for bit, repeatedly (5 passes, the caching allocator reusing freed blocks across streams
+    and autograd accumulating residual-branch gradients in place in between)."""
+    import contextlib
+    cpu = add_edges_cpu(make_samples(name, g), name)
+    gpu = _gpu_batch(cpu, name, g)
+    kw = arch_for(name, cpu)
+    em = hb.set_precision(hb.create_model(**kw).to(DEV), prec)
+    hi = [h.to(DEV) for h in hb.get_head_indices(em, gpu)]
+    mlip = bool(kw.get("enable_interatomic_potential"))
+
+    def grads():
+        em.zero_grad(set_to_none=True)
+        torch.manual_seed(7)                                     # the GPS layers draw dropout masks (train mode): same masks every pass
+        if mlip:
+            gpu.pos.requires_grad_(True)
+            loss, _ = em.energy_force_loss(em(gpu), gpu)
+        else:
+            loss, _ = em.loss(em(gpu), gpu.y, hi)
+        with (ops.deferred_weight_gradients() if deferred else contextlib.nullcontext()):
+            loss.backward()
+        return {k: p.grad.clone() for k, p in em.named_parameters() if p.grad is not None}
+
+    monkeypatch.setattr(ops, "WGRAD_OVERLAP", False)
+    want = grads()
+    monkeypatch.setattr(ops, "WGRAD_OVERLAP", True)
+    for _ in range(5):
+        got = grads()
+        assert set(got) == set(want)
+        for k in want:
+            assert torch.equal(got[k], want[k]), k
