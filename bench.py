@@ -218,6 +218,17 @@ def run_reference(args):
 # -----------------------------------------------------------------------------------------------------------
 # per-entry-point algorithmic bytes (fp32 storage), used for the roofline of the dominant kernel
 # -----------------------------------------------------------------------------------------------------------
+def _alg_flops(entry, a, ctx):
+    """ALGORITHMIC flops of the entries that are tensor- / FMA-bound rather than HBM-bound (None otherwise)."""
+    if entry == "hgb_mha_tc_fwd":             # S = Q K^T and O = P V over ONE dense sequence of n tokens: 2 n^2 f each
+        return 4.0 * a["n"] * a["n"] * a["f"]
+    if entry == "hgb_mha_tc_bwd":             # S again, dP = dO V^T, dV = P^T dO, dQ = dS K, dK = dS^T Q
+        return 10.0 * a["n"] * a["n"] * a["f"]
+    if entry in ("hgb_egnn_edge_fwd", "hgb_egnn_edge_bwd_data", "hgb_egnn_edge_wgrad"):
+        return 2.0 * ctx["E"] * a["h"] * a["h"]
+    return None
+
+
 def _alg_bytes(entry, a, ctx):
     """ALGORITHMIC bytes of one C-ABI call (DESIGN.md section 4 lists every formula).  ``a``: argument dict by header name."""
     N, E = ctx["N"], ctx["E"]
@@ -253,8 +264,10 @@ def _alg_bytes(entry, a, ctx):
         return 4 * a["count"] * 3
     if entry == "hgb_adamw_step":
         return 4 * a["count"] * 7
-    if entry in ("hgb_egnn_edge_fwd", "hgb_egnn_edge_bwd"):
-        return ctx.get("egnn_edge_bytes", lambda *_: None)(entry, a)
+    if entry == "hgb_egnn_edge_fwd":          # per edge: Q[col] row gathered + s, nbr, perm + the two mask words; per node: PQ read, sums written
+        return E * (4 * a["h"] + 28) + a["n"] * 3 * a["h"] * 4
+    if entry in ("hgb_egnn_edge_bwd_data", "hgb_egnn_edge_wgrad"):    # per edge: gz1 written (bwd) / Q[col] gathered (wgrad) + masks, s, perm
+        return E * (4 * a["h"] + 28) + a["n"] * 2 * a["h"] * 4
     if entry == "hgb_mace_tp_scatter_fwd":
         return None
     return None
@@ -391,13 +404,13 @@ def run_engine(args):
         one_graph = ws == 1 or capture_ar
         for d, hi, sz in zip(devb, hidx, sizes):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with ops.capture_graph(g):
                 l = step(d, hi, known=sz, with_opt=one_graph)
             graphs.append(g)
             losses.append(l)
         if not one_graph:
             g_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_opt):
+            with ops.capture_graph(g_opt):
                 opt.step(1.0 / ws)
 
     loss_host = torch.zeros(1).pin_memory()
@@ -572,15 +585,22 @@ def kernel_shares_and_roofline(step_fn, _lib, args, N, E, G):
     C-ABI call that launched them), and the roofline object of the DOMINANT one: achieved = its algorithmic bytes / its
     measured device time.  Measured outside the timed regions."""
     from torch.profiler import ProfilerActivity, profile
+    from hydragnn_b200 import ops as _ops
     hbm, tf, src = peaks()
-    for _ in range(2):
-        step_fn()
-    torch.cuda.synchronize()
-    _lib.trace_begin()
-    with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        step_fn()
+    # one stream for this step: with the weight-gradient kernels on their side stream two kernels share the SMs, their CUPTI
+    # durations stretch and start order != launch order; per-kernel figures are of the kernel running alone, like ncu's.
+    overlap, _ops.WGRAD_OVERLAP = _ops.WGRAD_OVERLAP, False
+    try:
+        for _ in range(2):
+            step_fn()
         torch.cuda.synchronize()
-    calls = _lib.trace_end()                               # [(entry, {arg: value}, n_kernel_launches)]
+        _lib.trace_begin()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step_fn()
+            torch.cuda.synchronize()
+        calls = _lib.trace_end()                               # [(entry, {arg: value}, n_kernel_launches)]
+    finally:
+        _ops.WGRAD_OVERLAP = overlap
     kern = [e for e in prof.events() if getattr(e, "device_type", None) is not None and "cuda" in str(e.device_type).lower()
             and e.name and not e.name.lower().startswith(("memcpy", "memset"))]
     kern.sort(key=lambda e: e.time_range.start)
@@ -597,6 +617,7 @@ def kernel_shares_and_roofline(step_fn, _lib, args, N, E, G):
     top_names = sorted(by_name.items(), key=lambda kv: -kv[1][0])[:12]
     shares = {"total_kernel_us": round(tot_us, 1), "libhgb_share": round(sum(e.time_range.elapsed_us() for e in ours) / max(tot_us, 1e-9), 4),
               "aten_share": round(sum(e.time_range.elapsed_us() for e in kern if is_aten(e.name)) / max(tot_us, 1e-9), 4),
+              "streams": "profiled step on ONE stream (side-stream weight gradients off); the timed steps overlap them",
               "by_kernel": [{"kernel": k, "us": round(v[0], 1), "launches": v[1], "share": round(v[0] / max(tot_us, 1e-9), 4)} for k, v in top_names]}
     # attribute our kernels to the C-ABI calls in launch order
     n_expected = sum(c[2] for c in calls)
@@ -607,9 +628,13 @@ def kernel_shares_and_roofline(step_fn, _lib, args, N, E, G):
         for entry, a, nl in calls:
             us = sum(e.time_range.elapsed_us() for e in ours[pos:pos + nl])
             pos += nl
-            t = by_entry.setdefault(entry, {"us": 0.0, "calls": 0, "bytes": 0, "unknown": False})
+            t = by_entry.setdefault(entry, {"us": 0.0, "calls": 0, "bytes": 0, "unknown": False, "flops": 0.0})
             t["us"] += us
             t["calls"] += 1
+            try:
+                t["flops"] += _alg_flops(entry, a, ctx) or 0.0
+            except Exception:                                  # noqa: BLE001 -- a reporting extra must never break the bench line
+                pass
             b = _alg_bytes(entry, a, ctx)
             if b is None:
                 t["unknown"] = True
@@ -620,6 +645,9 @@ def kernel_shares_and_roofline(step_fn, _lib, args, N, E, G):
                                "achieved_GBps": None if v["unknown"] or v["us"] == 0 else round(v["bytes"] / v["us"] * 1e-3, 1),
                                "frac_of_hbm_peak": None if v["unknown"] or v["us"] == 0 else round(v["bytes"] / v["us"] * 1e-3 / hbm, 4)}
                               for k, v in ranked[:12]]
+        for row, (k, v) in zip(shares["by_entry"], ranked[:12]):
+            if v["flops"] and v["us"]:
+                row["achieved_TFLOPs"] = round(v["flops"] / v["us"] * 1e-6, 2)       # algorithmic flops / device time
         top, tv = ranked[0]
         ach = None if tv["unknown"] else tv["bytes"] / tv["us"] * 1e-3
         roof = {"kernel": top, "selection": "largest share of the step's GPU time (%.1f %%), CUPTI kernel durations of one eager step" %
@@ -627,6 +655,17 @@ def kernel_shares_and_roofline(step_fn, _lib, args, N, E, G):
                 "frac": None if ach is None else ach / hbm, "traffic": None, "peak_source": src,
                 "algorithmic_bytes_per_launch": None if tv["unknown"] else tv["bytes"] / tv["calls"], "ms_per_launch": tv["us"] / tv["calls"] * 1e-3,
                 "launches_per_step": tv["calls"]}
+        if tv["flops"] and tv["us"]:
+            tfs = tv["flops"] / tv["us"] * 1e-6
+            roof["algorithmic_flops_per_launch"] = tv["flops"] / tv["calls"]
+            roof["achieved_TFLOPs"] = tfs
+            if top.startswith("hgb_mha_tc"):
+                # attention: no [n, n] matrix in HBM, the kernel is bound by the tensor / SFU pipes.  Peak = the measured dense bf16
+                # throughput / 2 (TF32 runs at half the bf16 rate); the fp32 configs issue three MMAs per product (3xTF32 split)
+                roof.update({"bound": "tensor", "achieved": tfs, "peak": tf / 2, "unit": "TFLOP/s", "frac": tfs / (tf / 2),
+                             "note": "algorithmic flops (4 n^2 f forward, 10 n^2 f backward); legacy mma.sync m16n8k8 TF32, 3 MMAs per product in fp32 mode"})
+            else:
+                roof["note"] = "SIMT fp32 FMA tile GEMMs (2 E H^2 flops): FMA-issue bound, HBM fraction reported on the algorithmic bytes"
     else:
         shares["attribution"] = "kernel count mismatch (%d traced launches vs %d profiled kernels): per-entry table skipped" % (n_expected, len(ours))
         roof = {"kernel": top_names[0][0] if top_names else None, "bound": "hbm", "achieved": None, "peak": hbm, "unit": "GB/s", "frac": None,

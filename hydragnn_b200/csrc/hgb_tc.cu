@@ -155,11 +155,9 @@ struct LinParams {
                         //    products hi*hi + lo*hi + hi*lo (3xTF32); four extra warps (10..13) split the A stages in shared memory
 };
 
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// round to TF32 (10 mantissa bits), nearest, ties away from zero -- what cvt.rna.tf32.f32 does, as two full-rate integer
+// instructions (the splitter warps run this on every operand element)
+__device__ __forceinline__ float tf32_rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
 constexpr int TILE_M = 128;
 
@@ -437,48 +435,65 @@ __global__ void __launch_bounds__(448, 1) tc_linear_kernel(const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // weight gradient: dW[NO, KO] (+ db[NO]) = sum_m dZ[m, NO]^T X[m, KO]
 // ------------------------------------------------------------------------------------------------
-constexpr int WG_ROWS = 64;            // rows of dZ / X per pipeline stage (8 MMA k-steps of 8 rows)
-constexpr int WG_CHUNK = WG_ROWS * 128;  // one [64 x 32 fp32] slab = 8 KB
-
 struct WgParams {
   int m, no, ko;
-  int chunks_per_cta;   // number of 64-row chunks each CTA reduces
+  int chunks_per_cta;   // number of `rows`-row chunks each CTA reduces
   int stages;
   int tmem_cols;
   int mblocks;          // ceil(no / 128)
   int nmma;             // ko + 16 (ones columns for the bias gradient)
+  int rows;             // rows of dZ / X per pipeline stage (a multiple of 8: one MMA k-step = 8 rows): 32, or 16 when the stage is big
+  int split;            // 1: fp32-accurate mode -- both operands are split into TF32 hi / lo twins in shared memory (warps 2..5, before
+                        //    they turn into the epilogue) and every k-step runs hi*hi + lo*hi + hi*lo
+  int nhh;              // split mode: TMEM accumulators the hi*hi products rotate through (the two cross terms own one more).  The
+                        //    tensor core truncates when it adds into the accumulator, so short chains of large terms keep the sum accurate
   float* part;          // [gridDim.x, no, ko + 1]
 };
 
-__global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz,
+__device__ __forceinline__ void split_f4(float4* hi_p, float4* lo_p) {
+  const float4 v = *hi_p;
+  float4 h, l;
+  h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+  l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+  *hi_p = h;
+  *lo_p = l;
+}
+
+__global__ void __launch_bounds__(320, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz,
                                                           const __grid_constant__ CUtensorMap tmap_x, const WgParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int R = p.rows;
+  const uint32_t CH = (uint32_t)R * 128;       // one [R x 32 fp32] slab
   const int a_chunks = p.mblocks * 4;          // allocated MN slabs of the A operand (>= no/32; the tail is never read back)
   const int b_chunks = (p.ko >> 5) + 1;        // + the ones slab
-  const uint32_t stage_bytes = (uint32_t)(a_chunks + b_chunks) * WG_CHUNK;
+  const uint32_t hi_bytes = (uint32_t)(a_chunks + b_chunks) * CH;
+  const uint32_t lo_bytes = p.split ? (uint32_t)(a_chunks + (p.ko >> 5)) * CH : 0u;   // lo twins (the ones slab has none: lo(1) = 0)
+  const uint32_t stage_bytes = hi_bytes + lo_bytes;
   const int S = p.stages;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
   uint64_t* empty = full + S;
-  uint64_t* done = empty + S;
+  uint64_t* full2 = empty + S;                 // split mode: "stage s is split" (the four splitter warps arrive)
+  uint64_t* done = full2 + S;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(done + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int total_chunks = (p.m + WG_ROWS - 1) / WG_ROWS;
+  const int total_chunks = (p.m + R - 1) / R;
   const int c_beg = blockIdx.x * p.chunks_per_cta;
   const int c_end = min(total_chunks, c_beg + p.chunks_per_cta);
   const int nchunks = max(0, c_end - c_beg);
+  const int KS = R >> 3;                       // MMA k-steps per stage
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(full2 + s, (blockDim.x >> 5) - 2); }
     mbar_init(done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_holder, (uint32_t)p.tmem_cols);
   // ones slab of every stage (all elements equal, so the swizzle does not matter)
   for (int s = 0; s < S; ++s) {
-    float* ones = reinterpret_cast<float*>(smem + (size_t)s * stage_bytes + (size_t)(a_chunks + b_chunks - 1) * WG_CHUNK);
-    for (int i = threadIdx.x; i < WG_CHUNK / 4; i += blockDim.x) ones[i] = 1.0f;
+    float* ones = reinterpret_cast<float*>(smem + (size_t)s * stage_bytes + (size_t)(a_chunks + b_chunks - 1) * CH);
+    for (int i = threadIdx.x; i < (int)(CH / 4); i += blockDim.x) ones[i] = 1.0f;
   }
   fence_proxy_async();
   tc_fence_before();
@@ -486,7 +501,9 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
   const uint32_t idesc = make_idesc(128, p.nmma, 1, 1);
-  const uint32_t tx_bytes = (uint32_t)((p.no >> 5) + (p.ko >> 5)) * WG_CHUNK;
+  const uint32_t idesc_ko = make_idesc(128, p.ko, 1, 1);     // hi(dZ) * lo(X): no ones columns
+  const uint32_t tx_bytes = (uint32_t)((p.no >> 5) + (p.ko >> 5)) * CH;
+  const int nused = min(p.nhh, nchunks * KS);                // hi*hi accumulators this CTA really wrote
 
   if (warp == 0) {
     if (lane == 0) {
@@ -496,9 +513,9 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
         mbar_wait(empty + s, ph ^ 1);
         mbar_expect_tx(full + s, tx_bytes);
         uint8_t* st = smem + (size_t)s * stage_bytes;
-        const int row0 = (c_beg + c) * WG_ROWS;
-        for (int j = 0; j < (p.no >> 5); ++j) tma_load_2d(st + (size_t)j * WG_CHUNK, &tmap_dz, full + s, j * 32, row0);
-        for (int j = 0; j < (p.ko >> 5); ++j) tma_load_2d(st + (size_t)(a_chunks + j) * WG_CHUNK, &tmap_x, full + s, j * 32, row0);
+        const int row0 = (c_beg + c) * R;
+        for (int j = 0; j < (p.no >> 5); ++j) tma_load_2d(st + (size_t)j * CH, &tmap_dz, full + s, j * 32, row0);
+        for (int j = 0; j < (p.ko >> 5); ++j) tma_load_2d(st + (size_t)(a_chunks + j) * CH, &tmap_x, full + s, j * 32, row0);
         if (++s == S) { s = 0; ph ^= 1; }
       }
     }
@@ -507,16 +524,30 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
       int s = 0;
       uint32_t ph = 0;
       const uint32_t base = smem_u32(smem);
+      int it = 0;                                // running k-step of this CTA
       for (int c = 0; c < nchunks; ++c) {
-        mbar_wait(full + s, ph);
+        mbar_wait(p.split ? full2 + s : full + s, ph);
         tc_fence_after();
         const uint32_t st = base + s * stage_bytes;
-#pragma unroll
-        for (int ks = 0; ks < WG_ROWS / 8; ++ks) {
-          const uint64_t bd = make_desc(st + a_chunks * WG_CHUNK + ks * 1024, WG_CHUNK, 512, 1);
-          for (int mb = 0; mb < p.mblocks; ++mb) {
-            const uint64_t ad = make_desc(st + mb * 4 * WG_CHUNK + ks * 1024, WG_CHUNK, 512, 1);
-            umma_tf32(tmem_base + (uint32_t)mb * p.nmma, ad, bd, idesc, (c | ks) != 0);
+        for (int ks = 0; ks < KS; ++ks, ++it) {
+          const uint64_t bd = make_desc(st + a_chunks * CH + ks * 1024, CH, 512, 1);
+          if (!p.split) {
+            for (int mb = 0; mb < p.mblocks; ++mb) {
+              const uint64_t ad = make_desc(st + mb * 4 * CH + ks * 1024, CH, 512, 1);
+              umma_tf32(tmem_base + (uint32_t)mb * p.nmma, ad, bd, idesc, it != 0);
+            }
+          } else {
+            const uint64_t bdl = make_desc(st + hi_bytes + a_chunks * CH + ks * 1024, CH, 512, 1);
+            const int a = it % p.nhh;
+            for (int mb = 0; mb < p.mblocks; ++mb) {
+              const uint64_t ad = make_desc(st + mb * 4 * CH + ks * 1024, CH, 512, 1);
+              const uint64_t adl = make_desc(st + hi_bytes + mb * 4 * CH + ks * 1024, CH, 512, 1);
+              const uint32_t d_hh = tmem_base + (uint32_t)(a * p.mblocks + mb) * p.nmma;
+              const uint32_t d_x = tmem_base + (uint32_t)(p.nhh * p.mblocks + mb) * p.nmma;
+              umma_tf32(d_x, adl, bd, idesc, it != 0);          // lo(dZ) * hi(X | 1)
+              umma_tf32(d_x, ad, bdl, idesc_ko, 1);             // hi(dZ) * lo(X)
+              umma_tf32(d_hh, ad, bd, idesc, it >= p.nhh);      // hi * hi (first use of an accumulator overwrites it)
+            }
           }
         }
         umma_commit(empty + s);
@@ -525,8 +556,30 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
       umma_commit(done);
     }
   } else {
-    // epilogue: after the whole reduction, dump this CTA's partial
+    if (p.split) {
+      // splitter: rewrite the landed stage as TF32 hi (in place) + lo (same swizzled offsets of the twin region)
+      int s = 0;
+      uint32_t ph = 0;
+      const int tl = threadIdx.x - 64, nt = blockDim.x - 64;       // warps 2.. (the launch has 8 of them in split mode)
+      const int nA4 = (p.no >> 5) * (int)(CH / 16), nB4 = (p.ko >> 5) * (int)(CH / 16);
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(full + s, ph);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        float4* ah = reinterpret_cast<float4*>(st);
+        float4* al = reinterpret_cast<float4*>(st + hi_bytes);
+        for (int i = tl; i < nA4; i += nt) split_f4(ah + i, al + i);
+        float4* bh = reinterpret_cast<float4*>(st + (size_t)a_chunks * CH);
+        float4* bl = reinterpret_cast<float4*>(st + hi_bytes + (size_t)a_chunks * CH);
+        for (int i = tl; i < nB4; i += nt) split_f4(bh + i, bl + i);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full2 + s);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+    // epilogue (warps 2..5, one per TMEM lane quarter): after the whole reduction, dump this CTA's partial
     const int q = warp & 3;
+    if (warp < 6) {
     mbar_wait(done, 0);
     tc_fence_after();
     float* part = p.part + (size_t)blockIdx.x * p.no * (p.ko + 1);
@@ -536,6 +589,17 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
       for (int c0 = 0; c0 < p.nmma; c0 += 32) {   // nmma = ko + 16: the last piece is read 32 wide and masked
         float v[32];
         tmem_ld32(taddr + c0, v);
+        if (p.split) {                            // sum of the accumulators, the two cross terms last (ordinary fp32 adds)
+          float t[32];
+          for (int a = 1; a < nused; ++a) {
+            tmem_ld32(taddr + (uint32_t)(a * p.mblocks) * p.nmma + c0, t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += t[j];
+          }
+          tmem_ld32(taddr + (uint32_t)(p.nhh * p.mblocks) * p.nmma + c0, t);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += t[j];
+        }
         if (row < p.no && nchunks > 0) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -550,6 +614,7 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
           }
         }
       }
+    }
     }
   }
   tc_fence_before();
@@ -710,42 +775,56 @@ extern "C" int64_t hgb_tc_wgrad_workspace_bytes(int32_t n_out, int32_t k_out) { 
 
 // dw[no, ko] (row stride lddw) (+)= dz[m, no]^T x[m, ko];  db[no] (+)= column sums of dz (db may be NULL)
 extern "C" int hgb_tc_wgrad(const float* dz, int64_t lddz, const float* x, int64_t ldx, int32_t m, int32_t n_out, int32_t k_out,
-                            float* dw, int64_t lddw, float* db, int32_t accumulate, void* workspace, int64_t workspace_bytes,
-                            hgb_stream_t stream) {
+                            float* dw, int64_t lddw, float* db, int32_t accumulate, int32_t exact, void* workspace,
+                            int64_t workspace_bytes, hgb_stream_t stream) {
   HGB_REQUIRE(dz && x && dw && workspace && m >= 128 && shape_ok(k_out, n_out) && k_out + 16 <= 256,
               "tc_wgrad: unsupported shape m=%d n=%d k=%d", m, n_out, k_out);
   HGB_REQUIRE(lddz % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)dz % 16 == 0) && ((uintptr_t)x % 16 == 0), "tc_wgrad: operands must be 16-byte aligned");
   HGB_REQUIRE(workspace_bytes >= hgb_tc_wgrad_workspace_bytes(n_out, k_out), "tc_wgrad: workspace too small");
-  CUtensorMap tdz, tx;
-  int rc = make_tmap(&tdz, dz, m, n_out, lddz, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-  if (rc) return rc;
-  rc = make_tmap(&tx, x, m, k_out, ldx, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-  if (rc) return rc;
   WgParams p;
   p.m = m; p.no = n_out; p.ko = k_out;
   p.mblocks = (n_out + 127) / 128;
   p.nmma = k_out + 16;
-  p.tmem_cols = pow2_cols(p.mblocks * p.nmma);
+  p.split = exact ? 1 : 0;
+  p.nhh = 1;
+  if (exact) {                                   // (nhh + 1) accumulators + the 16 columns the epilogue's last 32-wide read runs over
+    HGB_REQUIRE(2 * p.mblocks * p.nmma + 16 <= 512, "tc_wgrad: exact mode needs two accumulators in TMEM (n=%d k=%d)", n_out, k_out);
+    p.nhh = (512 - 16) / (p.mblocks * p.nmma) - 1;
+    if (p.nhh > 4) p.nhh = 4;
+  }
+  p.tmem_cols = pow2_cols((exact ? (p.nhh + 1) : 1) * p.mblocks * p.nmma + (exact ? 16 : 0));
   HGB_REQUIRE(p.tmem_cols <= 512, "tc_wgrad: accumulator does not fit TMEM");
   const int a_chunks = p.mblocks * 4, b_chunks = k_out / 32 + 1;
-  const size_t stage_bytes = (size_t)(a_chunks + b_chunks) * WG_CHUNK;
-  int stages = (int)((200 * 1024) / stage_bytes);
-  if (stages > 4) stages = 4;
+  const int slabs = a_chunks + b_chunks + (exact ? a_chunks + k_out / 32 : 0);
+  // TF32: 64-row stages (measured best: 36 us vs 39 us with 32-row stages at the C2 shapes); exact: the stage also holds the lo
+  // twins, so 32 rows, or 16 when three 32-row stages do not fit
+  const size_t budget = exact ? 227 * 1024 - 1024 - 512 : 200 * 1024;
+  int rows = exact ? 32 : 64;
+  if (exact && budget / ((size_t)slabs * rows * 128) < 3) rows = 16;
+  const size_t stage_bytes = (size_t)slabs * rows * 128;
+  int stages = (int)(budget / stage_bytes);
+  if (stages > (exact ? 6 : 4)) stages = exact ? 6 : 4;
   HGB_REQUIRE(stages >= 2, "tc_wgrad: stage does not fit shared memory");
+  p.rows = rows;
   p.stages = stages;
-  const int total_chunks = (m + WG_ROWS - 1) / WG_ROWS;
+  CUtensorMap tdz, tx;
+  int rc = make_tmap(&tdz, dz, m, n_out, lddz, rows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc) return rc;
+  rc = make_tmap(&tx, x, m, k_out, ldx, rows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc) return rc;
+  const int total_chunks = (m + rows - 1) / rows;
   int grid = total_chunks < HGB_NUM_SMS ? total_chunks : HGB_NUM_SMS;
   p.chunks_per_cta = (total_chunks + grid - 1) / grid;
   grid = (total_chunks + p.chunks_per_cta - 1) / p.chunks_per_cta;
   p.part = (float*)workspace;
-  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 1) * 8 + 16;
+  const size_t smem = 1024 + stages * stage_bytes + (3 * stages + 1) * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  tc_wgrad_kernel<<<grid, 192, smem, st>>>(tdz, tx, p);
+  tc_wgrad_kernel<<<grid, exact ? 320 : 192, smem, st>>>(tdz, tx, p);
   HGB_LAUNCH_CHECK("tc_wgrad");
   const int outs = n_out * (k_out + 1);
   tc_wgrad_reduce_kernel<<<(outs + 31) / 32, dim3(32, 8), 0, st>>>(p.part, grid, n_out, k_out, dw, lddw, db, accumulate);

@@ -250,6 +250,14 @@ class tensor_cores:
 
 
 EXACT_TC = os.environ.get("HGB_EXACT_TC", "1") == "1"     # fp32 mode: large-M Linears on tcgen05 with the 3xTF32 split (fp32-accurate)
+EXACT_WGRAD = os.environ.get("HGB_EXACT_WGRAD", "1") == "1"   # ... and their weight gradients (0: SIMT fp32 GEMM)
+
+
+def tc_wgrad_ok(m, n_out, k_out, *tensors):
+    """dW = dZ^T X on the tcgen05 kernel: always in TF32 mode, in fp32 mode when the split variant is enabled"""
+    if not (_TC["enabled"] or (EXACT_TC and EXACT_WGRAD)):
+        return False
+    return k_out + 16 <= 256 and tc_ok(m, n_out, k_out, *tensors)
 
 
 def tc_ok(m, n_out, k_red, *tensors):
@@ -279,13 +287,14 @@ def raw_tc_wgrad(dz, x2, want_bias=True, dw=None, db=None, accumulate=False):
         dw = torch.empty(n_out, k_out, dtype=dz.dtype, device=dz.device)
     if want_bias and db is None:
         db = torch.empty(n_out, dtype=dz.dtype, device=dz.device)
-    piece = 256 if k_out <= 96 else 128             # two pipeline stages of (dz piece + x) must fit shared memory
+    exact = 0 if _TC["enabled"] else 1              # fp32 mode: 3xTF32 split inside the kernel
+    piece = 256 if k_out <= 96 else 128             # the pipeline stages of (dz piece + x) must fit shared memory
     for c0 in range(0, n_out, piece):               # output-feature pieces (independent rows of dw)
         nc = min(piece, n_out - c0)
         nbytes = _lib.query("hgb_tc_wgrad_workspace_bytes", nc, k_out)
         ws = _ws(nbytes, dz.device)
         _lib.call("hgb_tc_wgrad", _p(dz[:, c0:]), dz.stride(0), _p(x2), x2.stride(0), m, nc, k_out, _p(dw[c0:]), dw.stride(0),
-                  _p(db[c0:]) if want_bias else None, int(accumulate), _p(ws), nbytes, _stream())
+                  _p(db[c0:]) if want_bias else None, int(accumulate), exact, _p(ws), nbytes, _stream())
     return dw, db
 
 
@@ -358,6 +367,35 @@ def _side_stream(device):
     if key not in _SIDE:
         _SIDE[key] = torch.cuda.Stream(device=key)
     return _SIDE[key]
+
+
+class capture_graph:
+    """``with capture_graph(g):`` = ``torch.cuda.graph(g)`` with Python's cyclic collector paused for the duration: a collection
+    that runs mid-capture may destroy an older CUDAGraph (or free event-carrying blocks), and those driver calls are not
+    permitted while a global-mode capture is open (seen as a flaky failed capture in a long test session)."""
+
+    def __init__(self, graph, **kw):
+        self.ctx = torch.cuda.graph(graph, **kw)
+
+    def __enter__(self):
+        import gc
+        self.gc_was_on = gc.isenabled()
+        gc.collect()
+        gc.disable()
+        try:
+            return self.ctx.__enter__()
+        except BaseException:
+            if self.gc_was_on:
+                gc.enable()
+            raise
+
+    def __exit__(self, *exc):
+        import gc
+        try:
+            return self.ctx.__exit__(*exc)
+        finally:
+            if self.gc_was_on:
+                gc.enable()
 
 
 _PENDING = {"keys": set(), "leaves": set(), "hold": [], "bytes": 0}
@@ -466,7 +504,7 @@ def linear_bwd_dispatch(dz, x2, w, need_x=True, need_w=True, need_b=True, dx_add
     dx = dw = db = None
     with fork_join(dz, x2, defer_for=leaves) as fj:
         if need_w or need_b:                                                     # side stream: the weight gradient
-            if _TC["enabled"] and tc_ok(m, n, k, dz, x2) and k + 16 <= 256:      # tc_wgrad has no fp32-accurate mode
+            if tc_wgrad_ok(m, n, k, dz, x2):
                 dw, db = fj.side(lambda: raw_tc_wgrad(dz, x2, want_bias=need_b))
             else:
                 dw, db = fj.side(lambda: ((raw_gemm(dz, x2, True, False) if need_w else None), (raw_colsum(dz) if need_b else None)))
@@ -530,11 +568,12 @@ class MatMul(torch.autograd.Function):
         ctx.b_is_weight = bool(b_is_weight)
         a2, b2 = _row_major_2d(a), _row_major_2d(b)
         if ctx.tc or EXACT_TC:      # precision "bf16": plain TF32; "fp32": the 3xTF32 split inside the same kernel (exact flag)
-            if not ta and tb and tc_ok(a2.shape[0], b2.shape[0], a2.shape[1], a2, b2):         # [m,k] x [n,k]^T
+            if not ta and tb and tc_ok(a2.shape[0], b2.shape[0], a2.shape[1], a2):             # [m,k] x [n,k]^T  (the small operand is staged
+                                                                                                 #  by plain loads: any row stride, e.g. a column slice)
                 return raw_tc_linear(a2, b2, False, None, b2.shape[0], a2.shape[1])[0]
-            if not ta and not tb and tc_ok(a2.shape[0], b2.shape[1], a2.shape[1], a2, b2):     # [m,n] x [n,k]
+            if not ta and not tb and tc_ok(a2.shape[0], b2.shape[1], a2.shape[1], a2):         # [m,n] x [n,k]
                 return raw_tc_linear(a2, b2, True, None, b2.shape[1], a2.shape[1])[0]
-            if ctx.tc and ta and not tb and tc_ok(a2.shape[0], a2.shape[1], b2.shape[1], a2, b2) and b2.shape[1] + 16 <= 256:
+            if ta and not tb and tc_wgrad_ok(a2.shape[0], a2.shape[1], b2.shape[1], a2, b2):
                 return raw_tc_wgrad(a2, b2, want_bias=False)[0]                                    # [m,n]^T x [m,k]
         return raw_gemm(a2, b2, ta, tb)
 

@@ -167,11 +167,11 @@ class PaddedGraphStep:
         torch.cuda.synchronize()
         one = self.ws == 1 or self.capture_allreduce
         self.g_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_fb):
+        with ops.capture_graph(self.g_fb):
             self._step_body(one)
         if not one:
             self.g_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_opt):
+            with ops.capture_graph(self.g_opt):
                 self.opt.step(1.0 / self.ws)
         self.opt.flat_p.copy_(keep[0])
         self.opt.m.copy_(keep[1])

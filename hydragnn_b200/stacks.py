@@ -13,7 +13,10 @@ Every conv has two execution modes, selected per forward call:
   differentiated again -- hydragnn/models/create.py:718-724 with ``create_graph=True``): the same math
   composed from the closed primitives GatherRows / SegmentSum / MatMul, with ATen only for elementwise glue.
 """
+import os
+
 import torch
+import torch.nn.functional as F
 from torch import nn
 
 from . import ops
@@ -92,33 +95,78 @@ class _Loss:
         return torch.sqrt(val) if self.sqrt else val
 
 
+PAD_MLP = os.environ.get("HGB_PAD_MLP", "1") == "1"
+PAD_MLP_MIN_ROWS = 32768      # below this the chain is launch-bound and the extra pad / slice kernels cost more than the GEMMs save
+
+
+def _round32(v):
+    return (int(v) + 31) // 32 * 32
+
+
+def _padded_chain(mods, x):
+    """Head MLPs carry the reference's widths (60, 20, 1 / 50, 25 / 200: examples/*.json) that the tensor-core Linear cannot take
+    (multiples of 32).  On many rows the chain is run with every width rounded up to a multiple of 32: weights / biases are
+    zero-padded (tiny, differentiable ``F.pad``), the activations between the layers stay padded, the result is sliced once at the
+    end.  Exact: the padded weight columns are zero, so whatever the activation makes of the padded columns meets a zero weight,
+    and the gradient of the padding is dropped by ``F.pad``'s own backward.  Returns [(weight, bias)] per Linear, or None."""
+    if not (PAD_MLP and x.is_cuda and (ops._TC["enabled"] or ops.EXACT_TC)):
+        return None
+    k0 = x.shape[-1]
+    rows = x.numel() // max(k0, 1)
+    lins = [m for m in mods if isinstance(m, nn.Linear)]
+    if rows < PAD_MLP_MIN_ROWS or not lins or k0 % 32 or not 32 <= k0 <= 1024 or lins[0].in_features != k0:
+        return None
+    if any((not isinstance(m, nn.Linear)) and _act_code(m) is None for m in mods):
+        return None
+    if all(l.out_features % 32 == 0 for l in lins) or any(l.out_features > 1024 for l in lins):
+        return None
+    out, kin = [], k0
+    for l in lins:
+        if l.in_features > kin or _round32(l.in_features) != kin:
+            return None                                   # not a plain chain
+        nout = _round32(l.out_features)
+        w = F.pad(l.weight, (0, kin - l.in_features, 0, nout - l.out_features))
+        b = F.pad(l.bias, (0, nout - l.out_features)) if l.bias is not None else None
+        out.append((w, b))
+        kin = nout
+    return out
+
+
 def run_mlp(seq, x, higher_order=False):
     """Execute an ``nn.Sequential`` of Linear / activation modules on the engine: every Linear (with the
     activation that follows it) is one fused kernel; in any-order mode it is MatMul + ATen glue."""
     mods = list(seq)
+    padded = _padded_chain(mods, x)
+    params = iter(padded) if padded is not None else None
+
+    def wb(lin):
+        return next(params) if params is not None else (lin.weight, lin.bias)
+
     i = 0
     while i < len(mods):
         m = mods[i]
         if isinstance(m, nn.Linear):
             code = _act_code(mods[i + 1]) if i + 1 < len(mods) else None
+            w, b = wb(m)
             if (not higher_order and code is not None and i + 2 < len(mods) and isinstance(mods[i + 2], nn.Linear)):
                 # Linear - act - Linear (- act): one autograd node, activation gradient folded into a GEMM epilogue
-                m2 = mods[i + 2]
+                w2, b2 = wb(mods[i + 2])
                 code2 = _act_code(mods[i + 3]) if i + 3 < len(mods) else None
-                x = ops.mlp2(x, m.weight, m.bias, code[0], code[1], m2.weight, m2.bias, code2[0] if code2 else None,
-                             code2[1] if code2 else 0.0)
+                x = ops.mlp2(x, w, b, code[0], code[1], w2, b2, code2[0] if code2 else None, code2[1] if code2 else 0.0)
                 i += 4 if code2 is not None else 3
                 continue
             if higher_order:
-                x = ops.linear_any_order(x, m.weight, m.bias)
+                x = ops.linear_any_order(x, w, b)
             elif code is not None:
-                x = ops.linear_act(x, m.weight, m.bias, code[0], code[1])
+                x = ops.linear_act(x, w, b, code[0], code[1])
                 i += 1
             else:
-                x = ops.linear_act(x, m.weight, m.bias)
+                x = ops.linear_act(x, w, b)
         else:
             x = m(x)
         i += 1
+    if padded is not None:
+        x = x[..., :[m for m in mods if isinstance(m, nn.Linear)][-1].out_features]
     return x
 
 

@@ -253,7 +253,7 @@ class GraphedTrainStep:
         self.g_opt = None
         self.g_fb = torch.cuda.CUDAGraph()
         one_graph = self.ws == 1 or self.capture_allreduce
-        with torch.cuda.graph(self.g_fb):
+        with ops.capture_graph(self.g_fb):
             self._fwd_bwd()
             if one_graph:
                 if self.ws > 1:
@@ -261,7 +261,7 @@ class GraphedTrainStep:
                 self.opt.step(1.0 / self.ws)
         if not one_graph:
             self.g_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_opt):
+            with ops.capture_graph(self.g_opt):
                 self.opt.step(1.0 / self.ws)
 
     def _fwd_bwd(self):

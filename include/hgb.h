@@ -218,10 +218,12 @@ int hgb_tc_linear(const float* a, int64_t lda, const float* w, int64_t ldw, int3
                   const float* addend, const float* gsrc, int32_t gact, int32_t exact, hgb_stream_t stream);
 /* dw[n_out,k_out] (row stride lddw) (+)= dz[m,n_out]^T . x[m,k_out] and db[n_out] (+)= column sums of dz
  * (db may be NULL) in one pass: both operands are consumed MN-major straight from the row-major tensors, the
- * bias gradient rides along as extra all-ones columns of the B operand.  Deterministic two-stage reduce.      */
+ * bias gradient rides along as extra all-ones columns of the B operand.  Deterministic two-stage reduce.
+ * exact = 1: fp32-accurate (both operands split into TF32 hi / lo twins in shared memory, three products per
+ * k-step, the large products rotating through several TMEM accumulators); exact = 0: plain TF32.             */
 int hgb_tc_wgrad(const float* dz, int64_t lddz, const float* x, int64_t ldx, int32_t m, int32_t n_out,
-                 int32_t k_out, float* dw, int64_t lddw, float* db, int32_t accumulate, void* workspace,
-                 int64_t workspace_bytes, hgb_stream_t stream);
+                 int32_t k_out, float* dw, int64_t lddw, float* db, int32_t accumulate, int32_t exact,
+                 void* workspace, int64_t workspace_bytes, hgb_stream_t stream);
 int64_t hgb_tc_wgrad_workspace_bytes(int32_t n_out, int32_t k_out);
 /* dz = dy * act'(.) evaluated from y (or from z for SiLU, which must then be non-NULL).           */
 int hgb_act_bwd(const float* dy, const float* y, const float* z, int64_t count, int32_t act,

@@ -641,3 +641,85 @@ def test_side_stream_weight_gradients_equal_single_stream(name, g, prec, deferre
         assert set(got) == set(want)
         for k in want:
             assert torch.equal(got[k], want[k]), k
+
+
+# ---- fp32-accurate tensor-core weight gradient (hgb_tc_wgrad, exact = 1) ------------------------------------------------------------
+@pytest.mark.parametrize("m,n,k,shift", [(130, 64, 64, 0.0), (5000, 64, 64, 0.0), (200000, 64, 128, 0.0), (200000, 128, 128, 0.5),
+                                         (60000, 192, 96, 0.5), (33000, 64, 224, 0.0), (9001, 384, 64, 0.5), (400000, 32, 32, 1.0)])
+def test_tc_wgrad_exact_mode_matches_fp64(m, n, k, shift):
+    """fp32 mode: dW = dZ^T X (+ db) on tcgen05 with both operands split into TF32 hi / lo twins in shared memory.  ``shift`` gives
+    the operands a non-zero mean, so every product has the same sign on average and a truncating accumulator would drift -- the
+    kernel rotates the large products through several TMEM accumulators to keep the chains short.  fp32-level agreement with
+    fp64 (the SIMT fp32 GEMM it replaces sits at the same level), bit-identical on repetition, pieces for wide outputs."""
+    g = torch.Generator().manual_seed(m + n + k)
+    dz, x = torch.randn(m, n, generator=g) + shift, torch.randn(m, k, generator=g) + shift
+    dzd, xd = dz.to(DEV), x.to(DEV)
+    assert not ops._TC["enabled"] and ops.tc_wgrad_ok(m, n, k, dzd, xd)
+    hb._lib.trace_begin()
+    dw, db = ops.raw_tc_wgrad(dzd, xd, want_bias=True)
+    calls = [c for c in hb._lib.trace_end() if c[0] == "hgb_tc_wgrad"]
+    assert calls and all(c[1]["exact"] == 1 for c in calls)
+    ref_w, ref_b = dz.double().t() @ x.double(), dz.double().sum(0)
+    e_w, e_b = rel_l2(dw, ref_w), rel_l2(db, ref_b)
+    simt = ops.raw_gemm(dzd, xd, True, False)
+    e_simt = rel_l2(simt, ref_w)
+    assert e_w < max(5e-6, 4 * e_simt), (e_w, e_simt)
+    assert e_b < 5e-6, e_b
+    assert float((dw.double().cpu() - ref_w).abs().max()) <= 2e-5 * float(ref_w.abs().max())
+    dw2, db2 = ops.raw_tc_wgrad(dzd, xd, want_bias=True)
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+    with ops.tensor_cores(True):                                   # the plain TF32 mode of the same kernel, for scale
+        dw32, _ = ops.raw_tc_wgrad(dzd, xd, want_bias=True)
+    assert rel_l2(dw32, ref_w) > 3 * e_w
+    # through autograd: a fused Linear's weight / bias gradients in fp32 mode come from this kernel
+    w = (torch.randn(n, k, generator=g) * 0.2).to(DEV).requires_grad_(True)
+    b = torch.zeros(n, device=DEV, requires_grad=True)
+    hb._lib.trace_begin()
+    (ops.linear_act(xd, w, b) * dzd).sum().backward()
+    assert any(c[0] == "hgb_tc_wgrad" and c[1]["exact"] == 1 for c in hb._lib.trace_end())
+    assert rel_l2(w.grad, ref_w) < max(5e-6, 4 * e_simt) and rel_l2(b.grad, ref_b) < 5e-6
+
+
+# ---- head MLPs with the reference's odd widths on the tensor-core Linear (stacks._padded_chain) --------------------------------------
+@pytest.mark.parametrize("name,g", [("md17_egnn", 256), ("lj_egnn", 256), ("qm9_painn", 4500)])
+def test_zero_padded_head_mlps_equal_the_unpadded_chain(name, g, monkeypatch):
+    """Widths 60 / 20 / 1 (node heads) and 5 (shared graph layers) are rounded up to multiples of 32 with zero-padded weights so the
+    chain runs on hgb_tc_linear; outputs, loss, forces and every parameter gradient (through the MLIP double backward) equal the
+    unpadded SIMT chain to fp32 rounding, and the padded path really is the tensor-core one."""
+    from hydragnn_b200 import stacks
+    cpu = add_edges_cpu(make_samples(name, g), name)
+    gpu = _gpu_batch(cpu, name, g)
+    kw = arch_for(name, cpu)
+    em = hb.create_model(**kw).to(DEV)
+    hi = [h.to(DEV) for h in hb.get_head_indices(em, gpu)]
+    mlip = bool(kw.get("enable_interatomic_potential"))
+
+    monkeypatch.setattr(stacks, "PAD_MLP_MIN_ROWS", 1024)          # the production threshold is 32768 rows
+
+    def run(pad):
+        monkeypatch.setattr(stacks, "PAD_MLP", pad)
+        em.zero_grad(set_to_none=True)
+        hb._lib.trace_begin()
+        if mlip:
+            gpu.pos.requires_grad_(True)
+            pred = em(gpu)
+            loss, _ = em.energy_force_loss(pred, gpu)
+        else:
+            pred = em(gpu)
+            loss, _ = em.loss(pred, gpu.y, hi)
+        loss.backward()
+        calls = hb._lib.trace_end()
+        return [p.detach().clone() for p in pred], loss.detach().clone(), {k: p.grad.clone() for k, p in em.named_parameters()}, calls
+
+    p0, l0, g0, c0 = run(False)
+    p1, l1, g1, c1 = run(True)
+    n_gemm = lambda cs: sum(1 for c in cs if c[0] == "hgb_gemm")            # noqa: E731
+    n_tc = lambda cs: sum(1 for c in cs if c[0] in ("hgb_tc_linear", "hgb_tc_wgrad"))   # noqa: E731
+    assert n_tc(c1) > n_tc(c0) and n_gemm(c1) < n_gemm(c0)
+    for a, b in zip(p1, p0):
+        assert a.shape == b.shape and rel_l2(a, b) < 2e-6
+    assert abs(float(l1) - float(l0)) <= 2e-6 * abs(float(l0))
+    assert set(g0) == set(g1)
+    for k in g0:
+        assert g1[k].shape == g0[k].shape
+        assert rel_l2(g1[k], g0[k]) < 2e-5 or float((g1[k] - g0[k]).abs().max()) < 1e-9, k
