@@ -383,3 +383,47 @@ def test_padded_batch_filler_layout():
     assert supported(m)
     kw = dict(ARCH["gfm_pnaeq_mini"], pna_deg=[0, 3, 5, 9])
     assert not supported(hb.create_model(use_gpu=False, **kw))                        # global attention: filler atoms would leak
+
+
+def test_zero_padded_head_chain_is_the_same_function_on_cpu():
+    """stacks._padded_chain (host logic of the tensor-core head MLPs): the reference's widths 64 -> 60 -> 20 -> 1 are rounded up to
+    multiples of 32 with zero-padded weights / biases; the padded chain, sliced at the end, is the same function of the ORIGINAL
+    parameters: same outputs, same gradients (the padding's gradient is dropped by F.pad's backward), for an activation with
+    act(0) != 0 as well.  The decision itself needs many rows, an aligned input width and at least one odd width."""
+    import torch.nn as nn
+    from hydragnn_b200 import stacks
+
+    class Rows:                      # the decision only looks at the shape of the input (and wants a CUDA tensor)
+        is_cuda = True
+
+        def __init__(self, rows, k):
+            self.shape = (rows, k)
+
+        def numel(self):
+            return self.shape[0] * self.shape[1]
+
+    torch.manual_seed(3)
+    for act in (nn.ReLU, nn.Sigmoid):
+        seq = nn.Sequential(nn.Linear(64, 60), act(), nn.Linear(60, 20), act(), nn.Linear(20, 1))
+        mods = list(seq)
+        assert stacks._padded_chain(mods, Rows(1000, 64)) is None                    # few rows: launch-bound, not worth it
+        assert stacks._padded_chain(mods, Rows(200000, 60)) is None                  # input width is not a multiple of 32
+        assert stacks._padded_chain(list(nn.Sequential(nn.Linear(64, 64), act(), nn.Linear(64, 32))), Rows(200000, 64)) is None
+        assert stacks._padded_chain(mods + [nn.Dropout(0.1)], Rows(200000, 64)) is None   # not a plain Linear / activation chain
+        padded = stacks._padded_chain(mods, Rows(200000, 64))
+        assert [tuple(w.shape) for w, _ in padded] == [(64, 64), (32, 64), (32, 32)]
+        assert [tuple(b.shape) for _, b in padded] == [(64,), (32,), (32,)]
+        x = torch.randn(50, 64)
+        want = seq(x)
+        h = x
+        for i, (w, b) in enumerate(padded):
+            h = torch.nn.functional.linear(h, w, b)
+            if i < 2:
+                h = act()(h)
+        got = h[:, :1]
+        torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-6)
+        gw = torch.autograd.grad(want.square().sum(), list(seq.parameters()))
+        gp = torch.autograd.grad(got.square().sum(), list(seq.parameters()))
+        for a, b in zip(gp, gw):
+            assert a.shape == b.shape
+            torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
